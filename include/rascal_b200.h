@@ -1,0 +1,241 @@
+/*
+ * rascal_b200 — C ABI of the B200-native calibration hot path.
+ *
+ * The reference (rascal v0.3.9) is pure Python and has no FFI; the drop-in
+ * boundary is its Python class API (rascal.calibrator.Calibrator /
+ * HoughTransform).  `rascal_b200/calibrator.py` presents that API and binds the
+ * entry points below with ctypes; a maintainer of the reference would add the
+ * same ctypes stub.  Each entry point cites the reference code
+ * it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer (the caller owns the memory:
+ *     torch tensors in this repo); h_* are host pointers;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - every call returns 0 or a negative rb2_status; nothing throws;
+ *   - every call is batched: a leading `n_problems` dimension, one descriptor
+ *     per problem (an array of plain structs in device memory, pointers inside
+ *     the structs are device pointers);
+ *   - all floating point is IEEE binary64; counts are uint32/int32.
+ */
+#ifndef RASCAL_B200_H
+#define RASCAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB2_ABI_VERSION 1
+#define RB2_MAX_DEG 7       /* polynomial degree of a hypothesis            */
+#define RB2_MAX_SAMPLE 16   /* sample_size + known pairs                    */
+#define RB2_MAX_TOPN 32     /* top_n_candidate                              */
+
+typedef enum {
+  RB2_OK = 0,
+  RB2_ERR_CUDA = -1,        /* a CUDA runtime call failed (see rb2_last_cuda_error) */
+  RB2_ERR_ARG = -2,         /* bad argument                                  */
+  RB2_ERR_CAPACITY = -3,    /* a device-side capacity was exceeded (flag in status word) */
+  RB2_ERR_NO_DEVICE = -4
+} rb2_status;
+
+/* ---- diagnostics ------------------------------------------------------- */
+int rb2_abi_version(void);
+const char *rb2_status_string(int status);
+const char *rb2_last_cuda_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of this). */
+int rb2_sm_count(int *out);
+/* sizeof() of the structs below, in declaration order (0 = rb2_hough_desc ...
+ * 5 = rb2_refit_result); lets a binding verify its layout. */
+int rb2_struct_size(int which);
+
+/* ======================================================================= *
+ * K1  Hough accumulation
+ *     replaces HoughTransform.generate_hough_points (houghtransform.py:60-92)
+ *     and HoughTransform.bin_hough_points (houghtransform.py:167-210), as
+ *     driven by Calibrator.do_hough_transform (calibrator.py:1425-1452).
+ * ======================================================================= */
+typedef struct {
+  double min_slope, max_slope;          /* HoughTransform.set_constraints   */
+  double min_intercept, max_intercept;
+  int32_t n_slopes;                     /* num_slopes                       */
+  int32_t xbins, ybins;                 /* gradient bins, intercept bins    */
+  int32_t n_pairs;
+  const double *d_pair_x;               /* pairs[:,0]  [n_pairs]            */
+  const double *d_pair_y;               /* pairs[:,1]  [n_pairs]            */
+  int32_t *d_lo, *d_hi;                 /* out: surviving slope interval per pair [n_pairs] */
+  double *d_xedges;                     /* out: [xbins+1] == np.histogram2d xedges */
+  double *d_yedges;                     /* out: [ybins+1]                   */
+  uint32_t *d_hist;                     /* out: [xbins*ybins] counts, row-major (x,y) */
+  int32_t *d_rank;                      /* out: [xbins*ybins] flat bin ids, canonical order */
+  int32_t *d_rankpos;                   /* out: [xbins*ybins] inverse of d_rank */
+  int32_t *d_sort_tmp;                  /* scratch: [xbins*ybins]           */
+} rb2_hough_desc;
+
+typedef struct {
+  double icpt_min, icpt_max;            /* min/max of surviving intercepts  */
+  double grad_min, grad_max;            /* min/max of surviving gradients   */
+  int64_t n_points;                     /* number of surviving Hough points */
+  int32_t slope_lo, slope_hi;           /* first/last slope index with survivors */
+  uint32_t max_count;                   /* largest histogram count          */
+  int32_t status;                       /* 0 or RB2_ERR_CAPACITY            */
+} rb2_hough_stats;
+
+/* Pass 1+2+3: intervals -> edges -> histogram -> canonical ranking.
+ * d_stats[n_problems] is written by the call.  slopes_per_cta = 0 lets the
+ * library choose. */
+int rb2_hough_accumulate(int n_problems, const rb2_hough_desc *d_desc,
+                         const rb2_hough_desc *h_desc, rb2_hough_stats *d_stats,
+                         int slopes_per_cta, void *stream);
+
+/* Lazy materialisation of HoughTransform.hough_points: [n_points,2]
+ * (gradient, intercept), slope-major, exactly the reference's row order.
+ * d_slope_off is scratch [n_slopes+2] int64. Needs d_lo/d_hi from
+ * rb2_hough_accumulate. One problem per call. */
+int rb2_hough_points(const rb2_hough_desc *h_desc, int64_t *d_slope_off,
+                     double *d_points, int64_t n_points, void *stream);
+
+/* ======================================================================= *
+ * K2  candidate vote
+ *     replaces Calibrator._get_candidate_points_linear (calibrator.py:219-261)
+ *     + Calibrator._get_most_common_candidates (calibrator.py:154-217),
+ *     including the W[argsort(-agg)] indexing quirk.
+ * ======================================================================= */
+typedef struct {
+  int32_t n_upeaks;                     /* unique peaks, ascending           */
+  int32_t n_uwaves;                     /* unique atlas wavelengths          */
+  int32_t xbins, ybins;
+  int32_t top_n;                        /* top_n_candidate                   */
+  int32_t weighted;                     /* candidate_weighted                */
+  double tol;                           /* fit(candidate_tolerance=)         */
+  double gauss_denom;                   /* 2*sigma**2 + 1e-9 (util.py:447)   */
+  const double *d_upeak_x;              /* [n_upeaks]                        */
+  const int32_t *d_pair_off;            /* [n_upeaks+1] CSR into the arrays below (original pair order inside a peak) */
+  const double *d_pair_y;               /* [n_pairs] wavelength of each pair */
+  const int32_t *d_pair_wid;            /* [n_pairs] id of that wavelength among the sorted unique wavelengths */
+  const double *d_xedges, *d_yedges;    /* from K1                           */
+  const int32_t *d_rankpos;             /* from K1                           */
+  double *d_cand_wave;                  /* out: [n_upeaks*top_n]             */
+  int32_t *d_cand_pair;                 /* out: [n_upeaks*top_n] pair index (global, CSR order) */
+  int32_t *d_cand_n;                    /* out: [n_upeaks] n = min(top_n, #distinct) */
+  double *d_agg;                        /* out: [n_upeaks*n_uwaves] aggregated weight (diagnostic / plotting) */
+  int32_t *d_cnt;                       /* out: [n_upeaks*n_uwaves] hit counts */
+  int32_t *d_status;                    /* out: [1] 0 or RB2_ERR_CAPACITY    */
+} rb2_vote_desc;
+
+int rb2_candidate_vote(int n_problems, const rb2_vote_desc *d_desc,
+                       const rb2_vote_desc *h_desc, void *stream);
+
+/* ======================================================================= *
+ * K3  batched RANSAC hypothesis draw / fit / test / score / reduce
+ *     replaces the loop body of Calibrator._solve_candidate_ransac
+ *     (calibrator.py:525-735): np.random.choice draws (:538-566), polyfit
+ *     (:575), intercept test (:578-582), monotonicity test (:585-600),
+ *     _match_bijective (:317-380), M-SAC cost with the Hough-density weight
+ *     (:610-633) and the best-so-far selection rule (:636, App. A.4).
+ * ======================================================================= */
+typedef struct {
+  /* candidate table (calibrator.py:488-495) */
+  int32_t n_upeaks;                     /* peaks that have candidates, ascending */
+  int32_t n_wids;                       /* distinct candidate wavelengths    */
+  int32_t n_cand;                       /* total candidate entries == d_cand_off[n_upeaks] */
+  int32_t pad0;
+  const double *d_peaks;                /* [n_upeaks]                        */
+  const int32_t *d_cand_off;            /* [n_upeaks+1]                      */
+  const double *d_cand_wave;            /* [n_cand]                          */
+  const int32_t *d_cand_wid;            /* [n_cand] id among sorted distinct candidate wavelengths */
+  const uint32_t *d_cdf32;              /* [n_upeaks] floor(cdf*2^32) of the sampling law (calibrator.py:521-523) */
+  /* known pairs (calibrator.py:569-571) */
+  int32_t n_known;
+  const double *d_known_x, *d_known_y;
+  /* model */
+  int32_t deg;                          /* fit_deg                           */
+  int32_t sample_size;                  /* drawn peaks per hypothesis        */
+  double min_intercept, max_intercept;  /* :578-582                          */
+  double pix_min, pix_max;              /* monotonic grid np.arange(pix_min,pix_max,1), :585-592 */
+  double tol;                           /* ransac_tolerance                  */
+  /* Hough-density weight (calibrator.py:497-506, 614-627) */
+  double hough_weight;
+  double gc_min, gc_max;                /* first / last gradient-bin centre  */
+  double ic_min;                        /* first intercept-bin centre        */
+  double h_lo, h_hi;                    /* spline value at (gc_min, ic_min) / (gc_max, ic_min) */
+  int32_t n_pp;                         /* pieces of the 1-D spline along the first intercept row */
+  const double *d_pp_breaks;            /* [n_pp+1]                          */
+  const double *d_pp_coef;              /* [n_pp*4] c0..c3 in (u - break)    */
+  int32_t n_pix;                        /* len(pixel_list)                   */
+  const double *d_pix;                  /* sorted pixel_list, or NULL == arange(n_pix) */
+  /* acceptance that does not need the refit (calibrator.py:640-649, 684-700) */
+  int32_t min_inliers;                  /* n_inliers >= this (max(deg+1, minimum_matches)) */
+  double min_inliers_frac;              /* n_inliers >= this (minimum_peak_utilisation*len(peaks)) */
+  double cost_ceiling;                  /* cost <= this (1e50, or the prior's cost, :512-515) */
+  double floor_cost;                    /* fall-through: only hypotheses ranked after (floor_cost, floor_id) */
+  int64_t floor_id;                     /* -1 = no floor                     */
+  /* work */
+  int64_t hyp_begin;                    /* first hypothesis id of this call  */
+  int64_t n_hyp;
+  uint64_t seed;                        /* Philox4x32-10 key                 */
+  const int32_t *d_replay_x;            /* [n_hyp*sample_size] peak indices, or NULL -> draw with Philox */
+  const int32_t *d_replay_y;            /* [n_hyp*sample_size] candidate indices inside that peak's list */
+  /* optional per-hypothesis outputs (NULL to skip) */
+  uint8_t *d_out_status;                /* [n_hyp] rb2_hyp_status            */
+  double *d_out_cost;                   /* [n_hyp]                           */
+  double *d_out_weight;                 /* [n_hyp]                           */
+  double *d_out_coeffs;                 /* [n_hyp*(deg+1)]                   */
+  int32_t *d_out_counts;                /* [n_hyp*2] n_match, n_inliers      */
+} rb2_ransac_desc;
+
+typedef enum {
+  RB2_HYP_ABORT = 0,        /* impossible draw, try consumed (:557-566)      */
+  RB2_HYP_INTERCEPT = 1,
+  RB2_HYP_MONOTONIC = 2,
+  RB2_HYP_EMPTY = 3,
+  RB2_HYP_SCORED = 4,
+  RB2_HYP_UNSUPPORTED = 5   /* weight outside the corner-clamped regime      */
+} rb2_hyp_status;
+
+typedef struct {
+  double cost;                          /* +inf when nothing eligible        */
+  int64_t hyp_id;                       /* -1 when nothing eligible          */
+  int32_t n_match, n_inliers;
+  double coeffs[RB2_MAX_DEG + 1];       /* hypothesis coefficients, low order first */
+  uint64_t counters[8];                 /* drawn, aborted, intercept, monotonic, empty, scored, eligible, unsupported */
+} rb2_ransac_result;
+
+/* blocks_per_problem = 0 lets the library choose (a multiple of the SM count
+ * for one problem).  d_block_scratch must hold rb2_ransac_scratch_bytes(). */
+size_t rb2_ransac_scratch_bytes(int n_problems, int blocks_per_problem);
+int rb2_ransac_batch(int n_problems, const rb2_ransac_desc *d_desc,
+                     const rb2_ransac_desc *h_desc, rb2_ransac_result *d_result,
+                     void *d_block_scratch, int blocks_per_problem, void *stream);
+
+/* ======================================================================= *
+ * K4  winner refit + acceptance
+ *     replaces Calibrator._match_bijective on the winner (calibrator.py:317-380),
+ *     the inlier selection (:640-643), models.robust_polyfit (models.py:70-123;
+ *     solved to the exact Huber optimum) and the residual / rms /
+ *     minimum_fit_error check (:664-679).
+ * ======================================================================= */
+typedef struct {
+  double coeffs[RB2_MAX_DEG + 1];       /* refit coefficients, low order first */
+  double rms;                           /* sqrt(mean(clipped residual^2))    */
+  int32_t n_inliers;
+  int32_t accepted;                     /* 1 if rms >= minimum_fit_error     */
+  int32_t huber_iters;                  /* 0 = pure least squares (all |r|<=1) */
+  int32_t pad;
+} rb2_refit_result;
+
+/* d_matched_x / d_matched_y / d_residual: [n_problems * max_upeaks] outputs
+ * (inliers sorted by wavelength, first n_inliers entries valid). */
+int rb2_refit_winners(int n_problems, const rb2_ransac_desc *d_desc,
+                      const rb2_ransac_desc *h_desc,
+                      const rb2_ransac_result *d_winner, double minimum_fit_error,
+                      rb2_refit_result *d_out, double *d_matched_x,
+                      double *d_matched_y, double *d_residual, int max_upeaks,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RASCAL_B200_H */

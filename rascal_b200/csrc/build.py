@@ -1,0 +1,62 @@
+"""Build librascal_b200.so (sm_100a only) in-tree with nvcc.
+
+    python -m rascal_b200.csrc.build
+
+The shared library lands next to the package (rascal_b200/librascal_b200.so) so
+it travels with the repo snapshot to the GPU box; nothing is JIT-compiled at
+import time.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "librascal_b200.so")
+SOURCES = ["abi.cu", "hough.cu", "vote.cu", "ransac.cu", "refit.cu"]
+HEADERS = ["common.cuh", os.path.join(PKG, "..", "include", "rascal_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--fmad=true",  # bit-exact paths use explicit __dmul_rn/__dadd_rn intrinsics
+]
+
+
+def _stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(HERE, s) for s in SOURCES] + [
+        h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objs = []
+    procs = []
+    bdir = os.path.join(HERE, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    for s in SOURCES:
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {s}")
+    cmd = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,517 @@
+// K1 — Hough accumulation for sm_100a.
+//
+// Replaces HoughTransform.generate_hough_points (houghtransform.py:60-92) and
+// HoughTransform.bin_hough_points (houghtransform.py:167-210) of the reference.
+//
+// The reference materialises all S*P (slope, pair) intercepts, masks them and
+// histograms the survivors.  Here nothing is materialised:
+//
+//   pass 1  hough_interval_kernel   per pair, the surviving slopes form ONE
+//           contiguous index interval [lo, hi] because fl(y - fl(s*x)) is
+//           monotone in the slope index; both ends are found by binary search
+//           with the reference's own arithmetic, so the decision is bit-exact.
+//           The data-dependent histogram range (np.histogram2d uses min/max of
+//           the survivors) falls out of the interval ends.
+//   pass 2  hough_edges_kernel      np.linspace edges, bit-exact; zero hist.
+//   pass 3  hough_bin_kernel        each CTA owns a contiguous slope range =
+//           a few whole gradient rows -> a private shared-memory sub-histogram;
+//           a thread walks one pair's surviving slopes, its intercept bin moves
+//           monotonically, and runs of equal bins are flushed with ONE shared
+//           atomicAdd(count) (thread-level run-length aggregation).  Work is
+//           N survivors (~15 % of S*P), not S*P.
+//   pass 4  hough_rank_kernel       canonical ranking of ALL bins (count
+//           descending, ties by descending flat index) = stable LSD radix sort.
+//
+// Lazy: hough_points materialisation in the reference's exact row order.
+#include "common.cuh"
+
+namespace rb2 {
+
+struct SlopeGen {
+  Linspace ls;
+  __device__ SlopeGen(const rb2_hough_desc& d) : ls(d.min_slope, d.max_slope, d.n_slopes) {}
+  __device__ __forceinline__ double at(int i) const { return ls.at(i); }
+};
+
+__global__ void hough_init_stats_kernel(rb2_hough_stats* stats, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rb2_hough_stats s;
+  s.icpt_min = CUDART_INF;
+  s.icpt_max = -CUDART_INF;
+  s.grad_min = 0.0;
+  s.grad_max = 0.0;
+  s.n_points = 0;
+  s.slope_lo = 0x7fffffff;
+  s.slope_hi = -1;
+  s.max_count = 0;
+  s.status = 0;
+  stats[i] = s;
+}
+
+// ---- pass 1 ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hough_interval_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int S = d.n_slopes;
+  SlopeGen sg(d);
+
+  int lo = 1, hi = 0;  // empty
+  double cmin = CUDART_INF, cmax = -CUDART_INF;
+  if (p < d.n_pairs) {
+    const double x = d.d_pair_x[p];
+    const double y = d.d_pair_y[p];
+    const double mn = d.min_intercept, mx = d.max_intercept;
+    auto icpt = [&](int i) { return sub(y, mul(sg.at(i), x)); };
+    // c(i) is non-increasing in i for x >= 0, non-decreasing for x < 0.
+    // In-range set {i : mn <= c(i) <= mx} is an interval [lo, hi].
+    const bool dec = !(x < 0.0);
+    // lo = first i with "entered": dec ? c <= mx : c >= mn
+    int a = 0, b = S;  // search in [0, S]
+    while (a < b) {
+      int m = (a + b) >> 1;
+      double c = icpt(m);
+      bool entered = dec ? (c <= mx) : (c >= mn);
+      if (entered) b = m; else a = m + 1;
+    }
+    lo = a;
+    // hi = last i with "not left": dec ? c >= mn : c <= mx
+    a = lo - 1; b = S - 1;  // search last true in [lo, S-1]; a = lo-1 means none
+    while (a < b) {
+      int m = (a + b + 1) >> 1;
+      double c = icpt(m);
+      bool inside = dec ? (c >= mn) : (c <= mx);
+      if (inside) a = m; else b = m - 1;
+    }
+    hi = a;
+    if (lo <= hi) {
+      double c0 = icpt(lo), c1 = icpt(hi);
+      // NaN inputs never survive the reference's mask
+      if (c0 >= mn && c0 <= mx && c1 >= mn && c1 <= mx) {
+        cmax = fmax(c0, c1);
+        cmin = fmin(c0, c1);
+      } else { lo = 1; hi = 0; }
+    }
+    if (lo > hi) { lo = 1; hi = 0; }
+    d.d_lo[p] = lo;
+    d.d_hi[p] = hi;
+  }
+  // block reduction
+  long long cnt = (lo <= hi) ? (long long)(hi - lo + 1) : 0;
+  int slo = (lo <= hi) ? lo : 0x7fffffff;
+  int shi = (lo <= hi) ? hi : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    slo = min(slo, __shfl_xor_sync(0xffffffffu, slo, o));
+    shi = max(shi, __shfl_xor_sync(0xffffffffu, shi, o));
+    cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+    cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+  }
+  if (lane_id() == 0 && cnt > 0) {
+    rb2_hough_stats* s = stats + blockIdx.y;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s->n_points), (unsigned long long)cnt);
+    atomicMin(&s->slope_lo, slo);
+    atomicMax(&s->slope_hi, shi);
+    atomic_min_double(&s->icpt_min, cmin);
+    atomic_max_double(&s->icpt_max, cmax);
+  }
+}
+
+// ---- pass 2 ------------------------------------------------------------------
+// grid (zero_blocks, n_problems): every block helps zeroing the histogram,
+// block x==0 also writes the edges.
+__global__ void __launch_bounds__(256)
+hough_edges_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  const int B = d.xbins * d.ybins;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) d.d_hist[i] = 0u;
+  if (blockIdx.x != 0) return;
+  rb2_hough_stats* s = stats + blockIdx.y;
+  SlopeGen sg(d);
+  double g0, g1, c0, c1;
+  if (s->n_points == 0) {  // numpy: empty sample -> range (0, 1)
+    g0 = 0.0; g1 = 1.0; c0 = 0.0; c1 = 1.0;
+  } else {
+    g0 = sg.at(s->slope_lo);
+    g1 = sg.at(s->slope_hi);
+    c0 = s->icpt_min;
+    c1 = s->icpt_max;
+    if (g0 == g1) { g0 -= 0.5; g1 += 0.5; }  // _get_outer_edges
+    if (c0 == c1) { c0 -= 0.5; c1 += 0.5; }
+  }
+  Linspace lx(g0, g1, d.xbins + 1), ly(c0, c1, d.ybins + 1);
+  for (int i = threadIdx.x; i <= d.xbins; i += blockDim.x) d.d_xedges[i] = lx.at(i);
+  for (int i = threadIdx.x; i <= d.ybins; i += blockDim.x) d.d_yedges[i] = ly.at(i);
+  if (threadIdx.x == 0) {
+    s->grad_min = (s->n_points == 0) ? 0.0 : sg.at(s->slope_lo);
+    s->grad_max = (s->n_points == 0) ? 0.0 : sg.at(s->slope_hi);
+  }
+}
+
+// ---- pass 3 ------------------------------------------------------------------
+// grid (n_chunks, pair_splits, n_problems), dynamic smem:
+//   double ye[ybins+1]; double slope_s[spc]; int row_s[spc]; uint32 sub[cap]
+__global__ void __launch_bounds__(512)
+hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats* __restrict__ stats,
+                 int spc, int sub_cap_words) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const rb2_hough_desc d = descs[blockIdx.z];
+  const rb2_hough_stats st = stats[blockIdx.z];
+  if (st.n_points == 0) return;
+  const int S = d.n_slopes, yb = d.ybins, xb = d.xbins;
+  int s0 = blockIdx.x * spc;
+  int s1 = min(S, s0 + spc);
+  s0 = max(s0, st.slope_lo);
+  s1 = min(s1, st.slope_hi + 1);
+  if (s0 >= s1) return;
+
+  double* ye = reinterpret_cast<double*>(smem_raw);
+  double* slope_s = ye + (yb + 1);
+  int* row_s = reinterpret_cast<int*>(slope_s + spc);
+  unsigned* subh = reinterpret_cast<unsigned*>(row_s + spc + (spc & 1));
+
+  for (int i = threadIdx.x; i <= yb; i += blockDim.x) ye[i] = d.d_yedges[i];
+  SlopeGen sg(d);
+  const double* __restrict__ xe = d.d_xedges;
+  const double inv_wx = (double)xb / (xe[xb] - xe[0]);
+  for (int k = threadIdx.x; k < s1 - s0; k += blockDim.x) {
+    double g = sg.at(s0 + k);
+    slope_s[k] = g;
+    row_s[k] = fix_bin(xe, xb, g, (int)((g - xe[0]) * inv_wx));
+  }
+  __syncthreads();
+  const int row_lo = row_s[0], row_hi = row_s[s1 - s0 - 1];
+  const int rows_cap = max(1, sub_cap_words / yb);
+  const double ye0 = ye[0];
+  const double inv_wy = (double)yb / (ye[yb] - ye0);
+
+  // contiguous pair range of this split
+  const int np = d.n_pairs;
+  const int per = (np + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(np, p0 + per);
+
+  for (int w0 = row_lo; w0 <= row_hi; w0 += rows_cap) {
+    const int w1 = min(row_hi, w0 + rows_cap - 1);
+    const int words = (w1 - w0 + 1) * yb;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) subh[i] = 0u;
+    __syncthreads();
+    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      const int a = max(d.d_lo[p], s0), b = min(d.d_hi[p], s1 - 1);
+      if (a > b) continue;
+      const double x = d.d_pair_x[p], y = d.d_pair_y[p];
+      int cur = -1;
+      unsigned run = 0;
+      int k = -1;
+      for (int i = a; i <= b; ++i) {
+        const int row = row_s[i - s0];
+        if (row < w0 || row > w1) continue;
+        const double c = sub(y, mul(slope_s[i - s0], x));
+        if (k < 0) k = (int)((c - ye0) * inv_wy);
+        k = fix_bin(ye, yb, c, k);
+        const int key = (row - w0) * yb + k;
+        if (key == cur) {
+          ++run;
+        } else {
+          if (run) atomicAdd(&subh[cur], run);
+          cur = key;
+          run = 1;
+        }
+      }
+      if (run) atomicAdd(&subh[cur], run);
+    }
+    __syncthreads();
+    unsigned* gh = d.d_hist + (size_t)w0 * yb;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) {
+      unsigned v = subh[i];
+      if (v) atomicAdd(&gh[i], v);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- pass 4: canonical ranking ----------------------------------------------
+// One CTA (1024 threads) per problem.  Stable LSD radix sort (8-bit digits) of
+// the bins visited in DESCENDING flat index, by DESCENDING count:
+//   == np.argsort(hist.ravel(), kind='stable')[::-1].
+__global__ void __launch_bounds__(1024)
+hough_rank_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+  __shared__ unsigned base[256];
+  __shared__ unsigned tile_tot[256];
+  __shared__ __align__(16) unsigned short wcnt[32][256];
+  __shared__ unsigned red[32];
+  const rb2_hough_desc d = descs[blockIdx.x];
+  const int B = d.xbins * d.ybins;
+  const unsigned* __restrict__ hist = d.d_hist;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // max count -> number of 8-bit passes
+  unsigned mx = 0;
+  for (int i = tid; i < B; i += 1024) mx = max(mx, hist[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    mx = red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) { red[0] = mx; stats[blockIdx.x].max_count = mx; }
+  }
+  __syncthreads();
+  mx = red[0];
+  int passes = 0;
+  while (passes < 4 && (mx >> (8 * passes)) != 0) ++passes;
+
+  if (passes == 0) {
+    for (int e = tid; e < B; e += 1024) d.d_rank[e] = B - 1 - e;
+  }
+  const int* src = nullptr;  // pass 0 reads the implicit reversed identity
+  for (int ps = 0; ps < passes; ++ps) {
+    const int sh = 8 * ps;
+    int* dst = (((passes - 1 - ps) & 1) == 0) ? d.d_rank : d.d_sort_tmp;  // last pass lands in d_rank
+    if (tid < 256) base[tid] = 0;
+    __syncthreads();
+    for (int e = tid; e < B; e += 1024) {
+      const int idx = src ? src[e] : (B - 1 - e);
+      atomicAdd(&base[255u - ((hist[idx] >> sh) & 255u)], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 256 digit counters
+      unsigned v[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[j] = base[lane * 8 + j]; sum += v[j]; }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      unsigned run = incl - sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { base[lane * 8 + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < B; t0 += 1024) {
+      reinterpret_cast<uint4*>(&wcnt[0][0])[tid] = make_uint4(0, 0, 0, 0);  // 16 KB / 1024 threads
+      __syncthreads();
+      const int e = t0 + tid;
+      const bool valid = e < B;
+      int idx = 0;
+      unsigned dg = 0;
+      if (valid) {
+        idx = src ? src[e] : (B - 1 - e);
+        dg = 255u - ((hist[idx] >> sh) & 255u);
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, valid);
+      unsigned rank_in_warp = 0;
+      if (valid) {
+        const unsigned peers = __match_any_sync(act, dg);
+        rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (rank_in_warp == 0) wcnt[warp][dg] = (unsigned short)__popc(peers);
+      }
+      __syncthreads();
+      // exclusive prefix over the 32 warps, per digit; warp w owns digits 8w..8w+7
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int dgt = warp * 8 + j;
+        const unsigned v = wcnt[lane][dgt];
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        wcnt[lane][dgt] = (unsigned short)(incl - v);
+        if (lane == 31) tile_tot[dgt] = incl;
+      }
+      __syncthreads();
+      if (valid) dst[base[dg] + wcnt[warp][dg] + rank_in_warp] = idx;
+      __syncthreads();
+      if (tid < 256) base[tid] += tile_tot[tid];
+      // next iteration's zeroing of wcnt + its barrier orders this update
+    }
+    __syncthreads();
+    src = dst;
+  }
+  __syncthreads();
+  for (int r = tid; r < B; r += 1024) d.d_rankpos[d.d_rank[r]] = r;
+}
+
+// ---- lazy materialisation of hough_points -----------------------------------
+__global__ void hough_slope_count_kernel(const rb2_hough_desc d, long long* __restrict__ off) {
+  // off[i+1] accumulates (#pairs with lo<=i) - (#pairs with hi<i) via a difference array
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.n_pairs) return;
+  int lo = d.d_lo[p], hi = d.d_hi[p];
+  if (lo > hi) return;
+  atomicAdd(reinterpret_cast<unsigned long long*>(&off[lo + 1]), 1ull);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&off[hi + 2]), (unsigned long long)(-1ll));
+}
+
+__global__ void __launch_bounds__(1024)
+hough_slope_scan_kernel(int S, long long* __restrict__ off) {
+  // single block: off[i+1] (difference) -> count[i] -> exclusive offsets in off[0..S]
+  __shared__ long long carry_cnt, carry_off;
+  __shared__ long long wsum[32], wsum2[32];
+  if (threadIdx.x == 0) { carry_cnt = 0; carry_off = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t0 = 0; t0 < S; t0 += 1024) {
+    int i = t0 + threadIdx.x;
+    long long dlt = (i < S) ? off[i + 1] : 0;
+    // inclusive scan of differences -> count[i]
+    long long v = dlt;
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = wsum[lane], iv = w;
+      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+      wsum[lane] = iv - w;
+    }
+    __syncthreads();
+    long long cnt = v + wsum[warp] + carry_cnt;  // count[i]
+    // inclusive scan of counts -> offsets
+    long long c = (i < S) ? cnt : 0;
+    long long u = c;
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += t; }
+    if (lane == 31) wsum2[warp] = u;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = wsum2[lane], iv = w;
+      for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+      wsum2[lane] = iv - w;
+    }
+    __syncthreads();
+    long long incl = u + wsum2[warp] + carry_off;
+    __syncthreads();
+    if (i < S) off[i + 1] = incl;  // exclusive offset of slope i+1
+    if (threadIdx.x == 1023 || i == S - 1) { carry_cnt = cnt; carry_off = incl; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[0] = 0;
+}
+
+// one block per slope (grid-stride); rows ordered by pair index inside a slope
+__global__ void __launch_bounds__(256)
+hough_points_kernel(const rb2_hough_desc d, const long long* __restrict__ off, double* __restrict__ out) {
+  __shared__ int wtot[8];
+  __shared__ long long base;
+  SlopeGen sg(d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = blockIdx.x; s < d.n_slopes; s += gridDim.x) {
+    const long long o0 = off[s], o1 = off[s + 1];
+    if (o0 == o1) continue;
+    const double g = sg.at(s);
+    if (threadIdx.x == 0) base = o0;
+    __syncthreads();
+    for (int p0 = 0; p0 < d.n_pairs; p0 += 256) {
+      const int p = p0 + threadIdx.x;
+      bool in = false;
+      double c = 0.0;
+      if (p < d.n_pairs) {
+        in = (d.d_lo[p] <= s) && (s <= d.d_hi[p]);
+        if (in) c = sub(d.d_pair_y[p], mul(g, d.d_pair_x[p]));
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) wtot[warp] = __popc(bal);
+      __syncthreads();
+      int pre = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { int t = wtot[w]; if (w < warp) pre += t; tot += t; }
+      if (in) {
+        long long r = base + pre + __popc(bal & ((1u << lane) - 1u));
+        out[2 * r] = g;
+        out[2 * r + 1] = c;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) base += tot;
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace rb2
+
+// ---- host entry points -------------------------------------------------------
+extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc, const rb2_hough_desc* h_desc,
+                                    rb2_hough_stats* d_stats, int slopes_per_cta, void* stream_) {
+  using namespace rb2;
+  if (n_problems <= 0 || !d_desc || !h_desc || !d_stats) return RB2_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int sms = 148;
+  if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
+
+  int max_pairs = 0, max_bins = 0, max_slopes = 0, max_yb = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    const rb2_hough_desc& h = h_desc[i];
+    if (h.n_slopes < 1 || h.xbins < 1 || h.ybins < 1 || h.n_pairs < 0) return RB2_ERR_ARG;
+    if (!(h.min_slope <= h.max_slope)) return RB2_ERR_ARG;
+    max_pairs = max(max_pairs, h.n_pairs);
+    max_bins = max(max_bins, h.xbins * h.ybins);
+    max_slopes = max(max_slopes, h.n_slopes);
+    max_yb = max(max_yb, h.ybins);
+  }
+  hough_init_stats_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(d_stats, n_problems);
+  if (max_pairs > 0) {
+    dim3 g1((max_pairs + 255) / 256, n_problems);
+    hough_interval_kernel<<<g1, 256, 0, stream>>>(d_desc, d_stats);
+  }
+  {
+    int zb = max(1, min(64, (max_bins + 256 * 16 - 1) / (256 * 16)));
+    dim3 g2(zb, n_problems);
+    hough_edges_kernel<<<g2, 256, 0, stream>>>(d_desc, d_stats);
+  }
+  if (max_pairs > 0) {
+    // chunking: aim at >= 4 CTAs per SM over the whole batch
+    int pair_splits = 1;
+    int target_chunks = (4 * sms + n_problems - 1) / n_problems;
+    if (target_chunks > max_slopes) {
+      pair_splits = min(8, max(1, target_chunks / max_slopes));
+      pair_splits = min(pair_splits, max(1, max_pairs / 2048));
+      target_chunks = max_slopes;
+    }
+    int spc = slopes_per_cta > 0 ? slopes_per_cta : (max_slopes + target_chunks - 1) / target_chunks;
+    spc = max(1, spc);
+    int n_chunks = (max_slopes + spc - 1) / spc;
+    // shared memory: edges + slope tables + sub-histogram (as large as useful, <= 160 KB)
+    size_t fixed = (size_t)(max_yb + 1) * 8 + (size_t)spc * 8 + (size_t)(spc + (spc & 1)) * 4;
+    size_t want_words = 0;
+    for (int i = 0; i < n_problems; ++i) {
+      const rb2_hough_desc& h = h_desc[i];
+      // rows a chunk can span: spc slopes over >= 1 surviving slope per row, at most xbins
+      size_t rows = (size_t)min(h.xbins, spc);
+      want_words = max(want_words, rows * (size_t)h.ybins);
+    }
+    size_t cap_bytes = 160 * 1024;
+    size_t sub_words = min(want_words, (cap_bytes - min(cap_bytes, fixed)) / 4);
+    if (sub_words < (size_t)max_yb) return RB2_ERR_ARG;  // ybins too large for one row in smem
+    size_t smem = fixed + sub_words * 4;
+    RB2_CHECK(cudaFuncSetAttribute(hough_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g3(n_chunks, pair_splits, n_problems);
+    hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words);
+  }
+  hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+
+extern "C" int rb2_hough_points(const rb2_hough_desc* h_desc, int64_t* d_slope_off, double* d_points,
+                                int64_t n_points, void* stream_) {
+  using namespace rb2;
+  if (!h_desc || !d_slope_off) return RB2_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const rb2_hough_desc d = *h_desc;
+  RB2_CHECK(cudaMemsetAsync(d_slope_off, 0, sizeof(int64_t) * (size_t)(d.n_slopes + 2), stream));
+  if (d.n_pairs == 0 || n_points == 0) return RB2_OK;
+  if (!d_points) return RB2_ERR_ARG;
+  hough_slope_count_kernel<<<(d.n_pairs + 255) / 256, 256, 0, stream>>>(d, (long long*)d_slope_off);
+  hough_slope_scan_kernel<<<1, 1024, 0, stream>>>(d.n_slopes, (long long*)d_slope_off);
+  int sms = 148;
+  rb2_sm_count(&sms);
+  hough_points_kernel<<<min(d.n_slopes, sms * 8), 256, 0, stream>>>(d, (const long long*)d_slope_off, d_points);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}

@@ -1,0 +1,285 @@
+// K2 — candidate vote for sm_100a.
+//
+// Replaces Calibrator._get_candidate_points_linear (calibrator.py:219-261) and
+// Calibrator._get_most_common_candidates (calibrator.py:154-217).
+//
+// The reference loops over ALL B = xbins*ybins ranked bin-centre lines and, for
+// each, tests all P pairs (B*P evaluations; 5e9 for a 1000x1000 histogram).
+// Here one CTA owns one unique peak and one thread one (peak, atlas-line) pair.
+// For a fixed pair and gradient row the predicate
+//       | fl(fl(g*x) + c_j) - lambda | <= tol
+// is monotone in the intercept-bin index j, so the hit bins of the row are one
+// short window that is located directly (float guess + exact fix-up with the
+// reference's own arithmetic): P*xbins window searches instead of B*P tests.
+//
+// Per peak the reference then needs
+//   agg[w]  = sum of Gaussian weights of every hit of wavelength w (any order),
+//   U       = sorted distinct hit wavelengths,  n = min(top_n, |U|),
+//   result  = W[argsort(-agg)[:n]]   -- W = the hit list ordered by (bin rank,
+//             pair order): indices into U applied to W (the App. A.3 quirk).
+// agg is accumulated per thread in a fixed (bin-index) order: deterministic, no
+// atomics on the value path.  Only the first max(j)+1 entries of W are needed:
+// a rank-bucket histogram finds the rank threshold that covers them, a second
+// enumeration collects just those hits and a shared-memory bitonic sort orders
+// them by (rank, pair).
+#include "common.cuh"
+
+namespace rb2 {
+
+constexpr int VOTE_THREADS = 256;
+constexpr int VOTE_NB = 4096;    // rank buckets
+constexpr int VOTE_CAP = 4096;   // collected (rank, pair) keys
+
+struct VoteCtx {
+  const double* ye;   // smem [yb+1]
+  const double* gc;   // smem [xb] gradient-bin centres
+  double hy, x, tol, inv_wy, c_first;
+  int xb, yb;
+};
+
+// Enumerate the hit bins of one pair; f(gi, j, pred) is called for every hit in
+// ascending flat bin index.
+template <class F>
+__device__ __forceinline__ void for_each_hit(const VoteCtx& c, double lam, F&& f) {
+  for (int gi = 0; gi < c.xb; ++gi) {
+    const double gx = mul(c.gc[gi], c.x);
+    // first j whose centre line is within reach: (gx + c_j) - lam >= -tol
+    int j = (int)floor(((lam - gx) - c.tol - c.c_first) * c.inv_wy) - 1;
+    j = max(0, min(c.yb, j));
+    while (j > 0) {  // guess too high: step back while the previous bin is not below the window
+      const double df = sub(add(gx, add(c.ye[j - 1], c.hy)), lam);
+      if (df < -c.tol) break;
+      --j;
+    }
+    for (; j < c.yb; ++j) {
+      const double pred = add(gx, add(c.ye[j], c.hy));
+      const double df = sub(pred, lam);
+      if (df > c.tol) break;
+      if (fabs(df) <= c.tol) f(gi, j, pred);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VOTE_THREADS)
+vote_kernel(const rb2_vote_desc* __restrict__ descs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const rb2_vote_desc d = descs[blockIdx.y];
+  const int u = blockIdx.x;
+  if (u >= d.n_upeaks) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int xb = d.xbins, yb = d.ybins, nw = d.n_uwaves;
+  const int B = xb * yb;
+
+  double* ye = reinterpret_cast<double*>(smem_raw);
+  double* gc = ye + (yb + 1);
+  double* wagg = gc + xb;
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(wagg + nw);
+  int* wcnt = reinterpret_cast<int*>(list + VOTE_CAP);
+  unsigned* rb_hist = reinterpret_cast<unsigned*>(wcnt + nw);
+  __shared__ int sel_wid[RB2_MAX_TOPN];
+  __shared__ int sel_j[RB2_MAX_TOPN];
+  __shared__ double red_v[VOTE_THREADS / 32];
+  __shared__ int red_i[VOTE_THREADS / 32];
+  __shared__ unsigned scan_s[VOTE_THREADS / 32];
+  __shared__ int s_L, s_tb, s_list_n, s_need;
+
+  const double hx = (d.d_xedges[1] - d.d_xedges[0]) / 2;  // houghtransform.py:197
+  const double hy = (d.d_yedges[1] - d.d_yedges[0]) / 2;  // houghtransform.py:198
+  for (int i = tid; i <= yb; i += VOTE_THREADS) ye[i] = d.d_yedges[i];
+  for (int i = tid; i < xb; i += VOTE_THREADS) gc[i] = add(d.d_xedges[i], hx);
+  for (int i = tid; i < nw; i += VOTE_THREADS) { wagg[i] = 0.0; wcnt[i] = 0; }
+  for (int i = tid; i < VOTE_NB; i += VOTE_THREADS) rb_hist[i] = 0u;
+  if (tid == 0) { s_list_n = 0; s_L = 0; }
+  __syncthreads();
+
+  int shift = 0;
+  while ((B >> shift) > VOTE_NB) ++shift;
+
+  VoteCtx c;
+  c.ye = ye; c.gc = gc; c.hy = hy; c.x = d.d_upeak_x[u]; c.tol = d.tol;
+  c.xb = xb; c.yb = yb;
+  c.c_first = ye[0] + hy;
+  c.inv_wy = (double)yb / (ye[yb] - ye[0]);
+
+  const int q0 = d.d_pair_off[u];
+  const int m = d.d_pair_off[u + 1] - q0;
+  const int* __restrict__ rankpos = d.d_rankpos;
+
+  // ---- phase 1: aggregate weights and counts, rank-bucket histogram ----------
+  for (int q = tid; q < m; q += VOTE_THREADS) {
+    const double lam = d.d_pair_y[q0 + q];
+    double agg = 0.0;
+    int cnt = 0;
+    for_each_hit(c, lam, [&](int gi, int j, double pred) {
+      const double t = sub(lam, pred);
+      const double w = exp(-mul(t, t) / d.gauss_denom);  // util.py:447, a = 1.0
+      agg = add(agg, w);
+      ++cnt;
+      atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
+    });
+    if (cnt) {
+      const int wid = d.d_pair_wid[q0 + q];
+      atomicAdd(&wagg[wid], d.weighted ? agg : (double)cnt);
+      atomicAdd(&wcnt[wid], cnt);
+    }
+  }
+  __syncthreads();
+  if (d.d_agg) {
+    for (int i = tid; i < nw; i += VOTE_THREADS) {
+      d.d_agg[(size_t)u * nw + i] = wagg[i];
+      d.d_cnt[(size_t)u * nw + i] = wcnt[i];
+    }
+  }
+  // L = number of distinct hit wavelengths
+  {
+    int l = 0;
+    for (int i = tid; i < nw; i += VOTE_THREADS) l += (wcnt[i] > 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0 && l) atomicAdd(&s_L, l);
+  }
+  __syncthreads();
+  const int L = s_L;
+  const int n = min(min(d.top_n, RB2_MAX_TOPN), L);
+  if (tid == 0) d.d_cand_n[u] = n;
+  if (n == 0) return;
+
+  // ---- phase 2: top-n wavelengths by aggregated weight (stable) --------------
+  for (int k = 0; k < n; ++k) {
+    double bv = -CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < nw; i += VOTE_THREADS) {
+      if (wcnt[i] > 0) {
+        const double v = wagg[i];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < VOTE_THREADS / 32; ++w)
+        if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+      sel_wid[k] = bi;
+      wcnt[bi] = -wcnt[bi];  // mark as taken (still counts as "hit" below via != 0)
+    }
+    __syncthreads();
+  }
+  // U-index of each selected wavelength = number of hit wavelengths with a smaller id
+  for (int k = warp; k < n; k += VOTE_THREADS / 32) {
+    const int wid = sel_wid[k];
+    int cntl = 0;
+    for (int i = lane; i < wid; i += 32) cntl += (wcnt[i] != 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntl += __shfl_xor_sync(0xffffffffu, cntl, o);
+    if (lane == 0) sel_j[k] = cntl;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int need = 0;
+    for (int k = 0; k < n; ++k) need = max(need, sel_j[k] + 1);
+    s_need = need;
+  }
+  __syncthreads();
+  const unsigned need = (unsigned)s_need;
+
+  // ---- phase 3: rank threshold that covers the first `need` entries of W -----
+  {
+    constexpr int PER = VOTE_NB / VOTE_THREADS;
+    unsigned loc[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { loc[j] = rb_hist[tid * PER + j]; sum += loc[j]; }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) scan_s[warp] = incl;
+    __syncthreads();
+    unsigned wpre = 0;
+    for (int w = 0; w < warp; ++w) wpre += scan_s[w];
+    unsigned run = wpre + incl - sum;  // exclusive prefix of this thread's first bucket
+    if (tid == 0) s_tb = VOTE_NB - 1;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const unsigned before = run;
+      run += loc[j];
+      if (before < need && run >= need) s_tb = tid * PER + j;  // unique writer
+    }
+    __syncthreads();
+  }
+  const int tb = s_tb;
+
+  // ---- phase 4: collect hits up to the threshold bucket, sort, pick W[j] ------
+  for (int q = tid; q < m; q += VOTE_THREADS) {
+    const double lam = d.d_pair_y[q0 + q];
+    for_each_hit(c, lam, [&](int gi, int j, double) {
+      const unsigned r = (unsigned)rankpos[gi * yb + j];
+      if ((int)(r >> shift) <= tb) {
+        const int pos = atomicAdd(&s_list_n, 1);
+        if (pos < VOTE_CAP) list[pos] = ((unsigned long long)r << 32) | (unsigned)q;
+      }
+    });
+  }
+  __syncthreads();
+  int ln = s_list_n;
+  if (ln > VOTE_CAP) {
+    if (tid == 0) atomicExch(d.d_status, (int)RB2_ERR_CAPACITY);
+    ln = VOTE_CAP;
+  }
+  int np2 = 1;
+  while (np2 < ln) np2 <<= 1;
+  for (int i = ln + tid; i < np2; i += VOTE_THREADS) list[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += VOTE_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = list[i], b = list[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { list[i] = b; list[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = tid; k < n; k += VOTE_THREADS) {
+    const int q = (int)(list[sel_j[k]] & 0xffffffffu);
+    d.d_cand_wave[(size_t)u * d.top_n + k] = d.d_pair_y[q0 + q];
+    d.d_cand_pair[(size_t)u * d.top_n + k] = q0 + q;
+  }
+}
+
+}  // namespace rb2
+
+extern "C" int rb2_candidate_vote(int n_problems, const rb2_vote_desc* d_desc, const rb2_vote_desc* h_desc,
+                                  void* stream_) {
+  using namespace rb2;
+  if (n_problems <= 0 || !d_desc || !h_desc) return RB2_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int max_up = 0;
+  size_t smem = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    const rb2_vote_desc& h = h_desc[i];
+    if (h.top_n < 1 || h.top_n > RB2_MAX_TOPN || h.xbins < 1 || h.ybins < 1) return RB2_ERR_ARG;
+    max_up = max(max_up, h.n_upeaks);
+    size_t s = (size_t)(h.ybins + 1) * 8 + (size_t)h.xbins * 8 + (size_t)h.n_uwaves * 8 + (size_t)VOTE_CAP * 8 +
+               (size_t)h.n_uwaves * 4 + (size_t)VOTE_NB * 4;
+    smem = max(smem, s);
+  }
+  if (max_up == 0) return RB2_OK;
+  if (smem > 200 * 1024) return RB2_ERR_ARG;
+  RB2_CHECK(cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(max_up, n_problems);
+  vote_kernel<<<grid, VOTE_THREADS, smem, stream>>>(d_desc);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
