@@ -1,0 +1,394 @@
+"""`rascal.calibrator.Calibrator` with the calibration hot path on the B200.
+
+Mirror of the reference class (src/rascal/calibrator.py:20-2324) for the path
+this repo accelerates: same constructor, setters, defaults, attributes, return
+tuples and error behaviour, so user code that does
+
+    c = Calibrator(peaks, spectrum)
+    c.set_hough_properties(...); c.set_ransac_properties(...)
+    c.set_atlas(atlas); c.do_hough_transform(); c.fit(max_tries=..., fit_deg=...)
+
+runs unchanged.  Host Python keeps what the reference keeps on the host
+(property setters :859-1283, pair enumeration :86-133, the RANSAC set-up
+:441-523, result assembly :1673-1715); the arithmetic runs in hand-written
+sm_100a kernels behind the C ABI (include/rascal_b200.h):
+
+    do_hough_transform  -> K1 rb2_hough_accumulate   (houghtransform.py:60-92, 167-210)
+    fit                 -> K2 rb2_candidate_vote     (calibrator.py:154-261)
+                           K3 rb2_ransac_batch       (calibrator.py:525-735)
+                           K4 rb2_refit_winners      (calibrator.py:636-720, models.py:70-123)
+
+There is no CPU fallback; without the built library or a CUDA device every hot
+call raises.
+"""
+from __future__ import annotations
+
+import copy
+import itertools
+import logging
+
+import numpy as np
+from scipy import interpolate
+
+from . import engine
+from .houghtransform import HoughTransform
+
+__all__ = ["Calibrator", "HoughTransform", "LineList"]
+
+
+class LineList:
+    """Minimal stand-in for rascal.atlas.Atlas holding user-supplied lines
+    (atlas.py:206-281 without the air/vacuum conversion).  Any object with
+    ``get_lines()`` and ``__len__`` - including the reference's own Atlas -
+    can be passed to ``Calibrator.set_atlas``."""
+
+    def __init__(self, wavelengths, elements=None, intensities=None):
+        self._lines = [float(w) for w in wavelengths]
+        self._elements = list(elements) if elements is not None else ["?"] * len(self._lines)
+        self._intensities = list(intensities) if intensities is not None else [0] * len(self._lines)
+
+    def get_lines(self):
+        return list(self._lines)
+
+    def get_elements(self):
+        return list(self._elements)
+
+    def get_intensities(self):
+        return list(self._intensities)
+
+    def __len__(self):
+        return len(self._lines)
+
+
+def _keep(new, old, default):
+    """The reference's setter rule: explicit value > previous value > default."""
+    if new is not None:
+        return new
+    return default if old is None else old
+
+
+class Calibrator:
+    def __init__(self, peaks, spectrum=None):
+        self.logger = None
+        self.log_level = None
+        self.peaks = copy.deepcopy(peaks)
+        self.spectrum = copy.deepcopy(spectrum)
+        self.atlas = None
+        self.pix_known = None
+        self.wave_known = None
+        self.hough_lines = None
+        self.hough_points = None
+        self.ht = HoughTransform()
+        self.pairs = []
+        self.num_pix = None
+        self.pixel_list = None
+        self.plotting_library = None
+        self.constrain_poly = None
+        self.num_slopes = self.xbins = self.ybins = None
+        self.min_wavelength = self.max_wavelength = None
+        self.range_tolerance = self.linearity_tolerance = None
+        self.sample_size = self.top_n_candidate = self.linear = self.filter_close = None
+        self.ransac_tolerance = self.candidate_weighted = self.hough_weight = None
+        self.minimum_matches = self.minimum_peak_utilisation = self.minimum_fit_error = None
+        self.matched_peaks = []
+        self.matched_atlas = []
+        self.fit_coeff = None
+        self.candidate_peak = self.candidate_arc = None
+        self.ransac_counters = None
+        self.seed = None
+        self.set_calibrator_properties()
+        self.set_hough_properties()
+        self.set_ransac_properties()
+
+    # ------------------------------------------------------------------ setters
+    def set_calibrator_properties(self, num_pix=None, pixel_list=None, plotting_library=None, seed=None,
+                                  logger_name="Calibrator", log_level="warning"):
+        """calibrator.py:859-982 (plotting-library selection is not part of this package)."""
+        self.logger = logging.getLogger(logger_name)
+        self.logger.propagate = False
+        level = logging.getLevelName(log_level.upper())
+        self.logger.setLevel(level)
+        self.log_level = level
+        if len(self.logger.handlers) == 0:
+            handler = logging.StreamHandler()
+            handler.setFormatter(logging.Formatter(
+                "[%(asctime)s] %(levelname)s [%(filename)s:%(lineno)d] %(message)s",
+                datefmt="%a, %d %b %Y %H:%M:%S"))
+            self.logger.addHandler(handler)
+        if num_pix is not None:
+            self.num_pix = num_pix
+        elif self.num_pix is None:
+            try:
+                self.num_pix = len(self.spectrum)
+            except Exception as e:
+                self.logger.warning(e)
+                self.logger.warning("Neither num_pix nor spectrum is given, it uses 1.1 times max(peaks) as "
+                                    "the maximum pixel value.")
+                self.num_pix = 1.1 * max(self.peaks)
+        if pixel_list is not None:
+            self.pixel_list = np.asarray(pixel_list)
+        elif self.pixel_list is None:
+            self.pixel_list = np.arange(self.num_pix)
+        self.pix_to_rawpix = interpolate.interp1d(self.pixel_list, np.arange(len(self.pixel_list)),
+                                                  fill_value="extrapolate")
+        if seed is not None:
+            self.seed = seed
+            np.random.seed(seed)
+        self.plotting_library = _keep(plotting_library, self.plotting_library, "matplotlib")
+
+    def set_hough_properties(self, num_slopes=None, xbins=None, ybins=None, min_wavelength=None,
+                             max_wavelength=None, range_tolerance=None, linearity_tolerance=None):
+        """calibrator.py:984-1119."""
+        self.num_slopes = int(_keep(num_slopes, self.num_slopes, 2000))
+        self.xbins = _keep(xbins, self.xbins, 100)
+        self.ybins = _keep(ybins, self.ybins, 100)
+        self.min_wavelength = _keep(min_wavelength, self.min_wavelength, 3000.0)
+        self.max_wavelength = _keep(max_wavelength, self.max_wavelength, 9000.0)
+        self.range_tolerance = _keep(range_tolerance, self.range_tolerance, 500)
+        self.linearity_tolerance = _keep(linearity_tolerance, self.linearity_tolerance, 100)
+        # start wavelength +/- tolerance; slope limits over the detector span (:1088-1116)
+        self.min_intercept = self.min_wavelength - self.range_tolerance
+        self.max_intercept = self.min_wavelength + self.range_tolerance
+        span = np.ptp(self.pixel_list)
+        self.min_slope = ((self.max_wavelength - self.range_tolerance - self.linearity_tolerance)
+                          - (self.min_intercept + self.range_tolerance + self.linearity_tolerance)) / span
+        self.max_slope = ((self.max_wavelength + self.range_tolerance + self.linearity_tolerance)
+                          - (self.min_intercept - self.range_tolerance - self.linearity_tolerance)) / span
+        if self.atlas is not None:
+            self._generate_pairs()
+
+    def set_ransac_properties(self, sample_size=None, top_n_candidate=None, linear=None, filter_close=None,
+                              ransac_tolerance=None, candidate_weighted=None, hough_weight=None,
+                              minimum_matches=None, minimum_peak_utilisation=None, minimum_fit_error=None):
+        """calibrator.py:1121-1283."""
+        self.sample_size = _keep(sample_size, self.sample_size, 5)
+        self.top_n_candidate = _keep(top_n_candidate, self.top_n_candidate, 5)
+        self.linear = _keep(linear, self.linear, True)
+        self.filter_close = _keep(filter_close, self.filter_close, False)
+        self.ransac_tolerance = _keep(ransac_tolerance, self.ransac_tolerance, 5)
+        self.candidate_weighted = _keep(candidate_weighted, self.candidate_weighted, True)
+        self.hough_weight = _keep(hough_weight, self.hough_weight, 1.0)
+        if minimum_matches is not None:
+            assert minimum_matches > 0
+        self.minimum_matches = _keep(minimum_matches, self.minimum_matches, 0)
+        if minimum_peak_utilisation is not None:
+            assert minimum_peak_utilisation >= 0 and minimum_peak_utilisation <= 1.0
+        self.minimum_peak_utilisation = _keep(minimum_peak_utilisation, self.minimum_peak_utilisation, 0)
+        if minimum_fit_error is not None:
+            assert minimum_fit_error >= 0
+        self.minimum_fit_error = _keep(minimum_fit_error, self.minimum_fit_error, 1e-4)
+
+    # ------------------------------------------------------------------ atlas / pairs
+    def _generate_pairs(self):
+        """calibrator.py:86-133: peak-major Cartesian product, optional polygon mask."""
+        pairs = [pair for pair in itertools.product(self.peaks, self.atlas.get_lines())]
+        if self.constrain_poly:
+            from scipy.spatial import Delaunay
+
+            px = self.pixel_list.max()
+            valid_area = Delaunay([
+                (0, self.max_intercept + self.candidate_tolerance),
+                (0, self.min_intercept - self.candidate_tolerance),
+                (px, self.max_wavelength - self.range_tolerance - self.candidate_tolerance),
+                (px, self.max_wavelength + self.range_tolerance + self.candidate_tolerance)])
+            mask = valid_area.find_simplex(pairs) >= 0
+            self.pairs = np.array(pairs)[mask]
+        else:
+            self.pairs = np.array(pairs)
+
+    def set_atlas(self, atlas, candidate_tolerance=10.0, constrain_poly=False):
+        """calibrator.py:1399-1423."""
+        self.atlas = atlas
+        self.candidate_tolerance = candidate_tolerance
+        self.constrain_poly = constrain_poly
+        self._generate_pairs()
+
+    def set_known_pairs(self, pix=(), wave=()):
+        """calibrator.py:1507-1550."""
+        pix = np.asarray(pix, dtype="float").reshape(-1)
+        wave = np.asarray(wave, dtype="float").reshape(-1)
+        assert pix.size == wave.size, ValueError(
+            "Please check the length of the input arrays. pix has size {} and wave has size {}.".format(
+                pix.size, wave.size))
+        if not all(isinstance(p, (float, int)) & (not np.isnan(p)) for p in pix):
+            raise ValueError("All pix elements have to be numeric.")
+        if not all(isinstance(w, (float, int)) & (not np.isnan(w)) for w in wave):
+            raise ValueError("All wave elements have to be numeric.")
+        self.pix_known = pix
+        self.wave_known = wave
+
+    # ------------------------------------------------------------------ Hough
+    def do_hough_transform(self, brute_force=False):
+        """calibrator.py:1425-1452."""
+        if len(self.pairs) == 0:
+            logging.warning("pairs list is empty. Try generating now.")
+            self._generate_pairs()
+            if len(self.pairs) == 0:
+                logging.error("pairs list is still empty.")
+        self.ht.set_constraints(self.min_slope, self.max_slope, self.min_intercept, self.max_intercept)
+        if brute_force:
+            self.ht.generate_hough_points_brute_force(self.pairs[:, 0], self.pairs[:, 1])
+        else:
+            self.ht.generate_hough_points(self.pairs[:, 0], self.pairs[:, 1], num_slopes=self.num_slopes)
+        self.ht.bin_hough_points(self.xbins, self.ybins)
+        self.hough_points = _LazyPoints(self.ht)
+        self.hough_lines = self.ht.hough_lines
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, max_tries=500, fit_deg=4, fit_coeff=None, fit_tolerance=5.0, fit_type="poly",
+            candidate_tolerance=2.0, brute_force=False, progress=True):
+        """calibrator.py:1552-1715; returns (fit_coeff, matched_peaks, matched_atlas, rms, residual,
+        peak_utilisation, atlas_utilisation)."""
+        self.max_tries = max_tries
+        self.fit_deg = fit_deg
+        self.fit_coeff = fit_coeff
+        if fit_coeff is not None:
+            self.fit_deg = len(fit_coeff) - 1
+        self.fit_tolerance = fit_tolerance
+        self.fit_type = fit_type
+        self.brute_force = brute_force
+        self.progress = progress
+        if self.fit_type == "poly":
+            self.polyfit = np.polynomial.polynomial.polyfit
+            self.polyval = np.polynomial.polynomial.polyval
+        elif self.fit_type in ("legendre", "chebyshev"):
+            raise NotImplementedError("fit_type '%s' is not on the accelerated path yet" % self.fit_type)
+        else:
+            raise ValueError("fit_type must be: (1) poly, (2) legendre or (3) chebyshev")
+        if brute_force:
+            raise NotImplementedError("brute_force sampling is not supported (it never terminates on a "
+                                      "rejected sample in the reference, calibrator.py:532-534)")
+        if not self.linear:
+            raise NotImplementedError("linear=False (experimental in the reference) is not on the accelerated path")
+        if self.sample_size > len(self.atlas):
+            self.logger.warning("Size of sample_size is larger than the size of atlas, the sample_size is set to "
+                                "match the size of atlas = " + str(len(self.atlas)) + ".")
+            self.sample_size = len(self.atlas)
+        if self.sample_size <= self.fit_deg:
+            self.sample_size = self.fit_deg + 1
+        if (self.hough_lines is None) or (self.hough_points is None):
+            self.do_hough_transform()
+        if self.minimum_matches > len(self.atlas):
+            self.logger.warning("Requested minimum matches is greater than the atlas size, setting the minimum "
+                                "number of matches to equal the atlas size = " + str(len(self.atlas)) + ".")
+            self.minimum_matches = len(self.atlas)
+        if self.minimum_matches > len(self.peaks):
+            self.logger.warning("Requested minimum matches is greater than the number of peaks detected, which "
+                                "has a size of size = " + str(len(self.peaks)) + ".")
+            self.minimum_matches = len(self.peaks)
+
+        fit_coeff, rms, residual, n_inliers, valid = self._solve_candidate_ransac(
+            fit_deg=self.fit_deg, fit_coeff=self.fit_coeff, max_tries=self.max_tries,
+            candidate_tolerance=candidate_tolerance)
+
+        peak_utilisation = n_inliers / len(self.peaks)
+        atlas_utilisation = n_inliers / len(self.atlas)
+        if not valid:
+            self.logger.warning("Invalid fit")
+        if rms > self.fit_tolerance:
+            self.logger.warning("RMS too large {} > {}".format(rms, self.fit_tolerance))
+        assert fit_coeff is not None, "Couldn't fit"
+        self.fit_coeff = fit_coeff
+        self.rms = rms
+        self.residual = residual
+        self.peak_utilisation = peak_utilisation
+        self.atlas_utilisation = atlas_utilisation
+        return (self.fit_coeff, self.matched_peaks, self.matched_atlas, self.rms, self.residual,
+                self.peak_utilisation, self.atlas_utilisation)
+
+    def _vote(self, candidate_tolerance):
+        """K2: _get_candidate_points_linear + _get_most_common_candidates (calibrator.py:154-261)."""
+        sigma = (self.range_tolerance + self.linearity_tolerance) * 1.1775  # :256
+        vb = engine.VoteBatch(self.ht._batch, [dict(
+            pairs=self.pairs, top_n=self.top_n_candidate, weighted=self.candidate_weighted,
+            tol=candidate_tolerance, gauss_denom=2 * sigma ** 2 + 1e-9)]).run()
+        cp, ca = vb.candidates(0)
+        self.candidate_peak, self.candidate_arc = list(cp), list(ca)
+
+    def _solve_candidate_ransac(self, fit_deg, fit_coeff, max_tries, candidate_tolerance):
+        """calibrator.py:382-752 as batched device work (order-independent rule)."""
+        if self.ht._batch is None:
+            raise NotImplementedError("fit() needs a Hough transform computed by do_hough_transform()")
+        self._vote(candidate_tolerance)
+        best = (None, 1e50, None, 0, False)
+        if fit_coeff is not None:
+            raise NotImplementedError("a prior fit_coeff (calibrator.py:512-515) is not on the accelerated path yet")
+        setup = engine.RansacSetup(
+            self.candidate_peak, self.candidate_arc, fit_deg=fit_deg, sample_size=self.sample_size,
+            ransac_tolerance=self.ransac_tolerance, min_intercept=self.min_intercept,
+            max_intercept=self.max_intercept, pixel_list=self.pixel_list, hist=self.ht.hist,
+            xedges=self.ht.xedges, yedges=self.ht.yedges, hough_weight=self.hough_weight,
+            filter_close=self.filter_close, minimum_matches=self.minimum_matches,
+            minimum_peak_utilisation=self.minimum_peak_utilisation, minimum_fit_error=self.minimum_fit_error,
+            n_peaks_total=len(self.peaks), pix_known=self.pix_known, wave_known=self.wave_known)
+        if not setup.enough:  # :468-469
+            return best
+        if self.sample_size >= len(setup.peaks):
+            raise NotImplementedError("sample_size >= number of candidate peaks switches the reference to its "
+                                      "brute-force sampler (calibrator.py:474-477), which is not supported")
+        # Philox key: drawn from the legacy global RNG so that seed= makes the fit reproducible
+        key = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+        rb = engine.RansacBatch([setup])
+        counters = dict.fromkeys(engine.N.COUNTER_NAMES, 0)
+        winner = None
+        done = 0
+        chunk = max(1 << 14, 64 * int(max_tries))
+        # `max_tries` counts completed tries of the reference loop: scored hypotheses (and
+        # impossible draws); rejected draws are redrawn for free (:578-600)
+        while counters["scored"] + counters["aborted"] < int(max_tries) and done < (1 << 40):
+            rb.run(done, chunk, seed=key)
+            r = rb.results()[0]
+            for k, v in engine.counters_dict(r).items():
+                counters[k] += v
+            if r.hyp_id >= 0 and (winner is None or r.cost < winner.cost
+                                  or (r.cost == winner.cost and r.hyp_id > winner.hyp_id)):
+                winner = engine.N.RansacResult.from_buffer_copy(bytes(r))
+            done += chunk
+            if counters["drawn"] == 0 and counters["aborted"] == 0:
+                break
+            chunk = min(chunk * 4, 1 << 28)
+        self.ransac_counters = counters
+        if counters["unsupported"]:
+            self.logger.warning("%d hypotheses left the corner-clamped Hough-weight regime and were skipped",
+                                counters["unsupported"])
+        # refit + refit-dependent acceptance (:652-679); fall through to the next best on failure
+        spans = done
+        for _ in range(16):
+            if winner is None:
+                return best
+            win = engine.N.struct_array(engine.N.RansacResult, 1)
+            win[0] = winner
+            out, mx, my, rs = rb.refit(win)
+            o = out[0]
+            if o.accepted:
+                m = o.n_inliers
+                self.matched_peaks = list(mx[0, :m])
+                self.matched_atlas = list(my[0, :m])
+                assert len(self.matched_atlas) == len(set(self.matched_atlas))
+                coeffs = np.array(o.coeffs[:fit_deg + 1])
+                return coeffs, o.rms, rs[0, :m].copy(), m, m > fit_deg + 1
+            rb.run(0, spans, seed=key, floors=[(winner.cost, winner.hyp_id)])
+            r = rb.results()[0]
+            winner = engine.N.RansacResult.from_buffer_copy(bytes(r)) if r.hyp_id >= 0 else None
+        return best
+
+
+class _LazyPoints:
+    """`Calibrator.hough_points`: materialised from the device on first use."""
+
+    def __init__(self, ht):
+        self._ht = ht
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._ht.hough_points
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, k):
+        return self._ht.hough_points[k]
+
+    def __len__(self):
+        return len(self._ht.hough_points)
+
+    @property
+    def shape(self):
+        return self._ht.hough_points.shape

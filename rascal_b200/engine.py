@@ -1,0 +1,554 @@
+"""Batched device engine: host-side packing + the C-ABI calls (include/rascal_b200.h).
+
+This is the layer between the reference-shaped facade (``calibrator.py`` /
+``houghtransform.py``) and ``librascal_b200.so``.  Every stage takes a *batch* of
+problems (leading ``n_problems`` dimension of the C ABI); a single spectrum is a
+batch of one.  PyTorch is used for device buffers and streams only.
+
+There is no CPU fallback: every entry point raises ``NativeError`` when the
+library is missing or no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+_ALIGN = 32
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise N.NativeError("rascal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def current_stream_ptr():
+    return int(_torch().cuda.current_stream().cuda_stream)
+
+
+class Arena:
+    """One contiguous device buffer assembled on the host.
+
+    ``add(arr)`` stages input data, ``reserve(nbytes)`` leaves room for an
+    output; ``upload()`` moves the staged bytes in ONE host->device copy (from
+    pinned memory) and returns the device base address.  Views of regions come
+    back as torch tensors / numpy arrays.
+    """
+
+    def __init__(self):
+        self._chunks = []  # (offset, ndarray)
+        self.size = 0
+        self.buf = None
+        self.host = None
+        self.h2d_bytes = 0
+
+    def _bump(self, nbytes):
+        off = self.size
+        self.size = (off + int(nbytes) + _ALIGN - 1) // _ALIGN * _ALIGN
+        return off
+
+    def add(self, arr):
+        a = np.ascontiguousarray(arr)
+        off = self._bump(max(a.nbytes, 1))
+        self._chunks.append((off, a))
+        return off
+
+    def reserve(self, nbytes):
+        return self._bump(max(int(nbytes), 1))
+
+    def upload(self, pinned=True):
+        torch = _torch()
+        n = max(self.size, _ALIGN)
+        staged = max((o + a.nbytes for o, a in self._chunks), default=0)
+        self.buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+        if staged:
+            host = torch.empty(staged, dtype=torch.uint8, pin_memory=pinned)
+            hv = host.numpy()
+            for off, a in self._chunks:
+                hv[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
+            self.buf[:staged].copy_(host, non_blocking=True)
+            self.host = host  # keep alive until the copy has run
+            self.h2d_bytes = staged
+        return self.ptr(0)
+
+    def ptr(self, off):
+        return self.buf.data_ptr() + off
+
+    def tensor(self, off, dtype, count):
+        torch = _torch()
+        esz = torch.empty(0, dtype=dtype).element_size()
+        return self.buf[off:off + count * esz].view(dtype)
+
+    def numpy(self, off, np_dtype, count):
+        nbytes = np.dtype(np_dtype).itemsize * count
+        return self.buf[off:off + nbytes].cpu().numpy().view(np_dtype)
+
+
+def _upload_structs(arr):
+    """ctypes struct array -> device uint8 tensor."""
+    torch = _torch()
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.cuda()
+
+
+def _download_structs(tensor, cls, n):
+    raw = tensor.cpu().numpy().tobytes()
+    return (cls * n).from_buffer_copy(raw)
+
+
+# ---------------------------------------------------------------------------
+# K1  Hough accumulation
+# ---------------------------------------------------------------------------
+
+
+class HoughBatch:
+    """Hough accumulate + bin + rank for a batch of spectra (rb2_hough_accumulate).
+
+    problems: sequence of dicts with keys pair_x, pair_y (float64 arrays),
+    min_slope, max_slope, min_intercept, max_intercept, n_slopes, xbins, ybins.
+    """
+
+    def __init__(self, problems):
+        self.lib = N.load()
+        _torch()
+        self.n = len(problems)
+        self.problems = problems
+        ar = Arena()
+        self.arena = ar
+        self.h_desc = N.struct_array(N.HoughDesc, self.n)
+        self._off = []
+        for i, p in enumerate(problems):
+            x = np.asarray(p["pair_x"], dtype=np.float64)
+            y = np.asarray(p["pair_y"], dtype=np.float64)
+            assert x.shape == y.shape and x.ndim == 1
+            P, xb, yb = x.size, int(p["xbins"]), int(p["ybins"])
+            B = xb * yb
+            o = dict(x=ar.add(x), y=ar.add(y), lo=ar.reserve(4 * P), hi=ar.reserve(4 * P),
+                     xe=ar.reserve(8 * (xb + 1)), ye=ar.reserve(8 * (yb + 1)), hist=ar.reserve(4 * B),
+                     rank=ar.reserve(4 * B), rankpos=ar.reserve(4 * B), tmp=ar.reserve(4 * B))
+            self._off.append(o)
+        self.o_stats = ar.reserve(C.sizeof(N.HoughStats) * self.n)
+        base = ar.upload()
+        for i, p in enumerate(problems):
+            o = self._off[i]
+            d = self.h_desc[i]
+            d.min_slope, d.max_slope = float(p["min_slope"]), float(p["max_slope"])
+            d.min_intercept, d.max_intercept = float(p["min_intercept"]), float(p["max_intercept"])
+            d.n_slopes, d.xbins, d.ybins = int(p["n_slopes"]), int(p["xbins"]), int(p["ybins"])
+            d.n_pairs = int(np.asarray(p["pair_x"]).size)
+            d.d_pair_x, d.d_pair_y = base + o["x"], base + o["y"]
+            d.d_lo, d.d_hi = base + o["lo"], base + o["hi"]
+            d.d_xedges, d.d_yedges = base + o["xe"], base + o["ye"]
+            d.d_hist, d.d_rank = base + o["hist"], base + o["rank"]
+            d.d_rankpos, d.d_sort_tmp = base + o["rankpos"], base + o["tmp"]
+        self.d_desc = _upload_structs(self.h_desc)
+        self._stats = None
+
+    def run(self, slopes_per_cta=0):
+        rc = self.lib.rb2_hough_accumulate(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
+                                           self.arena.ptr(self.o_stats), int(slopes_per_cta), current_stream_ptr())
+        N.check(rc, "rb2_hough_accumulate")
+        self._stats = None
+        return self
+
+    # ---- results -----------------------------------------------------------
+    @property
+    def stats(self):
+        if self._stats is None:
+            raw = self.arena.numpy(self.o_stats, np.uint8, C.sizeof(N.HoughStats) * self.n).tobytes()
+            self._stats = (N.HoughStats * self.n).from_buffer_copy(raw)
+            for s in self._stats:
+                if s.status != 0:
+                    N.check(s.status, "rb2_hough_accumulate (device status)")
+        return self._stats
+
+    def _dims(self, i):
+        p = self.problems[i]
+        return int(p["xbins"]), int(p["ybins"])
+
+    def hist(self, i=0):
+        xb, yb = self._dims(i)
+        return self.arena.numpy(self._off[i]["hist"], np.uint32, xb * yb).reshape(xb, yb)
+
+    def xedges(self, i=0):
+        return self.arena.numpy(self._off[i]["xe"], np.float64, self._dims(i)[0] + 1)
+
+    def yedges(self, i=0):
+        return self.arena.numpy(self._off[i]["ye"], np.float64, self._dims(i)[1] + 1)
+
+    def rank(self, i=0):
+        xb, yb = self._dims(i)
+        return self.arena.numpy(self._off[i]["rank"], np.int32, xb * yb)
+
+    def intervals(self, i=0):
+        P = self.h_desc[i].n_pairs
+        return (self.arena.numpy(self._off[i]["lo"], np.int32, P),
+                self.arena.numpy(self._off[i]["hi"], np.int32, P))
+
+    def dev_ptr(self, i, key):
+        return self.arena.ptr(self._off[i][key])
+
+    def points(self, i=0):
+        """HoughTransform.hough_points, materialised in the reference's row order."""
+        torch = _torch()
+        n_points = int(self.stats[i].n_points)
+        S = self.h_desc[i].n_slopes
+        off = torch.empty(S + 2, dtype=torch.int64, device="cuda")
+        out = torch.empty((max(n_points, 1), 2), dtype=torch.float64, device="cuda")
+        one = N.struct_array(N.HoughDesc, 1)
+        C.memmove(one, C.byref(self.h_desc[i]), C.sizeof(N.HoughDesc))
+        rc = self.lib.rb2_hough_points(C.addressof(one), off.data_ptr(), out.data_ptr(), n_points,
+                                       current_stream_ptr())
+        N.check(rc, "rb2_hough_points")
+        return out[:n_points].cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+# K2  candidate vote
+# ---------------------------------------------------------------------------
+
+
+def vote_layout(pairs):
+    """Host-side CSR layout of the pair list for K2.
+
+    Returns (upeaks, pair_off, order, pair_y_csr, pair_wid, uwaves): unique
+    peaks ascending, CSR offsets, the permutation pairs -> CSR (original order
+    inside a peak), the wavelengths in CSR order and their ids among the sorted
+    distinct wavelengths.
+    """
+    pairs = np.asarray(pairs, dtype=np.float64).reshape(-1, 2)
+    upeaks, inv = np.unique(pairs[:, 0], return_inverse=True)
+    order = np.argsort(inv, kind="stable")
+    counts = np.bincount(inv, minlength=len(upeaks))
+    pair_off = np.zeros(len(upeaks) + 1, dtype=np.int32)
+    np.cumsum(counts, out=pair_off[1:])
+    y = pairs[order, 1]
+    uwaves, wid = np.unique(y, return_inverse=True)
+    return upeaks, pair_off, order, y, wid.astype(np.int32), uwaves
+
+
+class VoteBatch:
+    """Per-peak candidate vote for a batch of spectra (rb2_candidate_vote).
+
+    `hough` is the HoughBatch that produced the histogram (its device buffers
+    are consumed in place); `settings[i]` = dict(pairs, top_n, weighted, tol,
+    gauss_denom).
+    """
+
+    def __init__(self, hough: HoughBatch, settings, diagnostics=False):
+        self.lib = N.load()
+        self.n = hough.n
+        assert len(settings) == self.n
+        self.hough = hough
+        ar = Arena()
+        self.arena = ar
+        self.h_desc = N.struct_array(N.VoteDesc, self.n)
+        self._off = []
+        self.layouts = []
+        for i, s in enumerate(settings):
+            upeaks, pair_off, order, y, wid, uwaves = vote_layout(s["pairs"])
+            self.layouts.append((upeaks, pair_off, order, y, wid, uwaves))
+            nu, nw, top_n = len(upeaks), len(uwaves), int(s["top_n"])
+            o = dict(ux=ar.add(upeaks), off=ar.add(pair_off), y=ar.add(y), wid=ar.add(wid),
+                     cw=ar.reserve(8 * nu * top_n), cp=ar.reserve(4 * nu * top_n), cn=ar.reserve(4 * nu),
+                     st=ar.add(np.zeros(1, np.int32)))
+            if diagnostics:
+                o["agg"] = ar.reserve(8 * nu * nw)
+                o["cnt"] = ar.reserve(4 * nu * nw)
+            self._off.append(o)
+        base = ar.upload()
+        for i, s in enumerate(settings):
+            o = self._off[i]
+            upeaks, pair_off, order, y, wid, uwaves = self.layouts[i]
+            d = self.h_desc[i]
+            hd = hough.h_desc[i]
+            d.n_upeaks, d.n_uwaves = len(upeaks), len(uwaves)
+            d.xbins, d.ybins = hd.xbins, hd.ybins
+            d.top_n, d.weighted = int(s["top_n"]), int(bool(s["weighted"]))
+            d.tol, d.gauss_denom = float(s["tol"]), float(s["gauss_denom"])
+            d.d_upeak_x, d.d_pair_off = base + o["ux"], base + o["off"]
+            d.d_pair_y, d.d_pair_wid = base + o["y"], base + o["wid"]
+            d.d_xedges, d.d_yedges, d.d_rankpos = hd.d_xedges, hd.d_yedges, hd.d_rankpos
+            d.d_cand_wave, d.d_cand_pair, d.d_cand_n = base + o["cw"], base + o["cp"], base + o["cn"]
+            d.d_agg = base + o["agg"] if diagnostics else None
+            d.d_cnt = base + o["cnt"] if diagnostics else None
+            d.d_status = base + o["st"]
+        self.d_desc = _upload_structs(self.h_desc)
+
+    def run(self):
+        rc = self.lib.rb2_candidate_vote(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
+                                         current_stream_ptr())
+        N.check(rc, "rb2_candidate_vote")
+        return self
+
+    def candidates(self, i=0):
+        """(candidate_peak, candidate_arc) as the reference's lists
+        (calibrator.py:174-217): ascending unique peaks, n entries each."""
+        o = self._off[i]
+        d = self.h_desc[i]
+        st = int(self.arena.numpy(o["st"], np.int32, 1)[0])
+        if st != 0:
+            N.check(st, "rb2_candidate_vote (device status)")
+        nu, top_n = d.n_upeaks, d.top_n
+        cn = self.arena.numpy(o["cn"], np.int32, nu)
+        cw = self.arena.numpy(o["cw"], np.float64, nu * top_n).reshape(nu, top_n)
+        upeaks = self.layouts[i][0]
+        keep = np.arange(top_n)[None, :] < cn[:, None]
+        cand_peak = np.repeat(upeaks, cn)
+        cand_arc = cw[keep]
+        return cand_peak, cand_arc
+
+    def aggregates(self, i=0):
+        o = self._off[i]
+        d = self.h_desc[i]
+        return (self.arena.numpy(o["agg"], np.float64, d.n_upeaks * d.n_uwaves).reshape(d.n_upeaks, d.n_uwaves),
+                self.arena.numpy(o["cnt"], np.int32, d.n_upeaks * d.n_uwaves).reshape(d.n_upeaks, d.n_uwaves))
+
+
+# ---------------------------------------------------------------------------
+# a7  RANSAC setup (host; calibrator.py:441-523) -> K3 inputs
+# ---------------------------------------------------------------------------
+
+
+class RansacSetup:
+    """Read-only inputs of the hypothesis loop, as the reference prepares them
+    at the top of _solve_candidate_ransac (calibrator.py:441-523)."""
+
+    def __init__(self, cand_peak, cand_arc, *, fit_deg, sample_size, ransac_tolerance, min_intercept,
+                 max_intercept, pixel_list, hist, xedges, yedges, hough_weight=1.0, filter_close=False,
+                 minimum_matches=0, minimum_peak_utilisation=0.0, minimum_fit_error=1e-4, n_peaks_total=None,
+                 pix_known=None, wave_known=None, cost_ceiling=1e50):
+        x = np.array(cand_peak, dtype=np.float64)
+        y = np.array(cand_arc, dtype=np.float64)
+        if filter_close:  # calibrator.py:457-464: drop the lower wavelength of every close pair
+            uy = np.unique(y)
+            close = uy[:-1][(uy[1:] - uy[:-1]) < 3 * ransac_tolerance]
+            keep = ~np.isin(y, close)
+            x, y = x[keep], y[keep]
+        self.x, self.y = x, y
+        self.deg = int(fit_deg)
+        self.sample_size = int(sample_size)
+        self.tol = float(ransac_tolerance)
+        self.min_intercept, self.max_intercept = float(min_intercept), float(max_intercept)
+        self.hough_weight = float(hough_weight)
+        self.minimum_matches = int(minimum_matches)
+        self.minimum_peak_utilisation = float(minimum_peak_utilisation)
+        self.minimum_fit_error = float(minimum_fit_error)
+        self.cost_ceiling = float(cost_ceiling)
+        self.peaks = np.unique(x)  # sorted
+        self.n_peaks_total = len(self.peaks) if n_peaks_total is None else int(n_peaks_total)
+        self.enough = len(self.peaks) > self.deg  # calibrator.py:468
+        self.known_x = np.zeros(0) if pix_known is None else np.asarray(pix_known, dtype=np.float64).reshape(-1)
+        self.known_y = np.zeros(0) if wave_known is None else np.asarray(wave_known, dtype=np.float64).reshape(-1)
+        # candidate table: CSR over ascending peaks, original order inside a peak (:494-495)
+        order = np.argsort(x, kind="stable")
+        self.cand_wave = y[order]
+        counts = np.searchsorted(x[order], self.peaks, side="right") - np.searchsorted(x[order], self.peaks, side="left")
+        self.cand_off = np.zeros(len(self.peaks) + 1, dtype=np.int32)
+        np.cumsum(counts, out=self.cand_off[1:])
+        self.uwaves, wid = np.unique(self.cand_wave, return_inverse=True)
+        self.cand_wid = wid.astype(np.int32)
+        # sampling law (:521-523), index -1 wrap-around kept
+        if self.enough:
+            h = np.histogram(self.peaks, bins=10)
+            prob = 1.0 / h[0][np.digitize(self.peaks, h[1], right=True) - 1]
+            prob = prob / np.sum(prob)
+            self.prob = prob
+            cdf = np.cumsum(prob)
+            cdf /= cdf[-1]
+            self.cdf32 = np.minimum(np.floor(cdf * 4294967296.0), 4294967295.0).astype(np.uint32)
+            self.cdf32[-1] = 0xFFFFFFFF
+        else:
+            self.prob = None
+            self.cdf32 = np.zeros(len(self.peaks), dtype=np.uint32)
+        ptp = np.ptp(self.peaks) if len(self.peaks) else 0.0
+        self.pix_min = float(self.peaks[0] - ptp * 0.2) if len(self.peaks) else 0.0  # :585
+        self.pix_max = float(self.peaks[-1] + ptp * 0.2) if len(self.peaks) else 0.0  # :586
+        # pixel list: NULL on the device when it is arange(n)
+        pl = np.asarray(pixel_list, dtype=np.float64)
+        self.n_pix = len(pl)
+        self.pixel_list = pl
+        self.pix_is_arange = bool(len(pl) and np.array_equal(pl, np.arange(len(pl), dtype=np.float64)))
+        self.pix_sorted = bool(np.all(np.diff(pl) > 0)) if len(pl) > 1 else True
+        # Hough-density weight (calibrator.py:497-506, 614-627)
+        self._weight_tables(np.asarray(hist, dtype=np.float64), np.asarray(xedges), np.asarray(yedges))
+
+    def _weight_tables(self, hist, xedges, yedges):
+        from scipy import interpolate
+
+        hx = (xedges[1] - xedges[0]) / 2.0
+        hy = (yedges[1] - yedges[0]) / 2.0
+        gc = xedges[1:] - hx
+        ic = yedges[1:] - hy
+        self.gc_min, self.gc_max, self.ic_min = float(gc[0]), float(gc[-1]), float(ic[0])
+        if not np.isfinite(self.hough_weight):
+            raise NotImplementedError("hough_weight must be finite")
+        # the reference's own spline object gives the two clamped corner values and the
+        # 1-D section along the first intercept row (evaluated as spline(t, ic_min))
+        spl = interpolate.RectBivariateSpline(gc, ic, hist)
+        self.h_lo = float(spl(gc[0], ic[0], grid=False))
+        self.h_hi = float(spl(gc[-1], ic[0], grid=False))
+        # pp-form of t -> spline(t, ic_min) between the FITPACK knots: a cubic on each knot
+        # interval, recovered exactly from 4 samples per interval
+        tx = spl.get_knots()[0]
+        brk = np.unique(tx)
+        npp = len(brk) - 1
+        coef = np.zeros((npp, 4))
+        for k in range(npp):
+            a, b = brk[k], brk[k + 1]
+            u = np.array([0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0])
+            v = spl(a + u * (b - a), np.full(4, ic[0]), grid=False)
+            coef[k] = np.linalg.solve(np.vander(u, 4, increasing=True), v) / (b - a) ** np.arange(4)
+        self.pp_breaks = brk.astype(np.float64)
+        self.pp_coef = coef.reshape(-1)
+
+    @property
+    def min_inliers(self):
+        # inliers > deg (calibrator.py:645), inliers >= minimum_matches (:684)
+        return max(self.deg + 1, self.minimum_matches)
+
+    @property
+    def min_inliers_frac(self):
+        return self.minimum_peak_utilisation * self.n_peaks_total  # :692-700
+
+
+class RansacBatch:
+    """K3 + K4 for a batch of prepared problems (rb2_ransac_batch / rb2_refit_winners)."""
+
+    def __init__(self, setups, blocks_per_problem=0):
+        self.lib = N.load()
+        _torch()
+        self.setups = list(setups)
+        self.n = len(self.setups)
+        ar = Arena()
+        self.arena = ar
+        self.h_desc = N.struct_array(N.RansacDesc, self.n)
+        self._off = []
+        for s in self.setups:
+            o = dict(peaks=ar.add(s.peaks), coff=ar.add(s.cand_off), cwave=ar.add(s.cand_wave),
+                     cwid=ar.add(s.cand_wid), cdf=ar.add(s.cdf32), kx=ar.add(s.known_x), ky=ar.add(s.known_y),
+                     ppb=ar.add(s.pp_breaks), ppc=ar.add(s.pp_coef))
+            if not s.pix_is_arange:
+                if not s.pix_sorted:
+                    raise NotImplementedError("pixel_list must be strictly increasing")
+                o["pix"] = ar.add(s.pixel_list)
+            self._off.append(o)
+        self.max_up = max((len(s.peaks) for s in self.setups), default=1)
+        base = ar.upload()
+        for i, s in enumerate(self.setups):
+            o = self._off[i]
+            d = self.h_desc[i]
+            d.n_upeaks, d.n_wids, d.n_cand = len(s.peaks), len(s.uwaves), len(s.cand_wave)
+            d.d_peaks, d.d_cand_off = base + o["peaks"], base + o["coff"]
+            d.d_cand_wave, d.d_cand_wid, d.d_cdf32 = base + o["cwave"], base + o["cwid"], base + o["cdf"]
+            d.n_known = len(s.known_x)
+            d.d_known_x, d.d_known_y = base + o["kx"], base + o["ky"]
+            d.deg, d.sample_size = s.deg, s.sample_size
+            d.min_intercept, d.max_intercept = s.min_intercept, s.max_intercept
+            d.pix_min, d.pix_max, d.tol = s.pix_min, s.pix_max, s.tol
+            d.hough_weight, d.gc_min, d.gc_max, d.ic_min = s.hough_weight, s.gc_min, s.gc_max, s.ic_min
+            d.h_lo, d.h_hi = s.h_lo, s.h_hi
+            d.n_pp = len(s.pp_breaks) - 1
+            d.d_pp_breaks, d.d_pp_coef = base + o["ppb"], base + o["ppc"]
+            d.n_pix = s.n_pix
+            d.d_pix = None if s.pix_is_arange else base + o["pix"]
+            d.min_inliers, d.min_inliers_frac = s.min_inliers, s.min_inliers_frac
+            d.cost_ceiling = s.cost_ceiling
+            d.floor_cost, d.floor_id = 0.0, -1
+        torch = _torch()
+        sms = C.c_int(0)
+        N.check(self.lib.rb2_sm_count(C.byref(sms)), "rb2_sm_count")
+        self.sm_count = sms.value
+        if blocks_per_problem <= 0:
+            # one problem: fill the machine; many problems: a few CTAs each
+            blocks_per_problem = max(1, min(4 * self.sm_count, (8 * self.sm_count + self.n - 1) // self.n))
+        self.blocks_per_problem = int(blocks_per_problem)
+        nbytes = self.lib.rb2_ransac_scratch_bytes(self.n, self.blocks_per_problem)
+        self.scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
+        self.d_result = torch.empty(C.sizeof(N.RansacResult) * self.n, dtype=torch.uint8, device="cuda")
+        self.d_refit = torch.empty(C.sizeof(N.RefitResult) * self.n, dtype=torch.uint8, device="cuda")
+        self.d_mx = torch.empty(self.n * self.max_up, dtype=torch.float64, device="cuda")
+        self.d_my = torch.empty(self.n * self.max_up, dtype=torch.float64, device="cuda")
+        self.d_res = torch.empty(self.n * self.max_up, dtype=torch.float64, device="cuda")
+        self.d_desc = None
+        self._keep = []
+
+    def _sync_desc(self):
+        self.d_desc = _upload_structs(self.h_desc)
+
+    def run(self, hyp_begin, n_hyp, seed=0, replay=None, per_hypothesis=False, floors=None):
+        """Evaluate hypothesis ids [hyp_begin, hyp_begin + n_hyp) of every problem.
+
+        replay: optional (x_idx[n_hyp, s], y_idx[n_hyp, s]) int arrays (parity
+        mode, one problem); per_hypothesis=True also returns status / cost /
+        weight / coefficients / counts of every hypothesis (one problem).
+        """
+        torch = _torch()
+        self._keep = []
+        outs = None
+        for i, s in enumerate(self.setups):
+            d = self.h_desc[i]
+            d.hyp_begin, d.n_hyp, d.seed = int(hyp_begin), int(n_hyp), int(seed)
+            d.d_replay_x = d.d_replay_y = None
+            d.d_out_status = d.d_out_cost = d.d_out_weight = d.d_out_coeffs = d.d_out_counts = None
+            if floors is not None:
+                d.floor_cost, d.floor_id = float(floors[i][0]), int(floors[i][1])
+            else:
+                d.floor_cost, d.floor_id = 0.0, -1
+        if replay is not None:
+            assert self.n == 1
+            rx = torch.from_numpy(np.ascontiguousarray(replay[0], dtype=np.int32)).cuda()
+            ry = torch.from_numpy(np.ascontiguousarray(replay[1], dtype=np.int32)).cuda()
+            assert rx.shape == (n_hyp, self.setups[0].sample_size)
+            self._keep += [rx, ry]
+            self.h_desc[0].d_replay_x, self.h_desc[0].d_replay_y = rx.data_ptr(), ry.data_ptr()
+        if per_hypothesis:
+            assert self.n == 1
+            nc = self.setups[0].deg + 1
+            outs = dict(status=torch.full((n_hyp,), 255, dtype=torch.uint8, device="cuda"),
+                        cost=torch.full((n_hyp,), float("nan"), dtype=torch.float64, device="cuda"),
+                        weight=torch.full((n_hyp,), float("nan"), dtype=torch.float64, device="cuda"),
+                        coeffs=torch.full((n_hyp, nc), float("nan"), dtype=torch.float64, device="cuda"),
+                        counts=torch.zeros((n_hyp, 2), dtype=torch.int32, device="cuda"))
+            d = self.h_desc[0]
+            d.d_out_status, d.d_out_cost = outs["status"].data_ptr(), outs["cost"].data_ptr()
+            d.d_out_weight, d.d_out_coeffs = outs["weight"].data_ptr(), outs["coeffs"].data_ptr()
+            d.d_out_counts = outs["counts"].data_ptr()
+        self._sync_desc()
+        rc = self.lib.rb2_ransac_batch(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
+                                       self.d_result.data_ptr(), self.scratch.data_ptr(), self.blocks_per_problem,
+                                       current_stream_ptr())
+        N.check(rc, "rb2_ransac_batch")
+        if outs is not None:
+            outs = {k: v.cpu().numpy() for k, v in outs.items()}
+        return outs
+
+    def results(self):
+        return _download_structs(self.d_result, N.RansacResult, self.n)
+
+    def refit(self, winners=None):
+        """K4 on the current winners (or on explicitly supplied RansacResult structs)."""
+        if winners is not None:
+            self.d_result.copy_(_upload_structs(winners))
+        mfe = self.setups[0].minimum_fit_error
+        if self.d_desc is None:
+            self._sync_desc()
+        rc = self.lib.rb2_refit_winners(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
+                                        self.d_result.data_ptr(), float(mfe), self.d_refit.data_ptr(),
+                                        self.d_mx.data_ptr(), self.d_my.data_ptr(), self.d_res.data_ptr(),
+                                        self.max_up, current_stream_ptr())
+        N.check(rc, "rb2_refit_winners")
+        out = _download_structs(self.d_refit, N.RefitResult, self.n)
+        mx = self.d_mx.cpu().numpy().reshape(self.n, self.max_up)
+        my = self.d_my.cpu().numpy().reshape(self.n, self.max_up)
+        rs = self.d_res.cpu().numpy().reshape(self.n, self.max_up)
+        return out, mx, my, rs
+
+
+def counters_dict(res):
+    return {k: int(res.counters[i]) for i, k in enumerate(N.COUNTER_NAMES)}

@@ -1,0 +1,90 @@
+"""The drop-in facade (rascal_b200.calibrator.Calibrator) end to end on the device;
+assertions follow the reference's own known-answer tests
+(test/test_polynomial_fit.py:60-65, 267-271; test/test_synthetic_calibration.py:60-62)."""
+import numpy as np
+import pytest
+
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def make_calibrator(g, **fit_over):
+    from rascal_b200.calibrator import Calibrator, LineList
+
+    cfg = g["config"]
+    c = Calibrator(g["peaks"])
+    c.set_calibrator_properties(pixel_list=g["pixel_list"], seed=cfg["seed"], **cfg["calib"])
+    c.set_hough_properties(**cfg["hough"])
+    c.set_ransac_properties(**cfg["ransac"])
+    c.set_atlas(LineList(g["lines"]), **cfg["atlas_kw"])
+    return c
+
+
+def test_facade_state_matches_reference(golden):
+    g = golden
+    c = make_calibrator(g)
+    assert np.array_equal(c.pairs, g["pairs"])
+    assert np.array_equal([c.min_slope, c.max_slope, c.min_intercept, c.max_intercept], g["limits"])
+    c.do_hough_transform()
+    assert np.array_equal(c.ht.hist, g["hist"].astype(float))
+    assert np.array_equal(c.ht.xedges, g["xedges"]) and np.array_equal(c.ht.yedges, g["yedges"])
+    assert len(c.hough_lines) == g["hist"].size
+    assert len(c.hough_points) == int(g["n_points"])
+    assert np.array_equal(np.asarray(c.hough_points)[:64], g["points_head"])
+
+
+def test_facade_fit_recovers_reference_solution(golden):
+    """Different RNG (Philox vs MT19937) => different draws; with the reference's try budget
+    the fit must land on the same wavelength solution."""
+    g = golden
+    c = make_calibrator(g)
+    f = dict(g["config"]["fit"])
+    f["max_tries"] = max(2000, f.get("max_tries", 500))
+    coeff, mp, ma, rms, residual, pu, au = c.fit(progress=False, **f)
+    assert np.array_equal(np.array(c.candidate_peak), g["candidate_peak"])
+    assert np.array_equal(np.array(c.candidate_arc), g["candidate_arc"])
+    assert len(coeff) == len(g["fit_coeff"])
+    assert len(mp) == len(ma) == len(residual) and len(mp) > len(coeff)
+    x = np.asarray(g["pixel_list"], dtype=float)
+    P = np.polynomial.polynomial
+    # same solution as the reference found: curves agree to a fraction of the tolerance
+    assert np.max(np.abs(P.polyval(g["peaks"], coeff) - P.polyval(g["peaks"], g["fit_coeff"]))) < 2.0
+    assert rms < 5.0
+    assert 0 < pu <= 1 and 0 < au <= 1
+    assert c.ransac_counters["scored"] >= f["max_tries"]
+    # seed => reproducible
+    c2 = make_calibrator(g)
+    coeff2 = c2.fit(progress=False, **f)[0]
+    assert np.array_equal(coeff, coeff2)
+
+
+def test_linear_known_answer():
+    """test/test_polynomial_fit.py:34-65: linear atlas 3000 + 5x."""
+    from rascal_b200.calibrator import Calibrator, LineList
+
+    np.random.seed(0)
+    peaks = np.sort(np.random.random(31) * 1000.0)
+    peaks = peaks[1:-1] if len(peaks) > 29 else peaks
+    wave = 3000.0 + 5.0 * peaks
+    c = Calibrator(peaks)
+    c.set_calibrator_properties(num_pix=1000)
+    c.set_hough_properties(num_slopes=1000, range_tolerance=500.0, xbins=200, ybins=200,
+                           min_wavelength=3000.0, max_wavelength=8000.0)
+    c.set_ransac_properties(minimum_matches=20, minimum_fit_error=1e-12)
+    c.set_atlas(LineList(wave))
+    coeff, mp, ma, rms, residual, pu, au = c.fit(max_tries=500, fit_deg=1, progress=False)
+    assert abs(coeff[1] - 5.0) / 5.0 < 0.001
+    assert abs(coeff[0] - 3000.0) / 3000.0 < 0.001
+    assert pu > 0.8 and au > 0.0
+
+
+def test_errors_match_reference():
+    from rascal_b200.calibrator import Calibrator, LineList
+
+    c = Calibrator(np.arange(10, 500, 25.0))
+    c.set_atlas(LineList(3000 + 5.0 * np.arange(10, 500, 25.0)))
+    with pytest.raises(ValueError):
+        c.fit(fit_type="spline", progress=False)
+    with pytest.raises(ValueError):
+        c.set_known_pairs([np.nan], [5000.0])
