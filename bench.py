@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark: RANSAC hypotheses/s on the synthetic 60-peak / 300-atlas-line
+degree-4 spectrum (BASELINE.json configs[2]; SURVEY.md 8d "C3 concrete input").
+
+    python bench.py --gpus N --steps K --warmup W           # this repo's CUDA path
+    python bench.py --impl reference ...                     # the reference's CPU algorithm
+
+A step = one pass of the hot path over one batch of hypotheses: H hypothesis ids of
+the Philox stream (default 1e8, the configuration the target is quoted on), split
+evenly over the N ranks (strong scaling: total work fixed), each rank running K3
+(draw -> fit -> intercept/monotonicity tests -> bijective match -> M-SAC cost ->
+block-best), ONE all-gather of the per-rank winner records, and K4 (winner refit).
+Hough + candidate vote (K1, K2) run once per spectrum and are part of the e2e leg,
+which goes through the public Calibrator API with host buffers every step.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ransac_hypotheses_per_sec"
+UNIT = "hypotheses/s"
+
+
+# ---------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------
+
+
+def c3_input():
+    rng = np.random.default_rng(1234)
+    npix = 4096
+    coeff = np.array([4000.0, 1.2, 2e-5, -3e-9, 1e-13])
+    lam = lambda x: np.polynomial.polynomial.polyval(x, coeff)  # noqa: E731
+    true_pix = np.sort(rng.uniform(50, npix - 50, 60))
+    peaks = true_pix + rng.normal(0, 0.05, 60)
+    atlas = np.sort(np.concatenate((lam(true_pix), rng.uniform(lam(0) - 400, lam(npix - 1) + 400, 240))))
+    return dict(peaks=peaks, atlas=atlas, npix=npix, truth=coeff,
+                hough=dict(num_slopes=2000, xbins=100, ybins=100, min_wavelength=float(lam(0)),
+                           max_wavelength=float(lam(npix - 1)), range_tolerance=500, linearity_tolerance=100),
+                ransac=dict(sample_size=5, top_n_candidate=5, ransac_tolerance=5),
+                fit=dict(fit_deg=4, candidate_tolerance=10.0))
+
+
+def flops_per_hypothesis(c, deg=4, s=5, n=60, k=5):
+    """F = F_fit + f_i*F_mono + f_m*F_score (FP64 flops, algorithmic)."""
+    d = deg
+    f_fit = s * (d - 1) + 2 * s * (d + 1) + (2.0 / 3.0) * (d + 1) ** 3 + 2 * (d + 1) ** 2
+    f_mono = 2 * (2 * d) * (2 * (d - 2) + 2) + 60
+    f_score = 2 * d * n + 2 * k * n + 3 * n + 600
+    drawn = max(1, c["drawn"])
+    f_i = (drawn - c["intercept"]) / drawn
+    f_m = (c["scored"] + c["empty"] + c["unsupported"]) / drawn
+    return f_fit + f_i * f_mono + f_m * f_score, f_i, f_m
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU legs (the oracle = a port of the reference's algorithm; test infrastructure)
+# ---------------------------------------------------------------------------
+
+
+def _cpu_worker(args):
+    seed, max_tries = args
+    from oracle import rascal_oracle as O
+
+    w = c3_input()
+    trace, tm = [], {}
+    O.run_path(w["peaks"], w["atlas"], num_pix=w["npix"], max_tries=max_tries, seed=seed, trace=trace,
+               timings=tm, **w["hough"], **w["ransac"], **w["fit"])
+    return len(trace), tm
+
+
+def cpu_baseline(max_tries=1200):
+    """Single-thread oracle port on a bounded sample of the same workload."""
+    n, tm = _cpu_worker((0, max_tries))
+    return {"value": n / tm["ransac"], "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "C3 spectrum, max_tries=%d (%d hypotheses drawn, %.1f s RANSAC loop; Hough %.2f s and "
+                      "candidate vote %.2f s not included)" % (max_tries, n, tm["ransac"], tm["hough"],
+                                                              tm["candidates"])}
+
+
+def reference_arm(args):
+    """The reference's CPU algorithm (oracle port; the reference itself is pure Python and
+    cannot travel) on all host cores: independent worker processes, distinct seeds."""
+    import multiprocessing as mp
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    max_tries = 150
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(args.warmup and 1):
+            pool.map(_cpu_worker, [(1000 + i, 20) for i in range(cores)])
+        times, hyps = [], []
+        for k in range(args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(k * cores + i, max_tries) for i in range(cores)])
+            dt = time.perf_counter() - t0
+            # hypotheses/s of the RANSAC loop itself: every worker's draws over the slowest loop
+            loop = max(tm["ransac"] for _, tm in res)
+            times.append(loop)
+            hyps.append(sum(n for n, _ in res))
+            del dt
+    value = sum(hyps) / sum(times)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample": "max_tries=%d per worker" % max_tries},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d worker processes x max_tries=%d x %d steps of the C3 spectrum "
+                                       "(RANSAC loop time only)" % (cores, max_tries, args.steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+WORKLOAD_NAME = "C3: synthetic 60-peak/300-atlas-line arc, degree 4, sample 5, top-5 candidates (BASELINE configs[2])"
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hyp", type=float, default=1e8, help="hypotheses per step over all ranks")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    group = None if world > 1 else False
+
+    import __graft_entry__
+
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from rascal_b200 import _native, engine, parallel
+    from rascal_b200.calibrator import Calibrator, LineList
+
+    lib = _native.load()
+    w = c3_input()
+    H = int(args.hyp)
+
+    def new_calibrator(seed):
+        c = Calibrator(w["peaks"], spectrum=np.zeros(w["npix"]))
+        c.set_calibrator_properties(seed=seed)
+        c.set_hough_properties(**w["hough"])
+        c.set_ransac_properties(**w["ransac"])
+        c.set_atlas(LineList(w["atlas"]), candidate_tolerance=10.0)
+        if world > 1:
+            c.use_distributed(None)
+        return c
+
+    # ---- device-resident leg: K1 + K2 + set-up once, then K3 (+ exchange + K4) per step ----
+    c = new_calibrator(0)
+    c.do_hough_transform()
+    c._vote(w["fit"]["candidate_tolerance"])
+    setup = engine.RansacSetup(
+        c.candidate_peak, c.candidate_arc, fit_deg=4, sample_size=5, ransac_tolerance=c.ransac_tolerance,
+        min_intercept=c.min_intercept, max_intercept=c.max_intercept, pixel_list=c.pixel_list, hist=c.ht.hist,
+        xedges=c.ht.xedges, yedges=c.ht.yedges, hough_weight=c.hough_weight, n_peaks_total=len(c.peaks))
+    rb = engine.RansacBatch([setup])
+    lo, hi = parallel.shard_range(H, rank, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step(k):
+        rb.run(k * H + lo, hi - lo, seed=2026)
+        win = parallel.allgather_winners([rb.results()[0]], group)[0]
+        one = _native.struct_array(_native.RansacResult, 1)
+        one[0] = win
+        out, mx, my, rs = rb.refit(one)
+        return win, out[0]
+
+    for k in range(args.warmup):
+        step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    counters = dict.fromkeys(_native.COUNTER_NAMES, 0)
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (inputs are KBs, far below L2)
+            ev[k][0].record()
+            kev[k][0].record()
+            rb.run((args.warmup + k) * H + lo, hi - lo, seed=2026)  # K3 main + finalize
+            kev[k][1].record()
+            win = parallel.allgather_winners([rb.results()[0]], group)[0]
+            one = _native.struct_array(_native.RansacResult, 1)
+            one[0] = win
+            out, mx, my, rs = rb.refit(one)  # K4
+            ev[k][1].record()
+            for name, v in engine.counters_dict(win).items():
+                counters[name] += v
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_kernel = [a.elapsed_time(b) for a, b in kev]
+    total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device="cuda")
+    kern_ms = torch.tensor([sum(ms_kernel)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(total_ms.item()), float(kern_ms.item())
+    value = args.steps * H / (total_ms * 1e-3)
+
+    # ---- FP64 roofline denominator (DFMA microbenchmark, same box, same run) ----
+    sink = torch.zeros(1, dtype=torch.float64, device="cuda")
+    sms = rb.sm_count
+    blocks, iters = sms * 16, 1 << 15
+    for _ in range(2):
+        lib.rb2_dfma_burn(blocks, iters, sink.data_ptr(), engine.current_stream_ptr())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    lib.rb2_dfma_burn(blocks, iters, sink.data_ptr(), engine.current_stream_ptr())
+    b.record()
+    torch.cuda.synchronize()
+    fp64_peak = 2.0 * 8 * iters * blocks * 256 / (a.elapsed_time(b) * 1e-3) / 1e12
+
+    # ---- e2e leg: the public Calibrator API with host buffers, every step ----
+    e2e = None
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    for k in range(1):
+        new_calibrator(5).fit(max_tries=50, progress=False, **w["fit"])  # warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    engine.TRANSFER["h2d"] = engine.TRANSFER["d2h"] = 0
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        cal = new_calibrator(100 + k)
+        cal.do_hough_transform()
+        res = cal.fit(progress=False, n_hypotheses=H, **w["fit"])
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_e2e = time.perf_counter() - t0
+    t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e_t.item())
+    e2e = {"value": e2e_steps * H / t_e2e, "unit": UNIT,
+           "h2d_bytes_per_step": engine.TRANSFER["h2d"] // e2e_steps,
+           "d2h_bytes_per_step": engine.TRANSFER["d2h"] // e2e_steps,
+           "ms_per_step": 1e3 * t_e2e / e2e_steps, "rms": float(res[3]), "n_matched": len(res[1])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    F, f_i, f_m = flops_per_hypothesis(counters)
+    per_rank_hyp = (hi - lo)
+    achieved = per_rank_hyp * args.steps * F / (kern_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d" % world,
+                   "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "traffic": None,
+                     "kernel": "ransac_kernel<4>", "flops_per_hypothesis": F, "f_intercept_pass": f_i,
+                     "f_scored": f_m, "peak_source": "DFMA microbenchmark in this run (rb2_dfma_burn); FP64 is not in MEASURED_PEAKS.json",
+                     "kernel_ms_per_step": kern_ms / args.steps},
+        "counters": counters,
+        "wall_s_timed_region": t_wall,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

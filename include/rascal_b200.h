@@ -50,6 +50,11 @@ int rb2_sm_count(int *out);
 /* sizeof() of the structs below, in declaration order (0 = rb2_hough_desc ...
  * 5 = rb2_refit_result); lets a binding verify its layout. */
 int rb2_struct_size(int which);
+/* Roofline denominator for the FP64-bound kernels (not in
+ * MEASURED_PEAKS.json): launches `blocks` CTAs of 256 threads doing 8*iters
+ * dependent-chain DFMAs each (2*8*iters*blocks*256 flops); the caller times it
+ * with CUDA events on `stream`. */
+int rb2_dfma_burn(int blocks, int iters, double *d_out, void *stream);
 
 /* ======================================================================= *
  * K1  Hough accumulation

@@ -98,6 +98,7 @@ EXPORTS = {
     "rb2_last_cuda_error": (C.c_char_p, []),
     "rb2_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rb2_struct_size": (C.c_int, [C.c_int]),
+    "rb2_dfma_burn": (C.c_int, [C.c_int, C.c_int, _vp, _vp]),
     "rb2_hough_accumulate": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_hough_points": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
     "rb2_candidate_vote": (C.c_int, [C.c_int, _vp, _vp, _vp]),

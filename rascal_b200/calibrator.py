@@ -96,6 +96,7 @@ class Calibrator:
         self.candidate_peak = self.candidate_arc = None
         self.ransac_counters = None
         self.seed = None
+        self.dist_group = False
         self.set_calibrator_properties()
         self.set_hough_properties()
         self.set_ransac_properties()
@@ -178,6 +179,11 @@ class Calibrator:
             assert minimum_fit_error >= 0
         self.minimum_fit_error = _keep(minimum_fit_error, self.minimum_fit_error, 1e-4)
 
+    def use_distributed(self, group=None):
+        """Shard the RANSAC hypotheses of fit() over the ranks of a torch.distributed process
+        group (None = the default group); one process per GPU."""
+        self.dist_group = group
+
     # ------------------------------------------------------------------ atlas / pairs
     def _generate_pairs(self):
         """calibrator.py:86-133: peak-major Cartesian product, optional polygon mask."""
@@ -236,9 +242,13 @@ class Calibrator:
 
     # ------------------------------------------------------------------ fit
     def fit(self, max_tries=500, fit_deg=4, fit_coeff=None, fit_tolerance=5.0, fit_type="poly",
-            candidate_tolerance=2.0, brute_force=False, progress=True):
+            candidate_tolerance=2.0, brute_force=False, progress=True, n_hypotheses=None):
         """calibrator.py:1552-1715; returns (fit_coeff, matched_peaks, matched_atlas, rms, residual,
-        peak_utilisation, atlas_utilisation)."""
+        peak_utilisation, atlas_utilisation).
+
+        Extension: `n_hypotheses` (keyword) replaces the `max_tries` stopping rule by an exact
+        budget of drawn hypotheses (ids 0..n-1 of the Philox stream), sharded over the ranks of
+        `use_distributed()`."""
         self.max_tries = max_tries
         self.fit_deg = fit_deg
         self.fit_coeff = fit_coeff
@@ -279,7 +289,7 @@ class Calibrator:
 
         fit_coeff, rms, residual, n_inliers, valid = self._solve_candidate_ransac(
             fit_deg=self.fit_deg, fit_coeff=self.fit_coeff, max_tries=self.max_tries,
-            candidate_tolerance=candidate_tolerance)
+            candidate_tolerance=candidate_tolerance, n_hypotheses=n_hypotheses)
 
         peak_utilisation = n_inliers / len(self.peaks)
         atlas_utilisation = n_inliers / len(self.atlas)
@@ -305,8 +315,15 @@ class Calibrator:
         cp, ca = vb.candidates(0)
         self.candidate_peak, self.candidate_arc = list(cp), list(ca)
 
-    def _solve_candidate_ransac(self, fit_deg, fit_coeff, max_tries, candidate_tolerance):
-        """calibrator.py:382-752 as batched device work (order-independent rule)."""
+    def _solve_candidate_ransac(self, fit_deg, fit_coeff, max_tries, candidate_tolerance, n_hypotheses=None):
+        """calibrator.py:382-752 as batched device work (order-independent rule).
+
+        With torch.distributed initialised (one process per GPU) every rank evaluates its own
+        slice of each hypothesis-id range and the per-rank winners are merged by ONE all-gather
+        (rascal_b200.parallel); the result is identical on every rank and independent of the
+        number of GPUs."""
+        from . import parallel
+
         if self.ht._batch is None:
             raise NotImplementedError("fit() needs a Hough transform computed by do_hough_transform()")
         self._vote(candidate_tolerance)
@@ -326,35 +343,40 @@ class Calibrator:
         if self.sample_size >= len(setup.peaks):
             raise NotImplementedError("sample_size >= number of candidate peaks switches the reference to its "
                                       "brute-force sampler (calibrator.py:474-477), which is not supported")
+        rank, world = parallel.rank_world(self.dist_group)
         # Philox key: drawn from the legacy global RNG so that seed= makes the fit reproducible
         key = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+        key = parallel.broadcast_int(key, self.dist_group)
         rb = engine.RansacBatch([setup])
-        counters = dict.fromkeys(engine.N.COUNTER_NAMES, 0)
-        winner = None
-        done = 0
-        chunk = max(1 << 14, 64 * int(max_tries))
-        # `max_tries` counts completed tries of the reference loop: scored hypotheses (and
-        # impossible draws); rejected draws are redrawn for free (:578-600)
-        while counters["scored"] + counters["aborted"] < int(max_tries) and done < (1 << 40):
-            rb.run(done, chunk, seed=key)
-            r = rb.results()[0]
-            for k, v in engine.counters_dict(r).items():
-                counters[k] += v
-            if r.hyp_id >= 0 and (winner is None or r.cost < winner.cost
-                                  or (r.cost == winner.cost and r.hyp_id > winner.hyp_id)):
-                winner = engine.N.RansacResult.from_buffer_copy(bytes(r))
-            done += chunk
-            if counters["drawn"] == 0 and counters["aborted"] == 0:
-                break
-            chunk = min(chunk * 4, 1 << 28)
-        self.ransac_counters = counters
-        if counters["unsupported"]:
+
+        def evaluate(begin, count, floors=None):
+            lo, hi = parallel.shard_range(count, rank, world)
+            rb.run(begin + lo, hi - lo, seed=key, floors=floors)
+            return parallel.allgather_winners([rb.results()[0]], self.dist_group)[0]
+
+        spans = []
+        if n_hypotheses is not None:
+            spans.append((0, int(n_hypotheses)))
+            winner = evaluate(0, int(n_hypotheses))
+        else:
+            # `max_tries` counts completed tries of the reference loop: scored hypotheses (and
+            # impossible draws); rejected draws are redrawn for free (:578-600)
+            winner = parallel.merge_winners([])
+            done, chunk = 0, max(1 << 14, 64 * int(max_tries))
+            while winner.counters[5] + winner.counters[1] < int(max_tries) and done < (1 << 40):
+                spans.append((done, chunk))
+                winner = parallel.merge_winners([winner, evaluate(done, chunk)])
+                done += chunk
+                if winner.counters[0] == 0 and winner.counters[1] == 0:
+                    break
+                chunk = min(chunk * 4, 1 << 28)
+        self.ransac_counters = engine.counters_dict(winner)
+        if self.ransac_counters["unsupported"]:
             self.logger.warning("%d hypotheses left the corner-clamped Hough-weight regime and were skipped",
-                                counters["unsupported"])
+                                self.ransac_counters["unsupported"])
         # refit + refit-dependent acceptance (:652-679); fall through to the next best on failure
-        spans = done
         for _ in range(16):
-            if winner is None:
+            if winner.hyp_id < 0:
                 return best
             win = engine.N.struct_array(engine.N.RansacResult, 1)
             win[0] = winner
@@ -366,10 +388,11 @@ class Calibrator:
                 self.matched_atlas = list(my[0, :m])
                 assert len(self.matched_atlas) == len(set(self.matched_atlas))
                 coeffs = np.array(o.coeffs[:fit_deg + 1])
+                self.best_cost = winner.cost
+                self.best_hypothesis = (winner.hyp_id, np.array(winner.coeffs[:fit_deg + 1]))
                 return coeffs, o.rms, rs[0, :m].copy(), m, m > fit_deg + 1
-            rb.run(0, spans, seed=key, floors=[(winner.cost, winner.hyp_id)])
-            r = rb.results()[0]
-            winner = engine.N.RansacResult.from_buffer_copy(bytes(r)) if r.hyp_id >= 0 else None
+            floor = (winner.cost, winner.hyp_id)
+            winner = parallel.merge_winners([evaluate(b, c, floors=[floor]) for b, c in spans])
         return best
 
 

@@ -48,3 +48,25 @@ extern "C" int rb2_struct_size(int which) {
     default: return -1;
   }
 }
+
+// FP64 roofline denominator: a DFMA-only kernel (8 independent chains per thread),
+// timed by the caller with CUDA events.  2 * 8 * iters * blocks * threads flops.
+__global__ void __launch_bounds__(256) dfma_burn_kernel(int iters, double* __restrict__ out) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+extern "C" int rb2_dfma_burn(int blocks, int iters, double* d_out, void* stream) {
+  if (blocks <= 0 || iters <= 0 || !d_out) return RB2_ERR_ARG;
+  dfma_burn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, d_out);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}

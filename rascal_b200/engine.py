@@ -18,6 +18,9 @@ from . import _native as N
 
 _ALIGN = 32
 
+# bytes moved across PCIe by this module (bench.py reads these for its e2e line)
+TRANSFER = {"h2d": 0, "d2h": 0}
+
 
 def _torch():
     import torch
@@ -74,6 +77,7 @@ class Arena:
             self.buf[:staged].copy_(host, non_blocking=True)
             self.host = host  # keep alive until the copy has run
             self.h2d_bytes = staged
+            TRANSFER["h2d"] += staged
         return self.ptr(0)
 
     def ptr(self, off):
@@ -86,6 +90,7 @@ class Arena:
 
     def numpy(self, off, np_dtype, count):
         nbytes = np.dtype(np_dtype).itemsize * count
+        TRANSFER["d2h"] += nbytes
         return self.buf[off:off + nbytes].cpu().numpy().view(np_dtype)
 
 
@@ -93,10 +98,12 @@ def _upload_structs(arr):
     """ctypes struct array -> device uint8 tensor."""
     torch = _torch()
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    TRANSFER["h2d"] += host.numel()
     return host.cuda()
 
 
 def _download_structs(tensor, cls, n):
+    TRANSFER["d2h"] += tensor.numel()
     raw = tensor.cpu().numpy().tobytes()
     return (cls * n).from_buffer_copy(raw)
 

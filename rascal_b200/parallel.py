@@ -1,0 +1,104 @@
+"""Multi-GPU plumbing: one process per GPU, hypotheses (or spectra) sharded by id
+range, ONE exchange per fit.
+
+RANSAC hypotheses are independent given the (tiny, replicated) candidate table, so
+rank r evaluates hypothesis ids ``shard_range(n, r, world)`` of the same Philox
+stream - the result does not depend on the number of GPUs.  The only collective
+is an all-gather of one fixed-size winner record per rank (cost, hypothesis id,
+counts, coefficients, counters: 160 bytes) followed by a local merge with the
+reference's tie rule (``cost <= best_cost``: the LATER hypothesis wins ties,
+calibrator.py:636).  Latency-bound; NCCL over NVLink on GPUs, gloo in CPU tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def shard_range(n, rank, world):
+    """Contiguous id range [begin, end) of `rank` when n ids are split over `world` ranks."""
+    n, rank, world = int(n), int(rank), int(world)
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def rank_world(group=False):
+    """(rank, world) of `group`; group=False means "not distributed"."""
+    if group is False:
+        return 0, 1
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def broadcast_int(value, group=False):
+    """Rank 0's 64-bit integer on every rank."""
+    if rank_world(group)[1] == 1:
+        return int(value)
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return int(t.item())
+
+
+def better(cost_a, id_a, cost_b, id_b):
+    """True if (cost_a, id_a) beats (cost_b, id_b): lower cost, later id on ties; id < 0 = none."""
+    if id_a < 0:
+        return False
+    if id_b < 0:
+        return True
+    return cost_a < cost_b or (cost_a == cost_b and id_a > id_b)
+
+
+def merge_winners(records):
+    """Merge per-rank / per-launch RansacResult structs: best winner, summed counters."""
+    out = N.RansacResult()
+    out.cost, out.hyp_id = float("inf"), -1
+    cnt = [0] * 8
+    for r in records:
+        for k in range(8):
+            cnt[k] += int(r.counters[k])
+        if better(r.cost, r.hyp_id, out.cost, out.hyp_id):
+            C.memmove(C.byref(out), C.byref(r), C.sizeof(N.RansacResult))
+    for k in range(8):
+        out.counters[k] = cnt[k]
+    return out
+
+
+def allgather_winners(local, group=False, device=None):
+    """All-gather one RansacResult per rank and merge.  `local` is a list of structs
+    (one per problem); returns the merged list, identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    if group is False or not (dist.is_available() and dist.is_initialized()):
+        return list(local)
+    world = dist.get_world_size(group)
+    if world == 1:
+        return list(local)
+    n = len(local)
+    sz = C.sizeof(N.RansacResult)
+    buf = np.empty(n * sz, dtype=np.uint8)
+    for i, r in enumerate(local):
+        buf[i * sz:(i + 1) * sz] = np.frombuffer(bytes(r), dtype=np.uint8)
+    t = torch.from_numpy(buf)
+    if device is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = t.to(device)
+    gathered = torch.empty(world * n * sz, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, t, group=group)
+    raw = gathered.cpu().numpy().reshape(world, n, sz)
+    merged = []
+    for i in range(n):
+        recs = [N.RansacResult.from_buffer_copy(raw[w, i].tobytes()) for w in range(world)]
+        merged.append(merge_winners(recs))
+    return merged

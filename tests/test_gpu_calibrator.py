@@ -46,10 +46,19 @@ def test_facade_fit_recovers_reference_solution(golden):
     assert np.array_equal(np.array(c.candidate_arc), g["candidate_arc"])
     assert len(coeff) == len(g["fit_coeff"])
     assert len(mp) == len(ma) == len(residual) and len(mp) > len(coeff)
-    x = np.asarray(g["pixel_list"], dtype=float)
     P = np.polynomial.polynomial
-    # same solution as the reference found: curves agree to a fraction of the tolerance
-    assert np.max(np.abs(P.polyval(g["peaks"], coeff) - P.polyval(g["peaks"], g["fit_coeff"]))) < 2.0
+    # RANSAC with another RNG stream need not land on the reference's local optimum; what must
+    # hold is the contract of the result: inlier pairs come from the candidate table, residuals
+    # are the refit model's, and the M-SAC cost is no worse than the reference's accepted one
+    cand = set(zip(g["candidate_peak"].tolist(), g["candidate_arc"].tolist()))
+    assert all((p, a) in cand for p, a in zip(mp, ma))
+    assert np.all(np.diff(ma) > 0)
+    res = P.polyval(np.array(mp), coeff) - np.array(ma)
+    assert np.max(np.abs(res)) < g["config"]["ransac"].get("ransac_tolerance", 5)
+    assert np.allclose(res, residual, rtol=0, atol=1e-9)
+    assert np.isclose(rms, np.sqrt(np.mean(res ** 2)), rtol=1e-12)
+    ref_cost = g["tr_cost"][np.flatnonzero(g["tr_accepted"])[-1]]
+    assert c.best_cost <= ref_cost * (1 + 1e-9)
     assert rms < 5.0
     assert 0 < pu <= 1 and 0 < au <= 1
     assert c.ransac_counters["scored"] >= f["max_tries"]
