@@ -218,17 +218,19 @@ int rb2_ransac_batch(int n_problems, const rb2_ransac_desc *d_desc,
 /* ======================================================================= *
  * K4  winner refit + acceptance
  *     replaces Calibrator._match_bijective on the winner (calibrator.py:317-380),
- *     the inlier selection (:640-643), models.robust_polyfit (models.py:70-123;
- *     solved to the exact Huber optimum) and the residual / rms /
- *     minimum_fit_error check (:664-679).
+ *     the inlier selection (:640-643), models.robust_polyfit (models.py:70-123)
+ *     and the residual / rms / minimum_fit_error check (:664-679).
+ *     mode 0 = the reference's solver restated step for step (SciPy TRF from
+ *     ones, Huber loss, 2-point Jacobian, diff_step 1e-5); mode 1 = the exact
+ *     Huber optimum that iteration approaches.
  * ======================================================================= */
 typedef struct {
   double coeffs[RB2_MAX_DEG + 1];       /* refit coefficients, low order first */
   double rms;                           /* sqrt(mean(clipped residual^2))    */
   int32_t n_inliers;
   int32_t accepted;                     /* 1 if rms >= minimum_fit_error     */
-  int32_t huber_iters;                  /* 0 = pure least squares (all |r|<=1) */
-  int32_t pad;
+  int32_t huber_iters;                  /* mode 0: SciPy nfev; mode 1: IRLS passes (0 = pure least squares) */
+  int32_t pad;                          /* mode 0: SciPy termination status (1 gtol, 2 ftol, 3 xtol, 4 both, 0 max_nfev) */
 } rb2_refit_result;
 
 /* d_matched_x / d_matched_y / d_residual: [n_problems * max_upeaks] outputs
@@ -236,7 +238,7 @@ typedef struct {
 int rb2_refit_winners(int n_problems, const rb2_ransac_desc *d_desc,
                       const rb2_ransac_desc *h_desc,
                       const rb2_ransac_result *d_winner, double minimum_fit_error,
-                      rb2_refit_result *d_out, double *d_matched_x,
+                      int mode, rb2_refit_result *d_out, double *d_matched_x,
                       double *d_matched_y, double *d_residual, int max_upeaks,
                       void *stream);
 

@@ -328,14 +328,17 @@ def _residual_fn(a, x, y, degree):
     return y - t
 
 
-def robust_polyfit(x, y, degree):
-    """SciPy TRF/Huber on std-normalised data; models.py:70-123 (x0=None)."""
+def robust_polyfit(x, y, degree, info=None):
+    """SciPy TRF/Huber on std-normalised data; models.py:70-123 (x0=None).
+    `info` (a dict) receives SciPy's nfev and termination status."""
     x = np.asarray(x, dtype=float)
     y = np.asarray(y, dtype=float)
     xs, ys = x.std(), y.std()
     res = scipy.optimize.least_squares(
         _residual_fn, np.ones(degree + 1), args=(x / xs, y / ys, degree),
         loss="huber", diff_step=1e-5)
+    if info is not None:
+        info.update(nfev=res.nfev, status=res.status)
     p = res.x
     p *= y.std()
     for i in range(0, degree):

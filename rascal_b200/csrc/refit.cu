@@ -6,13 +6,21 @@
 // minimum_fit_error test (:664-679).
 //
 // robust_polyfit minimises the Huber loss (f_scale = 1) of the residuals of a
-// polynomial in x/std(x) against y/std(y) with SciPy's TRF.  The loss is convex;
-// its minimiser is computed here directly: Householder QR least squares
-// (exact when every normalised residual is inside Huber's quadratic zone,
-// |r| <= 1 - always the case for inliers of a wavelength solution), followed by
-// IRLS with Huber weights only if some |r| > 1.  See DESIGN.md for why the
-// reference's own TRF iterate differs from this optimum by its stopping
-// tolerance and finite-difference Jacobian noise.
+// polynomial in x/std(x) against y/std(y) with SciPy's Trust Region Reflective
+// solver from x0 = ones on a forward-difference Jacobian.  Two modes:
+//   mode 0 (default, what the facade uses): the same iteration, step for step
+//       (scipy 1.18 optimize/_lsq/trf.py::trf_no_bounds, tr_solver='exact',
+//       common.py::solve_lsq_trust_region / update_tr_radius /
+//       check_termination, _numdiff '2-point' with rel_step 1e-5), with a
+//       one-sided Jacobi SVD in place of LAPACK gesdd.  TRF stops 1e-8..1e-5
+//       (relative, coefficients) short of the optimum and that distance is
+//       chaotic in the last bits of the iterates (FD-Jacobian noise 1e-11 x
+//       cond(J) 1e3..1e5), so agreement with a given SciPy build is at that
+//       level too - see DESIGN.md; what is reproduced is the algorithm, its
+//       number of function evaluations and the size of its inexactness (which
+//       the reference's minimum_fit_error test on exact data relies on).
+//   mode 1: the exact Huber optimum (Householder QR least squares + IRLS when a
+//       normalised residual leaves the quadratic zone).
 #include "common.cuh"
 
 namespace rb2 {
@@ -69,9 +77,277 @@ __device__ void warp_qr_solve(const double* x, const double* y, const double* sw
   __syncwarp();
 }
 
+
+// ---- SciPy TRF (no bounds, exact tr_solver, Huber loss), one warp ------------
+constexpr double TRF_EPS = 2.220446049250313e-16;
+
+struct TrfWs {        // shared-memory work space of one problem (m points, n params)
+  double *f_true, *f, *f_new, *js;   // [m]
+  double *J, *U;                     // [m*n] column-major
+};
+
+// models.py:10-54: y - (a[n-1] + sum_i a[n-1-i] * x**i), each power formed separately
+__device__ __forceinline__ double trf_residual(const double* a, int n, double x, double y) {
+  double t = a[n - 1];
+  double pw = x;
+  for (int i = 1; i < n; ++i) {
+    t = add(t, mul(a[n - 1 - i], pw));
+    pw = mul(pw, x);
+  }
+  return sub(y, t);
+}
+
+__device__ __forceinline__ void huber_rho(double f, double& r0, double& r1, double& r2) {
+  const double z = f * f;
+  if (z <= 1.0) { r0 = z; r1 = 1.0; r2 = 0.0; }
+  else { const double sq = sqrt(z); r0 = 2.0 * sq - 1.0; r1 = 1.0 / sq; r2 = -0.5 / (z * sq); }
+}
+
+// f_true (filled) -> J (2-point), robust scaling of J and f, returns cost; g = J^T f
+__device__ double trf_linearise(const double* a, int n, int m, const double* xn, const double* yn, TrfWs& w, double* g) {
+  const int lane = lane_id();
+  for (int j = 0; j < n; ++j) {  // _numdiff._compute_absolute_step / _dense_difference
+    const double sign = (a[j] >= 0.0) ? 1.0 : -1.0;
+    double h = 1e-5 * sign * fabs(a[j]);
+    if (sub(add(a[j], h), a[j]) == 0.0) h = sqrt(TRF_EPS) * sign * fmax(1.0, fabs(a[j]));
+    const double dx = sub(add(a[j], h), a[j]);
+    double a1[NCF];
+    for (int k = 0; k < n; ++k) a1[k] = a[k];
+    a1[j] = add(a[j], h);
+    for (int i = lane; i < m; i += 32) w.J[j * m + i] = sub(trf_residual(a1, n, xn[i], yn[i]), w.f_true[i]) / dx;
+  }
+  double c = 0.0;
+  for (int i = lane; i < m; i += 32) {  // common.scale_for_robust_loss_function
+    const double f = w.f_true[i];
+    double r0, r1, r2;
+    huber_rho(f, r0, r1, r2);
+    double s = r1 + 2.0 * r2 * f * f;
+    if (s < TRF_EPS) s = TRF_EPS;
+    s = sqrt(s);
+    w.js[i] = s;
+    w.f[i] = f * (r1 / s);
+    c += r0;
+  }
+  __syncwarp();
+  for (int j = 0; j < n; ++j) {
+    double gj = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double v = w.J[j * m + i] * w.js[i];
+      w.J[j * m + i] = v;
+      gj = fma(v, w.f[i], gj);
+    }
+    g[j] = warp_sum(gj);
+  }
+  __syncwarp();
+  return 0.5 * warp_sum(c);
+}
+
+// one-sided Jacobi SVD of w.J (copied to w.U): U columns normalised in place, s descending, V (n x n)
+__device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF]) {
+  const int lane = lane_id();
+  for (int i = lane; i < m * n; i += 32) w.U[i] = w.J[i];
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < n - 1; ++p) {
+      for (int q = p + 1; q < n; ++q) {
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int i = lane; i < m; i += 32) {
+          const double up = w.U[p * m + i], uq = w.U[q * m + i];
+          al = fma(up, up, al); be = fma(uq, uq, be); ga = fma(up, uq, ga);
+        }
+        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+        if (fabs(ga) <= 1e-300 || fabs(ga) <= TRF_EPS * sqrt(al * be)) continue;
+        rotated = true;
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int i = lane; i < m; i += 32) {
+          const double up = w.U[p * m + i], uq = w.U[q * m + i];
+          w.U[p * m + i] = c * up - sn * uq;
+          w.U[q * m + i] = sn * up + c * uq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vp = V[k][p], vq = V[k][q];
+          V[k][p] = c * vp - sn * vq;
+          V[k][q] = sn * vp + c * vq;
+        }
+        __syncwarp();
+      }
+    }
+    if (!rotated) break;
+  }
+  for (int j = 0; j < n; ++j) {
+    double ss = 0.0;
+    for (int i = lane; i < m; i += 32) ss = fma(w.U[j * m + i], w.U[j * m + i], ss);
+    s[j] = sqrt(warp_sum(ss));
+  }
+  // selection sort, descending (stable enough: n <= 8), permuting U columns and V columns
+  for (int a = 0; a < n - 1; ++a) {
+    int b = a;
+    for (int k = a + 1; k < n; ++k) if (s[k] > s[b]) b = k;
+    if (b != a) {
+      const double ts = s[a]; s[a] = s[b]; s[b] = ts;
+      for (int i = lane; i < m; i += 32) { const double tu = w.U[a * m + i]; w.U[a * m + i] = w.U[b * m + i]; w.U[b * m + i] = tu; }
+      for (int k = 0; k < n; ++k) { const double tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = tv; }
+    }
+  }
+  __syncwarp();
+  for (int j = 0; j < n; ++j) {
+    const double inv = (s[j] > 0.0) ? 1.0 / s[j] : 0.0;
+    for (int i = lane; i < m; i += 32) w.U[j * m + i] *= inv;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ double vnorm(const double* v, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s = fma(v[i], v[i], s);
+  return sqrt(s);
+}
+
+// common.solve_lsq_trust_region (scalar: every lane computes the same values)
+__device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, const double (*V)[NCF], double Delta,
+                             double& alpha, double* p) {
+  double suf[NCF];
+  for (int i = 0; i < n; ++i) suf[i] = s[i] * uf[i];
+  auto phi_and_derivative = [&](double al, double& phi, double& phi_prime) {
+    double pn = 0.0, sm = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double den = s[i] * s[i] + al;
+      const double q = suf[i] / den;
+      pn = fma(q, q, pn);
+      sm += suf[i] * suf[i] / (den * den * den);
+    }
+    pn = sqrt(pn);
+    phi = pn - Delta;
+    phi_prime = -sm / pn;
+  };
+  const bool full_rank = (m >= n) && (s[n - 1] > TRF_EPS * m * s[0]);
+  if (full_rank) {
+    for (int k = 0; k < n; ++k) {
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) acc = fma(V[k][i], uf[i] / s[i], acc);
+      p[k] = -acc;
+    }
+    if (vnorm(p, n) <= Delta) { alpha = 0.0; return; }
+  }
+  double alpha_upper = vnorm(suf, n) / Delta, alpha_lower = 0.0;
+  if (full_rank) {
+    double phi, phip;
+    phi_and_derivative(0.0, phi, phip);
+    alpha_lower = -phi / phip;
+  }
+  if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+  for (int it = 0; it < 10; ++it) {
+    if (alpha < alpha_lower || alpha > alpha_upper) alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+    double phi, phip;
+    phi_and_derivative(alpha, phi, phip);
+    if (phi < 0.0) alpha_upper = alpha;
+    const double ratio = phi / phip;
+    alpha_lower = fmax(alpha_lower, alpha - ratio);
+    alpha -= (phi + Delta) * ratio / Delta;
+    if (fabs(phi) < 0.01 * Delta) break;
+  }
+  for (int k = 0; k < n; ++k) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc = fma(V[k][i], suf[i] / (s[i] * s[i] + alpha), acc);
+    p[k] = -acc;
+  }
+  const double sc = Delta / vnorm(p, n);
+  for (int k = 0; k < n; ++k) p[k] *= sc;
+}
+
+// trf.trf_no_bounds; a[] = solution (high order first, as models.polynomial expects)
+__device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn, TrfWs& w, double* a, int& nfev_out,
+                               int& status_out) {
+  const int lane = lane_id();
+  const double ftol = 1e-8, xtol = 1e-8, gtol = 1e-8;
+  for (int k = 0; k < n; ++k) a[k] = 1.0;
+  for (int i = lane; i < m; i += 32) w.f_true[i] = trf_residual(a, n, xn[i], yn[i]);
+  __syncwarp();
+  int nfev = 1;
+  double g[NCF];
+  double cost = trf_linearise(a, n, m, xn, yn, w, g);
+  double Delta = vnorm(a, n);
+  if (Delta == 0.0) Delta = 1.0;
+  const int max_nfev = 100 * n;
+  double alpha = 0.0;
+  int status = -1;
+  double s[NCF], uf[NCF], step[NCF], a_new[NCF];
+  double V[NCF][NCF];
+  for (;;) {
+    double g_norm = 0.0;
+    for (int k = 0; k < n; ++k) g_norm = fmax(g_norm, fabs(g[k]));
+    if (g_norm < gtol) status = 1;
+    if (status >= 0 || nfev == max_nfev) break;
+    trf_svd(n, m, w, s, V);
+    for (int j = 0; j < n; ++j) {
+      double acc = 0.0;
+      for (int i = lane; i < m; i += 32) acc = fma(w.U[j * m + i], w.f[i], acc);
+      uf[j] = warp_sum(acc);
+    }
+    double actual_reduction = -1.0, cost_new = cost;
+    while (actual_reduction <= 0.0 && nfev < max_nfev) {
+      trf_solve_tr(n, m, uf, s, V, Delta, alpha, step);
+      double q = 0.0;  // evaluate_quadratic
+      for (int i = lane; i < m; i += 32) {
+        double js = 0.0;
+        for (int k = 0; k < n; ++k) js = fma(w.J[k * m + i], step[k], js);
+        q = fma(js, js, q);
+      }
+      q = warp_sum(q);
+      double l = 0.0;
+      for (int k = 0; k < n; ++k) l = fma(step[k], g[k], l);
+      const double predicted_reduction = -(0.5 * q + l);
+      for (int k = 0; k < n; ++k) a_new[k] = a[k] + step[k];
+      double c = 0.0;
+      int bad = 0;
+      for (int i = lane; i < m; i += 32) {
+        const double fn = trf_residual(a_new, n, xn[i], yn[i]);
+        w.f_new[i] = fn;
+        bad |= !isfinite(fn);
+        double r0, r1, r2;
+        huber_rho(fn, r0, r1, r2);
+        c += r0;
+      }
+      ++nfev;
+      const double step_norm = vnorm(step, n);
+      if (__any_sync(0xffffffffu, bad)) { Delta = 0.25 * step_norm; continue; }
+      cost_new = 0.5 * warp_sum(c);
+      actual_reduction = cost - cost_new;
+      double ratio;
+      if (predicted_reduction > 0.0) ratio = actual_reduction / predicted_reduction;
+      else if (predicted_reduction == 0.0 && actual_reduction == 0.0) ratio = 1.0;
+      else ratio = 0.0;
+      double Delta_new = Delta;
+      if (ratio < 0.25) Delta_new = 0.25 * step_norm;
+      else if (ratio > 0.75 && step_norm > 0.95 * Delta) Delta_new = Delta * 2.0;
+      const bool ftol_ok = (actual_reduction < ftol * cost) && (ratio > 0.25);
+      const bool xtol_ok = step_norm < xtol * (xtol + vnorm(a, n));
+      if (ftol_ok && xtol_ok) status = 4; else if (ftol_ok) status = 2; else if (xtol_ok) status = 3;
+      if (status >= 0) break;
+      alpha *= Delta / Delta_new;
+      Delta = Delta_new;
+    }
+    if (actual_reduction > 0.0) {
+      for (int k = 0; k < n; ++k) a[k] = a_new[k];
+      __syncwarp();
+      for (int i = lane; i < m; i += 32) w.f_true[i] = w.f_new[i];
+      __syncwarp();
+      cost = cost_new;
+      trf_linearise(a, n, m, xn, yn, w, g);
+    }
+  }
+  nfev_out = nfev;
+  status_out = status < 0 ? 0 : status;
+}
+
 __global__ void __launch_bounds__(32)
 refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result* __restrict__ winners,
-             double min_fit_error, rb2_refit_result* __restrict__ out, double* __restrict__ mx_out,
+             double min_fit_error, int mode, rb2_refit_result* __restrict__ out, double* __restrict__ mx_out,
              double* __restrict__ my_out, double* __restrict__ res_out, int max_up) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int p = blockIdx.x, lane = threadIdx.x;
@@ -92,8 +368,8 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
   double* xn = iy + n_u;                                                         // [n_u]
   double* yn = xn + n_u;                                                         // [n_u]
   double* sw = yn + n_u;                                                         // [n_u]
-  double* A = sw + n_u;                                                          // [n_u*(n+1)]
-  int* bpeak = reinterpret_cast<int*>(A + (size_t)n_u * (n + 1));                // [n_w]
+  double* A = sw + n_u;                                                          // [n_u*(n+1)] (QR) / J, U, f_true, f, f_new (TRF)
+  int* bpeak = reinterpret_cast<int*>(A + (size_t)n_u * (2 * n + 3));            // [n_w]
 
   double c[NCF];
   for (int i = 0; i < NCF; ++i) c[i] = w.coeffs[i];
@@ -161,32 +437,44 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
   __syncwarp();
   double a[NCF];
   for (int i = 0; i < NCF; ++i) a[i] = 0.0;
-  warp_qr_solve(xn, yn, nullptr, m, n, A, a);
-  // Huber (f_scale = 1): leave the quadratic zone only if some |r| > 1
   int iters = 0;
-  for (; iters < 100; ++iters) {
-    int nout = 0;
-    for (int i = lane; i < m; i += 32) {
-      double f = a[n - 1];
-      for (int j = n - 2; j >= 0; --j) f = fma(f, xn[i], a[j]);
-      const double rr = fabs(yn[i] - f);
-      sw[i] = (rr <= 1.0) ? 1.0 : sqrt(1.0 / rr);
-      nout += (rr > 1.0);
+  r.pad = 0;
+  if (mode == 0) {
+    TrfWs ws;
+    ws.J = A; ws.U = A + (size_t)m * n; ws.f_true = A + (size_t)2 * m * n;
+    ws.f = ws.f_true + m; ws.f_new = ws.f + m; ws.js = sw;
+    double ah[NCF];
+    int nfev = 0, status = 0;
+    trf_huber_warp(n, m, xn, yn, ws, ah, nfev, status);
+    for (int j = 0; j < n; ++j) a[j] = ah[n - 1 - j];  // low order first
+    iters = nfev;
+    r.pad = status;
+  } else {
+    warp_qr_solve(xn, yn, nullptr, m, n, A, a);
+    // Huber (f_scale = 1): leave the quadratic zone only if some |r| > 1
+    for (; iters < 100; ++iters) {
+      int nout = 0;
+      for (int i = lane; i < m; i += 32) {
+        double f = a[n - 1];
+        for (int j = n - 2; j >= 0; --j) f = fma(f, xn[i], a[j]);
+        const double rr = fabs(yn[i] - f);
+        sw[i] = (rr <= 1.0) ? 1.0 : sqrt(1.0 / rr);
+        nout += (rr > 1.0);
+      }
+      nout = __reduce_add_sync(0xffffffffu, nout);
+      __syncwarp();
+      if (nout == 0 && iters == 0) break;
+      double prev[NCF];
+      for (int i = 0; i < n; ++i) prev[i] = a[i];
+      warp_qr_solve(xn, yn, sw, m, n, A, a);
+      double dmax = 0.0, amax = 0.0;
+      for (int i = 0; i < n; ++i) { dmax = fmax(dmax, fabs(a[i] - prev[i])); amax = fmax(amax, fabs(a[i])); }
+      if (dmax <= 1e-15 * amax) { ++iters; break; }
     }
-    nout = __reduce_add_sync(0xffffffffu, nout);
-    __syncwarp();
-    if (nout == 0 && iters == 0) break;
-    double prev[NCF];
-    for (int i = 0; i < n; ++i) prev[i] = a[i];
-    warp_qr_solve(xn, yn, sw, m, n, A, a);
-    double dmax = 0.0, amax = 0.0;
-    for (int i = 0; i < n; ++i) { dmax = fmax(dmax, fabs(a[i] - prev[i])); amax = fmax(amax, fabs(a[i])); }
-    if (dmax <= 1e-15 * amax) { ++iters; break; }
   }
   r.huber_iters = iters;
   // un-normalise (models.py:117-123), low order first
-  double xp = 1.0;
-  for (int j = 0; j < n; ++j) { r.coeffs[j] = a[j] * ys / xp; xp *= xs; }
+  for (int j = 0; j < n; ++j) r.coeffs[j] = (j == 0) ? a[j] * ys : (a[j] * ys) / pow(xs, (double)j);
   // residual = polyval(matched_peaks, coeffs) - matched_atlas, clipped (:664-671)
   double ss = 0.0;
   for (int i = lane; i < m; i += 32) {
@@ -205,23 +493,23 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
 }  // namespace rb2
 
 extern "C" int rb2_refit_winners(int n_problems, const rb2_ransac_desc* d_desc, const rb2_ransac_desc* h_desc,
-                                 const rb2_ransac_result* d_winner, double minimum_fit_error,
+                                 const rb2_ransac_result* d_winner, double minimum_fit_error, int mode,
                                  rb2_refit_result* d_out, double* d_matched_x, double* d_matched_y,
                                  double* d_residual, int max_upeaks, void* stream_) {
   using namespace rb2;
-  if (n_problems <= 0 || !d_desc || !h_desc || !d_winner || !d_out) return RB2_ERR_ARG;
+  if (n_problems <= 0 || !d_desc || !h_desc || !d_winner || !d_out || mode < 0 || mode > 1) return RB2_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   size_t smem = 0;
   for (int i = 0; i < n_problems; ++i) {
     const rb2_ransac_desc& h = h_desc[i];
     if (h.n_upeaks > max_upeaks) return RB2_ERR_ARG;
     const size_t n = h.deg + 1;
-    size_t b = (size_t)h.n_wids * 16 + (size_t)h.n_upeaks * 8 * 5 + (size_t)h.n_upeaks * (n + 1) * 8 + (size_t)h.n_wids * 4;
+    size_t b = (size_t)h.n_wids * 16 + (size_t)h.n_upeaks * 8 * 5 + (size_t)h.n_upeaks * (2 * n + 3) * 8 + (size_t)h.n_wids * 4;
     smem = max(smem, b);
   }
   if (smem > 200 * 1024) return RB2_ERR_ARG;
   RB2_CHECK(cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  refit_kernel<<<n_problems, 32, smem, stream>>>(d_desc, d_winner, minimum_fit_error, d_out, d_matched_x,
+  refit_kernel<<<n_problems, 32, smem, stream>>>(d_desc, d_winner, minimum_fit_error, mode, d_out, d_matched_x,
                                                  d_matched_y, d_residual, max_upeaks);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;

@@ -538,7 +538,7 @@ class RansacBatch:
     def results(self):
         return _download_structs(self.d_result, N.RansacResult, self.n)
 
-    def refit(self, winners=None):
+    def refit(self, winners=None, mode=0):
         """K4 on the current winners (or on explicitly supplied RansacResult structs)."""
         if winners is not None:
             self.d_result.copy_(_upload_structs(winners))
@@ -546,7 +546,7 @@ class RansacBatch:
         if self.d_desc is None:
             self._sync_desc()
         rc = self.lib.rb2_refit_winners(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
-                                        self.d_result.data_ptr(), float(mfe), self.d_refit.data_ptr(),
+                                        self.d_result.data_ptr(), float(mfe), int(mode), self.d_refit.data_ptr(),
                                         self.d_mx.data_ptr(), self.d_my.data_ptr(), self.d_res.data_ptr(),
                                         self.max_up, current_stream_ptr())
         N.check(rc, "rb2_refit_winners")

@@ -73,7 +73,8 @@ def test_replay_reference_draws(golden):
     assert np.array_equal(out["counts"][sc, 0], g["tr_n_match"][sc])
     assert np.array_equal(out["counts"][sc, 1], g["tr_n_inl"][sc])
     # (atol: empty corner bins give a weight that is pure spline noise, << the 1e-9 the cost adds)
-    assert np.allclose(out["weight"][sc], g["tr_weight"][sc], rtol=1e-12, atol=1e-12)
+    dw = np.abs(out["weight"][sc] - g["tr_weight"][sc])
+    assert np.all(dw <= 1e-12 * np.abs(g["tr_weight"][sc]) + 1e-11), (dw.max(), out["weight"][sc][:3], g["tr_weight"][sc][:3])
     # cost = sum(err)/(n-d)/weight: relative 1e-8, or absolute = 1e-8 A of error per peak
     # (exact synthetic atlases give costs that are pure rounding noise)
     atol = 1e-8 / g["tr_weight"][sc]
@@ -104,7 +105,7 @@ def test_replay_selects_reference_winner(golden):
         assert g["tr_status"][win.hyp_id] == O.ST_SCORED
         assert abs(g["tr_cost"][win.hyp_id] - g["tr_cost"][ref_id]) <= 1e-8 / g["tr_weight"][ref_id]
         assert g["tr_n_inl"][win.hyp_id] == g["tr_n_inl"][ref_id]
-    out, mx, my, rs = rb.refit()
+    out, mx, my, rs = rb.refit()  # mode 0: SciPy's TRF iteration restated on the device
     o = out[0]
     assert o.accepted == 1
     m = o.n_inliers
@@ -112,13 +113,27 @@ def test_replay_selects_reference_winner(golden):
     assert np.array_equal(my[0, :m], g["matched_atlas"])
     deg = s.deg
     coeffs = np.array(o.coeffs[: deg + 1])
+    # same iteration path as SciPy on the same inlier set: number of function evaluations
+    info = {}
+    ref = O.robust_polyfit(g["matched_peaks"], g["matched_atlas"], deg, info=info)
+    assert abs(o.huber_iters - info["nfev"]) <= 2
+    # TRF stops 1e-8..1e-5 (relative) short of the optimum, chaotically in the last bits of its
+    # iterates: device vs this SciPy build agree at that level, and both sit that
+    # close to the exact optimum; the wavelength solution itself agrees far below 1e-6 A.
     exact = O.exact_refit(g["matched_peaks"], g["matched_atlas"], deg)
-    assert np.allclose(coeffs, exact, rtol=1e-9, atol=0)
-    # against the reference's own TRF result: same curve, same RMS
+    assert np.allclose(coeffs, exact, rtol=2e-5, atol=0)
+    assert np.allclose(ref, exact, rtol=2e-5, atol=0)
+    assert np.allclose(coeffs, g["fit_coeff"], rtol=2e-5, atol=0)
     assert np.max(np.abs(P.polyval(g["matched_peaks"], coeffs)
                          - P.polyval(g["matched_peaks"], g["fit_coeff"]))) < 1e-6
     assert abs(o.rms - float(g["rms"])) < 1e-6
     assert np.allclose(rs[0, :m], g["residual"], rtol=0, atol=1e-6)
+    # mode 1: the exact Huber optimum, 1e-9 relative against the closed-form least squares
+    out1, mx1, my1, rs1 = rb.refit(mode=1)
+    c1 = np.array(out1[0].coeffs[: deg + 1])
+    assert np.allclose(c1, exact, rtol=1e-9, atol=0)
+    assert out1[0].huber_iters == 0  # inliers never leave Huber's quadratic zone
+    assert np.array_equal(my1[0, :m], g["matched_atlas"])
 
 
 @pytest.mark.parametrize("case", ["c3_deg4", "fine_deg5", "poly_quadratic_deg2"])
@@ -215,3 +230,39 @@ def test_batched_problems_equal_single():
         one.run(0, n, seed=3)
         r = one.results()[0]
         assert (r.cost, r.hyp_id, r.n_inliers) == both[k]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_refit_random_inlier_sets_vs_scipy(seed):
+    """K4 on hand-made winners: noisy / exact / outlier-laden inlier sets, degrees 1-5, vs the
+    real scipy.optimize.least_squares call the reference makes."""
+    from rascal_b200 import _native, engine
+
+    rng = np.random.default_rng(40 + seed)
+    for deg in (1, 2, 3, 4, 5):
+        m = int(rng.integers(deg + 3, 60))
+        x = np.sort(rng.uniform(10, 4000, m))
+        c = np.array([rng.uniform(3500, 6000), rng.uniform(0.8, 2.5), rng.uniform(-5e-5, 5e-5),
+                      rng.uniform(-5e-9, 5e-9), rng.uniform(-5e-13, 5e-13), rng.uniform(-1e-17, 1e-17)])[: deg + 1]
+        y = P.polyval(x, c) + rng.normal(0, [0.0, 0.3, 1.5][seed], m)
+        # a problem whose candidate table is exactly these pairs; the "winner" is the true curve
+        hist = np.ones((4, 4))
+        e = np.linspace(1.0, 2.0, 5)
+        s = engine.RansacSetup(x, y, fit_deg=deg, sample_size=deg + 1, ransac_tolerance=8.0, min_intercept=0,
+                               max_intercept=1e5, pixel_list=np.arange(4096), hist=hist, xedges=e,
+                               yedges=e + 3000, minimum_fit_error=0.0)
+        rb = engine.RansacBatch([s])
+        rb.run(0, 0)  # uploads the descriptors
+        win = _native.struct_array(_native.RansacResult, 1)
+        win[0].cost, win[0].hyp_id = 1.0, 0
+        for k in range(deg + 1):
+            win[0].coeffs[k] = c[k]
+        out, mx, my, rs = rb.refit(win)
+        o = out[0]
+        assert o.n_inliers == m and o.accepted == 1
+        info = {}
+        ref = O.robust_polyfit(x, y, deg, info=info)
+        dev = np.array(o.coeffs[: deg + 1])
+        assert abs(o.huber_iters - info["nfev"]) <= 3, (deg, o.huber_iters, info)
+        assert np.max(np.abs(P.polyval(x, dev) - P.polyval(x, ref))) < 5e-6  # TRF's own stopping noise
+        assert abs(o.rms - np.sqrt(np.mean((P.polyval(x, ref) - y) ** 2))) < 1e-6

@@ -55,7 +55,7 @@ def test_argument_validation_without_device(lib):
     assert lib.rb2_hough_accumulate(0, None, None, None, 0, None) == -2
     assert lib.rb2_candidate_vote(1, None, None, None) == -2
     assert lib.rb2_ransac_batch(1, None, None, None, None, 0, None) == -2
-    assert lib.rb2_refit_winners(1, None, None, None, 0.0, None, None, None, None, 1, None) == -2
+    assert lib.rb2_refit_winners(1, None, None, None, 0.0, 0, None, None, None, None, 1, None) == -2
 
 
 def test_no_cpu_fallback():
