@@ -27,6 +27,7 @@
 // Selection rule (App. A.4): minimal cost among eligible hypotheses, the
 // LATEST hypothesis id among equal costs; per-warp -> per-CTA -> per-problem.
 #include "common.cuh"
+#include <stdio.h>
 
 namespace rb2 {
 
@@ -217,7 +218,7 @@ __device__ __forceinline__ int warp_first_true(int a, int b, Pred&& pred) {
       const int i = lo + lane;
       const bool p = (i < hi) ? pred(i) : true;
       const unsigned bal = __ballot_sync(0xffffffffu, p);
-      return lo + (__ffs(bal) - 1);  // lanes >= width vote true -> hi
+      return bal ? lo + (__ffs(bal) - 1) : hi;  // lanes >= width vote true -> hi; width == 32 and none true -> hi
     }
     const int step = (width + 31) / 32;
     int i = lo + (lane + 1) * step - 1;
@@ -328,7 +329,13 @@ __device__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int
       n_hi += f1 - ia; n_lo += ib + 1 - f2;
       i_mid0 = f1; i_mid1 = f2;
     }
-    for (int i = i_mid0 + lane; i < i_mid1; i += 32) mid += pp_eval(d, w.t_at(i));
+#ifdef RB2_DEBUG_WEIGHT
+    if (lane == 0) printf("piece %d: ia %d ib %d ca %d cb %d mid [%d,%d) n_hi %lld n_lo %lld nb %d brk0 %g\n", pc, ia, ib, ca, cb, i_mid0, i_mid1, n_hi, n_lo, nb, nb ? brk[0] : -1.0);
+#endif
+    for (int i = i_mid0 + lane; i < i_mid1; i += 32) {  // class re-checked per pixel: never extrapolate the pp-form
+      const double t = w.t_at(i);
+      mid += (t >= th_hi) ? d.h_hi : ((t <= th_lo) ? d.h_lo : pp_eval(d, t));
+    }
     ia = ib + 1;
   }
 #pragma unroll

@@ -72,9 +72,10 @@ def test_replay_reference_draws(golden):
     assert np.max(np.abs(dev - ref)) < 1e-6  # incl. the 20 % extrapolation beyond the outer peaks
     assert np.array_equal(out["counts"][sc, 0], g["tr_n_match"][sc])
     assert np.array_equal(out["counts"][sc, 1], g["tr_n_inl"][sc])
-    # (atol: empty corner bins give a weight that is pure spline noise, << the 1e-9 the cost adds)
+    # (atol: empty corner bins give a weight that is pure spline noise, << the 1e-9 the cost adds;
+    #  rtol: a pixel inside the spline window turns 1e-12 of coefficient noise into ~1e-11 of weight)
     dw = np.abs(out["weight"][sc] - g["tr_weight"][sc])
-    assert np.all(dw <= 1e-12 * np.abs(g["tr_weight"][sc]) + 1e-11), (dw.max(), out["weight"][sc][:3], g["tr_weight"][sc][:3])
+    assert np.all(dw <= 1e-10 * np.abs(g["tr_weight"][sc]) + 1e-11), (dw.max(), out["weight"][sc][:3], g["tr_weight"][sc][:3])
     # cost = sum(err)/(n-d)/weight: relative 1e-8, or absolute = 1e-8 A of error per peak
     # (exact synthetic atlases give costs that are pure rounding noise)
     atol = 1e-8 / g["tr_weight"][sc]
@@ -266,3 +267,32 @@ def test_refit_random_inlier_sets_vs_scipy(seed):
         assert abs(o.huber_iters - info["nfev"]) <= 3, (deg, o.huber_iters, info)
         assert np.max(np.abs(P.polyval(x, dev) - P.polyval(x, ref))) < 5e-6  # TRF's own stopping noise
         assert abs(o.rms - np.sqrt(np.mean((P.polyval(x, ref) - y) ** 2))) < 1e-6
+
+
+@pytest.mark.parametrize("seed", [9171440914760070181, 5])
+def test_winner_at_scale_is_the_oracles_minimum(seed):
+    """Min-selection amplifies any rare per-hypothesis glitch: over 2e6 Philox hypotheses the
+    winner record's cost must be what the oracle computes from its coefficients, and no scored
+    hypothesis may beat it (seed 9171440914760070181 / id 956017 once hit a 32-wide search bug)."""
+    from rascal_b200 import engine
+
+    g = load_golden("c3_deg4")
+    s = setup_from_golden(g)
+    prob = problem_from_golden(g)
+    n = 2_000_000
+    rb = engine.RansacBatch([s])
+    out = rb.run(0, n, seed=seed, per_hypothesis=True)
+    win = rb.results()[0]
+    sc = np.flatnonzero(out["status"] == O.ST_SCORED)
+    el = sc[out["counts"][sc, 1] >= s.min_inliers]
+    j = el[np.lexsort((-el, out["cost"][el]))[0]]
+    assert (win.hyp_id, win.cost) == (j, out["cost"][j])
+    assert np.all(out["weight"][sc] < 4096 * 700.0) and np.all(out["weight"][sc] > 0)
+    for i in list(el[np.argsort(out["cost"][el])][:40]):
+        c = out["coeffs"][i]
+        err, mx, my = O.match_bijective(prob, c)
+        err[err > prob.tol] = prob.tol
+        w = O.hough_weight_sum(prob, c)
+        cost = sum(err) / (len(err) - len(c) + 1) / (w + 1e-9)
+        assert np.isclose(out["weight"][i], w, rtol=1e-12, atol=0)
+        assert np.isclose(out["cost"][i], cost, rtol=1e-9, atol=0)
