@@ -189,6 +189,10 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # keep fd 1 for the ONE JSON line: libraries (NCCL's version banner) write to stdout too
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -236,12 +240,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step(k):
-        rb.run(k * H + lo, hi - lo, seed=2026)
-        win = parallel.allgather_winners([rb.results()[0]], group)[0]
-        one = _native.struct_array(_native.RansacResult, 1)
-        one[0] = win
-        out, mx, my, rs = rb.refit(one)
-        return win, out[0]
+        rb.run(k * H + lo, hi - lo, seed=2026)  # K3 main + per-problem finalize
+        rb.exchange(group)                      # NCCL all-gather + device merge (no-op at N=1)
+        rb.refit_async()                        # K4 on the device-resident winner
+        return rb.fetch()                       # the step's single D2H copy
 
     for k in range(args.warmup):
         step(k)
@@ -259,12 +261,11 @@ def main():
             kev[k][0].record()
             rb.run((args.warmup + k) * H + lo, hi - lo, seed=2026)  # K3 main + finalize
             kev[k][1].record()
-            win = parallel.allgather_winners([rb.results()[0]], group)[0]
-            one = _native.struct_array(_native.RansacResult, 1)
-            one[0] = win
-            out, mx, my, rs = rb.refit(one)  # K4
+            rb.exchange(group)
+            rb.refit_async()  # K4
+            win, fit, mx, my, rs = rb.fetch()
             ev[k][1].record()
-            for name, v in engine.counters_dict(win).items():
+            for name, v in engine.counters_dict(win[0]).items():
                 counters[name] += v
         if world > 1:
             dist.barrier()
@@ -335,7 +336,7 @@ def main():
                    "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
         "clocks": clocks.summary(),
         "e2e": e2e,
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": (3 + (1 if world > 1 else 0)) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": None,
                      "kernel": "ransac_kernel<4>", "flops_per_hypothesis": F, "f_intercept_pass": f_i,
@@ -346,7 +347,7 @@ def main():
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

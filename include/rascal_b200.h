@@ -215,6 +215,13 @@ int rb2_ransac_batch(int n_problems, const rb2_ransac_desc *d_desc,
                      const rb2_ransac_desc *h_desc, rb2_ransac_result *d_result,
                      void *d_block_scratch, int blocks_per_problem, void *stream);
 
+/* The one exchange of the multi-GPU path: merge n_sets record
+ * sets laid out [set][problem] - the ncclAllGather'ed per-rank winners, or the
+ * winners of successive launches - with the loop's own rule `cost <= best_cost`
+ * (calibrator.py:636): lower cost, LATER hypothesis id on ties; counters add. */
+int rb2_merge_winners(int n_problems, int n_sets, const rb2_ransac_result *d_sets,
+                      rb2_ransac_result *d_out, void *stream);
+
 /* ======================================================================= *
  * K4  winner refit + acceptance
  *     replaces Calibrator._match_bijective on the winner (calibrator.py:317-380),

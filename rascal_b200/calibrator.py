@@ -350,14 +350,23 @@ class Calibrator:
         rb = engine.RansacBatch([setup])
 
         def evaluate(begin, count, floors=None):
+            """K3 over this rank's slice + the one exchange; the merged winner stays on the device."""
             lo, hi = parallel.shard_range(count, rank, world)
             rb.run(begin + lo, hi - lo, seed=key, floors=floors)
-            return parallel.allgather_winners([rb.results()[0]], self.dist_group)[0]
+            rb.exchange(self.dist_group)
+
+        def one(struct):
+            arr = engine.N.struct_array(engine.N.RansacResult, 1)
+            arr[0] = struct
+            return arr
 
         spans = []
         if n_hypotheses is not None:
             spans.append((0, int(n_hypotheses)))
-            winner = evaluate(0, int(n_hypotheses))
+            evaluate(0, int(n_hypotheses))
+            rb.refit_async()  # K4 straight from the device-resident winner: one D2H for the whole fit
+            win, fit, mx, my, rs = rb.fetch()
+            winner = engine.N.RansacResult.from_buffer_copy(bytes(win[0]))
         else:
             # `max_tries` counts completed tries of the reference loop: scored hypotheses (and
             # impossible draws); rejected draws are redrawn for free (:578-600)
@@ -365,23 +374,22 @@ class Calibrator:
             done, chunk = 0, max(1 << 14, 64 * int(max_tries))
             while winner.counters[5] + winner.counters[1] < int(max_tries) and done < (1 << 40):
                 spans.append((done, chunk))
-                winner = parallel.merge_winners([winner, evaluate(done, chunk)])
+                evaluate(done, chunk)
+                winner = parallel.merge_winners([winner, rb.results()[0]])
                 done += chunk
                 if winner.counters[0] == 0 and winner.counters[1] == 0:
                     break
                 chunk = min(chunk * 4, 1 << 28)
+            fit, mx, my, rs = rb.refit(one(winner))
         self.ransac_counters = engine.counters_dict(winner)
         if self.ransac_counters["unsupported"]:
             self.logger.warning("%d hypotheses left the corner-clamped Hough-weight regime and were skipped",
                                 self.ransac_counters["unsupported"])
-        # refit + refit-dependent acceptance (:652-679); fall through to the next best on failure
+        # refit-dependent acceptance (:652-679); fall through to the next best on failure
         for _ in range(16):
             if winner.hyp_id < 0:
                 return best
-            win = engine.N.struct_array(engine.N.RansacResult, 1)
-            win[0] = winner
-            out, mx, my, rs = rb.refit(win)
-            o = out[0]
+            o = fit[0]
             if o.accepted:
                 m = o.n_inliers
                 self.matched_peaks = list(mx[0, :m])
@@ -390,9 +398,17 @@ class Calibrator:
                 coeffs = np.array(o.coeffs[:fit_deg + 1])
                 self.best_cost = winner.cost
                 self.best_hypothesis = (winner.hyp_id, np.array(winner.coeffs[:fit_deg + 1]))
+                self.refit_nfev = o.huber_iters
                 return coeffs, o.rms, rs[0, :m].copy(), m, m > fit_deg + 1
             floor = (winner.cost, winner.hyp_id)
-            winner = parallel.merge_winners([evaluate(b, c, floors=[floor]) for b, c in spans])
+            nxt = parallel.merge_winners([])
+            for b0, c0 in spans:
+                evaluate(b0, c0, floors=[floor])
+                nxt = parallel.merge_winners([nxt, rb.results()[0]])
+            for k in range(8):
+                nxt.counters[k] = winner.counters[k]
+            winner = nxt
+            fit, mx, my, rs = rb.refit(one(winner))
         return best
 
 

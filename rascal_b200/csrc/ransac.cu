@@ -737,20 +737,23 @@ ransac_kernel(const rb2_ransac_desc* __restrict__ descs, rb2_ransac_result* __re
   }
 }
 
-__global__ void ransac_finalize_kernel(const rb2_ransac_result* __restrict__ block_out, int blocks_per_problem,
-                                       rb2_ransac_result* __restrict__ result) {
-  // one warp per problem
+// one warp per problem: merge `count` records b[i * stride], b = records + p * base_mul
+// (per-CTA records: base_mul = count, stride = 1; per-rank record sets [set][problem]:
+//  base_mul = 1, stride = n_problems)
+__global__ void ransac_finalize_kernel(const rb2_ransac_result* __restrict__ records, int blocks_per_problem,
+                                       int base_mul, int stride, rb2_ransac_result* __restrict__ result) {
   const int p = blockIdx.x, lane = threadIdx.x;
-  const rb2_ransac_result* b = block_out + (size_t)p * blocks_per_problem;
+  const rb2_ransac_result* b0 = records + (size_t)p * base_mul;
+  auto rec = [&](int i) -> const rb2_ransac_result& { return b0[(size_t)i * stride]; };
   double bc = CUDART_INF;
   long long bid = -1;
   int bi = -1;
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = lane; i < blocks_per_problem; i += 32) {
-    const double c = b[i].cost;
-    const long long id = b[i].hyp_id;
+    const double c = rec(i).cost;
+    const long long id = rec(i).hyp_id;
     if (id >= 0 && ((c < bc) || (c == bc && id > bid) || bid < 0)) { bc = c; bid = id; bi = i; }
-    for (int k = 0; k < 8; ++k) cnt[k] += b[i].counters[k];
+    for (int k = 0; k < 8; ++k) cnt[k] += rec(i).counters[k];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -763,7 +766,7 @@ __global__ void ransac_finalize_kernel(const rb2_ransac_result* __restrict__ blo
   if (lane == 0) {
     rb2_ransac_result r;
     if (bi >= 0) {
-      r = b[bi];
+      r = rec(bi);
     } else {
       r.cost = CUDART_INF; r.hyp_id = -1; r.n_match = 0; r.n_inliers = 0;
       for (int i = 0; i < NCOEF; ++i) r.coeffs[i] = 0.0;
@@ -835,7 +838,19 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   else if (fast && deg == 5) rc = launch_ransac<5>(grid, smem, stream, d_desc, scratch);
   else rc = launch_ransac<0>(grid, smem, stream, d_desc, scratch);
   if (rc != RB2_OK) return rc;
-  ransac_finalize_kernel<<<n_problems, 32, 0, stream>>>(scratch, blocks_per_problem, d_result);
+  ransac_finalize_kernel<<<n_problems, 32, 0, stream>>>(scratch, blocks_per_problem, blocks_per_problem, 1, d_result);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+
+// Merge n_sets record sets (layout [set][problem], e.g. the all-gathered per-rank winners or
+// the winners of successive launches) with the same rule: lower cost, later id on ties;
+// counters are summed.  d_out may alias set 0 only if n_sets == 1.
+extern "C" int rb2_merge_winners(int n_problems, int n_sets, const rb2_ransac_result* d_sets,
+                                 rb2_ransac_result* d_out, void* stream_) {
+  using namespace rb2;
+  if (n_problems <= 0 || n_sets <= 0 || !d_sets || !d_out) return RB2_ERR_ARG;
+  ransac_finalize_kernel<<<n_problems, 32, 0, (cudaStream_t)stream_>>>(d_sets, n_sets, 1, n_problems, d_out);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }

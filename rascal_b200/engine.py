@@ -477,19 +477,39 @@ class RansacBatch:
         self.blocks_per_problem = int(blocks_per_problem)
         nbytes = self.lib.rb2_ransac_scratch_bytes(self.n, self.blocks_per_problem)
         self.scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
-        self.d_result = torch.empty(C.sizeof(N.RansacResult) * self.n, dtype=torch.uint8, device="cuda")
-        self.d_refit = torch.empty(C.sizeof(N.RefitResult) * self.n, dtype=torch.uint8, device="cuda")
-        self.d_mx = torch.empty(self.n * self.max_up, dtype=torch.float64, device="cuda")
-        self.d_my = torch.empty(self.n * self.max_up, dtype=torch.float64, device="cuda")
-        self.d_res = torch.empty(self.n * self.max_up, dtype=torch.float64, device="cuda")
-        self.d_desc = None
+        # every per-fit output lives in ONE device buffer so that a fit costs one D2H copy:
+        # [winner records | refit results | matched_x | matched_y | residual]
+        rsz, fsz = C.sizeof(N.RansacResult) * self.n, C.sizeof(N.RefitResult) * self.n
+        msz = 8 * self.n * self.max_up
+        self._o_res, self._o_fit, self._o_mx = 0, rsz, rsz + fsz
+        self._o_my, self._o_rs = self._o_mx + msz, self._o_mx + 2 * msz
+        self.d_out = torch.empty(rsz + fsz + 3 * msz, dtype=torch.uint8, device="cuda")
+        self.h_out = torch.empty(rsz + fsz + 3 * msz, dtype=torch.uint8, pin_memory=True)
+        self.d_result = self.d_out[:rsz]
+        self.d_refit = self.d_out[rsz:rsz + fsz]
+        self.d_desc = torch.empty(C.sizeof(N.RansacDesc) * self.n, dtype=torch.uint8, device="cuda")
+        self.h_desc_pinned = torch.empty(C.sizeof(N.RansacDesc) * self.n, dtype=torch.uint8, pin_memory=True)
+        self._desc_synced = False
+        self._desc_event = None
+        self.d_gather = None
         self._keep = []
 
     def _sync_desc(self):
-        self.d_desc = _upload_structs(self.h_desc)
+        """Descriptors -> device (pinned staging, async on the current stream)."""
+        torch = _torch()
+        nb = C.sizeof(N.RansacDesc) * self.n
+        if self._desc_event is not None:
+            self._desc_event.synchronize()  # the previous async copy has read the staging buffer
+        C.memmove(self.h_desc_pinned.data_ptr(), C.addressof(self.h_desc), nb)
+        self.d_desc.copy_(self.h_desc_pinned, non_blocking=True)
+        self._desc_event = torch.cuda.Event()
+        self._desc_event.record()
+        TRANSFER["h2d"] += nb
+        self._desc_synced = True
 
     def run(self, hyp_begin, n_hyp, seed=0, replay=None, per_hypothesis=False, floors=None):
-        """Evaluate hypothesis ids [hyp_begin, hyp_begin + n_hyp) of every problem.
+        """Evaluate hypothesis ids [hyp_begin, hyp_begin + n_hyp) of every problem; the winner
+        records stay on the device (results() / fetch() bring them back).
 
         replay: optional (x_idx[n_hyp, s], y_idx[n_hyp, s]) int arrays (parity
         mode, one problem); per_hypothesis=True also returns status / cost /
@@ -535,26 +555,67 @@ class RansacBatch:
             outs = {k: v.cpu().numpy() for k, v in outs.items()}
         return outs
 
+    def exchange(self, group=None):
+        """The ONE collective of a sharded fit: all-gather the per-rank winner records (NCCL,
+        device to device) and merge them on the device (rb2_merge_winners).  No-op when the
+        process group has a single rank."""
+        import torch.distributed as dist
+
+        torch = _torch()
+        if group is False or not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        if self.d_gather is None or self.d_gather.numel() != world * self.d_result.numel():
+            self.d_gather = torch.empty(world * self.d_result.numel(), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(self.d_gather, self.d_result, group=group)
+        rc = self.lib.rb2_merge_winners(self.n, world, self.d_gather.data_ptr(), self.d_result.data_ptr(),
+                                        current_stream_ptr())
+        N.check(rc, "rb2_merge_winners")
+
+    def set_winners(self, winners):
+        """Overwrite the device winner records with host structs (fall-through / tests)."""
+        self.d_result.copy_(_upload_structs(winners))
+
     def results(self):
         return _download_structs(self.d_result, N.RansacResult, self.n)
+
+    def refit_async(self, mode=0):
+        """K4 on the winner records currently on the device; nothing is copied back."""
+        mfe = self.setups[0].minimum_fit_error
+        if not self._desc_synced:
+            self._sync_desc()
+        base = self.d_out.data_ptr()
+        rc = self.lib.rb2_refit_winners(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
+                                        self.d_result.data_ptr(), float(mfe), int(mode), self.d_refit.data_ptr(),
+                                        base + self._o_mx, base + self._o_my, base + self._o_rs,
+                                        self.max_up, current_stream_ptr())
+        N.check(rc, "rb2_refit_winners")
+
+    def fetch(self):
+        """ONE device->host copy of everything a fit produced:
+        (winner records, refit results, matched_x, matched_y, residual)."""
+        torch = _torch()
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        TRANSFER["d2h"] += self.h_out.numel()
+        raw = self.h_out.numpy()
+        win = (N.RansacResult * self.n).from_buffer_copy(raw[self._o_res:self._o_fit].tobytes())
+        fit = (N.RefitResult * self.n).from_buffer_copy(raw[self._o_fit:self._o_mx].tobytes())
+        shp = (self.n, self.max_up)
+        mx = raw[self._o_mx:self._o_my].view(np.float64).reshape(shp).copy()
+        my = raw[self._o_my:self._o_rs].view(np.float64).reshape(shp).copy()
+        rs = raw[self._o_rs:].view(np.float64).reshape(shp).copy()
+        return win, fit, mx, my, rs
 
     def refit(self, winners=None, mode=0):
         """K4 on the current winners (or on explicitly supplied RansacResult structs)."""
         if winners is not None:
-            self.d_result.copy_(_upload_structs(winners))
-        mfe = self.setups[0].minimum_fit_error
-        if self.d_desc is None:
-            self._sync_desc()
-        rc = self.lib.rb2_refit_winners(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
-                                        self.d_result.data_ptr(), float(mfe), int(mode), self.d_refit.data_ptr(),
-                                        self.d_mx.data_ptr(), self.d_my.data_ptr(), self.d_res.data_ptr(),
-                                        self.max_up, current_stream_ptr())
-        N.check(rc, "rb2_refit_winners")
-        out = _download_structs(self.d_refit, N.RefitResult, self.n)
-        mx = self.d_mx.cpu().numpy().reshape(self.n, self.max_up)
-        my = self.d_my.cpu().numpy().reshape(self.n, self.max_up)
-        rs = self.d_res.cpu().numpy().reshape(self.n, self.max_up)
-        return out, mx, my, rs
+            self.set_winners(winners)
+        self.refit_async(mode)
+        _, fit, mx, my, rs = self.fetch()
+        return fit, mx, my, rs
 
 
 def counters_dict(res):

@@ -211,6 +211,24 @@ def test_philox_sharding_independent():
     b = (b.cost, b.hyp_id, list(b.counters))
     best = min([a, b], key=lambda t: (t[0], -t[1]))
     assert (whole.cost, whole.hyp_id) == (best[0], best[1])
+    # the device-side merge the NCCL path runs after its all-gather (two "ranks" = two record sets)
+    import ctypes as C
+
+    import torch
+
+    from rascal_b200 import _native
+
+    sets = _native.struct_array(_native.RansacResult, 2)
+    rb.run(0, n // 2, seed=7)
+    sets[0] = rb.results()[0]
+    rb.run(n // 2, n // 2, seed=7)
+    sets[1] = rb.results()[0]
+    d_sets = engine._upload_structs(sets)
+    d_out = torch.empty(C.sizeof(_native.RansacResult), dtype=torch.uint8, device="cuda")
+    _native.check(_native.load().rb2_merge_winners(1, 2, d_sets.data_ptr(), d_out.data_ptr(),
+                                                   engine.current_stream_ptr()), "rb2_merge_winners")
+    merged = engine._download_structs(d_out, _native.RansacResult, 1)[0]
+    assert bytes(merged) == bytes(whole)
     assert list(whole.counters) == [x + y for x, y in zip(a[2], b[2])]
     assert whole.hyp_id >= 0 and whole.n_inliers > s.deg
 
