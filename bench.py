@@ -53,6 +53,39 @@ def c3_input():
                 fit=dict(fit_deg=4, candidate_tolerance=10.0))
 
 
+def c4_input(i):
+    """SURVEY.md 8d "C4 concrete input": spectrum i of the 10k-spectrum batch."""
+    P = np.polynomial.polynomial
+    rng = np.random.default_rng(10_000 + i)
+    npix = int(rng.choice([1024, 2048, 4096]))
+    lam0 = rng.uniform(3500, 6500)
+    dlam = rng.uniform(1500, 5000)
+    while True:
+        a2, a3, a4 = rng.uniform(-0.05, 0.05), rng.uniform(-0.02, 0.02), rng.uniform(-0.01, 0.01)
+        cu = np.array([0.0, 1.0, a2, a3, a4]) / (1 + a2 + a3 + a4)
+        coeff = np.array([lam0] + [dlam * cu[k] / npix ** k for k in range(1, 5)])
+        if np.all(np.diff(P.polyval(np.arange(npix, dtype=float), coeff)) > 0):
+            break
+    n_peaks = int(rng.integers(30, 81))
+    # sorted uniform positions conditioned on >= 3 px separation (constructive, no rejection loop)
+    span = 0.98 * npix - 3.0 * (n_peaks - 1)
+    pix = 0.01 * npix + np.sort(rng.uniform(0, span, n_peaks)) + 3.0 * np.arange(n_peaks)
+    sigma = rng.uniform(0.02, 0.3)
+    peaks = pix + rng.normal(0, sigma, n_peaks)
+    spurious = rng.random(n_peaks) < rng.uniform(0, 0.3)
+    true_waves = P.polyval(pix[~spurious], coeff)
+    m = int(rng.integers(2, 6))
+    lo, hi = P.polyval(0.0, coeff) - 400, P.polyval(npix - 1.0, coeff) + 400
+    atlas = np.sort(np.concatenate((true_waves, rng.uniform(lo, hi, m * len(true_waves)))))
+    return dict(peaks=peaks, lines=atlas, num_pix=npix, truth=coeff,
+                hough=dict(num_slopes=2000, xbins=100, ybins=100,
+                           min_wavelength=float(P.polyval(0.0, coeff) + rng.uniform(-200, 200)),
+                           max_wavelength=float(P.polyval(npix - 1.0, coeff) + rng.uniform(-200, 200)),
+                           range_tolerance=500, linearity_tolerance=100),
+                ransac=dict(sample_size=5, top_n_candidate=5, ransac_tolerance=5),
+                fit=dict(fit_deg=4, candidate_tolerance=10.0))
+
+
 def flops_per_hypothesis(c, deg=4, s=5, n=60, k=5):
     """F = F_fit + f_i*F_mono + f_m*F_score (FP64 flops, algorithmic)."""
     d = deg

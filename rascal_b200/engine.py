@@ -48,6 +48,7 @@ class Arena:
         self.size = 0
         self.buf = None
         self.host = None
+        self.host_cache = None
         self.h2d_bytes = 0
 
     def _bump(self, nbytes):
@@ -63,6 +64,11 @@ class Arena:
 
     def reserve(self, nbytes):
         return self._bump(max(int(nbytes), 1))
+
+    def prefetch(self):
+        """ONE device->host copy of the whole arena; later numpy() calls read the host copy."""
+        self.host_cache = self.buf.cpu().numpy()
+        TRANSFER["d2h"] += self.host_cache.nbytes
 
     def upload(self, pinned=True):
         torch = _torch()
@@ -90,6 +96,8 @@ class Arena:
 
     def numpy(self, off, np_dtype, count):
         nbytes = np.dtype(np_dtype).itemsize * count
+        if self.host_cache is not None:
+            return self.host_cache[off:off + nbytes].view(np_dtype)
         TRANSFER["d2h"] += nbytes
         return self.buf[off:off + nbytes].cpu().numpy().view(np_dtype)
 
@@ -125,8 +133,8 @@ class HoughBatch:
         _torch()
         self.n = len(problems)
         self.problems = problems
-        ar = Arena()
-        self.arena = ar
+        ar, wk, sm = Arena(), Arena(), Arena()  # inputs (H2D) | device-only work | small outputs
+        self.arena, self.work, self.small = ar, wk, sm
         self.h_desc = N.struct_array(N.HoughDesc, self.n)
         self._off = []
         for i, p in enumerate(problems):
@@ -135,12 +143,12 @@ class HoughBatch:
             assert x.shape == y.shape and x.ndim == 1
             P, xb, yb = x.size, int(p["xbins"]), int(p["ybins"])
             B = xb * yb
-            o = dict(x=ar.add(x), y=ar.add(y), lo=ar.reserve(4 * P), hi=ar.reserve(4 * P),
-                     xe=ar.reserve(8 * (xb + 1)), ye=ar.reserve(8 * (yb + 1)), hist=ar.reserve(4 * B),
-                     rank=ar.reserve(4 * B), rankpos=ar.reserve(4 * B), tmp=ar.reserve(4 * B))
+            o = dict(x=ar.add(x), y=ar.add(y), lo=wk.reserve(4 * P), hi=wk.reserve(4 * P),
+                     xe=sm.reserve(8 * (xb + 1)), ye=sm.reserve(8 * (yb + 1)), hist=wk.reserve(4 * B),
+                     rank=wk.reserve(4 * B), rankpos=wk.reserve(4 * B), tmp=wk.reserve(4 * B))
             self._off.append(o)
-        self.o_stats = ar.reserve(C.sizeof(N.HoughStats) * self.n)
-        base = ar.upload()
+        self.o_stats = sm.reserve(C.sizeof(N.HoughStats) * self.n)
+        base, wbase, sbase = ar.upload(), wk.upload(), sm.upload()
         for i, p in enumerate(problems):
             o = self._off[i]
             d = self.h_desc[i]
@@ -149,16 +157,16 @@ class HoughBatch:
             d.n_slopes, d.xbins, d.ybins = int(p["n_slopes"]), int(p["xbins"]), int(p["ybins"])
             d.n_pairs = int(np.asarray(p["pair_x"]).size)
             d.d_pair_x, d.d_pair_y = base + o["x"], base + o["y"]
-            d.d_lo, d.d_hi = base + o["lo"], base + o["hi"]
-            d.d_xedges, d.d_yedges = base + o["xe"], base + o["ye"]
-            d.d_hist, d.d_rank = base + o["hist"], base + o["rank"]
-            d.d_rankpos, d.d_sort_tmp = base + o["rankpos"], base + o["tmp"]
+            d.d_lo, d.d_hi = wbase + o["lo"], wbase + o["hi"]
+            d.d_xedges, d.d_yedges = sbase + o["xe"], sbase + o["ye"]
+            d.d_hist, d.d_rank = wbase + o["hist"], wbase + o["rank"]
+            d.d_rankpos, d.d_sort_tmp = wbase + o["rankpos"], wbase + o["tmp"]
         self.d_desc = _upload_structs(self.h_desc)
         self._stats = None
 
     def run(self, slopes_per_cta=0):
         rc = self.lib.rb2_hough_accumulate(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
-                                           self.arena.ptr(self.o_stats), int(slopes_per_cta), current_stream_ptr())
+                                           self.small.ptr(self.o_stats), int(slopes_per_cta), current_stream_ptr())
         N.check(rc, "rb2_hough_accumulate")
         self._stats = None
         return self
@@ -167,7 +175,7 @@ class HoughBatch:
     @property
     def stats(self):
         if self._stats is None:
-            raw = self.arena.numpy(self.o_stats, np.uint8, C.sizeof(N.HoughStats) * self.n).tobytes()
+            raw = self.small.numpy(self.o_stats, np.uint8, C.sizeof(N.HoughStats) * self.n).tobytes()
             self._stats = (N.HoughStats * self.n).from_buffer_copy(raw)
             for s in self._stats:
                 if s.status != 0:
@@ -180,25 +188,42 @@ class HoughBatch:
 
     def hist(self, i=0):
         xb, yb = self._dims(i)
-        return self.arena.numpy(self._off[i]["hist"], np.uint32, xb * yb).reshape(xb, yb)
+        return self.work.numpy(self._off[i]["hist"], np.uint32, xb * yb).reshape(xb, yb)
 
     def xedges(self, i=0):
-        return self.arena.numpy(self._off[i]["xe"], np.float64, self._dims(i)[0] + 1)
+        return self.small.numpy(self._off[i]["xe"], np.float64, self._dims(i)[0] + 1)
 
     def yedges(self, i=0):
-        return self.arena.numpy(self._off[i]["ye"], np.float64, self._dims(i)[1] + 1)
+        return self.small.numpy(self._off[i]["ye"], np.float64, self._dims(i)[1] + 1)
 
     def rank(self, i=0):
         xb, yb = self._dims(i)
-        return self.arena.numpy(self._off[i]["rank"], np.int32, xb * yb)
+        return self.work.numpy(self._off[i]["rank"], np.int32, xb * yb)
 
     def intervals(self, i=0):
         P = self.h_desc[i].n_pairs
-        return (self.arena.numpy(self._off[i]["lo"], np.int32, P),
-                self.arena.numpy(self._off[i]["hi"], np.int32, P))
+        return (self.work.numpy(self._off[i]["lo"], np.int32, P),
+                self.work.numpy(self._off[i]["hi"], np.int32, P))
 
-    def dev_ptr(self, i, key):
-        return self.arena.ptr(self._off[i][key])
+    def prefetch(self):
+        """Bring every spectrum's edges + stats to the host in one copy (batch set-up)."""
+        self.small.prefetch()
+        self._stats = None
+
+    def first_rows(self):
+        """hist[:, 0] of every problem (the row the Hough-density weight needs),
+        gathered on the device and copied once: list of float64 arrays."""
+        torch = _torch()
+        idx, lens = [], []
+        for i in range(self.n):
+            xb, yb = self._dims(i)
+            idx.append(self._off[i]["hist"] // 4 + np.arange(xb, dtype=np.int64) * yb)
+            lens.append(xb)
+        flat = torch.from_numpy(np.concatenate(idx)).cuda()
+        TRANSFER["h2d"] += flat.numel() * 8
+        vals = self.work.buf.view(torch.int32)[flat].cpu().numpy().astype(np.float64)
+        TRANSFER["d2h"] += vals.size * 4
+        return np.split(vals, np.cumsum(lens)[:-1])
 
     def points(self, i=0):
         """HoughTransform.hough_points, materialised in the reference's row order."""
@@ -239,6 +264,20 @@ def vote_layout(pairs):
     return upeaks, pair_off, order, y, wid.astype(np.int32), uwaves
 
 
+def vote_layout_product(peaks, lines):
+    """vote_layout for pairs = product(peaks, lines) (calibrator.py:103-106) without building
+    the pair list, when the peaks are strictly increasing (else falls back to the general path)."""
+    peaks = np.asarray(peaks, dtype=np.float64)
+    lines = np.asarray(lines, dtype=np.float64)
+    n_p, n_a = len(peaks), len(lines)
+    if n_p > 1 and not np.all(np.diff(peaks) > 0):
+        return vote_layout(np.column_stack((np.repeat(peaks, n_a), np.tile(lines, n_p))))
+    uwaves, inv = np.unique(lines, return_inverse=True)
+    pair_off = (np.arange(n_p + 1, dtype=np.int64) * n_a).astype(np.int32)
+    return (peaks, pair_off, np.arange(n_p * n_a), np.tile(lines, n_p),
+            np.tile(inv.astype(np.int32), n_p), uwaves)
+
+
 class VoteBatch:
     """Per-peak candidate vote for a batch of spectra (rb2_candidate_vote).
 
@@ -252,23 +291,27 @@ class VoteBatch:
         self.n = hough.n
         assert len(settings) == self.n
         self.hough = hough
-        ar = Arena()
-        self.arena = ar
+        ar, out = Arena(), Arena()
+        self.arena, self.out = ar, out
         self.h_desc = N.struct_array(N.VoteDesc, self.n)
         self._off = []
         self.layouts = []
         for i, s in enumerate(settings):
-            upeaks, pair_off, order, y, wid, uwaves = vote_layout(s["pairs"])
+            if s.get("pairs") is None:
+                upeaks, pair_off, order, y, wid, uwaves = vote_layout_product(s["peaks"], s["lines"])
+            else:
+                upeaks, pair_off, order, y, wid, uwaves = vote_layout(s["pairs"])
             self.layouts.append((upeaks, pair_off, order, y, wid, uwaves))
             nu, nw, top_n = len(upeaks), len(uwaves), int(s["top_n"])
             o = dict(ux=ar.add(upeaks), off=ar.add(pair_off), y=ar.add(y), wid=ar.add(wid),
-                     cw=ar.reserve(8 * nu * top_n), cp=ar.reserve(4 * nu * top_n), cn=ar.reserve(4 * nu),
-                     st=ar.add(np.zeros(1, np.int32)))
+                     cw=out.reserve(8 * nu * top_n), cp=out.reserve(4 * nu * top_n), cn=out.reserve(4 * nu),
+                     st=out.reserve(4))
             if diagnostics:
-                o["agg"] = ar.reserve(8 * nu * nw)
-                o["cnt"] = ar.reserve(4 * nu * nw)
+                o["agg"] = out.reserve(8 * nu * nw)
+                o["cnt"] = out.reserve(4 * nu * nw)
             self._off.append(o)
-        base = ar.upload()
+        base, obase = ar.upload(), out.upload()
+        out.buf.zero_()
         for i, s in enumerate(settings):
             o = self._off[i]
             upeaks, pair_off, order, y, wid, uwaves = self.layouts[i]
@@ -281,10 +324,10 @@ class VoteBatch:
             d.d_upeak_x, d.d_pair_off = base + o["ux"], base + o["off"]
             d.d_pair_y, d.d_pair_wid = base + o["y"], base + o["wid"]
             d.d_xedges, d.d_yedges, d.d_rankpos = hd.d_xedges, hd.d_yedges, hd.d_rankpos
-            d.d_cand_wave, d.d_cand_pair, d.d_cand_n = base + o["cw"], base + o["cp"], base + o["cn"]
-            d.d_agg = base + o["agg"] if diagnostics else None
-            d.d_cnt = base + o["cnt"] if diagnostics else None
-            d.d_status = base + o["st"]
+            d.d_cand_wave, d.d_cand_pair, d.d_cand_n = obase + o["cw"], obase + o["cp"], obase + o["cn"]
+            d.d_agg = obase + o["agg"] if diagnostics else None
+            d.d_cnt = obase + o["cnt"] if diagnostics else None
+            d.d_status = obase + o["st"]
         self.d_desc = _upload_structs(self.h_desc)
 
     def run(self):
@@ -298,12 +341,12 @@ class VoteBatch:
         (calibrator.py:174-217): ascending unique peaks, n entries each."""
         o = self._off[i]
         d = self.h_desc[i]
-        st = int(self.arena.numpy(o["st"], np.int32, 1)[0])
+        st = int(self.out.numpy(o["st"], np.int32, 1)[0])
         if st != 0:
             N.check(st, "rb2_candidate_vote (device status)")
         nu, top_n = d.n_upeaks, d.top_n
-        cn = self.arena.numpy(o["cn"], np.int32, nu)
-        cw = self.arena.numpy(o["cw"], np.float64, nu * top_n).reshape(nu, top_n)
+        cn = self.out.numpy(o["cn"], np.int32, nu)
+        cw = self.out.numpy(o["cw"], np.float64, nu * top_n).reshape(nu, top_n)
         upeaks = self.layouts[i][0]
         keep = np.arange(top_n)[None, :] < cn[:, None]
         cand_peak = np.repeat(upeaks, cn)
@@ -313,8 +356,12 @@ class VoteBatch:
     def aggregates(self, i=0):
         o = self._off[i]
         d = self.h_desc[i]
-        return (self.arena.numpy(o["agg"], np.float64, d.n_upeaks * d.n_uwaves).reshape(d.n_upeaks, d.n_uwaves),
-                self.arena.numpy(o["cnt"], np.int32, d.n_upeaks * d.n_uwaves).reshape(d.n_upeaks, d.n_uwaves))
+        return (self.out.numpy(o["agg"], np.float64, d.n_upeaks * d.n_uwaves).reshape(d.n_upeaks, d.n_uwaves),
+                self.out.numpy(o["cnt"], np.int32, d.n_upeaks * d.n_uwaves).reshape(d.n_upeaks, d.n_uwaves))
+
+    def prefetch(self):
+        """Every spectrum's candidates to the host in one copy."""
+        self.out.prefetch()
 
 
 # ---------------------------------------------------------------------------
