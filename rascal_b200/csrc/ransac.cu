@@ -4,28 +4,18 @@
 // (calibrator.py:525-735).  One hypothesis = one minimal sample drawn and
 // fitted (= one polyfit call of the reference).
 //
-// Mapping.  A CTA serves one problem (one spectrum); its read-only tables
-// (<= a few KB: peaks, candidate lists, sampling CDF) live in shared memory.
-// Work is staged so that the three very different cost classes never diverge
-// inside a warp:
-//   stage A  (all 32 lanes, one hypothesis per lane)  counter-based Philox
-//            draw -> exact interpolation (Newton divided differences, one
-//            FP64 division per hypothesis) or least squares (Householder QR)
-//            -> intercept test.  ~85 % of hypotheses end here.  Survivors
-//            are pushed into a per-warp shared-memory ring.
-//   stage B  (32 lanes, one queued hypothesis per lane, run when >= 32 are
-//            queued) monotonicity test: instead of the reference's G ~ 1.4 *
-//            ptp(peaks) point grid, locate the critical points of
-//            q(k) = p(t_k + 1) - p(t_k) and evaluate the reference's own
-//            Horner arithmetic only at the grid points around them.
-//   stage C  (whole warp, one hypothesis at a time) bijective match: lanes
-//            take peaks, shared-memory atomicMin de-duplicates by wavelength
-//            id; M-SAC cost; Hough-density weight by locating the threshold
-//            crossings of the tangent-intercept polynomial with warp-parallel
-//            32-ary searches over the pixel list instead
-//            of evaluating a bicubic spline at every detector pixel.
-// Selection rule (App. A.4): minimal cost among eligible hypotheses, the
-// LATEST hypothesis id among equal costs; per-warp -> per-CTA -> per-problem.
+// Mapping.  The three very different cost classes of a hypothesis never share a warp:
+// they are separate small kernels connected by compacted survivor queues (see "The staged
+// pipeline" below): A draw + fit + intercept test (one thread per hypothesis; ~85 % end
+// here), B monotonicity test (one thread per survivor: instead of the reference's
+// G ~ 1.4 * ptp(peaks) point grid, locate the critical points of q(k) = p(t_k + 1) - p(t_k)
+// and evaluate the reference's own Horner arithmetic only at the grid points around them),
+// C score (one warp per survivor: lanes take peaks, shared-memory atomicMin de-duplicates by
+// wavelength id; M-SAC cost; Hough-density weight by locating the threshold crossings of the
+// tangent-intercept polynomial with warp-parallel 32-ary searches over the pixel list,
+// SURVEY.md App. A.5, instead of evaluating a bicubic spline at every detector pixel).
+// Selection rule (App. A.4): minimal cost among eligible hypotheses, the LATEST hypothesis id
+// among equal costs - a 128-bit atomic min on (sortable cost, ~id) per problem.
 #include "common.cuh"
 #include <stdio.h>
 
@@ -33,7 +23,6 @@ namespace rb2 {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int Q_CAP = 64;  // ring entries per warp
 constexpr int NCOEF = RB2_MAX_DEG + 1;
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter = (id_lo, id_hi, block, 0) ----
@@ -68,35 +57,43 @@ struct Philox {
   }
 };
 
-struct Tables {  // shared-memory views of one problem
-  const double* peaks;     // [n_u]
-  const double* cwave;     // [n_c]
-  const int* coff;         // [n_u+1]
-  const int* cwid;         // [n_c]
-  const unsigned* cdf32;   // [n_u]
-  int n_u, n_c, n_wids;
+// ---- compile-time-degree helpers ---------------------------------------------------------
+// DEG > 0: the degree is a template constant (loops unroll, coefficients live in registers);
+// DEG == 0: run-time degree `deg` (generic path).
+template <int DEG>
+struct Deg {
+  int rt;
+  __device__ __forceinline__ explicit Deg(int deg) : rt(deg) {}
+  __device__ __forceinline__ int get() const { return DEG > 0 ? DEG : rt; }
 };
+__host__ __device__ constexpr int deg_cap(int DEG) { return DEG > 0 ? DEG : RB2_MAX_DEG; }
 
-// first i with r < cdf32[i]  (== searchsorted(cdf, u, 'right')), clamped
-__device__ __forceinline__ int draw_peak(const Tables& t, unsigned r) {
-  int a = 0, b = t.n_u - 1;
-  while (a < b) {
-    const int m = (a + b) >> 1;
-    if (r < t.cdf32[m]) b = m; else a = m + 1;
+// Horner in the reference's arithmetic (np.polynomial.polynomial.polyval: separate mul and add)
+template <int CAP>
+__device__ __forceinline__ double horner_ref(const double (&c)[CAP + 1], int n, double x) {
+  double r = 0.0;
+#pragma unroll
+  for (int i = CAP; i >= 0; --i) {
+    if (i == n - 1) r = c[i];
+    else if (i < n - 1) r = add(c[i], mul(r, x));
   }
-  return a;
+  return r;
 }
-
-// ---- real roots of a polynomial of degree n <= 6 inside [lo, hi] -------------
-// Accuracy target is a fraction of a grid step: the callers re-check the grid
-// points around every root with the reference's arithmetic.
-__device__ __forceinline__ double horner_fma(const double* a, int n, double x) {
-  double r = a[n];
-  for (int i = n - 1; i >= 0; --i) r = fma(r, x, a[i]);
+template <int CAP>
+__device__ __forceinline__ double horner_fast(const double (&a)[CAP + 1], int n, double x) {  // degree n
+  double r = 0.0;
+#pragma unroll
+  for (int i = CAP; i >= 0; --i) {
+    if (i == n) r = a[i];
+    else if (i < n) r = fma(r, x, a[i]);
+  }
   return r;
 }
 
-__device__ int quad_roots(double a, double b, double c, double lo, double hi, double* out) {
+// ---- real roots inside (lo, hi) ------------------------------------------------------------
+// Accuracy target is a fraction of a grid step: the callers re-check the grid points around
+// every root with the reference's arithmetic.
+__device__ __forceinline__ int quad_roots(double a, double b, double c, double lo, double hi, double* out) {
   // a x^2 + b x + c
   int n = 0;
   if (a == 0.0) {
@@ -114,88 +111,90 @@ __device__ int quad_roots(double a, double b, double c, double lo, double hi, do
   return n;
 }
 
-// roots of sum_{i<=n} a[i] x^i in (lo, hi), ascending, via the derivative chain:
-// between consecutive roots of f' the function is monotone -> bisection.
-__device__ int real_roots(const double* a, int n, double lo, double hi, double* out) {
-  while (n > 0 && a[n] == 0.0) --n;
-  if (n <= 0) return 0;
-  if (n <= 2) return quad_roots(n == 2 ? a[2] : 0.0, a[1], a[0], lo, hi, out);
-  // derivative-chain polynomials: D_k = (n-k)-th derivative scaled, degree k
-  double prev[RB2_MAX_DEG], cur[RB2_MAX_DEG];
-  int nprev;
-  {
-    // degree-2 member of the chain: d^(n-2) f / dx^(n-2)
-    double c2[3];
-    for (int i = 0; i <= 2; ++i) {
-      double f = 1.0;
-      for (int j = 0; j < n - 2; ++j) f *= (double)(i + n - 2 - j);
-      c2[i] = a[i + n - 2] * f;
-    }
-    nprev = quad_roots(c2[2], c2[1], c2[0], lo, hi, prev);
-  }
-  for (int k = 3; k <= n; ++k) {
-    // coefficients of the (n-k)-th derivative, degree k
-    double ck[RB2_MAX_DEG + 1];
-    for (int i = 0; i <= k; ++i) {
-      double f = 1.0;
-      for (int j = 0; j < n - k; ++j) f *= (double)(i + n - k - j);
-      ck[i] = a[i + n - k] * f;
-    }
-    int ncur = 0;
-    double left = lo, fl = horner_fma(ck, k, left);
-    for (int s = 0; s <= nprev; ++s) {
-      const double right = (s < nprev) ? prev[s] : hi;
-      const double fr = horner_fma(ck, k, right);
-      if ((fl < 0.0) != (fr < 0.0) && right > left) {
-        double xa = left, xb = right, fa = fl;
-        for (int it = 0; it < 40 && (xb - xa) > 0.125; ++it) {
-          const double xm = 0.5 * (xa + xb);
-          const double fm = horner_fma(ck, k, xm);
-          if ((fm < 0.0) == (fa < 0.0)) { xa = xm; fa = fm; } else { xb = xm; }
+// roots of sum_{i<=n} a[i] x^i (n <= CAP) in (lo, hi), ascending: between consecutive roots of
+// f' the function is monotone -> bisection.  Recursion on the compile-time capacity.
+template <int CAP>
+__device__ __forceinline__ int real_roots(const double (&a)[CAP + 1], int n, double lo, double hi, double (&out)[CAP > 0 ? CAP : 1]) {
+  if constexpr (CAP <= 0) {
+    return 0;
+  } else if constexpr (CAP <= 2) {
+    const double a2 = (CAP >= 2 && n >= 2) ? a[CAP >= 2 ? 2 : 0] : 0.0;
+    const double a1 = (n >= 1) ? a[1] : 0.0;
+    if (n <= 0) return 0;
+    return quad_roots(a2, a1, a[0], lo, hi, out);
+  } else {
+    while (n > 0 && a[n] == 0.0) --n;
+    if (n <= 0) return 0;
+    if (n <= 2) return quad_roots(n == 2 ? a[2] : 0.0, a[1], a[0], lo, hi, out);
+    double da[CAP];           // derivative, degree n - 1 <= CAP - 1
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) da[i] = (i < n) ? (double)(i + 1) * a[i + 1] : 0.0;
+    double crit[CAP - 1 > 0 ? CAP - 1 : 1];
+    const int nc = real_roots<CAP - 1>(da, n - 1, lo, hi, crit);
+    int nout = 0;
+    double left = lo, fl = horner_fast<CAP>(a, n, left);
+#pragma unroll
+    for (int s = 0; s < CAP; ++s) {
+      if (s <= nc) {
+        const double right = (s < nc) ? crit[s < CAP - 1 ? s : 0] : hi;
+        const double fr = horner_fast<CAP>(a, n, right);
+        if ((fl < 0.0) != (fr < 0.0) && right > left) {
+          double xa = left, xb = right, fa = fl;
+          for (int it = 0; it < 40 && (xb - xa) > 0.125; ++it) {
+            const double xm = 0.5 * (xa + xb);
+            const double fm = horner_fast<CAP>(a, n, xm);
+            if ((fm < 0.0) == (fa < 0.0)) { xa = xm; fa = fm; } else { xb = xm; }
+          }
+          out[nout++] = 0.5 * (xa + xb);
         }
-        cur[ncur++] = 0.5 * (xa + xb);
+        left = right; fl = fr;
       }
-      left = right; fl = fr;
     }
-    nprev = ncur;
-    for (int i = 0; i < ncur; ++i) prev[i] = cur[i];
+    return nout;
   }
-  for (int i = 0; i < nprev; ++i) out[i] = prev[i];
-  return nprev;
 }
 
 // ---- monotonicity test (calibrator.py:585-600) -------------------------------
 // all(diff(polyval(arange(pix_min, pix_max, 1), c)) > 0)
-__device__ bool monotonic_test(const double* c, int deg, double pix_min, double pix_max) {
+template <int DEG>
+__device__ __forceinline__ bool monotonic_test(const double (&c)[deg_cap(DEG) + 1], int deg_rt, double pix_min, double pix_max) {
+  constexpr int CAP = deg_cap(DEG);
+  const int deg = DEG > 0 ? DEG : deg_rt;
   const double gl = ceil((pix_max - pix_min) / 1.0);  // numpy arange length
   if (!(gl >= 2.0)) return true;                      // diff of <2 points is empty
   const long long G = (long long)gl;
   const long long kmax = G - 2;                       // D_k for k in [0, kmax]
   auto D = [&](long long k) {
     const double t0 = add(pix_min, (double)k), t1 = add(pix_min, (double)(k + 1));
-    return sub(horner_unfused(c, deg + 1, t1), horner_unfused(c, deg + 1, t0));
+    return sub(horner_ref<CAP>(c, deg + 1, t1), horner_ref<CAP>(c, deg + 1, t0));
   };
   if (!(D(0) > 0.0) || !(D(kmax) > 0.0)) return false;
   if (deg <= 2) return true;  // q is linear: extremes at the ends
   // p~(tau) = p(pix_min + tau): Taylor shift
-  double ps[NCOEF];
-  for (int i = 0; i <= deg; ++i) ps[i] = c[i];
-  for (int i = 0; i < deg; ++i)
-    for (int j = deg - 1; j >= i; --j) ps[j] = fma(pix_min, ps[j + 1], ps[j]);
+  double ps[CAP + 1];
+#pragma unroll
+  for (int i = 0; i <= CAP; ++i) ps[i] = (i <= deg) ? c[i] : 0.0;
+#pragma unroll
+  for (int i = 0; i < CAP; ++i)
+#pragma unroll
+    for (int j = CAP - 1; j >= 0; --j)
+      if (j >= i && j < deg) ps[j] = fma(pix_min, ps[j + 1], ps[j]);
   // q(tau) = p~(tau+1) - p~(tau) = sum_i tau^i sum_{j>i} C(j,i) p~_j ; need q' (degree deg-2)
-  double q[NCOEF];
-  for (int i = 0; i < deg; ++i) {
+  double dq[(CAP - 2 > 0 ? CAP - 2 : 0) + 1];
+#pragma unroll
+  for (int i = 1; i < CAP; ++i) {
     double s = 0.0, binom = 1.0;  // C(j,i) for j = i.. : C(i,i)=1
-    for (int j = i + 1; j <= deg; ++j) {
-      binom = binom * (double)j / (double)(j - i);  // C(j,i)
-      s = fma(binom, ps[j], s);
+#pragma unroll
+    for (int j = 2; j <= CAP; ++j) {
+      if (j > i) {
+        binom = binom * (double)j / (double)(j - i);  // C(j,i)
+        if (j <= deg) s = fma(binom, ps[j], s);
+      }
     }
-    q[i] = s;
+    if (i - 1 <= CAP - 2) dq[i - 1 <= CAP - 2 ? i - 1 : 0] = (i < deg) ? (double)i * s : 0.0;
   }
-  double dq[NCOEF];
-  for (int i = 1; i < deg; ++i) dq[i - 1] = (double)i * q[i];
-  double roots[RB2_MAX_DEG];
-  const int nr = real_roots(dq, deg - 2, 0.0, (double)kmax, roots);
+  double roots[(CAP - 2 > 0 ? CAP - 2 : 1)];
+  const int nr = real_roots<(CAP - 2 > 0 ? CAP - 2 : 0)>(dq, deg - 2, 0.0, (double)kmax, roots);
   for (int r = 0; r < nr; ++r) {
     const long long kf = (long long)floor(roots[r]);
     for (long long k = kf - 1; k <= kf + 2; ++k) {
@@ -206,11 +205,35 @@ __device__ bool monotonic_test(const double* c, int deg, double pix_min, double 
   return true;
 }
 
-// ---- warp-parallel search: first index in [a, b] where pred(i) is true ------
-// pred must be monotone (false...false true...true); returns b+1 if none.
-template <class Pred>
-__device__ __forceinline__ int warp_first_true(int a, int b, Pred&& pred) {
+// ---- Hough-density weight (calibrator.py:497-506, 614-627) ---------------------
+template <int DEG>
+struct WeightCtx {
+  static constexpr int CAP = deg_cap(DEG);
+  double c[CAP + 1];   // coefficients (registers)
+  double dc[CAP + 1];  // derivative coefficients i*c[i] (degree deg-1), padded
+  int deg;
+  const double* pix;   // global or NULL
+  __device__ __forceinline__ double px(int i) const { return pix ? pix[i] : (double)i; }
+  // tangent intercept t(x) = p(x) - x p'(x), the reference's arithmetic (:614-618)
+  __device__ __forceinline__ double t_at(int i) const {
+    const double x = px(i);
+    const double wave = horner_ref<CAP>(c, deg + 1, x);
+    const double grad = (deg >= 1) ? horner_ref<CAP>(dc, deg, x) : 0.0;
+    return sub(wave, mul(grad, x));
+  }
+};
+
+enum { CMP_GT = 0, CMP_GE = 1, CMP_LT = 2, CMP_LE = 3 };
+
+// warp-parallel 32-ary search: first index i in [a, b] with cmp(t(i), th) true (the predicate is
+// monotone false...true on the piece); returns b + 1 if none.  ONE copy of the code (noinline).
+template <int DEG>
+__device__ __noinline__ int warp_first(const WeightCtx<DEG>& w, int a, int b, double th, int cmp) {
   const int lane = lane_id();
+  auto pred = [&](int i) {
+    const double t = w.t_at(i);
+    return cmp == CMP_GT ? (t > th) : cmp == CMP_GE ? (t >= th) : cmp == CMP_LT ? (t < th) : (t <= th);
+  };
   int lo = a, hi = b + 1;  // answer in [lo, hi]
   while (hi > lo) {
     const int width = hi - lo;
@@ -235,22 +258,7 @@ __device__ __forceinline__ int warp_first_true(int a, int b, Pred&& pred) {
   return lo;
 }
 
-struct WeightCtx {
-  const double* c;   // coefficients (smem)
-  double dc[NCOEF];  // derivative coefficients i*c[i]
-  int deg;
-  const double* pix; // global or NULL
-  __device__ __forceinline__ double px(int i) const { return pix ? pix[i] : (double)i; }
-  // tangent intercept t(x) = p(x) - x p'(x), the reference's arithmetic (:614-618)
-  __device__ __forceinline__ double t_at(int i) const {
-    const double x = px(i);
-    const double wave = horner_unfused(c, deg + 1, x);
-    const double grad = (deg >= 1) ? horner_unfused(dc, deg, x) : 0.0;
-    return sub(wave, mul(grad, x));
-  }
-};
-
-__device__ __forceinline__ double pp_eval(const rb2_ransac_desc& d, double t) {
+__device__ __noinline__ double pp_eval(const rb2_ransac_desc& d, double t) {
   // 1-D cubic spline along the first intercept row, pp-form
   int a = 0, b = d.n_pp - 1;
   while (a < b) {
@@ -262,28 +270,43 @@ __device__ __forceinline__ double pp_eval(const rb2_ransac_desc& d, double t) {
   return fma(fma(fma(k[3], dt, k[2]), dt, k[1]), dt, k[0]);
 }
 
-// Hough-density weight of one hypothesis (whole warp).  Returns false when the
-// hypothesis leaves the corner-clamped regime (gradient above the first
-// intercept-bin centre somewhere on the detector).
-__device__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int deg, double* out_weight) {
+// Hough-density weight of one hypothesis (whole warp).  Returns false when the hypothesis
+// leaves the corner-clamped regime (gradient above the first intercept-bin centre somewhere
+// on the detector).
+template <int DEG>
+__device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int deg_rt, double* out_weight) {
+  constexpr int CAP = deg_cap(DEG);
+  const int deg = DEG > 0 ? DEG : deg_rt;
   const int lane = lane_id();
   const int np = d.n_pix;
   if (np <= 0) { *out_weight = 0.0; return true; }
-  WeightCtx w;
-  w.c = c; w.deg = deg; w.pix = d.d_pix;
-  for (int i = 1; i <= deg; ++i) w.dc[i - 1] = mul((double)i, c[i]);
+  WeightCtx<DEG> w;
+  w.deg = deg; w.pix = d.d_pix;
+#pragma unroll
+  for (int i = 0; i <= CAP; ++i) w.c[i] = (i <= deg) ? c[i] : 0.0;
+#pragma unroll
+  for (int i = 0; i <= CAP; ++i) w.dc[i] = (i < deg) ? mul((double)(i + 1), w.c[i + 1 <= CAP ? i + 1 : CAP]) : 0.0;
   const double x0 = w.px(0), x1 = w.px(np - 1);
   // breakpoints of t: t'(x) = -x p''(x)
-  double brk[RB2_MAX_DEG + 1];
+  constexpr int P2 = CAP - 2 > 0 ? CAP - 2 : 0;   // capacity (degree) of p''
+  double brk[P2 + 2];
   int nb = 0;
-  double p2[NCOEF];
-  for (int i = 2; i <= deg; ++i) p2[i - 2] = (double)(i * (i - 1)) * c[i];
-  if (deg >= 3) nb = real_roots(p2, deg - 2, x0, x1, brk);
+  if (deg >= 3) {
+    double p2[P2 + 1];
+#pragma unroll
+    for (int i = 0; i <= P2; ++i) p2[i] = (i + 2 <= deg) ? (double)((i + 2) * (i + 1)) * w.c[i + 2 <= CAP ? i + 2 : CAP] : 0.0;
+    double rts[P2 > 0 ? P2 : 1];
+    nb = real_roots<P2>(p2, deg - 2, x0, x1, rts);
+#pragma unroll
+    for (int i = 0; i < (P2 > 0 ? P2 : 1); ++i) if (i < nb) brk[i] = rts[i];
+  }
   // regime check: max of p'(x) over [x0, x1] must stay <= first intercept-bin centre
   {
-    double gmax = fmax(horner_fma(w.dc, deg - 1 >= 0 ? deg - 1 : 0, x0), horner_fma(w.dc, deg - 1 >= 0 ? deg - 1 : 0, x1));
-    if (deg == 0) gmax = 0.0;
-    for (int r = 0; r < nb; ++r) gmax = fmax(gmax, horner_fma(w.dc, deg - 1, brk[r]));
+    double gmax = 0.0;
+    if (deg >= 1) {
+      gmax = fmax(horner_fast<CAP>(w.dc, deg - 1, x0), horner_fast<CAP>(w.dc, deg - 1, x1));
+      for (int r = 0; r < nb; ++r) gmax = fmax(gmax, horner_fast<CAP>(w.dc, deg - 1, brk[r]));
+    }
     if (!(gmax <= d.ic_min)) return false;
   }
   if (x0 < 0.0 && x1 > 0.0) {  // x = 0 is a breakpoint too
@@ -313,19 +336,21 @@ __device__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int
       ib = np - 1;
     }
     if (ib < ia) continue;
-    const int ca = cls(ia), cb = cls(ib);
+    // classes of the two ends, evaluated by two lanes at once
+    const int ce = cls(lane == 0 ? ia : ib);
+    const int ca = __shfl_sync(0xffffffffu, ce, 0), cb = __shfl_sync(0xffffffffu, ce, 1);
     int i_mid0, i_mid1;  // MID pixels are [i_mid0, i_mid1)
     if (ca == cb) {
       if (ca == 2) n_hi += ib - ia + 1; else if (ca == 0) n_lo += ib - ia + 1;
       i_mid0 = ia; i_mid1 = (ca == 1) ? ib + 1 : ia;
     } else if (ca < cb) {  // increasing: LO.. MID.. HI
-      const int f1 = warp_first_true(ia, ib, [&](int i) { return cls(i) >= 1; });
-      const int f2 = warp_first_true(f1, ib, [&](int i) { return cls(i) >= 2; });
+      const int f1 = warp_first<DEG>(w, ia, ib, th_lo, CMP_GT);
+      const int f2 = warp_first<DEG>(w, f1, ib, th_hi, CMP_GE);
       n_lo += f1 - ia; n_hi += ib + 1 - f2;
       i_mid0 = f1; i_mid1 = f2;
     } else {               // decreasing: HI.. MID.. LO
-      const int f1 = warp_first_true(ia, ib, [&](int i) { return cls(i) <= 1; });
-      const int f2 = warp_first_true(f1, ib, [&](int i) { return cls(i) <= 0; });
+      const int f1 = warp_first<DEG>(w, ia, ib, th_hi, CMP_LT);
+      const int f2 = warp_first<DEG>(w, f1, ib, th_lo, CMP_LE);
       n_hi += f1 - ia; n_lo += ib + 1 - f2;
       i_mid0 = f1; i_mid1 = f2;
     }
@@ -343,15 +368,6 @@ __device__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int
   *out_weight = d.hough_weight * ((double)n_hi * d.h_hi + (double)n_lo * d.h_lo + mid);
   return true;
 }
-
-struct Best {
-  double cost;
-  long long id;
-  int n_match, n_inl;
-  __device__ __forceinline__ bool worse_than(double c, long long i) const {
-    return (c < cost) || (c == cost && i > id);
-  }
-};
 
 // ---- least squares for the generic path: Householder QR on the Vandermonde in
 // a centred, scaled variable; returns monomial coefficients in x.
@@ -458,229 +474,282 @@ __device__ __forceinline__ void newton_fit(const double (&x)[DEG + 1], const dou
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The staged pipeline.  A chunk of hypothesis ids of every problem goes through four small
+// kernels connected by compacted survivor queues in global memory (L2-resident):
+//
+//   A  draw_fit     one thread per hypothesis: Philox draw (or replay) -> fit -> intercept test
+//                   survivors (~16 %) -> queue A          [int + FP64, no divergence by cost class]
+//   B  monotonic    one thread per queue-A entry: monotonicity test; survivors (~2 %) -> queue B
+//   C  score        one warp per queue-B entry: bijective match, M-SAC cost, Hough weight;
+//                   per-problem running best by a 128-bit atomic min on (cost key, ~id)
+//   D  record       one thread per queue-B entry: the entry that owns the running best writes
+//                   the winner record
+//
+// Queue entry = qs doubles: coefficients c[0..deg] + a tag (problem << 40 | local id).
+// ---------------------------------------------------------------------------------------
+
+struct alignas(16) BestKey { unsigned long long lo, hi; };  // hi = sortable cost, lo = ~global id
+
+__device__ __forceinline__ unsigned long long cost_key(double c) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(c);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ bool key_better(const BestKey& a, const BestKey& b) {
+  return (a.hi < b.hi) || (a.hi == b.hi && a.lo < b.lo);
+}
+
+constexpr unsigned long long TAG_ID_MASK = (1ull << 40) - 1ull;
+
+struct Rng {  // 32-bit words for the peak draws, 16-bit halves for the candidate picks
+  Philox p;
+  unsigned half;
+  bool has_half;
+  __device__ __forceinline__ void init(unsigned long long seed, unsigned long long id) { p.init(seed, id); has_half = false; half = 0; }
+  __device__ __forceinline__ unsigned next32() { return p.next(); }
+  __device__ __forceinline__ unsigned next16() {
+    if (has_half) { has_half = false; return half; }
+    const unsigned w = p.next();
+    half = w >> 16; has_half = true;
+    return w & 0xffffu;
+  }
+  // exactly uniform in [0, K), K <= 65536, from the 16-bit stream (Lemire's multiply-shift with
+  // the rare rejection that removes the bias; no division on the common path)
+  __device__ __forceinline__ int uniform(int K) {
+    unsigned x = next16() * (unsigned)K;
+    if ((x & 0xffffu) < (unsigned)K) {
+      const unsigned t = 65536u % (unsigned)K;
+      while ((x & 0xffffu) < t) x = next16() * (unsigned)K;
+    }
+    return (int)(x >> 16);
+  }
+};
+
+struct TablesA {  // shared-memory views of one problem (stage A)
+  const double* peaks; const double* cwave; const int* coff; const int* cwid;
+  const unsigned* cdf32; const unsigned short* lut;
+  int n_u;
+};
+
+// first i with r < cdf32[i] (== searchsorted(cdf, u, 'right')), clamped: 256-entry LUT + scan
+__device__ __forceinline__ int draw_peak_lut(const TablesA& t, unsigned r) {
+  int i = t.lut[r >> 24];
+  while (i < t.n_u - 1 && r >= t.cdf32[i]) ++i;
+  return i;
+}
+
+template <int S>
+__device__ __forceinline__ bool draw_sample(const TablesA& t, unsigned long long seed, unsigned long long gid,
+                                            int (&pi)[S], int (&ci)[S]) {
+  Rng rng;
+  rng.init(seed, gid);
+  // peaks: weighted, without replacement (np.random.choice(..., replace=False, p=prob), :538-540)
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    int idx;
+    bool dup;
+    do {
+      idx = draw_peak_lut(t, rng.next32());
+      dup = false;
+#pragma unroll
+      for (int j = 0; j < S; ++j) if (j < k) dup |= (pi[j] == idx);
+    } while (dup);
+    pi[k] = idx;
+  }
+  // one candidate wavelength per peak, no wavelength twice (:544-566)
+  int wi[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    const int o0 = t.coff[pi[k]], K = t.coff[pi[k] + 1] - o0;
+    bool checked = false;
+    for (;;) {
+      const int j = rng.uniform(K);
+      const int w = t.cwid[o0 + j];
+      bool dup = false;
+#pragma unroll
+      for (int q = 0; q < S; ++q) if (q < k) dup |= (wi[q] == w);
+      if (!dup) { wi[k] = w; ci[k] = o0 + j; break; }
+      if (!checked) {  // is any unused wavelength left for this peak?
+        bool possible = false;
+        for (int jj = 0; jj < K; ++jj) {
+          const int ww = t.cwid[o0 + jj];
+          bool used = false;
+#pragma unroll
+          for (int q = 0; q < S; ++q) if (q < k) used |= (wi[q] == ww);
+          possible |= !used;
+        }
+        if (!possible) return false;  // impossible draw: the try is consumed (:557-566)
+        checked = true;
+      }
+    }
+  }
+  return true;
+}
+
+// generic (run-time sample size) variant for the least-squares path
+__device__ bool draw_sample_dyn(const TablesA& t, unsigned long long seed, unsigned long long gid, int s, int* pi, int* ci) {
+  Rng rng;
+  rng.init(seed, gid);
+  int wi[RB2_MAX_SAMPLE];
+  for (int k = 0; k < s; ++k) {
+    int idx;
+    bool dup;
+    do {
+      idx = draw_peak_lut(t, rng.next32());
+      dup = false;
+      for (int j = 0; j < k; ++j) dup |= (pi[j] == idx);
+    } while (dup);
+    pi[k] = idx;
+  }
+  for (int k = 0; k < s; ++k) {
+    const int o0 = t.coff[pi[k]], K = t.coff[pi[k] + 1] - o0;
+    bool checked = false;
+    for (;;) {
+      const int j = rng.uniform(K);
+      const int w = t.cwid[o0 + j];
+      bool dup = false;
+      for (int q = 0; q < k; ++q) dup |= (wi[q] == w);
+      if (!dup) { wi[k] = w; ci[k] = o0 + j; break; }
+      if (!checked) {
+        bool possible = false;
+        for (int jj = 0; jj < K; ++jj) {
+          const int ww = t.cwid[o0 + jj];
+          bool used = false;
+          for (int q = 0; q < k; ++q) used |= (wi[q] == ww);
+          possible |= !used;
+        }
+        if (!possible) return false;
+        checked = true;
+      }
+    }
+  }
+  return true;
+}
+
+struct Pipe {  // device pointers of the staged pipeline (one per rb2_ransac_batch call)
+  double* qa; double* qb;           // queues, `cap` entries of qs doubles
+  unsigned* counts;                 // [0] = |queue A|, [1] = |queue B|
+  BestKey* best;                    // [n_problems]
+  double* res_cost; int2* res_cnt;  // per queue-B entry
+  unsigned cap; int qs;
+};
+
+__global__ void pipe_init_kernel(Pipe p, rb2_ransac_result* __restrict__ result, int n_problems) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2) p.counts[i] = 0u;
+  if (i >= n_problems) return;
+  p.best[i].hi = ~0ull; p.best[i].lo = ~0ull;
+  rb2_ransac_result r;
+  r.cost = CUDART_INF; r.hyp_id = -1; r.n_match = 0; r.n_inliers = 0;
+  for (int k = 0; k < NCOEF; ++k) r.coeffs[k] = 0.0;
+  for (int k = 0; k < 8; ++k) r.counters[k] = 0ull;
+  result[i] = r;
+}
+
+__global__ void pipe_reset_counts_kernel(Pipe p) { if (threadIdx.x < 2) p.counts[threadIdx.x] = 0u; }
+
+__device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigned v) {
+  if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&r->counters[k]), (unsigned long long)v);
+}
+
+// ---- stage A ---------------------------------------------------------------------------
 template <int DEG_T>
 __global__ void __launch_bounds__(RS_THREADS)
-ransac_kernel(const rb2_ransac_desc* __restrict__ descs, rb2_ransac_result* __restrict__ block_out) {
+ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
+                       rb2_ransac_result* __restrict__ result) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ rb2_ransac_desc s_desc;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned s_cnt[3];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int problem = blockIdx.y;
   {
-    static_assert(sizeof(rb2_ransac_desc) % 4 == 0, "descriptor must be word-sized");
-    const unsigned* src = reinterpret_cast<const unsigned*>(descs + blockIdx.y);
+    const unsigned* src = reinterpret_cast<const unsigned*>(descs + problem);
     unsigned* dst = reinterpret_cast<unsigned*>(&s_desc);
     for (int i = tid; i < (int)(sizeof(rb2_ransac_desc) / 4); i += RS_THREADS) dst[i] = src[i];
+    if (tid < 3) s_cnt[tid] = 0u;
   }
   __syncthreads();
   const rb2_ransac_desc& d = s_desc;
   const int deg = DEG_T > 0 ? DEG_T : d.deg;
   const int ncoef = deg + 1;
-  const int s = DEG_T > 0 ? DEG_T + 1 : d.sample_size;
-  const int n_u = d.n_upeaks, n_wids = d.n_wids;
-  const int n_c = d.n_cand;
+  const int n_u = d.n_upeaks, n_c = d.n_cand;
 
-  // ---- shared memory carve-up ----
   double* s_peaks = reinterpret_cast<double*>(smem_raw);
   double* s_cwave = s_peaks + n_u;
-  double* s_queue = s_cwave + n_c;                                    // [RS_WARPS][Q_CAP][ncoef+1]
-  unsigned long long* s_berr = reinterpret_cast<unsigned long long*>(s_queue + (size_t)RS_WARPS * Q_CAP * (ncoef + 1));  // [RS_WARPS][n_wids]
-  int* s_coff = reinterpret_cast<int*>(s_berr + (size_t)RS_WARPS * n_wids);
+  int* s_coff = reinterpret_cast<int*>(s_cwave + n_c);
   int* s_cwid = s_coff + (n_u + 1);
   unsigned* s_cdf = reinterpret_cast<unsigned*>(s_cwid + n_c);
-  __shared__ unsigned long long s_cnt[8];
-  __shared__ Best s_best[RS_WARPS];
-  __shared__ double s_bcoef[RS_WARPS][NCOEF];
-
+  unsigned short* s_lut = reinterpret_cast<unsigned short*>(s_cdf + n_u);
   for (int i = tid; i < n_u; i += RS_THREADS) { s_peaks[i] = d.d_peaks[i]; s_cdf[i] = d.d_cdf32 ? d.d_cdf32[i] : 0u; }
   for (int i = tid; i <= n_u; i += RS_THREADS) s_coff[i] = d.d_cand_off[i];
   for (int i = tid; i < n_c; i += RS_THREADS) { s_cwave[i] = d.d_cand_wave[i]; s_cwid[i] = d.d_cand_wid[i]; }
-  if (tid < 8) s_cnt[tid] = 0ull;
   __syncthreads();
-
-  Tables tb;
-  tb.peaks = s_peaks; tb.cwave = s_cwave; tb.coff = s_coff; tb.cwid = s_cwid; tb.cdf32 = s_cdf;
-  tb.n_u = n_u; tb.n_c = n_c; tb.n_wids = n_wids;
-
-  const int qstride = ncoef + 1;
-  double* q = s_queue + (size_t)warp * Q_CAP * qstride;
-  unsigned long long* berr = s_berr + (size_t)warp * n_wids;
-  int q_head = 0, q_count = 0;  // warp-uniform
-
-  Best best;
-  best.cost = CUDART_INF; best.id = -1; best.n_match = 0; best.n_inl = 0;
-  double best_coef[NCOEF];
-#pragma unroll
-  for (int i = 0; i < NCOEF; ++i) best_coef[i] = 0.0;
-  unsigned c_drawn = 0, c_abort = 0, c_icpt = 0, c_mono = 0, c_empty = 0, c_scored = 0, c_elig = 0, c_unsup = 0;
+  for (int b = tid; b < 256; b += RS_THREADS) {  // lut[b] = #{i : cdf32[i] <= b << 24}, clamped
+    const unsigned r = (unsigned)b << 24;
+    int lo = 0, hi = n_u - 1;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (r < s_cdf[m]) hi = m; else lo = m + 1; }
+    s_lut[b] = (unsigned short)lo;
+  }
+  __syncthreads();
+  TablesA tb;
+  tb.peaks = s_peaks; tb.cwave = s_cwave; tb.coff = s_coff; tb.cwid = s_cwid; tb.cdf32 = s_cdf; tb.lut = s_lut; tb.n_u = n_u;
 
   const bool replay = d.d_replay_x != nullptr;
+  const int s = DEG_T > 0 ? DEG_T + 1 : d.sample_size;
   const double min_i = d.min_intercept, max_i = d.max_intercept;
-  const double tol = d.tol;
   const long long n_hyp = d.n_hyp;
   const double lsq_xc = 0.5 * (d.pix_min + d.pix_max);
   const double lsq_xsc = (d.pix_max > d.pix_min) ? 2.0 / (d.pix_max - d.pix_min) : 1.0;
+  const int qs = pipe.qs;
+  unsigned c_drawn = 0, c_abort = 0, c_icpt = 0;
 
-  // ---- stage B + C: drain up to 32 queued hypotheses ----
-  auto drain = [&]() {
-    const int take = min(q_count, 32);
-    const bool have = lane < take;
-    const int slot = (q_head + lane) % Q_CAP;
-    const double* qc = q + (size_t)slot * qstride;
-    bool mono = false;
-    long long hid = -1;
-    if (have) {
-      hid = __double_as_longlong(qc[ncoef]);
-      mono = monotonic_test(qc, deg, d.pix_min, d.pix_max);
-      if (!mono && d.d_out_status) d.d_out_status[hid] = (uint8_t)RB2_HYP_MONOTONIC;
-    }
-    unsigned pass = __ballot_sync(0xffffffffu, have && mono);
-    c_mono += __popc(__ballot_sync(0xffffffffu, have && !mono));
-    while (pass) {
-      const int src = __ffs(pass) - 1;
-      pass &= pass - 1;
-      const int sl = (q_head + src) % Q_CAP;
-      const double* cc = q + (size_t)sl * qstride;
-      const long long id = __shfl_sync(0xffffffffu, hid, src);
-      // -- bijective match (calibrator.py:341-380) --
-      for (int i = lane; i < n_wids; i += 32) berr[i] = 0x7ff0000000000000ull;  // +inf = empty
-      __syncwarp();
-      for (int u = lane; u < n_u; u += 32) {
-        const double fit = horner_unfused(cc, ncoef, s_peaks[u]);
-        const int o0 = s_coff[u], o1 = s_coff[u + 1];
-        double be = CUDART_INF;
-        int bw = -1;
-        for (int k = o0; k < o1; ++k) {
-          const double e = fabs(sub(fit, s_cwave[k]));
-          if (e < be) { be = e; bw = s_cwid[k]; }  // first minimum wins
-        }
-        if (bw >= 0) atomicMin(&berr[bw], (unsigned long long)__double_as_longlong(be));
-      }
-      __syncwarp();
-      double esum = 0.0;
-      int nm = 0, ni = 0;
-      for (int i = lane; i < n_wids; i += 32) {
-        const unsigned long long bits = berr[i];
-        if (bits != 0x7ff0000000000000ull) {
-          double e = __longlong_as_double((long long)bits);
-          if (e > tol) e = tol;  // M-SAC clip (:611)
-          esum += e;
-          ++nm;
-          ni += (e < tol);
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        esum += __shfl_xor_sync(0xffffffffu, esum, o);
-        nm += __shfl_xor_sync(0xffffffffu, nm, o);
-        ni += __shfl_xor_sync(0xffffffffu, ni, o);
-      }
-      __syncwarp();
-      if (nm == 0) {  // :607-608
-        ++c_empty;
-        if (lane == 0 && d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY;
-        continue;
-      }
-      double weight;
-      const bool ok = hough_weight_warp(d, cc, deg, &weight);
-      if (!ok) {
-        ++c_unsup;
-        if (lane == 0 && d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED;
-        continue;
-      }
-      const double cost = esum / (double)(nm - ncoef + 1) / (weight + 1e-9);  // :629-633
-      ++c_scored;
-      if (lane == 0) {
-        if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
-        if (d.d_out_cost) d.d_out_cost[id] = cost;
-        if (d.d_out_weight) d.d_out_weight[id] = weight;
-        if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
-      }
-      const long long gid = d.hyp_begin + id;
-      bool elig = (ni >= d.min_inliers) && ((double)ni >= d.min_inliers_frac) && (cost <= d.cost_ceiling);
-      if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
-      if (elig) {
-        ++c_elig;
-        if (best.worse_than(cost, gid)) {
-          best.cost = cost; best.id = gid; best.n_match = nm; best.n_inl = ni;
-#pragma unroll
-          for (int i = 0; i < NCOEF; ++i) best_coef[i] = (i < ncoef) ? cc[i] : 0.0;
-        }
-      }
-    }
-    q_head = (q_head + take) % Q_CAP;
-    q_count -= take;
-  };
-
-  // ---- stage A over this warp's hypotheses ----
   const long long stride = (long long)gridDim.x * RS_THREADS;
-  for (long long base = (long long)blockIdx.x * RS_THREADS + warp * 32; base < n_hyp; base += stride) {
-    const long long id = base + lane;  // index inside this call
-    const bool active = id < n_hyp;
+  for (long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane); base < chunk_len; base += stride) {
+    const long long id = chunk_begin + base + lane;  // index inside this call
+    const bool active = (base + lane < chunk_len) && (id < n_hyp);
     bool pass = false, aborted = false;
     double cf[NCOEF];
 #pragma unroll
     for (int i = 0; i < NCOEF; ++i) cf[i] = 0.0;
     if (active) {
-      int pi[RB2_MAX_SAMPLE];
-      int wi[RB2_MAX_SAMPLE];
-      int ci[RB2_MAX_SAMPLE];
-      if (replay) {
-        for (int k = 0; k < s; ++k) {
-          pi[k] = d.d_replay_x[id * s + k];
-          ci[k] = tb.coff[pi[k]] + d.d_replay_y[id * s + k];
-        }
-      } else {
-        Philox rng;
-        rng.init(d.seed, (unsigned long long)(d.hyp_begin + id));
-        // peaks: weighted, without replacement (np.random.choice(..., replace=False, p=prob), :538-540)
-        for (int k = 0; k < s; ++k) {
-          int idx;
-          bool dup;
-          do {
-            idx = draw_peak(tb, rng.next());
-            dup = false;
-            for (int j = 0; j < k; ++j) dup |= (pi[j] == idx);
-          } while (dup);
-          pi[k] = idx;
-        }
-        // one candidate wavelength per peak, no wavelength twice (:544-566)
-        for (int k = 0; k < s && !aborted; ++k) {
-          const int o0 = tb.coff[pi[k]], K = tb.coff[pi[k] + 1] - o0;
-          bool checked = false;
-          for (;;) {
-            const int j = (int)__umulhi(rng.next(), (unsigned)K);
-            const int w = tb.cwid[o0 + j];
-            bool dup = false;
-            for (int t = 0; t < k; ++t) dup |= (wi[t] == w);
-            if (!dup) { wi[k] = w; ci[k] = o0 + j; break; }
-            if (!checked) {  // is any unused wavelength left for this peak?
-              bool possible = false;
-              for (int jj = 0; jj < K; ++jj) {
-                const int ww = tb.cwid[o0 + jj];
-                bool used = false;
-                for (int t = 0; t < k; ++t) used |= (wi[t] == ww);
-                possible |= !used;
-              }
-              if (!possible) { aborted = true; break; }
-              checked = true;
-            }
+      if constexpr (DEG_T > 0) {
+        int pi[DEG_T + 1], ci[DEG_T + 1];
+        if (replay) {
+#pragma unroll
+          for (int k = 0; k <= DEG_T; ++k) {
+            pi[k] = d.d_replay_x[id * (DEG_T + 1) + k];
+            ci[k] = tb.coff[pi[k]] + d.d_replay_y[id * (DEG_T + 1) + k];
           }
+        } else {
+          aborted = !draw_sample<DEG_T + 1>(tb, d.seed, (unsigned long long)(d.hyp_begin + id), pi, ci);
         }
-      }
-      if (!aborted) {
-        if constexpr (DEG_T > 0) {
+        if (!aborted) {
           double xs[DEG_T + 1], ys[DEG_T + 1], cc[DEG_T + 1];
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) { xs[k] = tb.peaks[pi[k]]; ys[k] = tb.cwave[ci[k]]; }
           newton_fit<DEG_T>(xs, ys, cc);
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) cf[k] = cc[k];
+        }
+      } else {
+        int pi[RB2_MAX_SAMPLE], ci[RB2_MAX_SAMPLE];
+        if (replay) {
+          for (int k = 0; k < s; ++k) {
+            pi[k] = d.d_replay_x[id * s + k];
+            ci[k] = tb.coff[pi[k]] + d.d_replay_y[id * s + k];
+          }
         } else {
+          aborted = !draw_sample_dyn(tb, d.seed, (unsigned long long)(d.hyp_begin + id), s, pi, ci);
+        }
+        if (!aborted) {
           double xs[RB2_MAX_SAMPLE], ys[RB2_MAX_SAMPLE];
           int m = 0;
           for (int k = 0; k < s; ++k) { xs[m] = tb.peaks[pi[k]]; ys[m] = tb.cwave[ci[k]]; ++m; }
           for (int k = 0; k < d.n_known && m < RB2_MAX_SAMPLE; ++k) { xs[m] = d.d_known_x[k]; ys[m] = d.d_known_y[k]; ++m; }
           lsq_polyfit(xs, ys, m, deg, lsq_xc, lsq_xsc, cf);
         }
+      }
+      if (!aborted) {
         pass = !((cf[0] < min_i) || (cf[0] > max_i));  // :578-582
         if (d.d_out_coeffs)
           for (int i = 0; i < ncoef; ++i) d.d_out_coeffs[id * ncoef + i] = cf[i];
@@ -690,50 +759,231 @@ ransac_kernel(const rb2_ransac_desc* __restrict__ descs, rb2_ransac_result* __re
       }
     }
     const unsigned pm = __ballot_sync(0xffffffffu, pass);
-    c_drawn += __popc(__ballot_sync(0xffffffffu, active && !aborted));
-    c_abort += __popc(__ballot_sync(0xffffffffu, aborted));
-    c_icpt += __popc(__ballot_sync(0xffffffffu, active && !aborted && !pass));
-    const int npass = __popc(pm);
-    if (q_count + npass > Q_CAP) drain();
-    if (pass) {
-      const int slot = (q_head + q_count + __popc(pm & ((1u << lane) - 1u))) % Q_CAP;
-      double* qc = q + (size_t)slot * qstride;
-      for (int i = 0; i < ncoef; ++i) qc[i] = cf[i];
-      qc[ncoef] = __longlong_as_double(id);
-    }
-    q_count += npass;
-    __syncwarp();
-    if (q_count >= 32) drain();
-  }
-  while (q_count > 0) drain();
-
-  // ---- per-warp -> per-CTA best, counters ----
-  if (lane == 0) {
-    s_best[warp] = best;
+    c_drawn += active && !aborted;
+    c_abort += aborted;
+    c_icpt += active && !aborted && !pass;
+    if (pm) {  // warp-aggregated push
+      unsigned slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(&pipe.counts[0], (unsigned)__popc(pm));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (pass) {
+        const unsigned slot = slot0 + __popc(pm & ((1u << lane) - 1u));
+        if (slot < pipe.cap) {
+          double* q = pipe.qa + (size_t)slot * qs;
 #pragma unroll
-    for (int i = 0; i < NCOEF; ++i) s_bcoef[warp][i] = best_coef[i];
-    atomicAdd(&s_cnt[0], (unsigned long long)c_drawn);
-    atomicAdd(&s_cnt[1], (unsigned long long)c_abort);
-    atomicAdd(&s_cnt[2], (unsigned long long)c_icpt);
-    atomicAdd(&s_cnt[3], (unsigned long long)c_mono);
-    atomicAdd(&s_cnt[4], (unsigned long long)c_empty);
-    atomicAdd(&s_cnt[5], (unsigned long long)c_scored);
-    atomicAdd(&s_cnt[6], (unsigned long long)c_elig);
-    atomicAdd(&s_cnt[7], (unsigned long long)c_unsup);
+          for (int i = 0; i < NCOEF; ++i) if (i < ncoef) q[i] = cf[i];
+          q[ncoef] = __longlong_as_double((long long)(((unsigned long long)problem << 40) | (unsigned long long)id));
+        }
+      }
+    }
   }
+  // counters: warp -> block -> global
+  c_drawn = __reduce_add_sync(0xffffffffu, c_drawn);
+  c_abort = __reduce_add_sync(0xffffffffu, c_abort);
+  c_icpt = __reduce_add_sync(0xffffffffu, c_icpt);
+  if (lane == 0) { atomicAdd(&s_cnt[0], c_drawn); atomicAdd(&s_cnt[1], c_abort); atomicAdd(&s_cnt[2], c_icpt); }
   __syncthreads();
   if (tid == 0) {
-    int bw = 0;
-    for (int w = 1; w < RS_WARPS; ++w)
-      if (s_best[bw].worse_than(s_best[w].cost, s_best[w].id) && s_best[w].id >= 0) bw = w;
-    rb2_ransac_result r;
-    r.cost = s_best[bw].cost;
-    r.hyp_id = s_best[bw].id;
-    r.n_match = s_best[bw].n_match;
-    r.n_inliers = s_best[bw].n_inl;
-    for (int i = 0; i < NCOEF; ++i) r.coeffs[i] = s_bcoef[bw][i];
-    for (int i = 0; i < 8; ++i) r.counters[i] = s_cnt[i];
-    block_out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = r;
+    add_counter(result + problem, 0, s_cnt[0]);
+    add_counter(result + problem, 1, s_cnt[1]);
+    add_counter(result + problem, 2, s_cnt[2]);
+  }
+}
+
+// ---- stage B ---------------------------------------------------------------------------
+template <int DEG_T>
+__global__ void __launch_bounds__(256)
+ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
+  const unsigned n = min(pipe.counts[0], pipe.cap);
+  const int lane = threadIdx.x & 31;
+  const int qs = pipe.qs;
+  const unsigned total = gridDim.x * blockDim.x;
+  int acc_problem = -1;
+  unsigned acc_n = 0;
+  for (unsigned i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += total) {
+    const unsigned i = i0 + lane;
+    const bool have = i < n;
+    bool mono = false;
+    int problem = -1;
+    double c[deg_cap(DEG_T) + 1];
+    unsigned long long tag = 0;
+    if (have) {
+      const double* q = pipe.qa + (size_t)i * qs;
+      const int ncoef = qs - 1;
+#pragma unroll
+      for (int k = 0; k <= deg_cap(DEG_T); ++k) c[k] = (k < ncoef) ? q[k] : 0.0;
+      tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+      problem = (int)(tag >> 40);
+      const rb2_ransac_desc* d = descs + problem;
+      const int deg = DEG_T > 0 ? DEG_T : d->deg;
+      mono = monotonic_test<DEG_T>(c, deg, d->pix_min, d->pix_max);
+      if (!mono && d->d_out_status) d->d_out_status[tag & TAG_ID_MASK] = (uint8_t)RB2_HYP_MONOTONIC;
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, have && mono);
+    if (have && !mono) {  // rejected: per-thread run-length counter, flushed when the problem changes
+      if (problem != acc_problem) {
+        if (acc_n) add_counter(result + acc_problem, 3, acc_n);
+        acc_problem = problem; acc_n = 0;
+      }
+      ++acc_n;
+    }
+    if (pm) {
+      unsigned slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(&pipe.counts[1], (unsigned)__popc(pm));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (have && mono) {
+        const unsigned slot = slot0 + __popc(pm & ((1u << lane) - 1u));
+        double* q = pipe.qb + (size_t)slot * qs;
+        const int ncoef = qs - 1;
+#pragma unroll
+        for (int k = 0; k <= deg_cap(DEG_T); ++k) if (k < ncoef) q[k] = c[k];
+        q[ncoef] = __longlong_as_double((long long)tag);
+      }
+    }
+  }
+  // final flush, aggregated over the lanes that hold the same problem
+  const unsigned holders = __ballot_sync(0xffffffffu, acc_n > 0);
+  if (acc_n > 0) {
+    const unsigned peers = __match_any_sync(holders, acc_problem);
+    const unsigned sum = __reduce_add_sync(peers, acc_n);
+    if ((peers & ((1u << lane) - 1u)) == 0) add_counter(result + acc_problem, 3, sum);
+  }
+}
+
+// ---- stage C ---------------------------------------------------------------------------
+// one warp per queue-B entry; dynamic smem: per warp  double coef[NCOEF]; u64 berr[max_wids]
+template <int DEG_T>
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_score_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result,
+                    int max_wids) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned n = pipe.counts[1];
+  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
+  double* s_coef = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (NCOEF + max_wids);
+  unsigned long long* berr = reinterpret_cast<unsigned long long*>(s_coef + NCOEF);
+  const unsigned total_warps = gridDim.x * RS_WARPS;
+  int acc_problem = -1;                 // lane 0: run-length counters of the current problem
+  unsigned acc[4] = {0u, 0u, 0u, 0u};   // empty, scored, eligible, unsupported
+  auto flush = [&]() {
+    if (acc_problem >= 0) {
+      add_counter(result + acc_problem, 4, acc[0]); add_counter(result + acc_problem, 5, acc[1]);
+      add_counter(result + acc_problem, 6, acc[2]); add_counter(result + acc_problem, 7, acc[3]);
+    }
+    acc[0] = acc[1] = acc[2] = acc[3] = 0u;
+  };
+  for (unsigned e = blockIdx.x * RS_WARPS + warp; e < n; e += total_warps) {
+    const double* q = pipe.qb + (size_t)e * qs;
+    __syncwarp();
+    if (lane < ncoef) s_coef[lane] = q[lane];
+    const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+    const int problem = (int)(tag >> 40);
+    const long long id = (long long)(tag & TAG_ID_MASK);
+    if (lane == 0 && problem != acc_problem) { flush(); acc_problem = problem; }
+    const rb2_ransac_desc& d = descs[problem];
+    const int n_u = d.n_upeaks, n_wids = d.n_wids;
+    const double tol = d.tol;
+    const double* __restrict__ g_peaks = d.d_peaks;
+    const int* __restrict__ g_coff = d.d_cand_off;
+    const double* __restrict__ g_cwave = d.d_cand_wave;
+    const int* __restrict__ g_cwid = d.d_cand_wid;
+    for (int i = lane; i < n_wids; i += 32) berr[i] = 0x7ff0000000000000ull;  // +inf = empty
+    __syncwarp();
+    const double* cc = s_coef;
+    double cr[deg_cap(DEG_T) + 1];
+#pragma unroll
+    for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? cc[k] : 0.0;
+    // -- bijective match (calibrator.py:341-380) --
+    for (int u = lane; u < n_u; u += 32) {
+      const double fit = horner_ref<deg_cap(DEG_T)>(cr, ncoef, g_peaks[u]);
+      const int o0 = g_coff[u], o1 = g_coff[u + 1];
+      double be = CUDART_INF;
+      int bw = -1;
+      for (int k = o0; k < o1; ++k) {
+        const double er = fabs(sub(fit, g_cwave[k]));
+        if (er < be) { be = er; bw = g_cwid[k]; }  // first minimum wins
+      }
+      if (bw >= 0) atomicMin(&berr[bw], (unsigned long long)__double_as_longlong(be));
+    }
+    __syncwarp();
+    double esum = 0.0;
+    int nm = 0, ni = 0;
+    for (int i = lane; i < n_wids; i += 32) {
+      const unsigned long long bits = berr[i];
+      if (bits != 0x7ff0000000000000ull) {
+        double er = __longlong_as_double((long long)bits);
+        if (er > tol) er = tol;  // M-SAC clip (:611)
+        esum += er;
+        ++nm;
+        ni += (er < tol);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      esum += __shfl_xor_sync(0xffffffffu, esum, o);
+      nm += __shfl_xor_sync(0xffffffffu, nm, o);
+      ni += __shfl_xor_sync(0xffffffffu, ni, o);
+    }
+    if (lane == 0) { pipe.res_cost[e] = CUDART_NAN; pipe.res_cnt[e] = make_int2(nm, ni); }
+    if (nm == 0) {  // :607-608
+      if (lane == 0) { ++acc[0]; if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY; }
+      continue;
+    }
+    double weight;
+    const bool ok = hough_weight_warp<DEG_T>(d, cc, deg, &weight);
+    if (!ok) {
+      if (lane == 0) { ++acc[3]; if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED; }
+      continue;
+    }
+    const double cost = esum / (double)(nm - ncoef + 1) / (weight + 1e-9);  // :629-633
+    const long long gid = d.hyp_begin + id;
+    bool elig = (ni >= d.min_inliers) && ((double)ni >= d.min_inliers_frac) && (cost <= d.cost_ceiling);
+    if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
+    if (lane == 0) {
+      ++acc[1];
+      if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
+      if (d.d_out_cost) d.d_out_cost[id] = cost;
+      if (d.d_out_weight) d.d_out_weight[id] = weight;
+      if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
+      if (elig) {
+        ++acc[2];
+        pipe.res_cost[e] = cost;
+        BestKey mine;
+        mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
+        BestKey* slot = pipe.best + problem;
+        BestKey cur;
+        cur.hi = *reinterpret_cast<volatile unsigned long long*>(&slot->hi);
+        cur.lo = *reinterpret_cast<volatile unsigned long long*>(&slot->lo);
+        while (key_better(mine, cur)) {
+          const BestKey old = atomicCAS(slot, cur, mine);
+          if (old.hi == cur.hi && old.lo == cur.lo) break;
+          cur = old;
+        }
+      }
+    }
+  }
+  if (lane == 0) flush();
+}
+
+// ---- stage D ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ransac_record_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
+  const unsigned n = pipe.counts[1];
+  const int qs = pipe.qs, ncoef = qs - 1;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const double cost = pipe.res_cost[e];
+    if (!(cost == cost)) continue;  // NaN = not eligible
+    const double* q = pipe.qb + (size_t)e * qs;
+    const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+    const int problem = (int)(tag >> 40);
+    const long long gid = descs[problem].hyp_begin + (long long)(tag & TAG_ID_MASK);
+    const BestKey b = pipe.best[problem];
+    if (b.hi != cost_key(cost) || b.lo != ~(unsigned long long)gid) continue;
+    rb2_ransac_result* r = result + problem;
+    r->cost = cost; r->hyp_id = gid;
+    const int2 c = pipe.res_cnt[e];
+    r->n_match = c.x; r->n_inliers = c.y;
+    for (int k = 0; k < NCOEF; ++k) r->coeffs[k] = (k < ncoef) ? q[k] : 0.0;
   }
 }
 
@@ -776,32 +1026,58 @@ __global__ void ransac_finalize_kernel(const rb2_ransac_result* __restrict__ rec
   }
 }
 
-static size_t ransac_smem_bytes(const rb2_ransac_desc& h, int n_c) {
-  const int ncoef = h.deg + 1;
-  size_t b = 0;
-  b += (size_t)h.n_upeaks * 8 + (size_t)n_c * 8;
-  b += (size_t)RS_WARPS * Q_CAP * (ncoef + 1) * 8;
-  b += (size_t)RS_WARPS * h.n_wids * 8;
-  b += (size_t)(h.n_upeaks + 1) * 4 + (size_t)n_c * 4 + (size_t)h.n_upeaks * 4;
-  return b;
+
+}  // namespace rb2
+
+namespace rb2 {
+
+constexpr unsigned PIPE_CHUNK = 1u << 22;  // hypotheses per chunk == queue capacity (worst case: all survive)
+
+struct PipeLayout { size_t counts, best, qa, qb, res_cost, res_cnt, total; };
+
+static PipeLayout pipe_layout(int n_problems) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  PipeLayout L;
+  size_t o = 0;
+  L.counts = o; o = up(o + 16);
+  L.best = o; o = up(o + (size_t)n_problems * sizeof(BestKey));
+  L.qa = o; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
+  L.qb = o; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
+  L.res_cost = o; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.res_cnt = o; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.total = o;
+  return L;
+}
+
+static size_t stage_a_smem(const rb2_ransac_desc& h) {
+  return (size_t)h.n_upeaks * 8 + (size_t)h.n_cand * 8 + (size_t)(h.n_upeaks + 1) * 4 + (size_t)h.n_cand * 4 +
+         (size_t)h.n_upeaks * 4 + 256 * 2 + 16;
+}
+
+template <int DEG_T>
+static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int sms, cudaStream_t stream,
+                        const rb2_ransac_desc* d_desc, const Pipe& pipe, long long chunk_begin, long long chunk_len,
+                        rb2_ransac_result* d_result) {
+  static bool configured = false;
+  if (!configured || true) {
+    RB2_CHECK(cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    RB2_CHECK(cudaFuncSetAttribute(ransac_score_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    configured = true;
+  }
+  pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(pipe);
+  ransac_draw_fit_kernel<DEG_T><<<grid_a, RS_THREADS, smem_a, stream>>>(d_desc, pipe, chunk_begin, chunk_len, d_result);
+  ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(d_desc, pipe, d_result);
+  ransac_score_kernel<DEG_T><<<sms * 4, RS_THREADS, smem_c, stream>>>(d_desc, pipe, d_result, max_wids);
+  ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(d_desc, pipe, d_result);
+  return RB2_OK;
 }
 
 }  // namespace rb2
 
 extern "C" size_t rb2_ransac_scratch_bytes(int n_problems, int blocks_per_problem) {
-  int sms = 148;
-  rb2_sm_count(&sms);
-  if (blocks_per_problem <= 0) blocks_per_problem = 4 * sms;
-  return (size_t)n_problems * blocks_per_problem * sizeof(rb2_ransac_result);
-}
-
-template <int DEG_T>
-static int launch_ransac(dim3 grid, size_t smem, cudaStream_t stream, const rb2_ransac_desc* d_desc,
-                         rb2_ransac_result* scratch) {
-  using namespace rb2;
-  RB2_CHECK(cudaFuncSetAttribute(ransac_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ransac_kernel<DEG_T><<<grid, RS_THREADS, smem, stream>>>(d_desc, scratch);
-  return RB2_OK;
+  (void)blocks_per_problem;
+  if (n_problems <= 0) return 0;
+  return rb2::pipe_layout(n_problems).total;
 }
 
 extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, const rb2_ransac_desc* h_desc,
@@ -809,14 +1085,16 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
                                 void* stream_) {
   using namespace rb2;
   if (n_problems <= 0 || !d_desc || !h_desc || !d_result || !d_block_scratch) return RB2_ERR_ARG;
+  if ((unsigned)n_problems > PIPE_CHUNK || n_problems >= (1 << 23)) return RB2_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   int sms = 148;
   if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
-  if (blocks_per_problem <= 0) blocks_per_problem = 4 * sms;
   // all problems of one call share degree / sample size (one kernel instantiation)
   const int deg = h_desc[0].deg, s = h_desc[0].sample_size;
   bool fast = true;
-  size_t smem = 0;
+  size_t smem_a = 0;
+  int max_wids = 1;
+  long long max_hyp = 0;
   for (int i = 0; i < n_problems; ++i) {
     const rb2_ransac_desc& h = h_desc[i];
     if (h.deg != deg || h.sample_size != s) return RB2_ERR_ARG;
@@ -824,21 +1102,47 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     if (h.sample_size + h.n_known > RB2_MAX_SAMPLE) return RB2_ERR_ARG;
     if (h.n_upeaks < h.sample_size && !h.d_replay_x) return RB2_ERR_ARG;
     if (h.sample_size != h.deg + 1 || h.n_known != 0) fast = false;
-    if (h.n_cand < h.n_upeaks || h.n_wids < 1) return RB2_ERR_ARG;
-    smem = max(smem, ransac_smem_bytes(h, h.n_cand));
+    if (h.n_cand < h.n_upeaks || h.n_wids < 1 || h.n_upeaks > 65535) return RB2_ERR_ARG;
+    if (h.n_hyp < 0 || h.n_hyp >= (1ll << 40)) return RB2_ERR_ARG;
+    smem_a = max(smem_a, stage_a_smem(h));
+    max_wids = max(max_wids, h.n_wids);
+    max_hyp = max(max_hyp, (long long)h.n_hyp);
   }
-  if (smem > 200 * 1024) return RB2_ERR_ARG;
-  dim3 grid(blocks_per_problem, n_problems);
-  rb2_ransac_result* scratch = (rb2_ransac_result*)d_block_scratch;
-  int rc;
-  if (fast && deg == 1) rc = launch_ransac<1>(grid, smem, stream, d_desc, scratch);
-  else if (fast && deg == 2) rc = launch_ransac<2>(grid, smem, stream, d_desc, scratch);
-  else if (fast && deg == 3) rc = launch_ransac<3>(grid, smem, stream, d_desc, scratch);
-  else if (fast && deg == 4) rc = launch_ransac<4>(grid, smem, stream, d_desc, scratch);
-  else if (fast && deg == 5) rc = launch_ransac<5>(grid, smem, stream, d_desc, scratch);
-  else rc = launch_ransac<0>(grid, smem, stream, d_desc, scratch);
-  if (rc != RB2_OK) return rc;
-  ransac_finalize_kernel<<<n_problems, 32, 0, stream>>>(scratch, blocks_per_problem, blocks_per_problem, 1, d_result);
+  const size_t smem_c = (size_t)RS_WARPS * (NCOEF + max_wids) * 8;
+  if (smem_a > 200 * 1024 || smem_c > 200 * 1024) return RB2_ERR_ARG;
+
+  const PipeLayout L = pipe_layout(n_problems);
+  unsigned char* base = (unsigned char*)d_block_scratch;
+  Pipe pipe;
+  pipe.counts = (unsigned*)(base + L.counts);
+  pipe.best = (BestKey*)(base + L.best);
+  pipe.qa = (double*)(base + L.qa);
+  pipe.qb = (double*)(base + L.qb);
+  pipe.res_cost = (double*)(base + L.res_cost);
+  pipe.res_cnt = (int2*)(base + L.res_cnt);
+  pipe.cap = PIPE_CHUNK;
+  pipe.qs = deg + 2;
+  pipe_init_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(pipe, d_result, n_problems);
+
+  const long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
+  for (long long c0 = 0; c0 < max_hyp; c0 += per_problem) {
+    const long long len = min(per_problem, max_hyp - c0);
+    int bpp = blocks_per_problem;
+    if (bpp <= 0) {
+      const long long want = (len + RS_THREADS * 8 - 1) / (RS_THREADS * 8);   // >= 8 passes per CTA
+      const long long fill = max(1ll, (long long)(8 * sms) / n_problems);      // ~8 CTAs per SM overall
+      bpp = (int)max(1ll, min(want, fill));
+    }
+    dim3 grid_a(bpp, n_problems);
+    int rc;
+    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    if (rc != RB2_OK) return rc;
+  }
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }

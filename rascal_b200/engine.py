@@ -518,10 +518,7 @@ class RansacBatch:
         sms = C.c_int(0)
         N.check(self.lib.rb2_sm_count(C.byref(sms)), "rb2_sm_count")
         self.sm_count = sms.value
-        if blocks_per_problem <= 0:
-            # one problem: fill the machine; many problems: a few CTAs each
-            blocks_per_problem = max(1, min(4 * self.sm_count, (8 * self.sm_count + self.n - 1) // self.n))
-        self.blocks_per_problem = int(blocks_per_problem)
+        self.blocks_per_problem = max(0, int(blocks_per_problem))  # stage-A CTAs per problem per chunk; 0 = auto
         nbytes = self.lib.rb2_ransac_scratch_bytes(self.n, self.blocks_per_problem)
         self.scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
         # every per-fit output lives in ONE device buffer so that a fit costs one D2H copy:
