@@ -104,38 +104,50 @@ def flops_per_hypothesis(c, deg=4, s=5, n=60, k=5):
 
 
 class ClockSampler:
+    """One long-running `nvidia-smi -lms 20` started before the timed region and stopped after
+    it (B200_PROFILING.md's clocks line); samples inside [t_begin, t_end] are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._read, daemon=True)
+            self._t.start()
+            time.sleep(0.25)  # let the first samples arrive before the timed region starts
+            self.skip = len(self.rows)
+        except Exception:
+            self.proc = None
+            self.skip = 0
         return self
 
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.strip().split(",")])
+
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[max(0, self.skip - 1):]
+        ok = [r for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        sm = [float(r[0]) for r in ok]
+        mx = [float(r[1]) for r in ok if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in ok for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 

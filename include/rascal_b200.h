@@ -169,6 +169,9 @@ typedef struct {
   int32_t n_pp;                         /* pieces of the 1-D spline along the first intercept row */
   const double *d_pp_breaks;            /* [n_pp+1]                          */
   const double *d_pp_coef;              /* [n_pp*4] c0..c3 in (u - break)    */
+  double w_upper;                       /* upper bound of the weight over ALL hypotheses (hough_weight *
+                                           n_pix * max of the section spline), or <= 0 if the spline
+                                           can go negative: lets K3 skip hypotheses that cannot win */
   int32_t n_pix;                        /* len(pixel_list)                   */
   const double *d_pix;                  /* sorted pixel_list, or NULL == arange(n_pix) */
   /* acceptance that does not need the refit (calibrator.py:640-649, 684-700) */

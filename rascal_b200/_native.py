@@ -62,7 +62,7 @@ class RansacDesc(C.Structure):
         ("hough_weight", C.c_double), ("gc_min", C.c_double), ("gc_max", C.c_double),
         ("ic_min", C.c_double), ("h_lo", C.c_double), ("h_hi", C.c_double),
         ("n_pp", C.c_int32), ("d_pp_breaks", _vp), ("d_pp_coef", _vp),
-        ("n_pix", C.c_int32), ("d_pix", _vp),
+        ("w_upper", C.c_double), ("n_pix", C.c_int32), ("d_pix", _vp),
         ("min_inliers", C.c_int32), ("min_inliers_frac", C.c_double),
         ("cost_ceiling", C.c_double), ("floor_cost", C.c_double), ("floor_id", C.c_int64),
         ("hyp_begin", C.c_int64), ("n_hyp", C.c_int64), ("seed", C.c_uint64),

@@ -274,7 +274,8 @@ __device__ __noinline__ double pp_eval(const rb2_ransac_desc& d, double t) {
 // leaves the corner-clamped regime (gradient above the first intercept-bin centre somewhere
 // on the detector).
 template <int DEG>
-__device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int deg_rt, double* out_weight) {
+__device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int deg_rt, bool need_value,
+                                                  double* out_weight) {
   constexpr int CAP = deg_cap(DEG);
   const int deg = DEG > 0 ? DEG : deg_rt;
   const int lane = lane_id();
@@ -309,6 +310,7 @@ __device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, cons
     }
     if (!(gmax <= d.ic_min)) return false;
   }
+  if (!need_value) { *out_weight = CUDART_NAN; return true; }  // regime established; the value cannot matter
   if (x0 < 0.0 && x1 > 0.0) {  // x = 0 is a breakpoint too
     int k = nb;
     while (k > 0 && brk[k - 1] > 0.0) { brk[k] = brk[k - 1]; --k; }
@@ -654,7 +656,7 @@ __device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigne
 
 // ---- stage A ---------------------------------------------------------------------------
 template <int DEG_T>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 ? 4 : 2)
 ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
                        rb2_ransac_result* __restrict__ result) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -853,7 +855,7 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
 // ---- stage C ---------------------------------------------------------------------------
 // one warp per queue-B entry; dynamic smem: per warp  double coef[NCOEF]; u64 berr[max_wids]
 template <int DEG_T>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 ? 4 : 2)
 ransac_score_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result,
                     int max_wids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -929,14 +931,14 @@ ransac_score_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ra
       if (lane == 0) { ++acc[0]; if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY; }
       continue;
     }
+    const long long gid = d.hyp_begin + id;
     double weight;
-    const bool ok = hough_weight_warp<DEG_T>(d, cc, deg, &weight);
+    const bool ok = hough_weight_warp<DEG_T>(d, cc, deg, true, &weight);
     if (!ok) {
       if (lane == 0) { ++acc[3]; if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED; }
       continue;
     }
     const double cost = esum / (double)(nm - ncoef + 1) / (weight + 1e-9);  // :629-633
-    const long long gid = d.hyp_begin + id;
     bool elig = (ni >= d.min_inliers) && ((double)ni >= d.min_inliers_frac) && (cost <= d.cost_ceiling);
     if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
     if (lane == 0) {

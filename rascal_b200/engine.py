@@ -471,6 +471,25 @@ class RansacSetup:
         return self.minimum_peak_utilisation * self.n_peaks_total  # :692-700
 
 
+def weight_upper_bound(s):
+    """Rigorous upper bound of the Hough-density weight of ANY hypothesis of problem `s`
+    (every pixel contributes h_lo, h_hi or a value of the section spline): the Bernstein
+    coefficients of each cubic piece enclose its range.  <= 0 disables K3's early skip (a
+    spline that can go negative makes the cost unbounded below)."""
+    c = np.asarray(s.pp_coef, dtype=np.float64).reshape(-1, 4)
+    h = np.diff(np.asarray(s.pp_breaks, dtype=np.float64))
+    b0 = c[:, 0]
+    b1 = c[:, 0] + c[:, 1] * h / 3.0
+    b2 = c[:, 0] + 2.0 * c[:, 1] * h / 3.0 + c[:, 2] * h * h / 3.0
+    b3 = c[:, 0] + c[:, 1] * h + c[:, 2] * h * h + c[:, 3] * h ** 3
+    bern = np.stack((b0, b1, b2, b3))
+    lo = min(float(bern.min()), s.h_lo, s.h_hi)
+    hi = max(float(bern.max()), s.h_lo, s.h_hi)
+    if not (lo >= 0.0 and hi > 0.0 and s.hough_weight > 0.0 and np.isfinite(hi)):
+        return -1.0
+    return float(s.hough_weight * s.n_pix * hi * (1.0 + 1e-9))
+
+
 class RansacBatch:
     """K3 + K4 for a batch of prepared problems (rb2_ransac_batch / rb2_refit_winners)."""
 
@@ -510,6 +529,7 @@ class RansacBatch:
             d.n_pp = len(s.pp_breaks) - 1
             d.d_pp_breaks, d.d_pp_coef = base + o["ppb"], base + o["ppc"]
             d.n_pix = s.n_pix
+            d.w_upper = weight_upper_bound(s)
             d.d_pix = None if s.pix_is_arange else base + o["pix"]
             d.min_inliers, d.min_inliers_frac = s.min_inliers, s.min_inliers_frac
             d.cost_ceiling = s.cost_ceiling

@@ -306,6 +306,11 @@ def test_winner_at_scale_is_the_oracles_minimum(seed):
     j = el[np.lexsort((-el, out["cost"][el]))[0]]
     assert (win.hyp_id, win.cost) == (j, out["cost"][j])
     assert np.all(out["weight"][sc] < 4096 * 700.0) and np.all(out["weight"][sc] > 0)
+    # production launch (no per-hypothesis outputs) -> same winner, same counters, bit for bit
+    rb.run(0, n, seed=seed)
+    fast = rb.results()[0]
+    assert bytes(fast) == bytes(win)
+    assert s.min_inliers <= win.n_inliers and engine.weight_upper_bound(s) >= out["weight"][sc].max()
     for i in list(el[np.argsort(out["cost"][el])][:40]):
         c = out["coeffs"][i]
         err, mx, my = O.match_bijective(prob, c)
