@@ -252,6 +252,57 @@ int rb2_refit_winners(int n_problems, const rb2_ransac_desc *d_desc,
                       double *d_matched_y, double *d_residual, int max_upeaks,
                       void *stream);
 
+/* models.robust_polyfit (models.py:70-123) on arbitrary point sets, batched: problem p owns
+ * points [off[p], off[p+1]) of d_x / d_y.  Used where the reference calls robust_polyfit
+ * outside the RANSAC loop (Calibrator.match_peaks calibrator.py:1915-1920, manual_refit
+ * :2113-2124).  rms = sqrt(mean((y - polyval(x))^2)) unclipped; n_inliers = point count;
+ * accepted = 0 when a problem has <= deg points.  mode as in rb2_refit_winners. */
+int rb2_robust_polyfit(int n_problems, const int32_t *d_off, const int32_t *h_off,
+                       const double *d_x, const double *d_y, int deg, int mode,
+                       rb2_refit_result *d_out, void *stream);
+
+/* ======================================================================= *
+ * K5  match_peaks: post-fit association of EVERY peak with the atlas
+ *     replaces the body of Calibrator.match_peaks (calibrator.py:1824-1956,
+ *     refine=False): per peak polyval -> atlas lines with |line - fit| <
+ *     tolerance (:1830-1838), polyfit of the association (:1890-1903), then
+ *     models.robust_polyfit on it (:1915-1920) and the signed residuals / rms
+ *     (:1936-1941).  The reference's permutation search (:1841-1876) only runs
+ *     to completion when every peak has at most ONE atlas line inside the
+ *     tolerance (otherwise it raises); for an ambiguous peak the
+ *     nearest line (first on ties) is taken and n_ambiguous counts such peaks.
+ * ======================================================================= */
+typedef struct {
+  const double *d_peaks;                /* [n_peaks] in the caller's order   */
+  const double *d_atlas;                /* [n_atlas] in atlas order          */
+  int32_t n_peaks, n_atlas;
+  double coeffs[RB2_MAX_DEG + 1];       /* solution to match with, low order first */
+  const double *d_coeffs;               /* if non-NULL: read the n_coef coefficients from the device
+                                           instead (e.g. rb2_refit_result.coeffs of K4: no host trip) */
+  int32_t n_coef;                       /* its length                        */
+  int32_t fit_deg;                      /* degree of polyfit / robust refit  */
+  double tolerance;
+  int32_t robust_refit;                 /* 0: stop after the polyfit         */
+  int32_t pad;
+} rb2_match_desc;
+
+typedef struct {
+  int32_t n_matched, n_ambiguous;
+  double polyfit_coeffs[RB2_MAX_DEG + 1]; /* :1893, low order first          */
+  double polyfit_err;                   /* sum |atlas - polyval| (:1896-1897) */
+  double polyfit_rms;                   /* :1908-1910                        */
+  rb2_refit_result refit;               /* robust refit; accepted = 0 if not run / too few points */
+} rb2_match_result;
+
+/* d_matched_x / d_matched_y / d_residual: [n_problems * max_peaks]; residual =
+ * atlas - polyval(peak, refit) (signed, :1936) when robust_refit, else
+ * |atlas - polyval(peak, polyfit)| (:1896). */
+int rb2_match_peaks(int n_problems, const rb2_match_desc *d_desc,
+                    const rb2_match_desc *h_desc, int mode,
+                    rb2_match_result *d_out, double *d_matched_x,
+                    double *d_matched_y, double *d_residual, int max_peaks,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -358,6 +358,55 @@ def exact_refit(x, y, degree):
     return c * ys / xs ** np.arange(degree + 1)
 
 
+
+def match_peaks(peaks, lines, fit_coeff, tolerance=10.0, fit_deg=None,
+                robust_refit=True, refit=None):
+    """Calibrator.match_peaks with refine=False (calibrator.py:1824-1956).
+
+    The reference's permutation search (:1841-1876) only completes when every
+    peak has at most one atlas line inside ``tolerance``: with an ambiguous
+    peak it raises (TypeError at :1867 under numpy >= 1.24; with that index
+    fixed, np.array() of a ragged list / a length mismatch in polyfit).  For
+    such a peak this restatement takes the NEAREST line (first on ties) and
+    counts it in ``n_ambiguous``; with n_ambiguous == 0 the result is the
+    reference's.  Returns a dict (fit_coeff, matched_peaks, matched_atlas,
+    rms, residuals, polyfit_coeff, polyfit_err, polyfit_rms, n_ambiguous)."""
+    polyfit = np.polynomial.polynomial.polyfit
+    polyval = np.polynomial.polynomial.polyval
+    fit_coeff = np.asarray(fit_coeff, dtype=np.float64)
+    if fit_deg is None:
+        fit_deg = len(fit_coeff) - 1  # :1795-1796
+    atlas_lines = np.asarray(lines, dtype=np.float64)
+    mp, ma, n_amb = [], [], 0
+    for p in peaks:  # :1830-1838
+        x = polyval(p, fit_coeff)
+        diff = atlas_lines - x
+        hit = np.abs(diff) < tolerance
+        if hit.any():
+            idx = np.flatnonzero(hit)
+            n_amb += len(idx) > 1
+            mp.append(p)
+            ma.append(atlas_lines[idx[np.argmin(np.abs(diff[idx]))]])
+    mp, ma = np.array(mp, dtype=np.float64), np.array(ma, dtype=np.float64)
+    out = dict(matched_peaks=mp, matched_atlas=ma, n_ambiguous=int(n_amb),
+               fit_coeff=None, rms=None, residuals=None,
+               polyfit_coeff=None, polyfit_err=None, polyfit_rms=None)
+    if len(mp) <= fit_deg:
+        return out
+    pc = polyfit(mp, ma, fit_deg)  # :1893
+    res = np.abs(ma - polyval(mp, pc))  # :1895-1897
+    out.update(polyfit_coeff=pc, polyfit_err=float(np.sum(res)),
+               polyfit_rms=float(np.sqrt(np.nansum(res ** 2.0) / len(res))))
+    if robust_refit:  # :1915-1941
+        c = (refit or robust_polyfit)(mp, ma, fit_deg)
+        r = ma - polyval(mp, c)
+        out.update(fit_coeff=np.asarray(c), residuals=r,
+                   rms=float(np.sqrt(np.nansum(r ** 2.0) / len(r))))
+    else:
+        out.update(residuals=res, rms=out["polyfit_rms"])
+    return out
+
+
 def acceptance(prob: RansacProblem, r, refit=robust_polyfit):
     """a14 checks after `cost <= best_cost`; calibrator.py:640-700.
 

@@ -88,7 +88,23 @@ class RefitResult(C.Structure):
     ]
 
 
-STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult]
+class MatchDesc(C.Structure):
+    _fields_ = [
+        ("d_peaks", _vp), ("d_atlas", _vp), ("n_peaks", C.c_int32), ("n_atlas", C.c_int32),
+        ("coeffs", C.c_double * NCOEF), ("d_coeffs", _vp), ("n_coef", C.c_int32), ("fit_deg", C.c_int32),
+        ("tolerance", C.c_double), ("robust_refit", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class MatchResult(C.Structure):
+    _fields_ = [
+        ("n_matched", C.c_int32), ("n_ambiguous", C.c_int32),
+        ("polyfit_coeffs", C.c_double * NCOEF), ("polyfit_err", C.c_double), ("polyfit_rms", C.c_double),
+        ("refit", RefitResult),
+    ]
+
+
+STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult, MatchDesc, MatchResult]
 COUNTER_NAMES = ("drawn", "aborted", "intercept", "monotonic", "empty", "scored", "eligible", "unsupported")
 
 # every symbol include/rascal_b200.h declares
@@ -105,6 +121,8 @@ EXPORTS = {
     "rb2_ransac_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rb2_ransac_batch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_merge_winners": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
+    "rb2_robust_polyfit": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "rb2_match_peaks": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_refit_winners": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_double, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
 }
 

@@ -166,13 +166,17 @@ class BatchResult(types.SimpleNamespace):
     pass
 
 
-def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=None):
+def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=None, match_tolerance=None):
     """do_hough_transform() + fit() for every spectrum of `spectra` in batched device calls.
 
     All spectra of one call must share fit_deg and sample size (one K3 instantiation).
     Returns a list of BatchResult(fit_coeff, matched_peaks, matched_atlas, rms, residual,
     peak_utilisation, atlas_utilisation, valid, cost, counters); fit_coeff is None where the
-    reference would raise "Couldn't fit"."""
+    reference would raise "Couldn't fit".
+
+    match_tolerance: if set, Calibrator.match_peaks(tolerance=match_tolerance) follows every fit
+    (K5), reading the refit coefficients straight from K4's device records; the result gains
+    `match` = BatchResult(fit_coeff, matched_peaks, matched_atlas, rms, residuals, n_ambiguous)."""
     import time
 
     torch = engine._torch()
@@ -201,12 +205,21 @@ def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=
     live = [i for i, s in enumerate(setups) if s.enough]
     results = [BatchResult(fit_coeff=None, matched_peaks=[], matched_atlas=[], rms=1e50, residual=None,
                            peak_utilisation=0.0, atlas_utilisation=0.0, valid=False, cost=float("inf"),
-                           counters=None) for _ in specs]
+                           counters=None, match=None) for _ in specs]
     if live:
         rb = engine.RansacBatch([setups[i] for i in live])
         rb.run(0, int(n_hypotheses), seed=seed)
         rb.refit_async(mode=refit_mode)
+        mb = None
+        if match_tolerance is not None:
+            stride = engine.C.sizeof(engine.N.RefitResult)
+            mb = engine.MatchBatch([dict(peaks=specs[i]["peaks"], lines=specs[i]["lines"],
+                                         d_coeffs=rb.d_refit.data_ptr() + k * stride, n_coef=setups[i].deg + 1,
+                                         fit_deg=setups[i].deg, tolerance=match_tolerance, robust_refit=True)
+                                    for k, i in enumerate(live)]).run(mode=refit_mode)
         win, fit, mx, my, rs = rb.fetch()
+        if mb is not None:
+            mres, mmx, mmy, mrs = mb.fetch()
         for k, i in enumerate(live):
             o, w, sp = fit[k], win[k], specs[i]
             res = results[i]
@@ -220,6 +233,11 @@ def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=
                 res.peak_utilisation = m / len(sp["peaks"])
                 res.atlas_utilisation = m / len(sp["lines"])
                 res.valid = m > d + 1
+                if mb is not None and mres[k].refit.accepted:
+                    q, mm = mres[k], mres[k].n_matched
+                    res.match = BatchResult(fit_coeff=np.array(q.refit.coeffs[:d + 1]), matched_peaks=mmx[k, :mm].copy(),
+                                            matched_atlas=mmy[k, :mm].copy(), rms=q.refit.rms,
+                                            residuals=mrs[k, :mm].copy(), n_ambiguous=q.n_ambiguous)
     torch.cuda.synchronize()
     t3 = time.perf_counter()
     if timings is not None:

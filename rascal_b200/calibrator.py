@@ -306,6 +306,58 @@ class Calibrator:
         return (self.fit_coeff, self.matched_peaks, self.matched_atlas, self.rms, self.residual,
                 self.peak_utilisation, self.atlas_utilisation)
 
+    def match_peaks(self, fit_coeff=None, n_delta=None, refine=False, tolerance=10.0, method="Nelder-Mead",
+                    convergence=1e-6, min_frac=0.5, robust_refit=True, fit_deg=None, refit_mode=0):
+        """calibrator.py:1717-1956 on the device (K5, rb2_match_peaks): every peak is associated
+        with the atlas lines within `tolerance` of the given solution, the association is
+        polyfit-ted and (robust_refit) re-fitted with models.robust_polyfit.
+
+        Where the reference is defined (no peak has two atlas lines inside the tolerance) the
+        7-tuple is the reference's.  Where it raises (an ambiguous peak: TypeError at :1867, see
+        DESIGN.md) the nearest line is taken and a warning is logged.  `refine=True` (the
+        experimental Nelder-Mead pre-step, :1797-1821) is not on the accelerated path."""
+        if fit_coeff is None:
+            fit_coeff = self.fit_coeff.copy()
+        if fit_deg is None:
+            fit_deg = len(fit_coeff) - 1
+        if refine:
+            raise NotImplementedError("match_peaks(refine=True) (experimental in the reference, "
+                                      "calibrator.py:1797-1821) is not on the accelerated path")
+        if getattr(self, "polyval", None) is None:
+            self.polyfit = np.polynomial.polynomial.polyfit
+            self.polyval = np.polynomial.polynomial.polyval
+        mb = engine.MatchBatch([dict(peaks=np.asarray(self.peaks, dtype=np.float64),
+                                     lines=np.asarray(self.atlas.get_lines(), dtype=np.float64),
+                                     coeffs=fit_coeff, tolerance=tolerance, fit_deg=fit_deg,
+                                     robust_refit=robust_refit)]).run(mode=refit_mode)
+        res, mx, my, rs = mb.fetch()
+        r = res[0]
+        m = r.n_matched
+        if m == 0:
+            raise TypeError("expected non-empty vector for x")  # np.polynomial.polyfit([], [], deg), :1893
+        if m <= fit_deg:
+            raise ValueError("match_peaks: %d matched peaks cannot constrain a degree-%d fit" % (m, fit_deg))
+        if r.n_ambiguous:
+            self.logger.warning("%d peaks have more than one atlas line within the tolerance; the nearest "
+                                "line is used (the reference raises here)." % r.n_ambiguous)
+        self.matched_peaks = mx[0, :m].copy()
+        self.matched_atlas = my[0, :m].copy()
+        self.match_ambiguous = int(r.n_ambiguous)
+        self.peak_utilisation = m / len(self.peaks)
+        self.atlas_utilisation = m / len(self.atlas)
+        self.residuals = rs[0, :m].copy()
+        if robust_refit:
+            self.fit_coeff = np.array(r.refit.coeffs[:fit_deg + 1])
+            self.rms = r.refit.rms
+            self.refit_nfev = r.refit.huber_iters
+        else:
+            # the reference assigns an undefined name here (:1944, UnboundLocalError unless
+            # refine=True); the documented intent is "the current solution": keep the input
+            self.fit_coeff = np.asarray(fit_coeff)
+            self.rms = r.polyfit_rms
+        return (self.fit_coeff, self.matched_peaks, self.matched_atlas, self.rms, self.residuals,
+                self.peak_utilisation, self.atlas_utilisation)
+
     def _vote(self, candidate_tolerance):
         """K2: _get_candidate_points_linear + _get_most_common_candidates (calibrator.py:154-261)."""
         sigma = (self.range_tolerance + self.linearity_tolerance) * 1.1775  # :256

@@ -45,6 +45,8 @@ extern "C" int rb2_struct_size(int which) {
     case 3: return (int)sizeof(rb2_ransac_desc);
     case 4: return (int)sizeof(rb2_ransac_result);
     case 5: return (int)sizeof(rb2_refit_result);
+    case 6: return (int)sizeof(rb2_match_desc);
+    case 7: return (int)sizeof(rb2_match_result);
     default: return -1;
   }
 }

@@ -345,6 +345,66 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
   status_out = status < 0 ? 0 : status;
 }
 
+// models.robust_polyfit (models.py:70-123) on m points (ix, iy) in shared memory, one warp.
+// xn, yn, sw: [m] scratch; A: [(2n+3)*m] scratch.  Fills r.coeffs (low order first),
+// r.huber_iters (nfev / IRLS passes) and r.pad (SciPy status).
+__device__ void robust_polyfit_warp(int m, int n, const double* ix, const double* iy, double* xn, double* yn, double* sw,
+                                    double* A, int mode, rb2_refit_result& r) {
+  const int lane = lane_id();
+  // models.normalise_input: population standard deviations
+  double sx = 0.0, sy = 0.0;
+  for (int i = lane; i < m; i += 32) { sx += ix[i]; sy += iy[i]; }
+  const double mxm = warp_sum(sx) / m, mym = warp_sum(sy) / m;
+  double vx = 0.0, vy = 0.0;
+  for (int i = lane; i < m; i += 32) {
+    const double dx = ix[i] - mxm, dy = iy[i] - mym;
+    vx = fma(dx, dx, vx); vy = fma(dy, dy, vy);
+  }
+  const double xs = sqrt(warp_sum(vx) / m), ys = sqrt(warp_sum(vy) / m);
+  for (int i = lane; i < m; i += 32) { xn[i] = ix[i] / xs; yn[i] = iy[i] / ys; }
+  __syncwarp();
+  double a[NCF];
+  for (int i = 0; i < NCF; ++i) a[i] = 0.0;
+  int iters = 0;
+  r.pad = 0;
+  if (mode == 0) {
+    TrfWs ws;
+    ws.J = A; ws.U = A + (size_t)m * n; ws.f_true = A + (size_t)2 * m * n;
+    ws.f = ws.f_true + m; ws.f_new = ws.f + m; ws.js = sw;
+    double ah[NCF];
+    int nfev = 0, status = 0;
+    trf_huber_warp(n, m, xn, yn, ws, ah, nfev, status);
+    for (int j = 0; j < n; ++j) a[j] = ah[n - 1 - j];  // low order first
+    iters = nfev;
+    r.pad = status;
+  } else {
+    warp_qr_solve(xn, yn, nullptr, m, n, A, a);
+    // Huber (f_scale = 1): leave the quadratic zone only if some |r| > 1
+    for (; iters < 100; ++iters) {
+      int nout = 0;
+      for (int i = lane; i < m; i += 32) {
+        double f = a[n - 1];
+        for (int j = n - 2; j >= 0; --j) f = fma(f, xn[i], a[j]);
+        const double rr = fabs(yn[i] - f);
+        sw[i] = (rr <= 1.0) ? 1.0 : sqrt(1.0 / rr);
+        nout += (rr > 1.0);
+      }
+      nout = __reduce_add_sync(0xffffffffu, nout);
+      __syncwarp();
+      if (nout == 0 && iters == 0) break;
+      double prev[NCF];
+      for (int i = 0; i < n; ++i) prev[i] = a[i];
+      warp_qr_solve(xn, yn, sw, m, n, A, a);
+      double dmax = 0.0, amax = 0.0;
+      for (int i = 0; i < n; ++i) { dmax = fmax(dmax, fabs(a[i] - prev[i])); amax = fmax(amax, fabs(a[i])); }
+      if (dmax <= 1e-15 * amax) { ++iters; break; }
+    }
+  }
+  r.huber_iters = iters;
+  // un-normalise (models.py:117-123), low order first
+  for (int j = 0; j < n; ++j) r.coeffs[j] = (j == 0) ? a[j] * ys : (a[j] * ys) / pow(xs, (double)j);
+}
+
 __global__ void __launch_bounds__(32)
 refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result* __restrict__ winners,
              double min_fit_error, int mode, rb2_refit_result* __restrict__ out, double* __restrict__ mx_out,
@@ -423,58 +483,7 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
     if (lane == 0) out[p] = r;
     return;
   }
-  // models.normalise_input: population standard deviations
-  double sx = 0.0, sy = 0.0;
-  for (int i = lane; i < m; i += 32) { sx += ix[i]; sy += iy[i]; }
-  const double mxm = warp_sum(sx) / m, mym = warp_sum(sy) / m;
-  double vx = 0.0, vy = 0.0;
-  for (int i = lane; i < m; i += 32) {
-    const double dx = ix[i] - mxm, dy = iy[i] - mym;
-    vx = fma(dx, dx, vx); vy = fma(dy, dy, vy);
-  }
-  const double xs = sqrt(warp_sum(vx) / m), ys = sqrt(warp_sum(vy) / m);
-  for (int i = lane; i < m; i += 32) { xn[i] = ix[i] / xs; yn[i] = iy[i] / ys; }
-  __syncwarp();
-  double a[NCF];
-  for (int i = 0; i < NCF; ++i) a[i] = 0.0;
-  int iters = 0;
-  r.pad = 0;
-  if (mode == 0) {
-    TrfWs ws;
-    ws.J = A; ws.U = A + (size_t)m * n; ws.f_true = A + (size_t)2 * m * n;
-    ws.f = ws.f_true + m; ws.f_new = ws.f + m; ws.js = sw;
-    double ah[NCF];
-    int nfev = 0, status = 0;
-    trf_huber_warp(n, m, xn, yn, ws, ah, nfev, status);
-    for (int j = 0; j < n; ++j) a[j] = ah[n - 1 - j];  // low order first
-    iters = nfev;
-    r.pad = status;
-  } else {
-    warp_qr_solve(xn, yn, nullptr, m, n, A, a);
-    // Huber (f_scale = 1): leave the quadratic zone only if some |r| > 1
-    for (; iters < 100; ++iters) {
-      int nout = 0;
-      for (int i = lane; i < m; i += 32) {
-        double f = a[n - 1];
-        for (int j = n - 2; j >= 0; --j) f = fma(f, xn[i], a[j]);
-        const double rr = fabs(yn[i] - f);
-        sw[i] = (rr <= 1.0) ? 1.0 : sqrt(1.0 / rr);
-        nout += (rr > 1.0);
-      }
-      nout = __reduce_add_sync(0xffffffffu, nout);
-      __syncwarp();
-      if (nout == 0 && iters == 0) break;
-      double prev[NCF];
-      for (int i = 0; i < n; ++i) prev[i] = a[i];
-      warp_qr_solve(xn, yn, sw, m, n, A, a);
-      double dmax = 0.0, amax = 0.0;
-      for (int i = 0; i < n; ++i) { dmax = fmax(dmax, fabs(a[i] - prev[i])); amax = fmax(amax, fabs(a[i])); }
-      if (dmax <= 1e-15 * amax) { ++iters; break; }
-    }
-  }
-  r.huber_iters = iters;
-  // un-normalise (models.py:117-123), low order first
-  for (int j = 0; j < n; ++j) r.coeffs[j] = (j == 0) ? a[j] * ys : (a[j] * ys) / pow(xs, (double)j);
+  robust_polyfit_warp(m, n, ix, iy, xn, yn, sw, A, mode, r);
   // residual = polyval(matched_peaks, coeffs) - matched_atlas, clipped (:664-671)
   double ss = 0.0;
   for (int i = lane; i < m; i += 32) {
@@ -487,6 +496,140 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
   }
   r.rms = sqrt(warp_sum(ss) / m);
   r.accepted = (r.rms < min_fit_error) ? 0 : 1;
+  if (lane == 0) out[p] = r;
+}
+
+// models.robust_polyfit for arbitrary point sets (Calibrator.match_peaks :1915-1920, manual_refit):
+// problem p owns points [off[p], off[p+1]).
+__global__ void __launch_bounds__(32)
+robust_polyfit_kernel(const int* __restrict__ off, const double* __restrict__ x, const double* __restrict__ y, int deg,
+                      int mode, int max_m, rb2_refit_result* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const int o0 = off[p], m = off[p + 1] - o0, n = deg + 1;
+  double* ix = reinterpret_cast<double*>(smem_raw);
+  double* iy = ix + max_m;
+  double* xn = iy + max_m;
+  double* yn = xn + max_m;
+  double* sw = yn + max_m;
+  double* A = sw + max_m;
+  rb2_refit_result r;
+  for (int i = 0; i < NCF; ++i) r.coeffs[i] = 0.0;
+  r.rms = 0.0; r.n_inliers = m; r.accepted = 0; r.huber_iters = 0; r.pad = 0;
+  if (m <= deg) {
+    if (lane == 0) out[p] = r;
+    return;
+  }
+  for (int i = lane; i < m; i += 32) { ix[i] = x[o0 + i]; iy[i] = y[o0 + i]; }
+  __syncwarp();
+  robust_polyfit_warp(m, n, ix, iy, xn, yn, sw, A, mode, r);
+  double ss = 0.0;
+  for (int i = lane; i < m; i += 32) {
+    const double res = sub(iy[i], horner_unfused(r.coeffs, n, ix[i]));
+    ss = fma(res, res, ss);
+  }
+  r.rms = sqrt(warp_sum(ss) / m);
+  r.accepted = 1;
+  if (lane == 0) out[p] = r;
+}
+
+// K5 - Calibrator.match_peaks (calibrator.py:1824-1956, refine=False), one warp per problem.
+__global__ void __launch_bounds__(32)
+match_peaks_kernel(const rb2_match_desc* __restrict__ descs, int mode, int max_p, int max_n,
+                   rb2_match_result* __restrict__ out, double* __restrict__ mx_out, double* __restrict__ my_out,
+                   double* __restrict__ res_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const rb2_match_desc& d = descs[p];
+  const int n_p = d.n_peaks, n_a = d.n_atlas, n = d.fit_deg + 1;
+  double* ix = reinterpret_cast<double*>(smem_raw);
+  double* iy = ix + max_p;
+  double* xn = iy + max_p;
+  double* yn = xn + max_p;
+  double* sw = yn + max_p;
+  double* A = sw + max_p;  // (2 max_n + 3) * max_p
+  (void)max_n;
+  rb2_match_result r;
+  r.n_matched = 0; r.n_ambiguous = 0; r.polyfit_err = 0.0; r.polyfit_rms = 0.0;
+  for (int i = 0; i < NCF; ++i) { r.polyfit_coeffs[i] = 0.0; r.refit.coeffs[i] = 0.0; }
+  r.refit.rms = 0.0; r.refit.n_inliers = 0; r.refit.accepted = 0; r.refit.huber_iters = 0; r.refit.pad = 0;
+  double cin[NCF];
+  for (int i = 0; i < NCF; ++i) cin[i] = (i < d.n_coef) ? (d.d_coeffs ? d.d_coeffs[i] : d.coeffs[i]) : 0.0;
+  // -- association (:1830-1838): lanes take peaks, every lane scans the atlas in order --
+  int m = 0, n_amb = 0;
+  for (int base = 0; base < n_p; base += 32) {
+    const int u = base + lane;
+    int hits = 0;
+    double bd = CUDART_INF, bw = 0.0, px = 0.0;
+    if (u < n_p) {
+      px = d.d_peaks[u];
+      const double x = horner_unfused(cin, d.n_coef, px);
+      for (int k = 0; k < n_a; ++k) {
+        const double w = d.d_atlas[k];
+        const double ad = fabs(sub(w, x));
+        if (ad < d.tolerance) {
+          ++hits;
+          if (ad < bd) { bd = ad; bw = w; }  // nearest, first on ties
+        }
+      }
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, hits > 0);
+    n_amb += __popc(__ballot_sync(0xffffffffu, hits > 1));
+    if (hits > 0) {
+      const int slot = m + __popc(hm & ((1u << lane) - 1u));
+      ix[slot] = px; iy[slot] = bw;
+    }
+    m += __popc(hm);
+  }
+  __syncwarp();
+  r.n_matched = m; r.n_ambiguous = n_amb;
+  for (int i = lane; i < m; i += 32) { mx_out[(size_t)p * max_p + i] = ix[i]; my_out[(size_t)p * max_p + i] = iy[i]; }
+  if (m < n) {  // np.polyfit of fewer points than coefficients is rank deficient: reported, not fitted
+    if (lane == 0) out[p] = r;
+    return;
+  }
+  // -- polyfit of the association (:1893): least squares in the normalised variables --
+  {
+    double sx = 0.0, sy = 0.0;
+    for (int i = lane; i < m; i += 32) { sx += ix[i]; sy += iy[i]; }
+    const double mxm = warp_sum(sx) / m, mym = warp_sum(sy) / m;
+    double vx = 0.0, vy = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double dx = ix[i] - mxm, dy = iy[i] - mym;
+      vx = fma(dx, dx, vx); vy = fma(dy, dy, vy);
+    }
+    double xs = sqrt(warp_sum(vx) / m), ys = sqrt(warp_sum(vy) / m);
+    if (!(xs > 0.0)) xs = 1.0;
+    if (!(ys > 0.0)) ys = 1.0;
+    for (int i = lane; i < m; i += 32) { xn[i] = ix[i] / xs; yn[i] = iy[i] / ys; }
+    __syncwarp();
+    double a[NCF];
+    for (int i = 0; i < NCF; ++i) a[i] = 0.0;
+    warp_qr_solve(xn, yn, nullptr, m, n, A, a);
+    double sc = ys;
+    for (int j = 0; j < n; ++j) { r.polyfit_coeffs[j] = a[j] * sc; sc /= xs; }
+    double se = 0.0, ss = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double res = fabs(sub(iy[i], horner_unfused(r.polyfit_coeffs, n, ix[i])));
+      if (!d.robust_refit) res_out[(size_t)p * max_p + i] = res;
+      se += res; ss = fma(res, res, ss);
+    }
+    r.polyfit_err = warp_sum(se);
+    r.polyfit_rms = sqrt(warp_sum(ss) / m);
+  }
+  if (d.robust_refit) {  // :1915-1941
+    __syncwarp();
+    robust_polyfit_warp(m, n, ix, iy, xn, yn, sw, A, mode, r.refit);
+    double ss = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double res = sub(iy[i], horner_unfused(r.refit.coeffs, n, ix[i]));
+      res_out[(size_t)p * max_p + i] = res;
+      ss = fma(res, res, ss);
+    }
+    r.refit.rms = sqrt(warp_sum(ss) / m);
+    r.refit.n_inliers = m;
+    r.refit.accepted = 1;
+  }
   if (lane == 0) out[p] = r;
 }
 
@@ -511,6 +654,49 @@ extern "C" int rb2_refit_winners(int n_problems, const rb2_ransac_desc* d_desc, 
   RB2_CHECK(cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   refit_kernel<<<n_problems, 32, smem, stream>>>(d_desc, d_winner, minimum_fit_error, mode, d_out, d_matched_x,
                                                  d_matched_y, d_residual, max_upeaks);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+
+extern "C" int rb2_robust_polyfit(int n_problems, const int32_t* d_off, const int32_t* h_off, const double* d_x,
+                                  const double* d_y, int deg, int mode, rb2_refit_result* d_out, void* stream_) {
+  using namespace rb2;
+  if (n_problems <= 0 || !d_off || !h_off || !d_x || !d_y || !d_out || deg < 1 || deg > RB2_MAX_DEG || mode < 0 || mode > 1)
+    return RB2_ERR_ARG;
+  int max_m = 1;
+  for (int i = 0; i < n_problems; ++i) {
+    if (h_off[i + 1] < h_off[i]) return RB2_ERR_ARG;
+    max_m = max(max_m, h_off[i + 1] - h_off[i]);
+  }
+  const size_t smem = (size_t)max_m * 8 * (5 + 2 * (deg + 1) + 3);
+  if (smem > 200 * 1024) return RB2_ERR_ARG;
+  RB2_CHECK(cudaFuncSetAttribute(robust_polyfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  robust_polyfit_kernel<<<n_problems, 32, smem, (cudaStream_t)stream_>>>(d_off, d_x, d_y, deg, mode, max_m, d_out);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+
+extern "C" int rb2_match_peaks(int n_problems, const rb2_match_desc* d_desc, const rb2_match_desc* h_desc, int mode,
+                               rb2_match_result* d_out, double* d_matched_x, double* d_matched_y, double* d_residual,
+                               int max_peaks, void* stream_) {
+  using namespace rb2;
+  if (n_problems <= 0 || !d_desc || !h_desc || !d_out || !d_matched_x || !d_matched_y || !d_residual || max_peaks <= 0 ||
+      mode < 0 || mode > 1)
+    return RB2_ERR_ARG;
+  int max_n = 2;
+  for (int i = 0; i < n_problems; ++i) {
+    const rb2_match_desc& h = h_desc[i];
+    if (h.n_peaks < 0 || h.n_peaks > max_peaks || h.n_atlas < 0 || h.n_coef < 1 || h.n_coef > RB2_MAX_DEG + 1 ||
+        h.fit_deg < 1 || h.fit_deg > RB2_MAX_DEG || !(h.tolerance >= 0.0))
+      return RB2_ERR_ARG;
+    if ((h.n_peaks && !h.d_peaks) || (h.n_atlas && !h.d_atlas)) return RB2_ERR_ARG;
+    max_n = max(max_n, h.fit_deg + 1);
+  }
+  const size_t smem = (size_t)max_peaks * 8 * (5 + 2 * max_n + 3);
+  if (smem > 200 * 1024) return RB2_ERR_ARG;
+  RB2_CHECK(cudaFuncSetAttribute(match_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  match_peaks_kernel<<<n_problems, 32, smem, (cudaStream_t)stream_>>>(d_desc, mode, max_peaks, max_n, d_out, d_matched_x,
+                                                                       d_matched_y, d_residual);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }

@@ -684,3 +684,94 @@ class RansacBatch:
 
 def counters_dict(res):
     return {k: int(res.counters[i]) for i, k in enumerate(N.COUNTER_NAMES)}
+
+
+def robust_polyfit(x, y, deg, mode=0):
+    """models.robust_polyfit (models.py:70-123) on the device for one point set or a list of
+    point sets; returns coefficients (low order first) [, ...] plus (rms, nfev, status)."""
+    torch = _torch()
+    lib = N.load()
+    single = np.ndim(x[0]) == 0
+    xs = [np.asarray(x, dtype=np.float64)] if single else [np.asarray(v, dtype=np.float64) for v in x]
+    ys = [np.asarray(y, dtype=np.float64)] if single else [np.asarray(v, dtype=np.float64) for v in y]
+    off = np.zeros(len(xs) + 1, dtype=np.int32)
+    np.cumsum([len(v) for v in xs], out=off[1:])
+    ar = Arena()
+    ox, oy, oo = ar.add(np.concatenate(xs)), ar.add(np.concatenate(ys)), ar.add(off)
+    base = ar.upload()
+    out = torch.empty(C.sizeof(N.RefitResult) * len(xs), dtype=torch.uint8, device="cuda")
+    rc = lib.rb2_robust_polyfit(len(xs), base + oo, off.ctypes.data, base + ox, base + oy, int(deg), int(mode),
+                                out.data_ptr(), current_stream_ptr())
+    N.check(rc, "rb2_robust_polyfit")
+    res = _download_structs(out, N.RefitResult, len(xs))
+    outs = [(np.array(r.coeffs[:deg + 1]) if r.accepted else np.full(deg + 1, np.nan), r.rms, r.huber_iters, r.pad)
+            for r in res]
+    return outs[0] if single else outs
+
+
+class MatchBatch:
+    """K5: Calibrator.match_peaks (calibrator.py:1824-1956, refine=False) for a batch of
+    solutions (rb2_match_peaks).
+
+    problems: list of dicts with peaks, lines, tolerance, fit_deg, robust_refit and either
+    coeffs (host array) or d_coeffs (device address of the coefficients, e.g. a K4 refit
+    record still on the device) + n_coef."""
+
+    def __init__(self, problems):
+        self.lib = N.load()
+        self.n = len(problems)
+        self.problems = problems
+        self.max_p = max(1, max(len(p["peaks"]) for p in problems))
+        ar = Arena()
+        offs = [(ar.add(np.asarray(p["peaks"], dtype=np.float64)), ar.add(np.asarray(p["lines"], dtype=np.float64)))
+                for p in problems]
+        self.h_desc = N.struct_array(N.MatchDesc, self.n)
+        o_desc = ar.reserve(C.sizeof(N.MatchDesc) * self.n)
+        self._o_res = ar.reserve(C.sizeof(N.MatchResult) * self.n)
+        self._o_mx = ar.reserve(8 * self.n * self.max_p)
+        self._o_my = ar.reserve(8 * self.n * self.max_p)
+        self._o_rs = ar.reserve(8 * self.n * self.max_p)
+        self._end = ar.size
+        base = ar.upload()
+        for i, p in enumerate(problems):
+            d = self.h_desc[i]
+            d.d_peaks, d.d_atlas = base + offs[i][0], base + offs[i][1]
+            d.n_peaks, d.n_atlas = len(p["peaks"]), len(p["lines"])
+            if p.get("d_coeffs"):
+                d.d_coeffs, d.n_coef = int(p["d_coeffs"]), int(p["n_coef"])
+            else:
+                c = np.asarray(p["coeffs"], dtype=np.float64)
+                d.d_coeffs, d.n_coef = None, len(c)
+                for k, v in enumerate(c):
+                    d.coeffs[k] = float(v)
+            d.fit_deg = int(p["fit_deg"]) if p.get("fit_deg") is not None else d.n_coef - 1
+            d.tolerance = float(p["tolerance"])
+            d.robust_refit = int(bool(p.get("robust_refit", True)))
+        torch = _torch()
+        self.arena = ar
+        self._desc_host = torch.empty(C.sizeof(N.MatchDesc) * self.n, dtype=torch.uint8, pin_memory=True)
+        C.memmove(self._desc_host.data_ptr(), C.addressof(self.h_desc), self._desc_host.numel())
+        ar.buf[o_desc:o_desc + self._desc_host.numel()].copy_(self._desc_host, non_blocking=True)
+        TRANSFER["h2d"] += self._desc_host.numel()
+        self._d_desc = base + o_desc
+        self._base = base
+
+    def run(self, mode=0):
+        b = self._base
+        rc = self.lib.rb2_match_peaks(self.n, self._d_desc, C.addressof(self.h_desc), int(mode), b + self._o_res,
+                                      b + self._o_mx, b + self._o_my, b + self._o_rs, self.max_p,
+                                      current_stream_ptr())
+        N.check(rc, "rb2_match_peaks")
+        return self
+
+    def fetch(self):
+        """ONE device->host copy: (match results, matched_x, matched_y, residual)."""
+        raw = self.arena.buf[self._o_res:self._end].cpu().numpy()
+        TRANSFER["d2h"] += raw.nbytes
+        o = self._o_res
+        res = (N.MatchResult * self.n).from_buffer_copy(raw[:C.sizeof(N.MatchResult) * self.n].tobytes())
+        shp, nb = (self.n, self.max_p), 8 * self.n * self.max_p
+        mx = raw[self._o_mx - o:self._o_mx - o + nb].view(np.float64).reshape(shp)
+        my = raw[self._o_my - o:self._o_my - o + nb].view(np.float64).reshape(shp)
+        rs = raw[self._o_rs - o:self._o_rs - o + nb].view(np.float64).reshape(shp)
+        return res, mx, my, rs
