@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
     os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
         o = os.path.join(bdir, s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, s), "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("RB2_NVCC_EXTRA", "").split(), "-c", os.path.join(HERE, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -18,6 +18,7 @@
 // among equal costs - a 128-bit atomic min on (sortable cost, ~id) per problem.
 #include "common.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace rb2 {
 
@@ -225,35 +226,17 @@ struct WeightCtx {
 
 enum { CMP_GT = 0, CMP_GE = 1, CMP_LT = 2, CMP_LE = 3 };
 
-// warp-parallel 32-ary search: first index i in [a, b] with cmp(t(i), th) true (the predicate is
-// monotone false...true on the piece); returns b + 1 if none.  ONE copy of the code (noinline).
+// first index i in [a, b] with cmp(t(i), th) true (the predicate is monotone false...true on
+// the piece); b + 1 if none.  Bisection over the pixel index, the reference's arithmetic at
+// every probe.  ONE copy of the code (noinline).
 template <int DEG>
-__device__ __noinline__ int warp_first(const WeightCtx<DEG>& w, int a, int b, double th, int cmp) {
-  const int lane = lane_id();
-  auto pred = [&](int i) {
-    const double t = w.t_at(i);
-    return cmp == CMP_GT ? (t > th) : cmp == CMP_GE ? (t >= th) : cmp == CMP_LT ? (t < th) : (t <= th);
-  };
-  int lo = a, hi = b + 1;  // answer in [lo, hi]
-  while (hi > lo) {
-    const int width = hi - lo;
-    if (width <= 32) {
-      const int i = lo + lane;
-      const bool p = (i < hi) ? pred(i) : true;
-      const unsigned bal = __ballot_sync(0xffffffffu, p);
-      return bal ? lo + (__ffs(bal) - 1) : hi;  // lanes >= width vote true -> hi; width == 32 and none true -> hi
-    }
-    const int step = (width + 31) / 32;
-    int i = lo + (lane + 1) * step - 1;
-    if (i >= hi) i = hi - 1;
-    const bool p = pred(i);
-    const unsigned bal = __ballot_sync(0xffffffffu, p);
-    if (bal == 0u) return hi;  // even the last probe (hi-1) is false
-    const int L = __ffs(bal) - 1;
-    const int probeL = min(lo + (L + 1) * step - 1, hi - 1);
-    const int probePrev = (L > 0) ? min(lo + L * step - 1, hi - 1) : lo - 1;
-    hi = probeL;  // pred(probeL) true -> answer <= probeL
-    lo = probePrev + 1;
+__device__ __noinline__ int first_index(const WeightCtx<DEG>& w, int a, int b, double th, int cmp) {
+  int lo = a, hi = b + 1;
+  while (lo < hi) {
+    const int m = (lo + hi) >> 1;
+    const double t = w.t_at(m);
+    const bool p = cmp == CMP_GT ? (t > th) : cmp == CMP_GE ? (t >= th) : cmp == CMP_LT ? (t < th) : (t <= th);
+    if (p) hi = m; else lo = m + 1;
   }
   return lo;
 }
@@ -270,15 +253,15 @@ __device__ __noinline__ double pp_eval(const rb2_ransac_desc& d, double t) {
   return fma(fma(fma(k[3], dt, k[2]), dt, k[1]), dt, k[0]);
 }
 
-// Hough-density weight of one hypothesis (whole warp).  Returns false when the hypothesis
-// leaves the corner-clamped regime (gradient above the first intercept-bin centre somewhere
-// on the detector).
+// Hough-density weight of one hypothesis, ONE THREAD (the work is scalar: roots, a few class
+// tests, bisections).  Returns false when the hypothesis leaves the corner-clamped regime
+// (gradient above the first intercept-bin centre somewhere on the detector).  need_value =
+// false: only the regime is established (*out_weight = NaN unless it comes for free).
 template <int DEG>
-__device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, const double* c, int deg_rt, bool need_value,
-                                                  double* out_weight) {
+__device__ __forceinline__ bool hough_weight_thread(const rb2_ransac_desc& d, const double* c, int deg_rt, bool need_value,
+                                                    double* out_weight) {
   constexpr int CAP = deg_cap(DEG);
   const int deg = DEG > 0 ? DEG : deg_rt;
-  const int lane = lane_id();
   const int np = d.n_pix;
   if (np <= 0) { *out_weight = 0.0; return true; }
   WeightCtx<DEG> w;
@@ -288,6 +271,7 @@ __device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, cons
 #pragma unroll
   for (int i = 0; i <= CAP; ++i) w.dc[i] = (i < deg) ? mul((double)(i + 1), w.c[i + 1 <= CAP ? i + 1 : CAP]) : 0.0;
   const double x0 = w.px(0), x1 = w.px(np - 1);
+  const double th_hi = d.gc_max, th_lo = d.gc_min;
   // breakpoints of t: t'(x) = -x p''(x)
   constexpr int P2 = CAP - 2 > 0 ? CAP - 2 : 0;   // capacity (degree) of p''
   double brk[P2 + 2];
@@ -317,7 +301,6 @@ __device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, cons
     brk[k] = 0.0;
     ++nb;
   }
-  const double th_hi = d.gc_max, th_lo = d.gc_min;
   auto cls = [&](int i) { const double t = w.t_at(i); return (t >= th_hi) ? 2 : ((t <= th_lo) ? 0 : 1); };
   long long n_hi = 0, n_lo = 0;
   double mid = 0.0;
@@ -338,35 +321,28 @@ __device__ __forceinline__ bool hough_weight_warp(const rb2_ransac_desc& d, cons
       ib = np - 1;
     }
     if (ib < ia) continue;
-    // classes of the two ends, evaluated by two lanes at once
-    const int ce = cls(lane == 0 ? ia : ib);
-    const int ca = __shfl_sync(0xffffffffu, ce, 0), cb = __shfl_sync(0xffffffffu, ce, 1);
+    const int ca = cls(ia), cb = (ib > ia) ? cls(ib) : ca;
     int i_mid0, i_mid1;  // MID pixels are [i_mid0, i_mid1)
     if (ca == cb) {
       if (ca == 2) n_hi += ib - ia + 1; else if (ca == 0) n_lo += ib - ia + 1;
       i_mid0 = ia; i_mid1 = (ca == 1) ? ib + 1 : ia;
     } else if (ca < cb) {  // increasing: LO.. MID.. HI
-      const int f1 = warp_first<DEG>(w, ia, ib, th_lo, CMP_GT);
-      const int f2 = warp_first<DEG>(w, f1, ib, th_hi, CMP_GE);
+      const int f1 = (ca == 0) ? first_index<DEG>(w, ia, ib, th_lo, CMP_GT) : ia;
+      const int f2 = (cb == 2) ? first_index<DEG>(w, f1, ib, th_hi, CMP_GE) : ib + 1;
       n_lo += f1 - ia; n_hi += ib + 1 - f2;
       i_mid0 = f1; i_mid1 = f2;
     } else {               // decreasing: HI.. MID.. LO
-      const int f1 = warp_first<DEG>(w, ia, ib, th_hi, CMP_LT);
-      const int f2 = warp_first<DEG>(w, f1, ib, th_lo, CMP_LE);
+      const int f1 = (ca == 2) ? first_index<DEG>(w, ia, ib, th_hi, CMP_LT) : ia;
+      const int f2 = (cb == 0) ? first_index<DEG>(w, f1, ib, th_lo, CMP_LE) : ib + 1;
       n_hi += f1 - ia; n_lo += ib + 1 - f2;
       i_mid0 = f1; i_mid1 = f2;
     }
-#ifdef RB2_DEBUG_WEIGHT
-    if (lane == 0) printf("piece %d: ia %d ib %d ca %d cb %d mid [%d,%d) n_hi %lld n_lo %lld nb %d brk0 %g\n", pc, ia, ib, ca, cb, i_mid0, i_mid1, n_hi, n_lo, nb, nb ? brk[0] : -1.0);
-#endif
-    for (int i = i_mid0 + lane; i < i_mid1; i += 32) {  // class re-checked per pixel: never extrapolate the pp-form
+    for (int i = i_mid0; i < i_mid1; ++i) {  // class re-checked per pixel: never extrapolate the pp-form
       const double t = w.t_at(i);
       mid += (t >= th_hi) ? d.h_hi : ((t <= th_lo) ? d.h_lo : pp_eval(d, t));
     }
     ia = ib + 1;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mid += __shfl_xor_sync(0xffffffffu, mid, o);
   *out_weight = d.hough_weight * ((double)n_hi * d.h_hi + (double)n_lo * d.h_lo + mid);
   return true;
 }
@@ -533,56 +509,117 @@ struct TablesA {  // shared-memory views of one problem (stage A)
   int n_u;
 };
 
-// first i with r < cdf32[i] (== searchsorted(cdf, u, 'right')), clamped: 256-entry LUT + scan
+// first i with r < cdf32[i] (== searchsorted(cdf, u, 'right')), clamped: LUT over the top
+// LUT_BITS bits + scan (almost always zero or one step)
+constexpr int LUT_BITS = 10;
 __device__ __forceinline__ int draw_peak_lut(const TablesA& t, unsigned r) {
-  int i = t.lut[r >> 24];
-  while (i < t.n_u - 1 && r >= t.cdf32[i]) ++i;
+  int i = t.lut[r >> (32 - LUT_BITS)];
+  const int last = t.n_u - 1;
+  if (i < last && r >= t.cdf32[i]) {
+    ++i;
+    while (i < last && r >= t.cdf32[i]) ++i;
+  }
   return i;
 }
 
+// One Philox4x32-10 block, stateless: counter = (id_lo, id_hi, blk, 0).
+__device__ __forceinline__ void philox_block(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned blk,
+                                             unsigned (&out)[4]) {
+  unsigned x0 = c0, x1 = c1, x2 = blk, x3 = 0u, a = k0, b = k1;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * x0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * x2;
+    const unsigned y0 = (unsigned)(p1 >> 32) ^ x1 ^ a, y2 = (unsigned)(p0 >> 32) ^ x3 ^ b;
+    x0 = y0; x1 = (unsigned)p1; x2 = y2; x3 = (unsigned)p0;
+    a += 0x9E3779B9u; b += 0xBB67AE85u;
+  }
+  out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+}
+// word `n` of the stream beyond the eager blocks (rare path; one copy of the code)
+__device__ __noinline__ unsigned philox_word(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned n) {
+  unsigned w[4];
+  philox_block(k0, k1, c0, c1, n >> 2, w);
+  const unsigned j = n & 3u;
+  return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+}
+
+// Fast-path sampler (sample size S = deg + 1 known at compile time).  All lanes generate the
+// same number of Philox blocks up front (no divergence in the generator): word k is the first
+// try of peak k, half-word k of the following words the first try of candidate k, the rest
+// are spares for the retries (duplicate peak / duplicate wavelength / Lemire rejection); only
+// a hypothesis that exhausts the spares continues with philox_word().  Same law as
+// draw_sample_dyn; the streams differ.
 template <int S>
 __device__ __forceinline__ bool draw_sample(const TablesA& t, unsigned long long seed, unsigned long long gid,
                                             int (&pi)[S], int (&ci)[S]) {
-  Rng rng;
-  rng.init(seed, gid);
+  constexpr int NWC = (S + 1) / 2;           // words holding the candidate half-words
+  constexpr int NB = (S + NWC + 2 + 3) / 4;  // eager blocks: at least two spare words
+  constexpr int NW = 4 * NB, SP0 = S + NWC, NSP = NW - SP0;
+  const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), c0 = (unsigned)gid, c1 = (unsigned)(gid >> 32);
+  unsigned w[NW];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    unsigned o[4];
+    philox_block(k0, k1, c0, c1, (unsigned)b, o);
+    w[4 * b] = o[0]; w[4 * b + 1] = o[1]; w[4 * b + 2] = o[2]; w[4 * b + 3] = o[3];
+  }
+  unsigned n_retry = 0;
+  auto retry_word = [&]() -> unsigned {
+    unsigned r = 0;
+    bool got = false;
+#pragma unroll
+    for (int j = 0; j < NSP; ++j) if (n_retry == (unsigned)j) { r = w[SP0 + j]; got = true; }
+    if (!got) r = philox_word(k0, k1, c0, c1, (unsigned)NW + (n_retry - (unsigned)NSP));
+    ++n_retry;
+    return r;
+  };
   // peaks: weighted, without replacement (np.random.choice(..., replace=False, p=prob), :538-540)
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    int idx;
-    bool dup;
-    do {
-      idx = draw_peak_lut(t, rng.next32());
-      dup = false;
+    int idx = draw_peak_lut(t, w[k]);
+    for (;;) {
+      bool dup = false;
 #pragma unroll
       for (int j = 0; j < S; ++j) if (j < k) dup |= (pi[j] == idx);
-    } while (dup);
+      if (!dup) break;
+      idx = draw_peak_lut(t, retry_word());
+    }
     pi[k] = idx;
   }
-  // one candidate wavelength per peak, no wavelength twice (:544-566)
+  // one candidate wavelength per peak, no wavelength twice (:544-566); exactly uniform in [0, K)
+  // from 16 bits by Lemire's multiply-shift with the rare rejection that removes the bias
   int wi[S];
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     const int o0 = t.coff[pi[k]], K = t.coff[pi[k] + 1] - o0;
+    unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
     bool checked = false;
     for (;;) {
-      const int j = rng.uniform(K);
-      const int w = t.cwid[o0 + j];
-      bool dup = false;
+      unsigned x = h * (unsigned)K;
+      bool redraw = false;
+      if ((x & 0xffffu) < (unsigned)K) redraw = (x & 0xffffu) < (65536u % (unsigned)K);
+      if (!redraw) {
+        const int j = (int)(x >> 16);
+        const int wv = t.cwid[o0 + j];
+        bool dup = false;
 #pragma unroll
-      for (int q = 0; q < S; ++q) if (q < k) dup |= (wi[q] == w);
-      if (!dup) { wi[k] = w; ci[k] = o0 + j; break; }
-      if (!checked) {  // is any unused wavelength left for this peak?
-        bool possible = false;
-        for (int jj = 0; jj < K; ++jj) {
-          const int ww = t.cwid[o0 + jj];
-          bool used = false;
+        for (int q = 0; q < S; ++q) if (q < k) dup |= (wi[q] == wv);
+        if (!dup) { wi[k] = wv; ci[k] = o0 + j; break; }
+        if (!checked) {  // is any unused wavelength left for this peak?
+          bool possible = false;
+          for (int jj = 0; jj < K; ++jj) {
+            const int ww = t.cwid[o0 + jj];
+            bool used = false;
 #pragma unroll
-          for (int q = 0; q < S; ++q) if (q < k) used |= (wi[q] == ww);
-          possible |= !used;
+            for (int q = 0; q < S; ++q) if (q < k) used |= (wi[q] == ww);
+            possible |= !used;
+          }
+          if (!possible) return false;  // impossible draw: the try is consumed (:557-566)
+          checked = true;
         }
-        if (!possible) return false;  // impossible draw: the try is consumed (:557-566)
-        checked = true;
       }
+      h = retry_word() & 0xffffu;
     }
   }
   return true;
@@ -632,7 +669,7 @@ struct Pipe {  // device pointers of the staged pipeline (one per rb2_ransac_bat
   double* qa; double* qb;           // queues, `cap` entries of qs doubles
   unsigned* counts;                 // [0] = |queue A|, [1] = |queue B|
   BestKey* best;                    // [n_problems]
-  double* res_cost; int2* res_cnt;  // per queue-B entry
+  double* res_cost; double* res_esum; int2* res_cnt;  // per queue-B entry
   unsigned cap; int qs;
 };
 
@@ -686,8 +723,8 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   for (int i = tid; i <= n_u; i += RS_THREADS) s_coff[i] = d.d_cand_off[i];
   for (int i = tid; i < n_c; i += RS_THREADS) { s_cwave[i] = d.d_cand_wave[i]; s_cwid[i] = d.d_cand_wid[i]; }
   __syncthreads();
-  for (int b = tid; b < 256; b += RS_THREADS) {  // lut[b] = #{i : cdf32[i] <= b << 24}, clamped
-    const unsigned r = (unsigned)b << 24;
+  for (int b = tid; b < (1 << LUT_BITS); b += RS_THREADS) {  // lut[b] = #{i : cdf32[i] <= b << (32 - LUT_BITS)}, clamped
+    const unsigned r = (unsigned)b << (32 - LUT_BITS);
     int lo = 0, hi = n_u - 1;
     while (lo < hi) { const int m = (lo + hi) >> 1; if (r < s_cdf[m]) hi = m; else lo = m + 1; }
     s_lut[b] = (unsigned short)lo;
@@ -852,50 +889,42 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
   }
 }
 
-// ---- stage C ---------------------------------------------------------------------------
-// one warp per queue-B entry; dynamic smem: per warp  double coef[NCOEF]; u64 berr[max_wids]
+// ---- stage C1 --------------------------------------------------------------------------
+// Bijective match, one warp per queue-B entry; dynamic smem per warp:
+//   u64 berr[max_wids] (all +inf between entries); double be[max_up]; int bw[max_up]
+// De-duplication by wavelength (calibrator.py:356-376): every peak posts its nearest-candidate
+// error with an atomicMin on the wavelength's slot, then the peak whose error IS the minimum
+// claims the slot with a CAS that also resets it (equal errors: either peak, same cost).
+// Output per entry: sum of the clipped errors, match count, inlier count.
 template <int DEG_T>
-__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 ? 4 : 2)
-ransac_score_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result,
-                    int max_wids) {
+__global__ void __launch_bounds__(RS_THREADS, 4)
+ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned n = pipe.counts[1];
-  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
-  double* s_coef = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (NCOEF + max_wids);
-  unsigned long long* berr = reinterpret_cast<unsigned long long*>(s_coef + NCOEF);
+  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1;
+  const size_t per_warp = (size_t)max_wids + max_up + (max_up + 1) / 2;  // in doubles
+  unsigned long long* berr = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * per_warp;
+  double* s_be = reinterpret_cast<double*>(berr + max_wids);
+  int* s_bw = reinterpret_cast<int*>(s_be + max_up);
+  for (int i = lane; i < max_wids; i += 32) berr[i] = INF_BITS;  // +inf = empty
+  __syncwarp();
   const unsigned total_warps = gridDim.x * RS_WARPS;
-  int acc_problem = -1;                 // lane 0: run-length counters of the current problem
-  unsigned acc[4] = {0u, 0u, 0u, 0u};   // empty, scored, eligible, unsupported
-  auto flush = [&]() {
-    if (acc_problem >= 0) {
-      add_counter(result + acc_problem, 4, acc[0]); add_counter(result + acc_problem, 5, acc[1]);
-      add_counter(result + acc_problem, 6, acc[2]); add_counter(result + acc_problem, 7, acc[3]);
-    }
-    acc[0] = acc[1] = acc[2] = acc[3] = 0u;
-  };
   for (unsigned e = blockIdx.x * RS_WARPS + warp; e < n; e += total_warps) {
     const double* q = pipe.qb + (size_t)e * qs;
-    __syncwarp();
-    if (lane < ncoef) s_coef[lane] = q[lane];
+    double cr[deg_cap(DEG_T) + 1];
+#pragma unroll
+    for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? q[k] : 0.0;
     const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
-    const int problem = (int)(tag >> 40);
-    const long long id = (long long)(tag & TAG_ID_MASK);
-    if (lane == 0 && problem != acc_problem) { flush(); acc_problem = problem; }
-    const rb2_ransac_desc& d = descs[problem];
-    const int n_u = d.n_upeaks, n_wids = d.n_wids;
+    const rb2_ransac_desc& d = descs[(int)(tag >> 40)];
+    const int n_u = d.n_upeaks;
     const double tol = d.tol;
     const double* __restrict__ g_peaks = d.d_peaks;
     const int* __restrict__ g_coff = d.d_cand_off;
     const double* __restrict__ g_cwave = d.d_cand_wave;
     const int* __restrict__ g_cwid = d.d_cand_wid;
-    for (int i = lane; i < n_wids; i += 32) berr[i] = 0x7ff0000000000000ull;  // +inf = empty
-    __syncwarp();
-    const double* cc = s_coef;
-    double cr[deg_cap(DEG_T) + 1];
-#pragma unroll
-    for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? cc[k] : 0.0;
-    // -- bijective match (calibrator.py:341-380) --
+    // -- nearest candidate per peak (calibrator.py:341-354) --
     for (int u = lane; u < n_u; u += 32) {
       const double fit = horner_ref<deg_cap(DEG_T)>(cr, ncoef, g_peaks[u]);
       const int o0 = g_coff[u], o1 = g_coff[u + 1];
@@ -905,66 +934,123 @@ ransac_score_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ra
         const double er = fabs(sub(fit, g_cwave[k]));
         if (er < be) { be = er; bw = g_cwid[k]; }  // first minimum wins
       }
+      s_be[u] = be; s_bw[u] = bw;
       if (bw >= 0) atomicMin(&berr[bw], (unsigned long long)__double_as_longlong(be));
     }
     __syncwarp();
     double esum = 0.0;
     int nm = 0, ni = 0;
-    for (int i = lane; i < n_wids; i += 32) {
-      const unsigned long long bits = berr[i];
-      if (bits != 0x7ff0000000000000ull) {
-        double er = __longlong_as_double((long long)bits);
-        if (er > tol) er = tol;  // M-SAC clip (:611)
-        esum += er;
-        ++nm;
-        ni += (er < tol);
-      }
+    for (int u = lane; u < n_u; u += 32) {
+      const int bw = s_bw[u];
+      if (bw < 0) continue;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(s_be[u]);
+      if (berr[bw] != bits) continue;
+      if (atomicCAS(&berr[bw], bits, INF_BITS) != bits) continue;  // claimed by an equal error
+      double er = __longlong_as_double((long long)bits);
+      if (er > tol) er = tol;  // M-SAC clip (:611)
+      esum += er;
+      ++nm;
+      ni += (er < tol);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      esum += __shfl_xor_sync(0xffffffffu, esum, o);
-      nm += __shfl_xor_sync(0xffffffffu, nm, o);
-      ni += __shfl_xor_sync(0xffffffffu, ni, o);
-    }
-    if (lane == 0) { pipe.res_cost[e] = CUDART_NAN; pipe.res_cnt[e] = make_int2(nm, ni); }
-    if (nm == 0) {  // :607-608
-      if (lane == 0) { ++acc[0]; if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY; }
-      continue;
-    }
-    const long long gid = d.hyp_begin + id;
-    double weight;
-    const bool ok = hough_weight_warp<DEG_T>(d, cc, deg, true, &weight);
-    if (!ok) {
-      if (lane == 0) { ++acc[3]; if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED; }
-      continue;
-    }
-    const double cost = esum / (double)(nm - ncoef + 1) / (weight + 1e-9);  // :629-633
-    bool elig = (ni >= d.min_inliers) && ((double)ni >= d.min_inliers_frac) && (cost <= d.cost_ceiling);
-    if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
-    if (lane == 0) {
-      ++acc[1];
-      if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
-      if (d.d_out_cost) d.d_out_cost[id] = cost;
-      if (d.d_out_weight) d.d_out_weight[id] = weight;
-      if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
-      if (elig) {
-        ++acc[2];
-        pipe.res_cost[e] = cost;
-        BestKey mine;
-        mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
-        BestKey* slot = pipe.best + problem;
-        BestKey cur;
-        cur.hi = *reinterpret_cast<volatile unsigned long long*>(&slot->hi);
-        cur.lo = *reinterpret_cast<volatile unsigned long long*>(&slot->lo);
-        while (key_better(mine, cur)) {
-          const BestKey old = atomicCAS(slot, cur, mine);
-          if (old.hi == cur.hi && old.lo == cur.lo) break;
-          cur = old;
+    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+    nm = __reduce_add_sync(0xffffffffu, nm);
+    ni = __reduce_add_sync(0xffffffffu, ni);
+    if (lane == 0) { pipe.res_esum[e] = esum; pipe.res_cnt[e] = make_int2(nm, ni); }
+    __syncwarp();
+  }
+}
+
+// ---- stage C2 --------------------------------------------------------------------------
+// M-SAC cost of every matched entry, one THREAD per queue-B entry: regime test, Hough-density
+// weight, cost, eligibility, per-problem running best (128-bit atomic min).
+// Early skip: cost >= sum(err) / (m - deg) / (w_upper + 1e-9); when that bound already exceeds the
+// problem's running best (or the hypothesis lacks the inliers to be eligible) the weight cannot
+// change the outcome and only its regime test is run.  Selection and counters are unaffected
+// (the `eligible` counter counts the inlier criteria only).
+template <int DEG_T>
+__global__ void __launch_bounds__(256, 2)
+ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
+  const unsigned n = pipe.counts[1];
+  const int lane = threadIdx.x & 31;
+  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
+  const unsigned total = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < n; e0 += total) {
+    const unsigned e = e0 + lane;
+    int kind = -1;  // 0 empty, 1 scored, 2 scored + enough inliers, 3 unsupported
+    int problem = -1;
+    if (e < n) {
+      const double* q = pipe.qb + (size_t)e * qs;
+      double cr[deg_cap(DEG_T) + 1];
+#pragma unroll
+      for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? q[k] : 0.0;
+      const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+      problem = (int)(tag >> 40);
+      const long long id = (long long)(tag & TAG_ID_MASK);
+      const rb2_ransac_desc& d = descs[problem];
+      const int2 cnt = pipe.res_cnt[e];
+      const int nm = cnt.x, ni = cnt.y;
+      const double esum = pipe.res_esum[e];
+      pipe.res_cost[e] = CUDART_NAN;
+      if (nm == 0) {  // :607-608
+        kind = 0;
+        if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY;
+      } else {
+        const long long gid = d.hyp_begin + id;
+        const bool counts_ok = (ni >= d.min_inliers) && ((double)ni >= d.min_inliers_frac);
+        const bool wants_all = d.d_out_cost || d.d_out_weight;  // parity / diagnostics: every cost is reported
+        bool need_value = wants_all || counts_ok;
+        const double denom = (double)(nm - ncoef + 1);
+        if (need_value && !wants_all && d.w_upper > 0.0) {
+          const double lb = esum / denom / (d.w_upper + 1e-9);
+          const unsigned long long best_hi = *reinterpret_cast<volatile unsigned long long*>(&pipe.best[problem].hi);
+          if (cost_key(lb) > best_hi || lb > d.cost_ceiling) need_value = false;
+        }
+        double weight;
+        const bool ok = hough_weight_thread<DEG_T>(d, cr, deg, need_value, &weight);
+        if (!ok) {
+          kind = 3;
+          if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED;
+        } else {
+          kind = counts_ok ? 2 : 1;
+          if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
+          if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
+          if (need_value) {
+            const double cost = esum / denom / (weight + 1e-9);  // :629-633
+            bool elig = counts_ok && (cost <= d.cost_ceiling);
+            if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
+            if (d.d_out_cost) d.d_out_cost[id] = cost;
+            if (d.d_out_weight) d.d_out_weight[id] = weight;
+            if (elig) {
+              pipe.res_cost[e] = cost;
+              BestKey mine;
+              mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
+              BestKey* slot = pipe.best + problem;
+              BestKey cur;
+              cur.hi = *reinterpret_cast<volatile unsigned long long*>(&slot->hi);
+              cur.lo = *reinterpret_cast<volatile unsigned long long*>(&slot->lo);
+              while (key_better(mine, cur)) {
+                const BestKey old = atomicCAS(slot, cur, mine);
+                if (old.hi == cur.hi && old.lo == cur.lo) break;
+                cur = old;
+              }
+            }
+          }
         }
       }
     }
+    // counters (empty, scored, eligible, unsupported), aggregated over the lanes of one problem
+    const unsigned have = __ballot_sync(0xffffffffu, kind >= 0);
+    if (kind >= 0) {
+      const unsigned peers = __match_any_sync(have, problem);
+      const unsigned m_empty = __ballot_sync(peers, kind == 0), m_sc = __ballot_sync(peers, kind == 1 || kind == 2);
+      const unsigned m_el = __ballot_sync(peers, kind == 2), m_un = __ballot_sync(peers, kind == 3);
+      if ((peers & ((1u << lane) - 1u)) == 0) {
+        add_counter(result + problem, 4, __popc(m_empty)); add_counter(result + problem, 5, __popc(m_sc));
+        add_counter(result + problem, 6, __popc(m_el)); add_counter(result + problem, 7, __popc(m_un));
+      }
+    }
   }
-  if (lane == 0) flush();
 }
 
 // ---- stage D ---------------------------------------------------------------------------
@@ -1035,7 +1121,7 @@ namespace rb2 {
 
 constexpr unsigned PIPE_CHUNK = 1u << 22;  // hypotheses per chunk == queue capacity (worst case: all survive)
 
-struct PipeLayout { size_t counts, best, qa, qb, res_cost, res_cnt, total; };
+struct PipeLayout { size_t counts, best, qa, qb, res_cost, res_esum, res_cnt, total; };
 
 static PipeLayout pipe_layout(int n_problems) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1046,6 +1132,7 @@ static PipeLayout pipe_layout(int n_problems) {
   L.qa = o; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
   L.qb = o; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
   L.res_cost = o; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.res_esum = o; o = up(o + (size_t)PIPE_CHUNK * 8);
   L.res_cnt = o; o = up(o + (size_t)PIPE_CHUNK * 8);
   L.total = o;
   return L;
@@ -1053,24 +1140,37 @@ static PipeLayout pipe_layout(int n_problems) {
 
 static size_t stage_a_smem(const rb2_ransac_desc& h) {
   return (size_t)h.n_upeaks * 8 + (size_t)h.n_cand * 8 + (size_t)(h.n_upeaks + 1) * 4 + (size_t)h.n_cand * 4 +
-         (size_t)h.n_upeaks * 4 + 256 * 2 + 16;
+         (size_t)h.n_upeaks * 4 + (size_t)(1 << LUT_BITS) * 2 + 16;
 }
 
 template <int DEG_T>
-static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int sms, cudaStream_t stream,
+static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int max_up, int sms, cudaStream_t stream,
                         const rb2_ransac_desc* d_desc, const Pipe& pipe, long long chunk_begin, long long chunk_len,
                         rb2_ransac_result* d_result) {
   static bool configured = false;
   if (!configured || true) {
     RB2_CHECK(cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    RB2_CHECK(cudaFuncSetAttribute(ransac_score_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     configured = true;
   }
+  static const bool dbg = getenv("RB2_DEBUG_SYNC") != nullptr;  // diagnostics: name the stage that faults
+  auto stage_ok = [&](const char* name) {
+    if (!dbg) return true;
+    const cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { fprintf(stderr, "rb2: stage %s failed: %s\n", name, cudaGetErrorString(e)); return false; }
+    return true;
+  };
   pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(pipe);
   ransac_draw_fit_kernel<DEG_T><<<grid_a, RS_THREADS, smem_a, stream>>>(d_desc, pipe, chunk_begin, chunk_len, d_result);
+  if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
   ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(d_desc, pipe, d_result);
-  ransac_score_kernel<DEG_T><<<sms * 4, RS_THREADS, smem_c, stream>>>(d_desc, pipe, d_result, max_wids);
+  if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
+  ransac_match_kernel<DEG_T><<<sms * 4, RS_THREADS, smem_c, stream>>>(d_desc, pipe, max_wids, max_up);
+  if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
+  ransac_cost_kernel<DEG_T><<<sms * 2, 256, 0, stream>>>(d_desc, pipe, d_result);
+  if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
   ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(d_desc, pipe, d_result);
+  if (!stage_ok("D record")) return RB2_ERR_CUDA;
   return RB2_OK;
 }
 
@@ -1095,7 +1195,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   const int deg = h_desc[0].deg, s = h_desc[0].sample_size;
   bool fast = true;
   size_t smem_a = 0;
-  int max_wids = 1;
+  int max_wids = 1, max_up = 1;
   long long max_hyp = 0;
   for (int i = 0; i < n_problems; ++i) {
     const rb2_ransac_desc& h = h_desc[i];
@@ -1108,9 +1208,10 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     if (h.n_hyp < 0 || h.n_hyp >= (1ll << 40)) return RB2_ERR_ARG;
     smem_a = max(smem_a, stage_a_smem(h));
     max_wids = max(max_wids, h.n_wids);
+    max_up = max(max_up, h.n_upeaks);
     max_hyp = max(max_hyp, (long long)h.n_hyp);
   }
-  const size_t smem_c = (size_t)RS_WARPS * (NCOEF + max_wids) * 8;
+  const size_t smem_c = (size_t)RS_WARPS * ((size_t)max_wids + max_up + (max_up + 1) / 2) * 8;
   if (smem_a > 200 * 1024 || smem_c > 200 * 1024) return RB2_ERR_ARG;
 
   const PipeLayout L = pipe_layout(n_problems);
@@ -1121,6 +1222,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   pipe.qa = (double*)(base + L.qa);
   pipe.qb = (double*)(base + L.qb);
   pipe.res_cost = (double*)(base + L.res_cost);
+  pipe.res_esum = (double*)(base + L.res_esum);
   pipe.res_cnt = (int2*)(base + L.res_cnt);
   pipe.cap = PIPE_CHUNK;
   pipe.qs = deg + 2;
@@ -1137,12 +1239,12 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     }
     dim3 grid_a(bpp, n_problems);
     int rc;
-    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
-    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, sms, stream, d_desc, pipe, c0, len, d_result);
+    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
+    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
     if (rc != RB2_OK) return rc;
   }
   RB2_CHECK(cudaGetLastError());

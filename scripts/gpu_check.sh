@@ -1,10 +1,12 @@
-# usage: bash scripts/gpu_check.sh TAG   -> tests + 1-GPU bench into gpurun_out/
+#!/bin/bash
+# usage (on the GPU box): bash scripts/gpu_check.sh TAG   -> gpurun_out/pytest_TAG.log, bench_TAG.json
 TAG=${1:-x}
-mkdir -p gpurun_out
-timeout 800 python -m pytest tests -m gpu -q --timeout 180 -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo exit=$? >> gpurun_out/pytest_gpu_$TAG.log
-tail -3 gpurun_out/pytest_gpu_$TAG.log
-timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench_rc=$?
-python -c "
-import json; d=json.load(open('gpurun_out/bench_$TAG.json'))
-print('value %.4g ms/step %.3f e2e %.4g (%.2f ms) frac %.4f kernel_ms %.3f cpu %.0f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms_per_step'], d.get('cpu_baseline',{}).get('value',0)))"
-tail -3 gpurun_out/bench_$TAG.err
+timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_$TAG.log 2>&1; echo pytest_exit=$?
+tail -5 gpurun_out/pytest_$TAG.log
+timeout 900 python bench.py --no-cpu > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench_exit=$?
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_$TAG.json").read().strip().splitlines()[-1])
+print("value %.4g  e2e %.4g  ms/step %.3f  kernel_ms %.3f frac %.4f" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["kernel_ms_per_step"], d["roofline"]["frac"]))
+print(d["counters"]); print(d.get("stage_ms"))
+PY
