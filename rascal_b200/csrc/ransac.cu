@@ -226,21 +226,6 @@ struct WeightCtx {
 
 enum { CMP_GT = 0, CMP_GE = 1, CMP_LT = 2, CMP_LE = 3 };
 
-// first index i in [a, b] with cmp(t(i), th) true (the predicate is monotone false...true on
-// the piece); b + 1 if none.  Bisection over the pixel index, the reference's arithmetic at
-// every probe.  ONE copy of the code (noinline).
-template <int DEG>
-__device__ __noinline__ int first_index(const WeightCtx<DEG>& w, int a, int b, double th, int cmp) {
-  int lo = a, hi = b + 1;
-  while (lo < hi) {
-    const int m = (lo + hi) >> 1;
-    const double t = w.t_at(m);
-    const bool p = cmp == CMP_GT ? (t > th) : cmp == CMP_GE ? (t >= th) : cmp == CMP_LT ? (t < th) : (t <= th);
-    if (p) hi = m; else lo = m + 1;
-  }
-  return lo;
-}
-
 __device__ __noinline__ double pp_eval(const rb2_ransac_desc& d, double t) {
   // 1-D cubic spline along the first intercept row, pp-form
   int a = 0, b = d.n_pp - 1;
@@ -326,16 +311,30 @@ __device__ __forceinline__ bool hough_weight_thread(const rb2_ransac_desc& d, co
     if (ca == cb) {
       if (ca == 2) n_hi += ib - ia + 1; else if (ca == 0) n_lo += ib - ia + 1;
       i_mid0 = ia; i_mid1 = (ca == 1) ? ib + 1 : ia;
-    } else if (ca < cb) {  // increasing: LO.. MID.. HI
-      const int f1 = (ca == 0) ? first_index<DEG>(w, ia, ib, th_lo, CMP_GT) : ia;
-      const int f2 = (cb == 2) ? first_index<DEG>(w, f1, ib, th_hi, CMP_GE) : ib + 1;
-      n_lo += f1 - ia; n_hi += ib + 1 - f2;
-      i_mid0 = f1; i_mid1 = f2;
-    } else {               // decreasing: HI.. MID.. LO
-      const int f1 = (ca == 2) ? first_index<DEG>(w, ia, ib, th_hi, CMP_LT) : ia;
-      const int f2 = (cb == 0) ? first_index<DEG>(w, f1, ib, th_lo, CMP_LE) : ib + 1;
-      n_hi += f1 - ia; n_lo += ib + 1 - f2;
-      i_mid0 = f1; i_mid1 = f2;
+    } else {
+      // increasing piece: LO.. MID.. HI, decreasing piece: HI.. MID.. LO.  Two bisections over the
+      // pixel index (first pixel past the first class, first pixel of the last class), the
+      // reference's arithmetic at every probe; ONE inlined copy of the loop, coefficients in registers.
+      const bool inc = ca < cb;
+      int f[2];
+#pragma unroll 1
+      for (int sidx = 0; sidx < 2; ++sidx) {
+        const bool first = (sidx == 0);
+        const bool needed = first ? (ca != 1) : (cb != 1);
+        int lo = first ? ia : f[0], hi = ib + 1;
+        if (!needed) { lo = first ? ia : ib + 1; hi = lo; }
+        const double th = (first == inc) ? th_lo : th_hi;
+        while (lo < hi) {
+          const int m = (lo + hi) >> 1;
+          const double t = w.t_at(m);
+          // inc: first  t > th_lo, then  t >= th_hi ; dec: first  t < th_hi, then  t <= th_lo
+          const bool pr = inc ? (first ? (t > th) : (t >= th)) : (first ? (t < th) : (t <= th));
+          if (pr) hi = m; else lo = m + 1;
+        }
+        if (first) f[0] = lo; else f[1] = lo;
+      }
+      if (inc) { n_lo += f[0] - ia; n_hi += ib + 1 - f[1]; } else { n_hi += f[0] - ia; n_lo += ib + 1 - f[1]; }
+      i_mid0 = f[0]; i_mid1 = f[1];
     }
     for (int i = i_mid0; i < i_mid1; ++i) {  // class re-checked per pixel: never extrapolate the pp-form
       const double t = w.t_at(i);
@@ -515,10 +514,8 @@ constexpr int LUT_BITS = 10;
 __device__ __forceinline__ int draw_peak_lut(const TablesA& t, unsigned r) {
   int i = t.lut[r >> (32 - LUT_BITS)];
   const int last = t.n_u - 1;
-  if (i < last && r >= t.cdf32[i]) {
-    ++i;
-    while (i < last && r >= t.cdf32[i]) ++i;
-  }
+  i += (i < last && r >= t.cdf32[i]);  // at most one boundary per LUT cell unless a peak is rarer than 2^-LUT_BITS
+  while (i < last && r >= t.cdf32[i]) ++i;
   return i;
 }
 
@@ -595,6 +592,7 @@ __device__ __forceinline__ bool draw_sample(const TablesA& t, unsigned long long
     const int o0 = t.coff[pi[k]], K = t.coff[pi[k] + 1] - o0;
     unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
     bool checked = false;
+    int n_dup = 0;
     for (;;) {
       unsigned x = h * (unsigned)K;
       bool redraw = false;
@@ -606,7 +604,7 @@ __device__ __forceinline__ bool draw_sample(const TablesA& t, unsigned long long
 #pragma unroll
         for (int q = 0; q < S; ++q) if (q < k) dup |= (wi[q] == wv);
         if (!dup) { wi[k] = wv; ci[k] = o0 + j; break; }
-        if (!checked) {  // is any unused wavelength left for this peak?
+        if (!checked && ++n_dup >= 3) {  // after a few duplicates: is any unused wavelength left for this peak?
           bool possible = false;
           for (int jj = 0; jj < K; ++jj) {
             const int ww = t.cwid[o0 + jj];
@@ -741,6 +739,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   const double lsq_xsc = (d.pix_max > d.pix_min) ? 2.0 / (d.pix_max - d.pix_min) : 1.0;
   const int qs = pipe.qs;
   unsigned c_drawn = 0, c_abort = 0, c_icpt = 0;
+  const bool diag = d.d_out_status != nullptr || d.d_out_coeffs != nullptr;  // parity / diagnostics launches only
 
   const long long stride = (long long)gridDim.x * RS_THREADS;
   for (long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane); base < chunk_len; base += stride) {
@@ -788,13 +787,15 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
           lsq_polyfit(xs, ys, m, deg, lsq_xc, lsq_xsc, cf);
         }
       }
-      if (!aborted) {
-        pass = !((cf[0] < min_i) || (cf[0] > max_i));  // :578-582
-        if (d.d_out_coeffs)
-          for (int i = 0; i < ncoef; ++i) d.d_out_coeffs[id * ncoef + i] = cf[i];
-        if (!pass && d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_INTERCEPT;
-      } else if (d.d_out_status) {
-        d.d_out_status[id] = (uint8_t)RB2_HYP_ABORT;
+      if (!aborted) pass = !((cf[0] < min_i) || (cf[0] > max_i));  // :578-582
+      if (diag) {
+        if (!aborted) {
+          if (d.d_out_coeffs)
+            for (int i = 0; i < ncoef; ++i) d.d_out_coeffs[id * ncoef + i] = cf[i];
+          if (!pass && d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_INTERCEPT;
+        } else if (d.d_out_status) {
+          d.d_out_status[id] = (uint8_t)RB2_HYP_ABORT;
+        }
       }
     }
     const unsigned pm = __ballot_sync(0xffffffffu, pass);
@@ -898,7 +899,7 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
 // Output per entry: sum of the clipped errors, match count, inlier count.
 template <int DEG_T>
 __global__ void __launch_bounds__(RS_THREADS, 4)
-ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up) {
+ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up, int single) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -909,6 +910,25 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
   double* s_be = reinterpret_cast<double*>(berr + max_wids);
   int* s_bw = reinterpret_cast<int*>(s_be + max_up);
   for (int i = lane; i < max_wids; i += 32) berr[i] = INF_BITS;  // +inf = empty
+  // one problem in the call (the many-hypotheses case): its tables are staged in shared memory once
+  // per CTA; a many-spectra batch reads them through L1 instead
+  int n_u = 0;
+  double tol = 0.0;
+  const double* t_peaks = nullptr; const int* t_coff = nullptr; const double* t_cwave = nullptr; const int* t_cwid = nullptr;
+  if (single) {
+    const rb2_ransac_desc& d = descs[0];
+    n_u = d.n_upeaks; tol = d.tol;
+    const int n_c = d.n_cand;
+    double* sp = reinterpret_cast<double*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)RS_WARPS * per_warp);
+    double* sw = sp + n_u;
+    int* so = reinterpret_cast<int*>(sw + n_c);
+    int* si = so + (n_u + 1);
+    for (int i = threadIdx.x; i < n_u; i += RS_THREADS) sp[i] = d.d_peaks[i];
+    for (int i = threadIdx.x; i <= n_u; i += RS_THREADS) so[i] = d.d_cand_off[i];
+    for (int i = threadIdx.x; i < n_c; i += RS_THREADS) { sw[i] = d.d_cand_wave[i]; si[i] = d.d_cand_wid[i]; }
+    t_peaks = sp; t_coff = so; t_cwave = sw; t_cwid = si;
+    __syncthreads();
+  }
   __syncwarp();
   const unsigned total_warps = gridDim.x * RS_WARPS;
   for (unsigned e = blockIdx.x * RS_WARPS + warp; e < n; e += total_warps) {
@@ -916,24 +936,27 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
     double cr[deg_cap(DEG_T) + 1];
 #pragma unroll
     for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? q[k] : 0.0;
-    const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
-    const rb2_ransac_desc& d = descs[(int)(tag >> 40)];
-    const int n_u = d.n_upeaks;
-    const double tol = d.tol;
-    const double* __restrict__ g_peaks = d.d_peaks;
-    const int* __restrict__ g_coff = d.d_cand_off;
-    const double* __restrict__ g_cwave = d.d_cand_wave;
-    const int* __restrict__ g_cwid = d.d_cand_wid;
+    if (!single) {
+      const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+      const rb2_ransac_desc& d = descs[(int)(tag >> 40)];
+      n_u = d.n_upeaks; tol = d.tol;
+      t_peaks = d.d_peaks; t_coff = d.d_cand_off; t_cwave = d.d_cand_wave; t_cwid = d.d_cand_wid;
+    }
+    const double* __restrict__ g_peaks = t_peaks;
+    const int* __restrict__ g_coff = t_coff;
+    const double* __restrict__ g_cwave = t_cwave;
+    const int* __restrict__ g_cwid = t_cwid;
     // -- nearest candidate per peak (calibrator.py:341-354) --
     for (int u = lane; u < n_u; u += 32) {
       const double fit = horner_ref<deg_cap(DEG_T)>(cr, ncoef, g_peaks[u]);
       const int o0 = g_coff[u], o1 = g_coff[u + 1];
       double be = CUDART_INF;
-      int bw = -1;
+      int bk = -1;
       for (int k = o0; k < o1; ++k) {
         const double er = fabs(sub(fit, g_cwave[k]));
-        if (er < be) { be = er; bw = g_cwid[k]; }  // first minimum wins
+        if (er < be) { be = er; bk = k; }  // first minimum wins
       }
+      const int bw = (bk >= 0) ? g_cwid[bk] : -1;
       s_be[u] = be; s_bw[u] = bw;
       if (bw >= 0) atomicMin(&berr[bw], (unsigned long long)__double_as_longlong(be));
     }
@@ -969,7 +992,7 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
 // change the outcome and only its regime test is run.  Selection and counters are unaffected
 // (the `eligible` counter counts the inlier criteria only).
 template <int DEG_T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(128, 4)
 ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
   const unsigned n = pipe.counts[1];
   const int lane = threadIdx.x & 31;
@@ -1144,7 +1167,7 @@ static size_t stage_a_smem(const rb2_ransac_desc& h) {
 }
 
 template <int DEG_T>
-static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int max_up, int sms, cudaStream_t stream,
+static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int max_up, int single, int sms, cudaStream_t stream,
                         const rb2_ransac_desc* d_desc, const Pipe& pipe, long long chunk_begin, long long chunk_len,
                         rb2_ransac_result* d_result) {
   static bool configured = false;
@@ -1165,9 +1188,9 @@ static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids,
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
   ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(d_desc, pipe, d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
-  ransac_match_kernel<DEG_T><<<sms * 4, RS_THREADS, smem_c, stream>>>(d_desc, pipe, max_wids, max_up);
+  ransac_match_kernel<DEG_T><<<sms * 4, RS_THREADS, smem_c, stream>>>(d_desc, pipe, max_wids, max_up, single);
   if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
-  ransac_cost_kernel<DEG_T><<<sms * 2, 256, 0, stream>>>(d_desc, pipe, d_result);
+  ransac_cost_kernel<DEG_T><<<sms * 8, 128, 0, stream>>>(d_desc, pipe, d_result);
   if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
   ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(d_desc, pipe, d_result);
   if (!stage_ok("D record")) return RB2_ERR_CUDA;
@@ -1211,7 +1234,9 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     max_up = max(max_up, h.n_upeaks);
     max_hyp = max(max_hyp, (long long)h.n_hyp);
   }
-  const size_t smem_c = (size_t)RS_WARPS * ((size_t)max_wids + max_up + (max_up + 1) / 2) * 8;
+  const int single = (n_problems == 1);
+  size_t smem_c = (size_t)RS_WARPS * ((size_t)max_wids + max_up + (max_up + 1) / 2) * 8;
+  if (single) smem_c += (size_t)h_desc[0].n_upeaks * 8 + (size_t)h_desc[0].n_cand * 12 + (size_t)(h_desc[0].n_upeaks + 1) * 4 + 16;
   if (smem_a > 200 * 1024 || smem_c > 200 * 1024) return RB2_ERR_ARG;
 
   const PipeLayout L = pipe_layout(n_problems);
@@ -1239,12 +1264,12 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     }
     dim3 grid_a(bpp, n_problems);
     int rc;
-    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
-    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, sms, stream, d_desc, pipe, c0, len, d_result);
+    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
+    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
     if (rc != RB2_OK) return rc;
   }
   RB2_CHECK(cudaGetLastError());
