@@ -213,6 +213,16 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def k3_traffic():
+    """DRAM bytes (read + write) of the K3 stage kernels per 2^22-hypothesis chunk from the committed
+    `ncu --set full` capture (profiles/k3_traffic.json, written by scripts/ncu_summary.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_chunk"]
+    except Exception:
+        return None
+
+
 WORKLOAD_NAME = "C3: synthetic 60-peak/300-atlas-line arc, degree 4, sample 5, top-5 candidates (BASELINE configs[2])"
 
 
@@ -230,6 +240,7 @@ def main():
     ap.add_argument("--hyp", type=float, default=1e8, help="hypotheses per step over all ranks")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--spectra", type=int, default=256, help="C4 spectra per rank in the many-spectra leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -366,12 +377,43 @@ def main():
            "d2h_bytes_per_step": engine.TRANSFER["d2h"] // e2e_steps,
            "ms_per_step": 1e3 * t_e2e / e2e_steps, "rms": float(res[3]), "n_matched": len(res[1])}
 
+    # ---- many-spectra leg (BASELINE configs[3] shape, bounded sample): spectra calibrated/s through
+    # rascal_b200.batch.calibrate_batch (K1..K5 per spectrum, host buffers in, results out) ----
+    spectra = None
+    if args.spectra > 0:
+        from rascal_b200 import batch
+
+        specs = [c4_input(rank + world * i) for i in range(args.spectra)]  # spectrum i -> rank i mod world
+        batch.calibrate_batch(specs[:16], n_hypotheses=10_000, seed=1, match_tolerance=5.0)  # warm
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tm = {}
+        t0 = time.perf_counter()
+        bres = batch.calibrate_batch(specs, n_hypotheses=10_000, seed=1, match_tolerance=5.0, timings=tm)
+        torch.cuda.synchronize()
+        t_b = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+        P = np.polynomial.polynomial
+        good = 0
+        for sp, r in zip(specs, bres):
+            if r.fit_coeff is not None:
+                x = np.linspace(0, sp["num_pix"] - 1, 256)
+                good += bool(np.sqrt(np.mean((P.polyval(x, r.fit_coeff) - P.polyval(x, sp["truth"])) ** 2)) < 1.0)
+        spectra = {"value": world * args.spectra / float(t_b.item()), "unit": "spectra/s",
+                   "sample": "%d C4 spectra per rank x 1e4 hypotheses each, Hough 2000x(100x100), match_peaks after the fit"
+                             % args.spectra,
+                   "fitted_rank0": sum(r.fit_coeff is not None for r in bres), "within_1A_of_truth_rank0": good,
+                   "stage_s_rank0": {k: round(v, 4) for k, v in tm.items()}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     F, f_i, f_m = flops_per_hypothesis(counters)
     per_rank_hyp = (hi - lo)
+    n_chunks = -(-per_rank_hyp // (1 << 22))
     achieved = per_rank_hyp * args.steps * F / (kern_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -381,15 +423,21 @@ def main():
                    "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
         "clocks": clocks.summary(),
         "e2e": e2e,
-        "gpu_launches": (3 + (1 if world > 1 else 0)) * args.steps,
+        # K3 = pipe_init + 6 kernels (reset, draw_fit, monotonic, match, cost, record) per 2^22-hypothesis
+        # chunk; + merge after the all-gather (N > 1) + K4 refit
+        "gpu_launches": (1 + 6 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak, "traffic": None,
-                     "kernel": "ransac_kernel<4>", "flops_per_hypothesis": F, "f_intercept_pass": f_i,
+                     "frac": achieved / fp64_peak, "traffic": k3_traffic(),
+                     "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant, ~60 % of K3 time) + "
+                               "monotonic + match + cost + record, timed together per step",
+                     "flops_per_hypothesis": F, "f_intercept_pass": f_i,
                      "f_scored": f_m, "peak_source": "DFMA microbenchmark in this run (rb2_dfma_burn); FP64 is not in MEASURED_PEAKS.json",
                      "kernel_ms_per_step": kern_ms / args.steps},
         "counters": counters,
         "wall_s_timed_region": t_wall,
     }
+    if spectra is not None:
+        line["spectra_per_sec"] = spectra
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

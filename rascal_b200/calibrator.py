@@ -24,7 +24,6 @@ call raises.
 from __future__ import annotations
 
 import copy
-import itertools
 import logging
 
 import numpy as np
@@ -187,7 +186,9 @@ class Calibrator:
     # ------------------------------------------------------------------ atlas / pairs
     def _generate_pairs(self):
         """calibrator.py:86-133: peak-major Cartesian product, optional polygon mask."""
-        pairs = [pair for pair in itertools.product(self.peaks, self.atlas.get_lines())]
+        peaks = np.asarray(self.peaks, dtype=np.float64)
+        lines = np.asarray(self.atlas.get_lines(), dtype=np.float64)
+        pairs = np.column_stack((np.repeat(peaks, len(lines)), np.tile(lines, len(peaks))))  # itertools.product order
         if self.constrain_poly:
             from scipy.spatial import Delaunay
 
@@ -198,9 +199,9 @@ class Calibrator:
                 (px, self.max_wavelength - self.range_tolerance - self.candidate_tolerance),
                 (px, self.max_wavelength + self.range_tolerance + self.candidate_tolerance)])
             mask = valid_area.find_simplex(pairs) >= 0
-            self.pairs = np.array(pairs)[mask]
+            self.pairs = pairs[mask]
         else:
-            self.pairs = np.array(pairs)
+            self.pairs = pairs
 
     def set_atlas(self, atlas, candidate_tolerance=10.0, constrain_poly=False):
         """calibrator.py:1399-1423."""

@@ -690,8 +690,11 @@ __device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigne
 }
 
 // ---- stage A ---------------------------------------------------------------------------
+#ifndef RB2_A_CTAS
+#define RB2_A_CTAS 4
+#endif
 template <int DEG_T>
-__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 ? 4 : 2)
+__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 ? RB2_A_CTAS : 2)
 ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
                        rb2_ransac_result* __restrict__ result) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1259,7 +1262,8 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     int bpp = blocks_per_problem;
     if (bpp <= 0) {
       const long long want = (len + RS_THREADS * 8 - 1) / (RS_THREADS * 8);   // >= 8 passes per CTA
-      const long long fill = max(1ll, (long long)(8 * sms) / n_problems);      // ~8 CTAs per SM overall
+      static const int ctas_per_sm = getenv("RB2_A_CTAS_PER_SM") ? atoi(getenv("RB2_A_CTAS_PER_SM")) : 8;
+      const long long fill = max(1ll, (long long)(ctas_per_sm * sms) / n_problems);  // CTAs per SM overall
       bpp = (int)max(1ll, min(want, fill));
     }
     dim3 grid_a(bpp, n_problems);

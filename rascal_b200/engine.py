@@ -452,12 +452,10 @@ class RansacSetup:
         tx = spl.get_knots()[0]
         brk = np.unique(tx)
         npp = len(brk) - 1
-        coef = np.zeros((npp, 4))
-        for k in range(npp):
-            a, b = brk[k], brk[k + 1]
-            u = np.array([0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0])
-            v = spl(a + u * (b - a), np.full(4, ic[0]), grid=False)
-            coef[k] = np.linalg.solve(np.vander(u, 4, increasing=True), v) / (b - a) ** np.arange(4)
+        u = np.array([0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0])
+        a, w = brk[:-1], np.diff(brk)
+        v = spl((a[:, None] + u[None, :] * w[:, None]).ravel(), np.full(4 * npp, ic[0]), grid=False).reshape(npp, 4)
+        coef = np.linalg.solve(np.vander(u, 4, increasing=True), v.T).T / w[:, None] ** np.arange(4)[None, :]
         self.pp_breaks = brk.astype(np.float64)
         self.pp_coef = coef.reshape(-1)
 
