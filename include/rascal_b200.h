@@ -303,6 +303,57 @@ int rb2_match_peaks(int n_problems, const rb2_match_desc *d_desc,
                     double *d_matched_y, double *d_residual, int max_peaks,
                     void *stream);
 
+/* ======================================================================= *
+ * Device-resident glue of the many-spectra path: the host work the reference
+ * does between its stages, on the device, so that a batch of spectra goes
+ * peaks/lines -> pairs -> K1 -> K2 -> prepare -> K3 -> K4 -> K5 with no host
+ * round trip.
+ * ======================================================================= */
+/* Calibrator._generate_pairs (calibrator.py:86-107, no polygon mask): the
+ * peak-major Cartesian product peaks x lines, plus the per-peak CSR view of it
+ * that K2 reads (d_pair_off / d_pair_wid may be NULL; wid = line index, i.e.
+ * the lines must be strictly increasing). */
+typedef struct {
+  const double *d_peaks, *d_lines;
+  int32_t n_peaks, n_lines;
+  double *d_pair_x, *d_pair_y;          /* out: [n_peaks*n_lines]            */
+  int32_t *d_pair_wid;                  /* out: [n_peaks*n_lines] or NULL    */
+  int32_t *d_pair_off;                  /* out: [n_peaks+1] or NULL          */
+} rb2_pairs_desc;
+
+int rb2_expand_pairs(int n_problems, const rb2_pairs_desc *d_desc,
+                     const rb2_pairs_desc *h_desc, void *stream);
+
+/* The set-up at the top of Calibrator._solve_candidate_ransac
+ * (calibrator.py:441-523, filter_close=False) from K1/K2 outputs that are
+ * still on the device.  d_ransac_desc[i] must already hold every pointer and
+ * every host-known scalar (deg, sample_size, tolerances, n_pix, hough_weight,
+ * min_inliers..., n_hyp, and d_peaks/d_cand_off/d_cand_wave/d_cand_wid/
+ * d_cdf32/d_pp_breaks/d_pp_coef sized for n_peaks, n_peaks+1,
+ * n_peaks*top_n (x2), n_peaks, n_pp+1, 4*n_pp); the kernel fills those tables
+ * and the data-dependent scalars (n_upeaks, n_cand, n_wids, pix_min/max,
+ * gc_min/max, ic_min, h_lo/h_hi, w_upper) and sets n_hyp = 0 where the
+ * reference would return before the loop (:468-469; d_enough[0] = 0). */
+typedef struct {
+  const double *d_upeak_x;              /* [n_peaks] ascending (K2's input)  */
+  const double *d_cand_wave;            /* [n_peaks*top_n] K2 output         */
+  const int32_t *d_cand_n;              /* [n_peaks]       K2 output         */
+  int32_t n_peaks, top_n;
+  const double *d_xedges, *d_yedges;    /* K1 outputs                        */
+  const uint32_t *d_hist;               /* K1 output [xbins*ybins]           */
+  int32_t xbins, ybins;
+  const double *d_spline_op;            /* [4*n_pp][xbins]: pp-form (Taylor coefficients at the left breaks,
+                                           integer grid) of the interpolating cubic spline as a linear map of
+                                           the data; depends on xbins only                                    */
+  const double *d_spline_brk;           /* [n_pp+1] breaks on the integer grid */
+  int32_t n_pp, pad;
+  int32_t *d_enough;                    /* out: [1] or NULL                  */
+} rb2_prepare_desc;
+
+int rb2_ransac_prepare(int n_problems, const rb2_prepare_desc *d_desc,
+                       const rb2_prepare_desc *h_desc,
+                       rb2_ransac_desc *d_ransac_desc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,7 +104,23 @@ class MatchResult(C.Structure):
     ]
 
 
-STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult, MatchDesc, MatchResult]
+class PairsDesc(C.Structure):
+    _fields_ = [
+        ("d_peaks", _vp), ("d_lines", _vp), ("n_peaks", C.c_int32), ("n_lines", C.c_int32),
+        ("d_pair_x", _vp), ("d_pair_y", _vp), ("d_pair_wid", _vp), ("d_pair_off", _vp),
+    ]
+
+
+class PrepareDesc(C.Structure):
+    _fields_ = [
+        ("d_upeak_x", _vp), ("d_cand_wave", _vp), ("d_cand_n", _vp), ("n_peaks", C.c_int32), ("top_n", C.c_int32),
+        ("d_xedges", _vp), ("d_yedges", _vp), ("d_hist", _vp), ("xbins", C.c_int32), ("ybins", C.c_int32),
+        ("d_spline_op", _vp), ("d_spline_brk", _vp), ("n_pp", C.c_int32), ("pad", C.c_int32), ("d_enough", _vp),
+    ]
+
+
+STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult, MatchDesc, MatchResult,
+           PairsDesc, PrepareDesc]
 COUNTER_NAMES = ("drawn", "aborted", "intercept", "monotonic", "empty", "scored", "eligible", "unsupported")
 
 # every symbol include/rascal_b200.h declares
@@ -122,6 +138,8 @@ EXPORTS = {
     "rb2_ransac_batch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_merge_winners": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "rb2_robust_polyfit": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "rb2_expand_pairs": (C.c_int, [C.c_int, _vp, _vp, _vp]),
+    "rb2_ransac_prepare": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
     "rb2_match_peaks": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_refit_winners": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_double, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
 }

@@ -17,7 +17,7 @@ import types
 
 import numpy as np
 
-from . import engine
+from . import engine, pipeline
 
 HOUGH_DEFAULTS = dict(num_slopes=2000, xbins=100, ybins=100, min_wavelength=3000.0, max_wavelength=9000.0,
                       range_tolerance=500, linearity_tolerance=100)
@@ -65,19 +65,7 @@ def _spline_tables(hist0, gc0, gcn):
 
 def _sampling_cdf(peaks):
     """calibrator.py:521-523 incl. the index -1 wrap-around; returns uint32 CDF."""
-    lo, hi = peaks[0], peaks[-1]
-    if lo == hi:
-        lo, hi = lo - 0.5, hi + 0.5
-    edges = np.linspace(lo, hi, 11)
-    idx = np.minimum(np.searchsorted(edges, peaks, side="right") - 1, 9)  # np.histogram bins
-    counts = np.bincount(idx, minlength=10)
-    dig = np.searchsorted(edges, peaks, side="left") - 1  # np.digitize(right=True) - 1
-    prob = 1.0 / counts[dig]
-    cdf = np.cumsum(prob / np.sum(prob))
-    cdf /= cdf[-1]
-    c32 = np.minimum(np.floor(cdf * 4294967296.0), 4294967295.0).astype(np.uint32)
-    c32[-1] = 0xFFFFFFFF
-    return c32
+    return engine.sampling_cdf32(peaks)[1]
 
 
 def ransac_setups(specs, hough, vote):
@@ -166,13 +154,18 @@ class BatchResult(types.SimpleNamespace):
     pass
 
 
-def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=None, match_tolerance=None):
+def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=None, match_tolerance=None,
+                    device_pipeline=True):
     """do_hough_transform() + fit() for every spectrum of `spectra` in batched device calls.
 
     All spectra of one call must share fit_deg and sample size (one K3 instantiation).
     Returns a list of BatchResult(fit_coeff, matched_peaks, matched_atlas, rms, residual,
     peak_utilisation, atlas_utilisation, valid, cost, counters); fit_coeff is None where the
     reference would raise "Couldn't fit".
+
+    device_pipeline: batches that qualify (pipeline.eligible: shared Hough / RANSAC shape, increasing
+    peaks and lines, pixel_list = arange) run device-resident end to end (rascal_b200.pipeline: one
+    H2D, one D2H, K3's tables built by rb2_ransac_prepare); others take the staged path below.
 
     match_tolerance: if set, Calibrator.match_peaks(tolerance=match_tolerance) follows every fit
     (K5), reading the refit coefficients straight from K4's device records; the result gains
@@ -182,6 +175,9 @@ def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=
     torch = engine._torch()
     t0 = time.perf_counter()
     specs = [normalise_spec(sp) for sp in spectra]
+    if device_pipeline and pipeline.eligible(specs):
+        return pipeline.run(specs, n_hypotheses, seed=seed, refit_mode=refit_mode, match_tolerance=match_tolerance,
+                            timings=timings)
     hp, vs = [], []
     for sp in specs:
         n_p, n_a = len(sp["peaks"]), len(sp["lines"])

@@ -47,6 +47,8 @@ extern "C" int rb2_struct_size(int which) {
     case 5: return (int)sizeof(rb2_refit_result);
     case 6: return (int)sizeof(rb2_match_desc);
     case 7: return (int)sizeof(rb2_match_result);
+    case 8: return (int)sizeof(rb2_pairs_desc);
+    case 9: return (int)sizeof(rb2_prepare_desc);
     default: return -1;
   }
 }

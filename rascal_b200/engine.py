@@ -369,6 +369,26 @@ class VoteBatch:
 # ---------------------------------------------------------------------------
 
 
+def sampling_cdf32(peaks):
+    """The reference's sampling law (calibrator.py:521-523: inverse 10-bin density of the peaks,
+    incl. the index -1 wrap-around of np.digitize(...) - 1) as (prob, uint32 CDF).  Every sum is
+    sequential so that rb2_ransac_prepare reproduces the table bit for bit on the device."""
+    lo, hi = peaks[0], peaks[-1]
+    if lo == hi:
+        lo, hi = lo - 0.5, hi + 0.5
+    edges = np.linspace(lo, hi, 11)  # np.histogram(peaks, bins=10)[1]
+    idx = np.minimum(np.searchsorted(edges, peaks, side="right") - 1, 9)
+    counts = np.bincount(idx, minlength=10)
+    dig = np.searchsorted(edges, peaks, side="left") - 1  # np.digitize(peaks, edges, right=True) - 1
+    w = 1.0 / counts[dig]
+    prob = w / np.cumsum(w)[-1]
+    cdf = np.cumsum(prob)
+    cdf /= cdf[-1]
+    c32 = np.minimum(np.floor(cdf * 4294967296.0), 4294967295.0).astype(np.uint32)
+    c32[-1] = 0xFFFFFFFF
+    return prob, c32
+
+
 class RansacSetup:
     """Read-only inputs of the hypothesis loop, as the reference prepares them
     at the top of _solve_candidate_ransac (calibrator.py:441-523)."""
@@ -409,14 +429,7 @@ class RansacSetup:
         self.cand_wid = wid.astype(np.int32)
         # sampling law (:521-523), index -1 wrap-around kept
         if self.enough:
-            h = np.histogram(self.peaks, bins=10)
-            prob = 1.0 / h[0][np.digitize(self.peaks, h[1], right=True) - 1]
-            prob = prob / np.sum(prob)
-            self.prob = prob
-            cdf = np.cumsum(prob)
-            cdf /= cdf[-1]
-            self.cdf32 = np.minimum(np.floor(cdf * 4294967296.0), 4294967295.0).astype(np.uint32)
-            self.cdf32[-1] = 0xFFFFFFFF
+            self.prob, self.cdf32 = sampling_cdf32(self.peaks)
         else:
             self.prob = None
             self.cdf32 = np.zeros(len(self.peaks), dtype=np.uint32)

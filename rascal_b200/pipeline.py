@@ -1,0 +1,332 @@
+"""Device-resident many-spectra pipeline (BASELINE configs[3]).
+
+    peaks/lines --H2D--> rb2_expand_pairs -> K1 rb2_hough_accumulate -> K2 rb2_candidate_vote
+        -> rb2_ransac_prepare -> K3 rb2_ransac_batch -> K4 rb2_refit_winners -> K5 rb2_match_peaks
+        --D2H--> results
+
+ONE host->device copy (peaks, lines, descriptors) and ONE device->host copy (results) per batch;
+every intermediate (pairs, Hough histogram and ranking, candidates, K3 tables) stays in HBM.  The
+host side is vectorised NumPy over the whole batch: descriptor arrays are structured arrays with
+the C ABI's layout (np.dtype of the ctypes structs), filled column-wise.
+
+Eligibility (else `batch.calibrate_batch` keeps its staged host path): all spectra share
+num_slopes / xbins / ybins / top_n / fit_deg / sample size / candidate_weighted, no filter_close,
+pixel_list = arange(num_pix), peaks and lines strictly increasing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import types
+
+import numpy as np
+
+from . import _native as N
+from . import engine
+
+_ALIGN = 16
+_CACHE = {}  # device-resident constants and scratch reused across calls
+
+
+def _dt(struct):
+    return np.dtype(struct)
+
+
+def spline_operator(xb):
+    """pp-form of the interpolating (not-a-knot) cubic spline on the integer grid 0..xb-1 as a linear
+    map of the data: op[(j, k), i] = d^k/dt^k (spline of e_i)(left break j) / k!  (what
+    batch._spline_tables gets from SciPy, applied to the identity)."""
+    from scipy import interpolate
+
+    b = interpolate.make_interp_spline(np.arange(xb, dtype=np.float64), np.eye(xb), k=3)
+    brk = np.unique(b.t)
+    left = brk[:-1]
+    fact = (1.0, 1.0, 2.0, 6.0)
+    op = np.empty((len(left), 4, xb))
+    for k in range(4):
+        op[:, k, :] = b(left, nu=k) / fact[k]
+    return np.ascontiguousarray(op.reshape(-1, xb)), brk.astype(np.float64)
+
+
+class _Layout:
+    """Bump allocator over one device buffer; vectorised over spectra."""
+
+    def __init__(self):
+        self.size = 0
+
+    def one(self, nbytes):
+        off = self.size
+        self.size += (int(nbytes) + _ALIGN - 1) // _ALIGN * _ALIGN
+        return off
+
+    def many(self, nbytes):
+        nb = (np.asarray(nbytes, dtype=np.int64) + _ALIGN - 1) // _ALIGN * _ALIGN
+        off = self.size + np.concatenate(([0], np.cumsum(nb)[:-1]))
+        self.size += int(nb.sum())
+        return off.astype(np.int64)
+
+
+class BatchResults:
+    """Sequence of per-spectrum results backed by the batch's columnar arrays."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+    def k3_tables(self, i):
+        """The K3 inputs rb2_ransac_prepare built for spectrum i (device -> host; tests / diagnostics)."""
+        t = self._tables
+        b = t["buf"]
+
+        def rd(off, dtype, count):
+            nb = np.dtype(dtype).itemsize * count
+            return b[int(off):int(off) + nb].cpu().numpy().view(dtype)
+
+        d = rd(t["desc"] + i * np.dtype(N.RansacDesc).itemsize, np.dtype(N.RansacDesc), 1)[0]
+        nu, nc = int(d["n_upeaks"]), int(d["n_cand"])
+        return dict(desc=d, peaks=rd(t["up"][i], np.float64, nu), cand_off=rd(t["coff"][i], np.int32, nu + 1),
+                    cand_wave=rd(t["cwave"][i], np.float64, nc), cand_wid=rd(t["cwid"][i], np.int32, nc),
+                    cdf32=rd(t["cdf"][i], np.uint32, nu), pp_breaks=rd(t["ppb"][i], np.float64, t["npp"] + 1),
+                    pp_coef=rd(t["ppc"][i], np.float64, 4 * t["npp"]))
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += self.n
+        r = types.SimpleNamespace(fit_coeff=None, matched_peaks=[], matched_atlas=[], rms=1e50, residual=None,
+                                  peak_utilisation=0.0, atlas_utilisation=0.0, valid=False, cost=float("inf"),
+                                  counters=None, match=None)
+        if not self.enough[i]:
+            return r
+        r.counters = {k: int(self.counters[i, j]) for j, k in enumerate(N.COUNTER_NAMES)}
+        r.cost = float(self.cost[i])
+        if self.ok[i]:
+            m, d = int(self.n_inliers[i]), self.deg
+            r.fit_coeff = self.coeffs[i, :d + 1].copy()
+            r.matched_peaks, r.matched_atlas = self.mx[i, :m].copy(), self.my[i, :m].copy()
+            r.rms, r.residual = float(self.rms[i]), self.rs[i, :m].copy()
+            r.peak_utilisation = m / int(self.n_p[i])
+            r.atlas_utilisation = m / int(self.n_a[i])
+            r.valid = m > d + 1
+            if self.match_ok is not None and self.match_ok[i]:
+                mm = int(self.m_n[i])
+                r.match = types.SimpleNamespace(fit_coeff=self.m_coeffs[i, :d + 1].copy(),
+                                                matched_peaks=self.mmx[i, :mm].copy(),
+                                                matched_atlas=self.mmy[i, :mm].copy(), rms=float(self.m_rms[i]),
+                                                residuals=self.mrs[i, :mm].copy(), n_ambiguous=int(self.m_amb[i]))
+        return r
+
+
+def eligible(specs):
+    """specs: output of batch.normalise_spec.  True if the device pipeline can take the batch."""
+    if not specs:
+        return False
+    s0 = specs[0]
+    keys_h = ("num_slopes", "xbins", "ybins")
+    for sp in specs:
+        if not sp["pix_is_arange"] or sp["ransac"]["filter_close"]:
+            return False
+        if any(sp["hough"][k] != s0["hough"][k] for k in keys_h):
+            return False
+        if (sp["ransac"]["top_n_candidate"] != s0["ransac"]["top_n_candidate"]
+                or bool(sp["ransac"]["candidate_weighted"]) != bool(s0["ransac"]["candidate_weighted"])
+                or sp["fit"]["fit_deg"] != s0["fit"]["fit_deg"] or sp["sample_size"] != s0["sample_size"]):
+            return False
+        p, a = sp["peaks"], sp["lines"]
+        if len(p) < 1 or len(a) < 1 or (len(p) > 1 and not np.all(p[1:] > p[:-1])) or \
+                (len(a) > 1 and not np.all(a[1:] > a[:-1])):
+            return False
+    if int(s0["hough"]["xbins"]) < 8 or s0["sample_size"] != s0["fit"]["fit_deg"] + 1:
+        return False
+    return True
+
+
+def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None):
+    """The whole path for `specs` (normalised, eligible) in batched device calls."""
+    import time
+
+    torch = engine._torch()
+    lib = N.load()
+    t0 = time.perf_counter()
+    n = len(specs)
+    s0 = specs[0]
+    S, xb, yb = int(s0["hough"]["num_slopes"]), int(s0["hough"]["xbins"]), int(s0["hough"]["ybins"])
+    B = xb * yb
+    top_n, deg, ssz = int(s0["ransac"]["top_n_candidate"]), int(s0["fit"]["fit_deg"]), int(s0["sample_size"])
+    weighted = int(bool(s0["ransac"]["candidate_weighted"]))
+    n_p = np.fromiter((len(sp["peaks"]) for sp in specs), dtype=np.int64, count=n)
+    n_a = np.fromiter((len(sp["lines"]) for sp in specs), dtype=np.int64, count=n)
+    P = n_p * n_a
+    lim = np.array([sp["limits"] for sp in specs], dtype=np.float64)  # min_slope, max_slope, min_i, max_i
+    rtol = np.fromiter((sp["hough"]["range_tolerance"] for sp in specs), dtype=np.float64, count=n)
+    ltol = np.fromiter((sp["hough"]["linearity_tolerance"] for sp in specs), dtype=np.float64, count=n)
+    ctol = np.fromiter((sp["fit"]["candidate_tolerance"] for sp in specs), dtype=np.float64, count=n)
+    tol = np.fromiter((sp["ransac"]["ransac_tolerance"] for sp in specs), dtype=np.float64, count=n)
+    hw = np.fromiter((sp["ransac"]["hough_weight"] for sp in specs), dtype=np.float64, count=n)
+    mm = np.fromiter((sp["ransac"]["minimum_matches"] for sp in specs), dtype=np.int64, count=n)
+    mpu = np.fromiter((sp["ransac"]["minimum_peak_utilisation"] for sp in specs), dtype=np.float64, count=n)
+    mfe = float(s0["ransac"]["minimum_fit_error"])
+    n_pix = np.fromiter((len(sp["pixel_list"]) for sp in specs), dtype=np.int64, count=n)
+    sigma = (rtol + ltol) * 1.1775
+
+    key = ("spline", xb)
+    if key not in _CACHE:
+        op, brk = spline_operator(xb)
+        _CACHE[key] = (torch.from_numpy(op).cuda(), torch.from_numpy(brk).cuda(), len(brk) - 1)
+    d_op, d_brk, npp = _CACHE[key]
+    max_p = int(n_p.max())
+
+    # ---- layout: [inputs | descriptors] (H2D)  [work] (device only)  [results] (D2H) ----
+    L = _Layout()
+    o_peaks, o_lines = L.many(8 * n_p), L.many(8 * n_a)
+    dts = dict(pairs=_dt(N.PairsDesc), hough=_dt(N.HoughDesc), vote=_dt(N.VoteDesc), prep=_dt(N.PrepareDesc),
+               ransac=_dt(N.RansacDesc), match=_dt(N.MatchDesc))
+    o_desc = {k: L.one(dt.itemsize * n) for k, dt in dts.items()}
+    h2d_bytes = L.size
+    o_px, o_py, o_pwid = L.many(8 * P), L.many(8 * P), L.many(4 * P)
+    o_poff, o_lo, o_hi = L.many(4 * (n_p + 1)), L.many(4 * P), L.many(4 * P)
+    o_hist, o_rank, o_rpos, o_tmp = (L.one(4 * B * n) + 4 * B * np.arange(n) for _ in range(4))
+    o_xe, o_ye = L.one(8 * (xb + 1) * n) + 8 * (xb + 1) * np.arange(n), L.one(8 * (yb + 1) * n) + 8 * (yb + 1) * np.arange(n)
+    zero_begin = L.size
+    o_cw, o_cp, o_cn = L.many(8 * n_p * top_n), L.many(4 * n_p * top_n), L.many(4 * n_p)
+    zero_end = L.size
+    o_up, o_coff, o_cwave = L.many(8 * n_p), L.many(4 * (n_p + 1)), L.many(8 * n_p * top_n)
+    o_cwid, o_cdf = L.many(4 * n_p * top_n), L.many(4 * n_p)
+    o_ppb, o_ppc = L.one(8 * (npp + 1) * n) + 8 * (npp + 1) * np.arange(n), L.one(32 * npp * n) + 32 * npp * np.arange(n)
+    res_begin = L.size
+    rsz, fsz, msz = C.sizeof(N.RansacResult), C.sizeof(N.RefitResult), C.sizeof(N.MatchResult)
+    o_res, o_fit = L.one(rsz * n), L.one(fsz * n)
+    o_mx, o_my, o_rs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
+    o_mres = L.one(msz * n)
+    o_mmx, o_mmy, o_mrs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
+    o_enough, o_vstat = L.one(4 * n), L.one(4 * n)
+    o_hstat = L.one(C.sizeof(N.HoughStats) * n)
+    res_end = L.size
+
+    buf = torch.empty(L.size, dtype=torch.uint8, device="cuda")
+    base = buf.data_ptr()
+    host = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    # peaks / lines: offsets are 16-byte aligned, so scatter by index arrays
+    pk = np.concatenate([sp["peaks"] for sp in specs])
+    ln = np.concatenate([sp["lines"] for sp in specs])
+    h64 = hv.view(np.float64)
+    idx_p = np.repeat(o_peaks // 8 - np.concatenate(([0], np.cumsum(n_p)[:-1])), n_p) + np.arange(len(pk))
+    idx_l = np.repeat(o_lines // 8 - np.concatenate(([0], np.cumsum(n_a)[:-1])), n_a) + np.arange(len(ln))
+    h64[idx_p] = pk
+    h64[idx_l] = ln
+
+    hv[min(o_desc.values()):h2d_bytes] = 0  # descriptor fields not set below are NULL / 0 (pinned memory is recycled)
+
+    def view(name):
+        o = o_desc[name]
+        return hv[o:o + dts[name].itemsize * n].view(dts[name])
+
+    dp, dh, dv, dr, dk, dm = (view(k) for k in ("pairs", "hough", "vote", "prep", "ransac", "match"))
+    u = lambda a: (base + np.asarray(a, dtype=np.int64)).astype(np.uint64)  # noqa: E731
+    dp["d_peaks"], dp["d_lines"], dp["n_peaks"], dp["n_lines"] = u(o_peaks), u(o_lines), n_p, n_a
+    dp["d_pair_x"], dp["d_pair_y"], dp["d_pair_wid"], dp["d_pair_off"] = u(o_px), u(o_py), u(o_pwid), u(o_poff)
+
+    dh["min_slope"], dh["max_slope"], dh["min_intercept"], dh["max_intercept"] = lim[:, 0], lim[:, 1], lim[:, 2], lim[:, 3]
+    dh["n_slopes"], dh["xbins"], dh["ybins"], dh["n_pairs"] = S, xb, yb, P
+    dh["d_pair_x"], dh["d_pair_y"], dh["d_lo"], dh["d_hi"] = u(o_px), u(o_py), u(o_lo), u(o_hi)
+    dh["d_xedges"], dh["d_yedges"], dh["d_hist"], dh["d_rank"] = u(o_xe), u(o_ye), u(o_hist), u(o_rank)
+    dh["d_rankpos"], dh["d_sort_tmp"] = u(o_rpos), u(o_tmp)
+
+    dv["n_upeaks"], dv["n_uwaves"], dv["xbins"], dv["ybins"] = n_p, n_a, xb, yb
+    dv["top_n"], dv["weighted"], dv["tol"], dv["gauss_denom"] = top_n, weighted, ctol, 2 * sigma ** 2 + 1e-9
+    dv["d_upeak_x"], dv["d_pair_off"], dv["d_pair_y"], dv["d_pair_wid"] = u(o_peaks), u(o_poff), u(o_py), u(o_pwid)
+    dv["d_xedges"], dv["d_yedges"], dv["d_rankpos"] = u(o_xe), u(o_ye), u(o_rpos)
+    dv["d_cand_wave"], dv["d_cand_pair"], dv["d_cand_n"] = u(o_cw), u(o_cp), u(o_cn)
+    dv["d_agg"], dv["d_cnt"], dv["d_status"] = 0, 0, u(o_vstat + 4 * np.arange(n))
+
+    dr["d_upeak_x"], dr["d_cand_wave"], dr["d_cand_n"], dr["n_peaks"], dr["top_n"] = u(o_peaks), u(o_cw), u(o_cn), n_p, top_n
+    dr["d_xedges"], dr["d_yedges"], dr["d_hist"], dr["xbins"], dr["ybins"] = u(o_xe), u(o_ye), u(o_hist), xb, yb
+    dr["d_spline_op"], dr["d_spline_brk"], dr["n_pp"] = d_op.data_ptr(), d_brk.data_ptr(), npp
+    dr["d_enough"] = u(o_enough + 4 * np.arange(n))
+
+    # K3 descriptors: pointers + host-known scalars; sizes are upper bounds until rb2_ransac_prepare ran
+    dk["n_upeaks"], dk["n_wids"], dk["n_cand"] = np.maximum(n_p, ssz), n_p * top_n, np.maximum(n_p, ssz) * top_n
+    dk["d_peaks"], dk["d_cand_off"], dk["d_cand_wave"], dk["d_cand_wid"] = u(o_up), u(o_coff), u(o_cwave), u(o_cwid)
+    dk["d_cdf32"], dk["deg"], dk["sample_size"] = u(o_cdf), deg, ssz
+    dk["min_intercept"], dk["max_intercept"], dk["tol"], dk["hough_weight"] = lim[:, 2], lim[:, 3], tol, hw
+    dk["n_pp"], dk["d_pp_breaks"], dk["d_pp_coef"] = npp, u(o_ppb), u(o_ppc)
+    dk["n_pix"], dk["d_pix"] = n_pix, 0
+    dk["min_inliers"] = np.maximum(deg + 1, np.minimum(np.minimum(mm, n_a), n_p))
+    dk["min_inliers_frac"], dk["cost_ceiling"], dk["floor_cost"], dk["floor_id"] = mpu * n_p, 1e50, 0.0, -1
+    dk["hyp_begin"], dk["n_hyp"], dk["seed"] = 0, int(n_hypotheses), int(seed)
+
+    if match_tolerance is not None:
+        dm["d_peaks"], dm["d_atlas"], dm["n_peaks"], dm["n_atlas"] = u(o_peaks), u(o_lines), n_p, n_a
+        dm["d_coeffs"], dm["n_coef"], dm["fit_deg"] = u(o_fit + fsz * np.arange(n)), deg + 1, deg
+        dm["tolerance"], dm["robust_refit"] = float(match_tolerance), 1
+
+    buf[:h2d_bytes].copy_(host, non_blocking=True)
+    engine.TRANSFER["h2d"] += h2d_bytes
+    buf[zero_begin:zero_end].zero_()
+    buf[o_vstat:o_vstat + 4 * n].zero_()
+    stream = engine.current_stream_ptr()
+    hptr = lambda name: hv.ctypes.data + o_desc[name]  # noqa: E731
+    dptr = lambda name: base + o_desc[name]  # noqa: E731
+    t1 = time.perf_counter()
+
+    N.check(lib.rb2_expand_pairs(n, dptr("pairs"), hptr("pairs"), stream), "rb2_expand_pairs")
+    N.check(lib.rb2_hough_accumulate(n, dptr("hough"), hptr("hough"), base + o_hstat, 0, stream), "rb2_hough_accumulate")
+    N.check(lib.rb2_candidate_vote(n, dptr("vote"), hptr("vote"), stream), "rb2_candidate_vote")
+    N.check(lib.rb2_ransac_prepare(n, dptr("prep"), hptr("prep"), dptr("ransac"), stream), "rb2_ransac_prepare")
+    nbytes = lib.rb2_ransac_scratch_bytes(n, 0)
+    if _CACHE.get("scratch") is None or _CACHE["scratch"].numel() < nbytes:
+        _CACHE["scratch"] = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + o_res, _CACHE["scratch"].data_ptr(), 0, stream),
+            "rb2_ransac_batch")
+    N.check(lib.rb2_refit_winners(n, dptr("ransac"), hptr("ransac"), base + o_res, mfe, int(refit_mode), base + o_fit,
+                                  base + o_mx, base + o_my, base + o_rs, max_p, stream), "rb2_refit_winners")
+    if match_tolerance is not None:
+        N.check(lib.rb2_match_peaks(n, dptr("match"), hptr("match"), int(refit_mode), base + o_mres, base + o_mmx,
+                                    base + o_mmy, base + o_mrs, max_p, stream), "rb2_match_peaks")
+    raw = torch.empty(res_end - res_begin, dtype=torch.uint8, pin_memory=True)
+    raw.copy_(buf[res_begin:res_end], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    engine.TRANSFER["d2h"] += raw.numel()
+    t2 = time.perf_counter()
+    r = raw.numpy()
+
+    def region(off, nbytes):
+        return r[off - res_begin:off - res_begin + nbytes]
+
+    hstat = region(o_hstat, C.sizeof(N.HoughStats) * n).view(_dt(N.HoughStats))
+    vstat = region(o_vstat, 4 * n).view(np.int32)
+    for st, what in ((hstat["status"], "rb2_hough_accumulate"), (vstat, "rb2_candidate_vote")):
+        bad = np.flatnonzero(st != 0)
+        if len(bad):
+            N.check(int(st[bad[0]]), what + " (device status)")
+    win = region(o_res, rsz * n).view(_dt(N.RansacResult))
+    fit = region(o_fit, fsz * n).view(_dt(N.RefitResult))
+    out = BatchResults(n)
+    out.deg, out.n_p, out.n_a = deg, n_p, n_a
+    out.enough = region(o_enough, 4 * n).view(np.int32) != 0
+    out.counters, out.cost = win["counters"], win["cost"]
+    out.ok = out.enough & (win["hyp_id"] >= 0) & (fit["accepted"] != 0)
+    out.coeffs, out.rms, out.n_inliers = fit["coeffs"], fit["rms"], fit["n_inliers"]
+    shp = (n, max_p)
+    out.mx = region(o_mx, 8 * n * max_p).view(np.float64).reshape(shp)
+    out.my = region(o_my, 8 * n * max_p).view(np.float64).reshape(shp)
+    out.rs = region(o_rs, 8 * n * max_p).view(np.float64).reshape(shp)
+    out.match_ok = None
+    if match_tolerance is not None:
+        mres = region(o_mres, msz * n).view(_dt(N.MatchResult))
+        out.match_ok = out.ok & (mres["refit"]["accepted"] != 0)
+        out.m_n, out.m_amb = mres["n_matched"], mres["n_ambiguous"]
+        out.m_coeffs, out.m_rms = mres["refit"]["coeffs"], mres["refit"]["rms"]
+        out.mmx = region(o_mmx, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.mmy = region(o_mmy, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.mrs = region(o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
+    out._keep = (raw, buf, host)
+    out._tables = dict(buf=buf, up=o_up, coff=o_coff, cwave=o_cwave, cwid=o_cwid, cdf=o_cdf, ppb=o_ppb, ppc=o_ppc,
+                       npp=npp, desc=o_desc["ransac"], top_n=top_n)
+    if timings is not None:
+        timings.update(pack=t1 - t0, device=t2 - t1, unpack=time.perf_counter() - t2)
+    return out
