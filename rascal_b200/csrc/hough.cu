@@ -152,7 +152,12 @@ hough_edges_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __
 
 // ---- pass 3 ------------------------------------------------------------------
 // grid (n_chunks, pair_splits, n_problems), dynamic smem:
-//   double ye[ybins+1]; double slope_s[spc]; int row_s[spc]; uint32 sub[cap]
+//   double ye[ybins+1]; int row_s[spc]; int row_last[xbins]; uint32 sub[cap]
+// A thread walks the surviving slopes of one pair.  The inner loop touches shared memory only
+// when something changes: the slope comes from np.linspace's own arithmetic in registers, the
+// gradient row from a per-row "last slope" table (one load per ~S/xbins slopes), the intercept
+// bin from its two edges kept in registers (reloaded when c leaves [e_lo, e_hi)); equal-bin runs
+// are flushed with one shared atomicAdd(count).
 __global__ void __launch_bounds__(512)
 hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats* __restrict__ stats,
                  int spc, int sub_cap_words) {
@@ -168,21 +173,25 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
   if (s0 >= s1) return;
 
   double* ye = reinterpret_cast<double*>(smem_raw);
-  double* slope_s = ye + (yb + 1);
-  int* row_s = reinterpret_cast<int*>(slope_s + spc);
-  unsigned* subh = reinterpret_cast<unsigned*>(row_s + spc + (spc & 1));
+  int* row_s = reinterpret_cast<int*>(ye + (yb + 1));
+  int* row_last = row_s + spc;
+  unsigned* subh = reinterpret_cast<unsigned*>(row_last + xb);
 
   for (int i = threadIdx.x; i <= yb; i += blockDim.x) ye[i] = d.d_yedges[i];
-  SlopeGen sg(d);
+  const SlopeGen sg(d);
+  const bool lin_fast = (S > 1) && !sg.ls.step_zero;  // np.linspace's common case: i * step + start, last = stop
   const double* __restrict__ xe = d.d_xedges;
   const double inv_wx = (double)xb / (xe[xb] - xe[0]);
-  for (int k = threadIdx.x; k < s1 - s0; k += blockDim.x) {
-    double g = sg.at(s0 + k);
-    slope_s[k] = g;
+  const int ns = s1 - s0;
+  for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+    const double g = sg.at(s0 + k);
     row_s[k] = fix_bin(xe, xb, g, (int)((g - xe[0]) * inv_wx));
   }
   __syncthreads();
-  const int row_lo = row_s[0], row_hi = row_s[s1 - s0 - 1];
+  for (int k = threadIdx.x; k < ns; k += blockDim.x)
+    if (k == ns - 1 || row_s[k + 1] != row_s[k]) row_last[row_s[k]] = s0 + k;  // rows are non-decreasing in the slope
+  __syncthreads();
+  const int row_lo = row_s[0], row_hi = row_s[ns - 1];
   const int rows_cap = max(1, sub_cap_words / yb);
   const double ye0 = ye[0];
   const double inv_wy = (double)yb / (ye[yb] - ye0);
@@ -197,26 +206,55 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
     const int words = (w1 - w0 + 1) * yb;
     for (int i = threadIdx.x; i < words; i += blockDim.x) subh[i] = 0u;
     __syncthreads();
-    for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-      const int a = max(d.d_lo[p], s0), b = min(d.d_hi[p], s1 - 1);
-      if (a > b) continue;
-      const double x = d.d_pair_x[p], y = d.d_pair_y[p];
+    // A warp takes 32 consecutive pairs (one peak, neighbouring atlas lines: heavily overlapping
+    // slope intervals) and walks the slope index in LOCKSTEP: slope, gradient row and row boundary
+    // are warp-uniform, a lane is active while the index is inside its pair's interval.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int pb = p0 + warp * 32; pb < p1; pb += n_warps * 32) {
+      const int p = pb + lane;
+      int a = 1, b = 0;
+      double x = 0.0, y = 0.0;
+      if (p < p1) {
+        a = max(d.d_lo[p], s0); b = min(d.d_hi[p], s1 - 1);
+        x = d.d_pair_x[p]; y = d.d_pair_y[p];
+      }
+      const bool any = a <= b;
+      const int ia = __reduce_min_sync(0xffffffffu, any ? a : 0x7fffffff);
+      const int ib = __reduce_max_sync(0xffffffffu, any ? b : -1);
+      if (ia > ib) continue;
       int cur = -1;
       unsigned run = 0;
       int k = -1;
-      for (int i = a; i <= b; ++i) {
+      double e_lo = 0.0, e_hi = 0.0;
+      int i = ia;
+      while (i <= ib) {
         const int row = row_s[i - s0];
-        if (row < w0 || row > w1) continue;
-        const double c = sub(y, mul(slope_s[i - s0], x));
-        if (k < 0) k = (int)((c - ye0) * inv_wy);
-        k = fix_bin(ye, yb, c, k);
-        const int key = (row - w0) * yb + k;
-        if (key == cur) {
-          ++run;
-        } else {
-          if (run) atomicAdd(&subh[cur], run);
-          cur = key;
-          run = 1;
+        const int iend = min(ib, row_last[row]);
+        if (row < w0 || row > w1) { i = iend + 1; continue; }
+        const int key_row = (row - w0) * yb;
+        for (; i <= iend; ++i) {
+          const double g = lin_fast ? ((i == S - 1) ? sg.ls.stop : add(mul((double)i, sg.ls.step), sg.ls.start)) : sg.at(i);
+          if (i >= a && i <= b) {
+            const double c = sub(y, mul(g, x));
+            if (k < 0) {
+              k = fix_bin(ye, yb, c, (int)((c - ye0) * inv_wy));
+              e_lo = ye[k]; e_hi = ye[k + 1];
+            } else if (c < e_lo && k > 0) {  // one bin down (the common move for x > 0), more only for steep pairs
+              --k; e_hi = e_lo; e_lo = ye[k];
+              if (c < e_lo) { k = fix_bin(ye, yb, c, k); e_lo = ye[k]; e_hi = ye[k + 1]; }
+            } else if (!(c < e_hi) && k < yb - 1) {
+              ++k; e_lo = e_hi; e_hi = ye[k + 1];
+              if (!(c < e_hi) && k < yb - 1) { k = fix_bin(ye, yb, c, k); e_lo = ye[k]; e_hi = ye[k + 1]; }
+            }
+            const int key = key_row + k;
+            if (key == cur) {
+              ++run;
+            } else {
+              if (run) atomicAdd(&subh[cur], run);
+              cur = key;
+              run = 1;
+            }
+          }
         }
       }
       if (run) atomicAdd(&subh[cur], run);
@@ -477,7 +515,9 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
     spc = max(1, spc);
     int n_chunks = (max_slopes + spc - 1) / spc;
     // shared memory: edges + slope tables + sub-histogram (as large as useful, <= 160 KB)
-    size_t fixed = (size_t)(max_yb + 1) * 8 + (size_t)spc * 8 + (size_t)(spc + (spc & 1)) * 4;
+    int max_xb = 1;
+    for (int i = 0; i < n_problems; ++i) max_xb = max(max_xb, h_desc[i].xbins);
+    size_t fixed = (size_t)(max_yb + 1) * 8 + (size_t)spc * 4 + (size_t)max_xb * 4 + 8;
     size_t want_words = 0;
     for (int i = 0; i < n_problems; ++i) {
       const rb2_hough_desc& h = h_desc[i];
