@@ -21,7 +21,9 @@ def test_ransac_setup_tables(golden):
     assert np.array_equal(s.peaks, p.peaks)
     assert np.array_equal(s.cand_wave, np.concatenate(p.cands))
     assert np.array_equal(np.diff(s.cand_off), [len(c) for c in p.cands])
-    assert np.array_equal(s.prob, p.prob)
+    # the normalising sum is sequential here (so that rb2_ransac_prepare reproduces the table on the
+    # device bit for bit), np.sum's pairwise order in the reference: last-bit differences only
+    assert np.allclose(s.prob, p.prob, rtol=1e-14, atol=0)
     assert (s.pix_min, s.pix_max) == (p.pix_min, p.pix_max)
     assert np.array_equal(s.uwaves[s.cand_wid], s.cand_wave)
     # CDF table reproduces searchsorted(cdf, u, 'right') of the sampling law
