@@ -102,6 +102,26 @@ int rb2_hough_accumulate(int n_problems, const rb2_hough_desc *d_desc,
 int rb2_hough_points(const rb2_hough_desc *h_desc, int64_t *d_slope_off,
                      double *d_points, int64_t n_points, void *stream);
 
+/* HoughTransform.generate_hough_points_brute_force (houghtransform.py:94-140):
+ * the line through every pair of (pixel, wavelength) pairs i < j of the
+ * x-sorted input, kept iff gradient and intercept are strictly inside the
+ * constraints.  Two calls: d_points == NULL counts (d_row_off[n-1] = total
+ * after the call, d_row_cnt / d_row_off are [n] / [n+1] int64 scratch), then
+ * with d_points [total*2] the rows are written in the reference's order. */
+int rb2_hough_brute_force(const double *d_x_sorted, const double *d_y_sorted, int n,
+                          double min_slope, double max_slope, double min_intercept,
+                          double max_intercept, int64_t *d_row_cnt, int64_t *d_row_off,
+                          double *d_points, void *stream);
+
+/* HoughTransform.bin_hough_points (houghtransform.py:167-210) for EXPLICIT
+ * points (brute force, add_hough_points, load): np.histogram2d with the
+ * data-dependent range + canonical ranking.  Uses rb2_hough_desc with
+ * d_pair_x = gradients, d_pair_y = intercepts, n_pairs = number of points;
+ * slopes / limits / d_lo / d_hi are ignored. */
+int rb2_hough_bin_points(int n_problems, const rb2_hough_desc *d_desc,
+                         const rb2_hough_desc *h_desc, rb2_hough_stats *d_stats,
+                         void *stream);
+
 /* ======================================================================= *
  * K2  candidate vote
  *     replaces Calibrator._get_candidate_points_linear (calibrator.py:219-261)

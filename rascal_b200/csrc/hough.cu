@@ -33,14 +33,14 @@ struct SlopeGen {
   __device__ __forceinline__ double at(int i) const { return ls.at(i); }
 };
 
-__global__ void hough_init_stats_kernel(rb2_hough_stats* stats, int n) {
+__global__ void hough_init_stats_kernel(rb2_hough_stats* stats, int n, bool points = false) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   rb2_hough_stats s;
   s.icpt_min = CUDART_INF;
   s.icpt_max = -CUDART_INF;
-  s.grad_min = 0.0;
-  s.grad_max = 0.0;
+  s.grad_min = points ? CUDART_INF : 0.0;   // explicit points: min / max are reduced over the data
+  s.grad_max = points ? -CUDART_INF : 0.0;
   s.n_points = 0;
   s.slope_lo = 0x7fffffff;
   s.slope_hi = -1;
@@ -533,6 +533,190 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
     dim3 g3(n_chunks, pair_splits, n_problems);
     hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words);
   }
+  hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+
+
+// =====================================================================================
+// Explicit Hough points: HoughTransform.generate_hough_points_brute_force
+// (houghtransform.py:94-140) and the binning of externally supplied points
+// (add_hough_points :142-165, load :291-339 followed by bin_hough_points :167-210).
+// =====================================================================================
+namespace rb2 {
+
+struct BfLimits { double min_slope, max_slope, min_icpt, max_icpt; };
+
+// gradient / intercept of the line through sorted points i < j, the reference's arithmetic (:121-122)
+__device__ __forceinline__ bool bf_line(const double* __restrict__ x, const double* __restrict__ y, int i, int j,
+                                        const BfLimits& L, double& g, double& c) {
+  g = (y[j] - y[i]) / (x[j] - x[i]);
+  c = sub(y[j], mul(g, x[j]));
+  return (g > L.min_slope) && (g < L.max_slope) && (c > L.min_icpt) && (c < L.max_icpt);  // strict (:130-135)
+}
+
+// one CTA per row i: ordered compaction of the valid j > i; points == NULL -> count only
+__global__ void __launch_bounds__(256)
+bf_rows_kernel(const double* __restrict__ x, const double* __restrict__ y, int n, BfLimits L,
+               long long* __restrict__ row_cnt, const long long* __restrict__ row_off, double* __restrict__ points) {
+  __shared__ int wtot[8];
+  __shared__ long long base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = blockIdx.x; i < n - 1; i += gridDim.x) {
+    if (threadIdx.x == 0) base_s = points ? row_off[i] : 0;
+    __syncthreads();
+    for (int j0 = i + 1; j0 < n; j0 += 256) {
+      const int j = j0 + threadIdx.x;
+      double g = 0.0, c = 0.0;
+      const bool ok = (j < n) && bf_line(x, y, i, j, L, g, c);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) wtot[warp] = __popc(m);
+      __syncthreads();
+      int pre = 0, tot = 0;
+      for (int w = 0; w < 8; ++w) { if (w < warp) pre += wtot[w]; tot += wtot[w]; }
+      if (ok && points) {
+        const long long slot = base_s + pre + __popc(m & ((1u << lane) - 1u));
+        points[2 * slot] = g;
+        points[2 * slot + 1] = c;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) base_s += tot;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0 && !points) row_cnt[i] = base_s;
+  }
+}
+
+// single block: counts[0..n) -> exclusive offsets off[0..n]
+__global__ void __launch_bounds__(1024)
+bf_scan_kernel(int n, const long long* __restrict__ cnt, long long* __restrict__ off) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    const long long v0 = (i < n) ? cnt[i] : 0;
+    long long v = v0;
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      const long long w = wsum[lane];
+      long long iv = w;
+      for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+      wsum[lane] = iv - w;
+    }
+    __syncthreads();
+    const long long incl = v + wsum[warp] + carry;
+    if (i < n) off[i] = incl - v0;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[n] = carry;
+}
+
+// ---- np.histogram2d of explicit points: d_pair_x = gradients, d_pair_y = intercepts -----------
+__global__ void __launch_bounds__(256)
+points_minmax_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  double g0 = CUDART_INF, g1 = -CUDART_INF, c0 = CUDART_INF, c1 = -CUDART_INF;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pairs; i += gridDim.x * blockDim.x) {
+    const double g = d.d_pair_x[i], c = d.d_pair_y[i];
+    g0 = fmin(g0, g); g1 = fmax(g1, g); c0 = fmin(c0, c); c1 = fmax(c1, c);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    g0 = fmin(g0, __shfl_xor_sync(0xffffffffu, g0, o)); g1 = fmax(g1, __shfl_xor_sync(0xffffffffu, g1, o));
+    c0 = fmin(c0, __shfl_xor_sync(0xffffffffu, c0, o)); c1 = fmax(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+  }
+  if (lane_id() == 0 && g0 <= g1) {
+    rb2_hough_stats* s = stats + blockIdx.y;
+    atomic_min_double(&s->grad_min, g0); atomic_max_double(&s->grad_max, g1);
+    atomic_min_double(&s->icpt_min, c0); atomic_max_double(&s->icpt_max, c1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+points_edges_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  const int B = d.xbins * d.ybins;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) d.d_hist[i] = 0u;
+  if (blockIdx.x != 0) return;
+  rb2_hough_stats* s = stats + blockIdx.y;
+  double g0 = s->grad_min, g1 = s->grad_max, c0 = s->icpt_min, c1 = s->icpt_max;
+  if (d.n_pairs == 0) { g0 = 0.0; g1 = 1.0; c0 = 0.0; c1 = 1.0; }  // numpy: empty sample -> range (0, 1)
+  if (g0 == g1) { g0 -= 0.5; g1 += 0.5; }  // _get_outer_edges
+  if (c0 == c1) { c0 -= 0.5; c1 += 0.5; }
+  Linspace lx(g0, g1, d.xbins + 1), ly(c0, c1, d.ybins + 1);
+  for (int i = threadIdx.x; i <= d.xbins; i += blockDim.x) d.d_xedges[i] = lx.at(i);
+  for (int i = threadIdx.x; i <= d.ybins; i += blockDim.x) d.d_yedges[i] = ly.at(i);
+  if (threadIdx.x == 0) s->n_points = d.n_pairs;
+}
+
+__global__ void __launch_bounds__(256)
+points_bin_kernel(const rb2_hough_desc* __restrict__ descs) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  const int xb = d.xbins, yb = d.ybins;
+  const double* __restrict__ xe = d.d_xedges;
+  const double* __restrict__ ye = d.d_yedges;
+  const double inv_wx = (double)xb / (xe[xb] - xe[0]), inv_wy = (double)yb / (ye[yb] - ye[0]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_pairs; i += gridDim.x * blockDim.x) {
+    const double g = d.d_pair_x[i], c = d.d_pair_y[i];
+    const int kx = fix_bin(xe, xb, g, (int)((g - xe[0]) * inv_wx));
+    const int ky = fix_bin(ye, yb, c, (int)((c - ye[0]) * inv_wy));
+    atomicAdd(&d.d_hist[(size_t)kx * yb + ky], 1u);
+  }
+}
+
+}  // namespace rb2
+
+extern "C" int rb2_hough_brute_force(const double* d_x, const double* d_y, int n, double min_slope, double max_slope,
+                                     double min_intercept, double max_intercept, int64_t* d_row_cnt,
+                                     int64_t* d_row_off, double* d_points, void* stream_) {
+  using namespace rb2;
+  if (n < 0 || !d_row_cnt || !d_row_off || (n > 0 && (!d_x || !d_y))) return RB2_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const BfLimits L{min_slope, max_slope, min_intercept, max_intercept};
+  int sms = 148;
+  if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
+  const int rows = max(n - 1, 0);
+  const int grid = max(1, min(rows, sms * 8));
+  if (!d_points) {  // pass 1: per-row counts and their exclusive scan (total in d_row_off[rows])
+    if (rows > 0)
+      bf_rows_kernel<<<grid, 256, 0, stream>>>(d_x, d_y, n, L, (long long*)d_row_cnt, nullptr, nullptr);
+    bf_scan_kernel<<<1, 1024, 0, stream>>>(rows, (const long long*)d_row_cnt, (long long*)d_row_off);
+  } else if (rows > 0) {  // pass 2: the points, in the reference's order (row i, then j ascending)
+    bf_rows_kernel<<<grid, 256, 0, stream>>>(d_x, d_y, n, L, (long long*)d_row_cnt, (const long long*)d_row_off, d_points);
+  }
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+
+extern "C" int rb2_hough_bin_points(int n_problems, const rb2_hough_desc* d_desc, const rb2_hough_desc* h_desc,
+                                    rb2_hough_stats* d_stats, void* stream_) {
+  using namespace rb2;
+  if (n_problems <= 0 || !d_desc || !h_desc || !d_stats) return RB2_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int max_n = 0, max_bins = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    const rb2_hough_desc& h = h_desc[i];
+    if (h.xbins < 1 || h.ybins < 1 || h.n_pairs < 0) return RB2_ERR_ARG;
+    if (h.n_pairs > 0 && (!h.d_pair_x || !h.d_pair_y)) return RB2_ERR_ARG;
+    max_n = max(max_n, h.n_pairs);
+    max_bins = max(max_bins, h.xbins * h.ybins);
+  }
+  int sms = 148;
+  if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
+  hough_init_stats_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(d_stats, n_problems, true);
+  const int gx = max(1, min((max_n + 255) / 256, max(1, 8 * sms / n_problems)));
+  if (max_n > 0) points_minmax_kernel<<<dim3(gx, n_problems), 256, 0, stream>>>(d_desc, d_stats);
+  const int zb = max(1, min(64, (max_bins + 256 * 16 - 1) / (256 * 16)));
+  points_edges_kernel<<<dim3(zb, n_problems), 256, 0, stream>>>(d_desc, d_stats);
+  if (max_n > 0) points_bin_kernel<<<dim3(gx, n_problems), 256, 0, stream>>>(d_desc);
   hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;

@@ -240,6 +240,79 @@ class HoughBatch:
         return out[:n_points].cpu().numpy()
 
 
+class PointsHoughBatch(HoughBatch):
+    """bin_hough_points for EXPLICIT Hough points (brute force / add_hough_points / load):
+    rb2_hough_bin_points.  problems: dicts with points ([N, 2] gradient, intercept), xbins, ybins.
+    Same result interface as HoughBatch (hist / edges / rank, consumed in place by VoteBatch)."""
+
+    def __init__(self, problems):
+        self.lib = N.load()
+        _torch()
+        self.n = len(problems)
+        self.problems = problems
+        ar, wk, sm = Arena(), Arena(), Arena()
+        self.arena, self.work, self.small = ar, wk, sm
+        self.h_desc = N.struct_array(N.HoughDesc, self.n)
+        self._off = []
+        for p in problems:
+            pts = np.asarray(p["points"], dtype=np.float64).reshape(-1, 2)
+            if not np.all(np.isfinite(pts)):  # np.histogram2d: "autodetected range of [nan, nan] is not finite"
+                raise ValueError("hough_points must be finite")
+            xb, yb = int(p["xbins"]), int(p["ybins"])
+            B = xb * yb
+            self._off.append(dict(x=ar.add(np.ascontiguousarray(pts[:, 0])), y=ar.add(np.ascontiguousarray(pts[:, 1])),
+                                  n=len(pts), xe=sm.reserve(8 * (xb + 1)), ye=sm.reserve(8 * (yb + 1)),
+                                  hist=wk.reserve(4 * B), rank=wk.reserve(4 * B), rankpos=wk.reserve(4 * B),
+                                  tmp=wk.reserve(4 * B)))
+        self.o_stats = sm.reserve(C.sizeof(N.HoughStats) * self.n)
+        base, wbase, sbase = ar.upload(), wk.upload(), sm.upload()
+        for i, p in enumerate(problems):
+            o, d = self._off[i], self.h_desc[i]
+            d.n_slopes, d.xbins, d.ybins, d.n_pairs = 0, int(p["xbins"]), int(p["ybins"]), o["n"]
+            d.d_pair_x, d.d_pair_y = base + o["x"], base + o["y"]
+            d.d_xedges, d.d_yedges = sbase + o["xe"], sbase + o["ye"]
+            d.d_hist, d.d_rank = wbase + o["hist"], wbase + o["rank"]
+            d.d_rankpos, d.d_sort_tmp = wbase + o["rankpos"], wbase + o["tmp"]
+        self.d_desc = _upload_structs(self.h_desc)
+        self._stats = None
+
+    def run(self, slopes_per_cta=0):
+        rc = self.lib.rb2_hough_bin_points(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
+                                           self.small.ptr(self.o_stats), current_stream_ptr())
+        N.check(rc, "rb2_hough_bin_points")
+        self._stats = None
+        return self
+
+    def points(self, i=0):
+        return np.asarray(self.problems[i]["points"], dtype=np.float64).reshape(-1, 2)
+
+
+def brute_force_points(x, y, min_slope, max_slope, min_intercept, max_intercept):
+    """HoughTransform.generate_hough_points_brute_force (houghtransform.py:94-140) on the device:
+    [N, 2] (gradient, intercept) rows in the reference's order for a STABLE sort of x (np.argsort's
+    default is not stable; the multiset of points does not depend on the tie order)."""
+    torch = _torch()
+    lib = N.load()
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    order = np.argsort(x, kind="stable")
+    dx, dy = torch.from_numpy(x[order]).cuda(), torch.from_numpy(y[order]).cuda()
+    TRANSFER["h2d"] += 16 * len(x)
+    n = len(x)
+    cnt = torch.zeros(max(n, 1), dtype=torch.int64, device="cuda")
+    off = torch.zeros(max(n, 1) + 1, dtype=torch.int64, device="cuda")
+    args = (dx.data_ptr(), dy.data_ptr(), n, float(min_slope), float(max_slope), float(min_intercept),
+            float(max_intercept), cnt.data_ptr(), off.data_ptr())
+    N.check(lib.rb2_hough_brute_force(*args, None, current_stream_ptr()), "rb2_hough_brute_force")
+    total = int(off[max(n - 1, 0)].item())
+    TRANSFER["d2h"] += 8
+    pts = torch.empty((max(total, 1), 2), dtype=torch.float64, device="cuda")
+    if total:
+        N.check(lib.rb2_hough_brute_force(*args, pts.data_ptr(), current_stream_ptr()), "rb2_hough_brute_force")
+    TRANSFER["d2h"] += 16 * total
+    return pts[:total].cpu().numpy()
+
+
 # ---------------------------------------------------------------------------
 # K2  candidate vote
 # ---------------------------------------------------------------------------

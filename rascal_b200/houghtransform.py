@@ -57,9 +57,13 @@ class HoughTransform:
         self._batch = None
         self._external = False
 
+    # ---- reference: houghtransform.py:94-140 -------------------------------
     def generate_hough_points_brute_force(self, x, y):
-        raise NotImplementedError(
-            "generate_hough_points_brute_force (houghtransform.py:94-140) is not on the accelerated path yet")
+        """The line through every two (pixel, wavelength) pairs, constrained strictly inside the
+        slope / intercept limits, on the device (rb2_hough_brute_force)."""
+        self.hough_points = engine.brute_force_points(x, y, self.min_slope, self.max_slope, self.min_intercept,
+                                                      self.max_intercept)
+        self._batch = None
 
     def _problem(self, xbins, ybins):
         x, y, S = self._pending
@@ -99,11 +103,10 @@ class HoughTransform:
     def bin_hough_points(self, xbins, ybins):
         assert (self._pending is not None) or (self._points is not None), \
             "Please load an hough_points or create an hough_points with hough_points() first."
-        if self._external or self._pending is None:
-            raise NotImplementedError(
-                "binning externally supplied hough_points (add_hough_points / load) is not on the "
-                "accelerated path yet; call generate_hough_points first")
-        batch = engine.HoughBatch([self._problem(xbins, ybins)]).run()
+        if self._external or self._pending is None:  # brute force / add_hough_points / load: explicit points
+            batch = engine.PointsHoughBatch([dict(points=self._points, xbins=int(xbins), ybins=int(ybins))]).run()
+        else:
+            batch = engine.HoughBatch([self._problem(xbins, ybins)]).run()
         self._batch = batch
         self.hist = batch.hist(0).astype(np.float64)
         self.xedges = batch.xedges(0)
