@@ -381,8 +381,6 @@ class Calibrator:
             raise NotImplementedError("fit() needs a Hough transform computed by do_hough_transform()")
         self._vote(candidate_tolerance)
         best = (None, 1e50, None, 0, False)
-        if fit_coeff is not None:
-            raise NotImplementedError("a prior fit_coeff (calibrator.py:512-515) is not on the accelerated path yet")
         setup = engine.RansacSetup(
             self.candidate_peak, self.candidate_arc, fit_deg=fit_deg, sample_size=self.sample_size,
             ransac_tolerance=self.ransac_tolerance, min_intercept=self.min_intercept,
@@ -393,6 +391,8 @@ class Calibrator:
             n_peaks_total=len(self.peaks), pix_known=self.pix_known, wave_known=self.wave_known)
         if not setup.enough:  # :468-469
             return best
+        if fit_coeff is not None:  # :512-515: only hypotheses that beat the pre-existing fit count
+            setup.cost_ceiling = setup.prior_cost(fit_coeff)
         if self.sample_size >= len(setup.peaks):
             raise NotImplementedError("sample_size >= number of candidate peaks switches the reference to its "
                                       "brute-force sampler (calibrator.py:474-477), which is not supported")

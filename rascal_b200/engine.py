@@ -545,6 +545,21 @@ class RansacSetup:
         self.pp_breaks = brk.astype(np.float64)
         self.pp_coef = coef.reshape(-1)
 
+    def prior_cost(self, fit_coeff):
+        """The initial cost of a pre-existing fit (calibrator.py:512-515): the plain sum of the
+        bijective-match errors of `fit_coeff` (unweighted, unclipped) - the ceiling a hypothesis has to
+        beat.  Part of the loop's set-up, evaluated once on the host."""
+        c = np.asarray(fit_coeff, dtype=np.float64)
+        fit = np.polynomial.polynomial.polyval(self.peaks, c)
+        best_e, best_w = np.empty(len(self.peaks)), np.empty(len(self.peaks))
+        for k in range(len(self.peaks)):
+            cand = self.cand_wave[self.cand_off[k]:self.cand_off[k + 1]]
+            e = np.abs(fit[k] - cand)
+            i = int(np.argmin(e))  # first minimum (:349-351)
+            best_e[k], best_w[k] = e[i], cand[i]
+        err = [np.min(best_e[best_w == w]) for w in np.unique(best_w)]  # one peak per wavelength (:356-376)
+        return float(sum(err))
+
     @property
     def min_inliers(self):
         # inliers > deg (calibrator.py:645), inliers >= minimum_matches (:684)

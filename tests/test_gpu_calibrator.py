@@ -97,3 +97,27 @@ def test_errors_match_reference():
         c.fit(fit_type="spline", progress=False)
     with pytest.raises(ValueError):
         c.set_known_pairs([np.nan], [5000.0])
+
+
+def test_fit_with_prior_coefficients():
+    """fit(fit_coeff=prior) (calibrator.py:512-515, 1599-1601): the degree comes from the prior, its
+    plain sum of match errors is the cost a hypothesis has to beat; a ceiling nothing can beat ends in
+    the reference's "Couldn't fit"."""
+    g = load_golden("c3_deg4")
+    c = make_calibrator(g)
+    f = dict(g["config"]["fit"])
+    f.pop("fit_deg", None)
+    f["max_tries"] = 2000
+    coeff, mp, ma, rms = c.fit(progress=False, fit_coeff=g["fit_coeff"], **f)[:4]
+    assert c.fit_deg == len(g["fit_coeff"]) - 1 and len(coeff) == len(g["fit_coeff"])
+    assert rms < 5.0 and len(mp) > len(coeff)  # another RNG stream may settle on another local optimum
+    from rascal_b200 import engine
+
+    orig = engine.RansacSetup.prior_cost
+    engine.RansacSetup.prior_cost = lambda self, co: -1.0  # nothing beats a negative cost
+    try:
+        c2 = make_calibrator(g)
+        with pytest.raises(AssertionError, match="Couldn't fit"):
+            c2.fit(progress=False, fit_coeff=g["fit_coeff"], **f)
+    finally:
+        engine.RansacSetup.prior_cost = orig

@@ -103,3 +103,13 @@ def test_facade_setters_follow_reference_defaults():
         c.set_ransac_properties(minimum_matches=0)
     with pytest.raises(AssertionError):
         c.set_ransac_properties(minimum_peak_utilisation=1.5)
+
+
+def test_prior_cost_is_the_reference_initial_cost(golden):
+    """calibrator.py:512-515: best_cost = sum(_match_bijective(candidates, peaks, fit_coeff)[0])."""
+    g = golden
+    s = _setup(g)
+    p = problem_from_golden(g)
+    for coeffs in (g["fit_coeff"], g["tr_coeffs"][0]):
+        err, _, _ = O.match_bijective(p, coeffs)
+        assert s.prior_cost(coeffs) == float(sum(err))
