@@ -10,6 +10,7 @@ def oracle_from_golden(g, refit=O.robust_polyfit, max_tries=None, trace=None):
     kw = {}
     kw.update(cfg["hough"])
     kw.update(cfg["ransac"])
+    assert kw.pop("linear", True)  # the linear candidate search is the path restated here
     kw.update(cfg["fit"])
     if max_tries is not None:
         kw["max_tries"] = max_tries
