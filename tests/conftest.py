@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["c3_deg4", "poly_linear_deg1", "poly_quadratic_deg2", "fine_deg5", "c1_sprat_xe", "c5_deimos"]
+GOLDEN_CASES = ["c3_deg4", "poly_linear_deg1", "poly_quadratic_deg2", "fine_deg5", "c1_sprat_xe", "c5_deimos", "c2_gmos_cuar"]
 
 
 def pytest_configure(config):

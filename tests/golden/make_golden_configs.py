@@ -82,8 +82,29 @@ def c5_deimos():
                   fit=dict(max_tries=300), seed=0)
 
 
+def c2_gmos():
+    """BASELINE configs[1]: Gemini GMOS longslit CuAr arc, degree 5.  The example's FITS frame is not
+    shipped; the reference's own ground-truth effective-pixel spectrum of the same
+    instrument is (test/ground_truth/gmos-effective-pixel-spectrum.txt), with the example's settings
+    (examples/example_gemini_gmos_longslit.py:37-61) and fit_deg=5."""
+    d = np.loadtxt("/root/reference/test/ground_truth/gmos-effective-pixel-spectrum.txt", delimiter=",")
+    spectrum = d[:, 1]
+    peaks, _ = find_peaks(spectrum, height=1000, prominence=500, distance=5)
+    peaks = util.refine_peaks(spectrum.copy(), peaks, window_width=3)
+    atlas = Atlas(elements=["Cu", "Ar"], min_intensity=80, min_distance=5, range_tolerance=500.0, pressure=70000.0,
+                  temperature=280.0, min_atlas_wavelength=5000.0, max_atlas_wavelength=9500.0)
+    G.record_case("c2_gmos_cuar", np.asarray(peaks, float), np.asarray(atlas.get_lines(), float),
+                  spectrum=np.zeros(len(spectrum)),
+                  hough=dict(num_slopes=5000, range_tolerance=500.0, xbins=200, ybins=200,
+                             min_wavelength=5000.0, max_wavelength=9500.0),
+                  ransac=dict(sample_size=6, top_n_candidate=5),
+                  fit=dict(max_tries=300, fit_deg=5), seed=0)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c5"]
+    which = sys.argv[1:] or ["c1", "c2", "c5"]
+    if "c2" in which:
+        c2_gmos()
     if "c1" in which:
         c1_sprat()
     if "c5" in which:

@@ -36,7 +36,7 @@ TOLERANCES = (10.0, 5.0, 2.0, 1.0, 0.5, 0.1)
 
 
 def main():
-    for case in (sys.argv[1:] or ("c3_deg4", "fine_deg5", "poly_linear_deg1", "poly_quadratic_deg2", "c1_sprat_xe", "c5_deimos")):
+    for case in (sys.argv[1:] or ("c3_deg4", "fine_deg5", "poly_linear_deg1", "poly_quadratic_deg2", "c1_sprat_xe", "c5_deimos", "c2_gmos_cuar")):
         g = np.load(os.path.join(HERE, case + ".npz"), allow_pickle=True)
         peaks, lines, coeff = g["peaks"], g["lines"], g["fit_coeff"]
         c = Calibrator(peaks, spectrum=np.zeros(len(g["pixel_list"])))
