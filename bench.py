@@ -424,8 +424,8 @@ def main():
         "clocks": clocks.summary(),
         "e2e": e2e,
         # K3 = pipe_init + 6 kernels (reset, draw_fit, monotonic, match, cost, record) per 2^22-hypothesis
-        # chunk; + merge after the all-gather (N > 1) + K4 refit
-        "gpu_launches": (1 + 6 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
+        # chunk + pipe_join; + merge after the all-gather (N > 1) + K4 refit
+        "gpu_launches": (2 + 6 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": k3_traffic(),
                      "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant, ~60 % of K3 time) + "

@@ -668,19 +668,41 @@ struct Pipe {  // device pointers of the staged pipeline (one per rb2_ransac_bat
   unsigned* counts;                 // [0] = |queue A|, [1] = |queue B|
   BestKey* best;                    // [n_problems]
   double* res_cost; double* res_esum; int2* res_cnt;  // per queue-B entry
+  rb2_ransac_result* win;           // [n_problems] winner records written by THIS lane's stage D
   unsigned cap; int qs;
 };
 
-__global__ void pipe_init_kernel(Pipe p, rb2_ransac_result* __restrict__ result, int n_problems) {
+constexpr int PIPE_MAX_LANES = 4;
+struct PipeSet { Pipe p[PIPE_MAX_LANES]; int n; };
+
+__global__ void pipe_init_kernel(PipeSet ps, rb2_ransac_result* __restrict__ result, int n_problems) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2) p.counts[i] = 0u;
+  if (i < 2) for (int l = 0; l < ps.n; ++l) ps.p[l].counts[i] = 0u;
   if (i >= n_problems) return;
-  p.best[i].hi = ~0ull; p.best[i].lo = ~0ull;
+  ps.p[0].best[i].hi = ~0ull; ps.p[0].best[i].lo = ~0ull;  // the running best is shared by all lanes
   rb2_ransac_result r;
   r.cost = CUDART_INF; r.hyp_id = -1; r.n_match = 0; r.n_inliers = 0;
   for (int k = 0; k < NCOEF; ++k) r.coeffs[k] = 0.0;
   for (int k = 0; k < 8; ++k) r.counters[k] = 0ull;
   result[i] = r;
+  for (int l = 0; l < ps.n; ++l) ps.p[l].win[i] = r;
+}
+
+// after all lanes have drained: the best of the lane winners (lower cost, later id on ties,
+// calibrator.py:636) becomes the problem's record; the counters already live in `result`
+__global__ void pipe_join_kernel(PipeSet ps, rb2_ransac_result* __restrict__ result, int n_problems) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_problems) return;
+  int best = 0;
+  for (int l = 1; l < ps.n; ++l) {
+    const rb2_ransac_result& a = ps.p[best].win[i];
+    const rb2_ransac_result& b = ps.p[l].win[i];
+    if (b.hyp_id >= 0 && (a.hyp_id < 0 || b.cost < a.cost || (b.cost == a.cost && b.hyp_id > a.hyp_id))) best = l;
+  }
+  const rb2_ransac_result& w = ps.p[best].win[i];
+  rb2_ransac_result* r = result + i;
+  r->cost = w.cost; r->hyp_id = w.hyp_id; r->n_match = w.n_match; r->n_inliers = w.n_inliers;
+  for (int k = 0; k < NCOEF; ++k) r->coeffs[k] = w.coeffs[k];
 }
 
 __global__ void pipe_reset_counts_kernel(Pipe p) { if (threadIdx.x < 2) p.counts[threadIdx.x] = 0u; }
@@ -1081,7 +1103,7 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
 
 // ---- stage D ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ransac_record_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
+ransac_record_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe) {
   const unsigned n = pipe.counts[1];
   const int qs = pipe.qs, ncoef = qs - 1;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -1093,7 +1115,7 @@ ransac_record_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_r
     const long long gid = descs[problem].hyp_begin + (long long)(tag & TAG_ID_MASK);
     const BestKey b = pipe.best[problem];
     if (b.hi != cost_key(cost) || b.lo != ~(unsigned long long)gid) continue;
-    rb2_ransac_result* r = result + problem;
+    rb2_ransac_result* r = pipe.win + problem;
     r->cost = cost; r->hyp_id = gid;
     const int2 c = pipe.res_cnt[e];
     r->n_match = c.x; r->n_inliers = c.y;
@@ -1147,21 +1169,54 @@ namespace rb2 {
 
 constexpr unsigned PIPE_CHUNK = 1u << 22;  // hypotheses per chunk == queue capacity (worst case: all survive)
 
-struct PipeLayout { size_t counts, best, qa, qb, res_cost, res_esum, res_cnt, total; };
+// Two LANES: consecutive chunks alternate between two independent sets of queues on two streams,
+// so that the issue-bound draw/fit stage of one chunk overlaps the latency-bound match / cost
+// stages of the other.  The running best is shared; each lane records its own winners.
+static int pipe_lanes() {
+  static const int n = [] {
+    const char* e = getenv("RB2_PIPE_LANES");
+    const int v = e ? atoi(e) : 3;  // measured on B200 (C3, 1e8 hypotheses): 1 lane 1.37e10, 2: 1.52e10, 3: 1.60e10, 4: 1.58e10 hyp/s
+    return v < 1 ? 1 : (v > PIPE_MAX_LANES ? PIPE_MAX_LANES : v);
+  }();
+  return n;
+}
+struct PipeLayout { size_t best, lane0, lane_bytes, counts, win, qa, qb, res_cost, res_esum, res_cnt, total; };
 
 static PipeLayout pipe_layout(int n_problems) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   PipeLayout L;
   size_t o = 0;
-  L.counts = o; o = up(o + 16);
   L.best = o; o = up(o + (size_t)n_problems * sizeof(BestKey));
-  L.qa = o; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
-  L.qb = o; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
-  L.res_cost = o; o = up(o + (size_t)PIPE_CHUNK * 8);
-  L.res_esum = o; o = up(o + (size_t)PIPE_CHUNK * 8);
-  L.res_cnt = o; o = up(o + (size_t)PIPE_CHUNK * 8);
-  L.total = o;
+  const size_t lane0 = o;
+  L.lane0 = lane0;
+  L.counts = o - lane0; o = up(o + 16);
+  L.win = o - lane0; o = up(o + (size_t)n_problems * sizeof(rb2_ransac_result));
+  L.qa = o - lane0; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
+  L.qb = o - lane0; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
+  L.res_cost = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.res_esum = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.res_cnt = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.lane_bytes = o - lane0;
+  L.total = lane0 + (size_t)pipe_lanes() * L.lane_bytes;
   return L;
+}
+
+// extra streams + fork / join events, created once per process
+struct LaneStreams {
+  cudaStream_t aux[PIPE_MAX_LANES - 1] = {};
+  cudaEvent_t fork = nullptr, join[PIPE_MAX_LANES - 1] = {};
+  bool ok = false;
+};
+static LaneStreams& lane_streams() {
+  static LaneStreams ls;
+  if (!ls.ok) {
+    bool good = cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < PIPE_MAX_LANES - 1 && good; ++l)
+      good = cudaStreamCreateWithFlags(&ls.aux[l], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ls.join[l], cudaEventDisableTiming) == cudaSuccess;
+    ls.ok = good;
+  }
+  return ls;
 }
 
 static size_t stage_a_smem(const rb2_ransac_desc& h) {
@@ -1195,7 +1250,7 @@ static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids,
   if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
   ransac_cost_kernel<DEG_T><<<sms * 8, 128, 0, stream>>>(d_desc, pipe, d_result);
   if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
-  ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(d_desc, pipe, d_result);
+  ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(d_desc, pipe);
   if (!stage_ok("D record")) return RB2_ERR_CUDA;
   return RB2_OK;
 }
@@ -1244,21 +1299,38 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
 
   const PipeLayout L = pipe_layout(n_problems);
   unsigned char* base = (unsigned char*)d_block_scratch;
-  Pipe pipe;
-  pipe.counts = (unsigned*)(base + L.counts);
-  pipe.best = (BestKey*)(base + L.best);
-  pipe.qa = (double*)(base + L.qa);
-  pipe.qb = (double*)(base + L.qb);
-  pipe.res_cost = (double*)(base + L.res_cost);
-  pipe.res_esum = (double*)(base + L.res_esum);
-  pipe.res_cnt = (int2*)(base + L.res_cnt);
-  pipe.cap = PIPE_CHUNK;
-  pipe.qs = deg + 2;
-  pipe_init_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(pipe, d_result, n_problems);
+  PipeSet ps;
+  ps.n = pipe_lanes();
+  for (int l = 0; l < ps.n; ++l) {
+    unsigned char* lb = base + L.lane0 + (size_t)l * L.lane_bytes;
+    Pipe& pipe = ps.p[l];
+    pipe.best = (BestKey*)(base + L.best);
+    pipe.counts = (unsigned*)(lb + L.counts);
+    pipe.win = (rb2_ransac_result*)(lb + L.win);
+    pipe.qa = (double*)(lb + L.qa);
+    pipe.qb = (double*)(lb + L.qb);
+    pipe.res_cost = (double*)(lb + L.res_cost);
+    pipe.res_esum = (double*)(lb + L.res_esum);
+    pipe.res_cnt = (int2*)(lb + L.res_cnt);
+    pipe.cap = PIPE_CHUNK;
+    pipe.qs = deg + 2;
+  }
+  pipe_init_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(ps, d_result, n_problems);
 
   const long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
-  for (long long c0 = 0; c0 < max_hyp; c0 += per_problem) {
+  const long long n_chunks = (max_hyp + per_problem - 1) / per_problem;
+  LaneStreams& ls = lane_streams();
+  const int n_lanes = (ls.ok && n_chunks > 1) ? (int)min((long long)ps.n, n_chunks) : 1;
+  if (n_lanes > 1) {  // fork: the extra streams start after everything already queued on the caller's stream
+    RB2_CHECK(cudaEventRecord(ls.fork, stream));
+    for (int l = 1; l < n_lanes; ++l) RB2_CHECK(cudaStreamWaitEvent(ls.aux[l - 1], ls.fork, 0));
+  }
+  long long chunk_index = 0;
+  for (long long c0 = 0; c0 < max_hyp; c0 += per_problem, ++chunk_index) {
     const long long len = min(per_problem, max_hyp - c0);
+    const int lane_id_ = (int)(chunk_index % n_lanes);
+    const Pipe& pipe = ps.p[lane_id_];
+    cudaStream_t cstream = lane_id_ ? ls.aux[lane_id_ - 1] : stream;
     int bpp = blocks_per_problem;
     if (bpp <= 0) {
       const long long want = (len + RS_THREADS * 8 - 1) / (RS_THREADS * 8);   // >= 8 passes per CTA
@@ -1268,14 +1340,19 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     }
     dim3 grid_a(bpp, n_problems);
     int rc;
-    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
-    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, stream, d_desc, pipe, c0, len, d_result);
+    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
     if (rc != RB2_OK) return rc;
   }
+  for (int l = 1; l < n_lanes; ++l) {  // join: the caller's stream continues after every lane
+    RB2_CHECK(cudaEventRecord(ls.join[l - 1], ls.aux[l - 1]));
+    RB2_CHECK(cudaStreamWaitEvent(stream, ls.join[l - 1], 0));
+  }
+  pipe_join_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(ps, d_result, n_problems);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }
