@@ -384,7 +384,7 @@ def main():
         from rascal_b200 import batch
 
         specs = [c4_input(rank + world * i) for i in range(args.spectra)]  # spectrum i -> rank i mod world
-        batch.calibrate_batch(specs[:64], n_hypotheses=10_000, seed=1, match_tolerance=5.0)  # warm
+        batch.calibrate_batch(specs, n_hypotheses=10_000, seed=1, match_tolerance=5.0)  # warm (untimed)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

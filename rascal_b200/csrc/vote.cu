@@ -33,7 +33,7 @@ constexpr int VOTE_CAP = 4096;   // collected (rank, pair) keys
 struct VoteCtx {
   const double* ye;   // smem [yb+1]
   const double* gc;   // smem [xb] gradient-bin centres
-  double hy, x, tol, inv_wy, c_first;
+  double hy, x, tol, inv_wy, c_first, c_last, inv_dg;
   int xb, yb;
 };
 
@@ -41,7 +41,24 @@ struct VoteCtx {
 // ascending flat bin index.
 template <class F>
 __device__ __forceinline__ void for_each_hit(const VoteCtx& c, double lam, F&& f) {
-  for (int gi = 0; gi < c.xb; ++gi) {
+  // Rows that can hold a hit: g*x + c_j within tol of lam for some bin centre c_j in [c_first, c_last]
+  // <=> g*x in [lam - c_last - tol, lam - c_first + tol].  The centres gc[] are equally spaced and
+  // increasing, so that is ONE contiguous row range, located arithmetically with a row of slack on
+  // each side (the exact window test below decides; skipped rows have no hits, the visiting order
+  // of the others is unchanged).
+  int g_begin = 0, g_end = c.xb;
+  if (c.xb > 2 && c.x != 0.0 && c.inv_dg > 0.0) {
+    const double lo_t = lam - c.c_last - c.tol, hi_t = lam - c.c_first + c.tol;
+    double ga = lo_t / c.x, gb = hi_t / c.x;
+    if (ga > gb) { const double t = ga; ga = gb; gb = t; }
+    const double slack = 1e-9 * (fabs(ga) + fabs(gb)) + 1e-300;
+    const double ra = ((ga - slack) - c.gc[0]) * c.inv_dg, rb = ((gb + slack) - c.gc[0]) * c.inv_dg;
+    if (ra == ra && rb == rb) {  // NaN / inf inputs keep the full range
+      g_begin = (int)fmax(0.0, fmin((double)c.xb, floor(ra) - 1.0));
+      g_end = (int)fmax(0.0, fmin((double)c.xb, ceil(rb) + 2.0));
+    }
+  }
+  for (int gi = g_begin; gi < g_end; ++gi) {
     const double gx = mul(c.gc[gi], c.x);
     // first j whose centre line is within reach: (gx + c_j) - lam >= -tol
     int j = (int)floor(((lam - gx) - c.tol - c.c_first) * c.inv_wy) - 1;
@@ -99,6 +116,8 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   c.ye = ye; c.gc = gc; c.hy = hy; c.x = d.d_upeak_x[u]; c.tol = d.tol;
   c.xb = xb; c.yb = yb;
   c.c_first = ye[0] + hy;
+  c.c_last = ye[yb - 1] + hy;
+  c.inv_dg = (xb > 1 && gc[xb - 1] > gc[0]) ? (double)(xb - 1) / (gc[xb - 1] - gc[0]) : 0.0;
   c.inv_wy = (double)yb / (ye[yb] - ye[0]);
 
   const int q0 = d.d_pair_off[u];

@@ -78,7 +78,8 @@ class BatchResults:
         return (self[i] for i in range(self.n))
 
     def k3_tables(self, i):
-        """The K3 inputs rb2_ransac_prepare built for spectrum i (device -> host; tests / diagnostics)."""
+        """The K3 inputs rb2_ransac_prepare built for spectrum i (device -> host; tests / diagnostics).
+        Valid until the next pipeline.run() call (the device arena is reused)."""
         t = self._tables
         b = t["buf"]
 
@@ -206,9 +207,17 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     o_hstat = L.one(C.sizeof(N.HoughStats) * n)
     res_end = L.size
 
-    buf = torch.empty(L.size, dtype=torch.uint8, device="cuda")
+    # grow-only device arena and pinned staging buffers, reused across calls (cudaHostAlloc of tens of MB
+    # costs more than the whole batch); results own their memory, only k3_tables() reads the arena later
+    def cached(name, nbytes, **kw):
+        t = _CACHE.get(name)
+        if t is None or t.numel() < nbytes:
+            t = _CACHE[name] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, **kw)
+        return t
+
+    buf = cached("arena", L.size, device="cuda")[:L.size]
     base = buf.data_ptr()
-    host = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    host = cached("stage_in", h2d_bytes, pin_memory=True)[:h2d_bytes]
     hv = host.numpy()
     # peaks / lines: offsets are 16-byte aligned, so scatter by index arrays
     pk = np.concatenate([sp["peaks"] for sp in specs])
@@ -287,12 +296,12 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     if match_tolerance is not None:
         N.check(lib.rb2_match_peaks(n, dptr("match"), hptr("match"), int(refit_mode), base + o_mres, base + o_mmx,
                                     base + o_mmy, base + o_mrs, max_p, stream), "rb2_match_peaks")
-    raw = torch.empty(res_end - res_begin, dtype=torch.uint8, pin_memory=True)
+    raw = cached("stage_out", res_end - res_begin, pin_memory=True)[:res_end - res_begin]
     raw.copy_(buf[res_begin:res_end], non_blocking=True)
     torch.cuda.current_stream().synchronize()
     engine.TRANSFER["d2h"] += raw.numel()
     t2 = time.perf_counter()
-    r = raw.numpy()
+    r = raw.numpy().copy()
 
     def region(off, nbytes):
         return r[off - res_begin:off - res_begin + nbytes]
@@ -324,7 +333,6 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
         out.mmx = region(o_mmx, 8 * n * max_p).view(np.float64).reshape(shp)
         out.mmy = region(o_mmy, 8 * n * max_p).view(np.float64).reshape(shp)
         out.mrs = region(o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
-    out._keep = (raw, buf, host)
     out._tables = dict(buf=buf, up=o_up, coff=o_coff, cwave=o_cwave, cwid=o_cwid, cdf=o_cdf, ppb=o_ppb, ppc=o_ppc,
                        npp=npp, desc=o_desc["ransac"], top_n=top_n)
     if timings is not None:
