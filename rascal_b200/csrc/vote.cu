@@ -37,6 +37,24 @@ struct VoteCtx {
   int xb, yb;
 };
 
+// exp(z) for the Gaussian vote weight, z = -(lam - pred)^2 / (2 sigma^2 + 1e-9) <= 0.  With the
+// reference's sigma = 1.1775 * (range_tolerance + linearity_tolerance) (hundreds of Angstrom) against a
+// candidate tolerance of a few Angstrom, |z| is ~1e-4: there the degree-6 Taylor polynomial is exact
+// to the last bit or two (truncation z^7/5040 < 1e-22 for |z| < 2^-9), the same 1-ulp class as exp();
+// libdevice's exp() costs ~10x more and was 28 % of the kernel's instructions.
+__device__ __forceinline__ double gauss_weight(double z) {
+  if (z > -0.001953125) {
+    double p = 1.0 / 720.0;
+    p = fma(p, z, 1.0 / 120.0);
+    p = fma(p, z, 1.0 / 24.0);
+    p = fma(p, z, 1.0 / 6.0);
+    p = fma(p, z, 0.5);
+    p = fma(p, z, 1.0);
+    return fma(p, z, 1.0);
+  }
+  return exp(z);
+}
+
 // Enumerate the hit bins of one pair; f(gi, j, pred) is called for every hit in
 // ascending flat bin index.
 template <class F>
@@ -95,8 +113,6 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   unsigned* rb_hist = reinterpret_cast<unsigned*>(wcnt + nw);
   __shared__ int sel_wid[RB2_MAX_TOPN];
   __shared__ int sel_j[RB2_MAX_TOPN];
-  __shared__ double red_v[VOTE_THREADS / 32];
-  __shared__ int red_i[VOTE_THREADS / 32];
   __shared__ unsigned scan_s[VOTE_THREADS / 32];
   __shared__ int s_L, s_tb, s_list_n, s_need;
 
@@ -131,7 +147,7 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
     int cnt = 0;
     for_each_hit(c, lam, [&](int gi, int j, double pred) {
       const double t = sub(lam, pred);
-      const double w = exp(-mul(t, t) / d.gauss_denom);  // util.py:447, a = 1.0
+      const double w = gauss_weight(-mul(t, t) / d.gauss_denom);  // util.py:447, a = 1.0
       agg = add(agg, w);
       ++cnt;
       atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
@@ -164,31 +180,31 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   if (n == 0) return;
 
   // ---- phase 2: top-n wavelengths by aggregated weight (stable) --------------
-  for (int k = 0; k < n; ++k) {
-    double bv = -CUDART_INF;
-    int bi = 0x7fffffff;
-    for (int i = tid; i < nw; i += VOTE_THREADS) {
-      if (wcnt[i] > 0) {
-        const double v = wagg[i];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  // one warp does the n arg-max passes over the (few hundred) wavelengths: no block barriers
+  if (warp == 0) {
+    for (int k = 0; k < n; ++k) {
+      double bv = -CUDART_INF;
+      int bi = 0x7fffffff;
+      for (int i = lane; i < nw; i += 32) {
+        if (wcnt[i] > 0) {
+          const double v = wagg[i];
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        sel_wid[k] = bi;
+        wcnt[bi] = -wcnt[bi];  // mark as taken (still counts as "hit" below via != 0)
+      }
+      __syncwarp();
     }
-    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < VOTE_THREADS / 32; ++w)
-        if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
-      sel_wid[k] = bi;
-      wcnt[bi] = -wcnt[bi];  // mark as taken (still counts as "hit" below via != 0)
-    }
-    __syncthreads();
   }
+  __syncthreads();
   // U-index of each selected wavelength = number of hit wavelengths with a smaller id
   for (int k = warp; k < n; k += VOTE_THREADS / 32) {
     const int wid = sel_wid[k];
@@ -252,6 +268,23 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   if (ln > VOTE_CAP) {
     if (tid == 0) atomicExch(d.d_status, (int)RB2_ERR_CAPACITY);
     ln = VOTE_CAP;
+  }
+  if (ln <= 1024) {
+    // only the entries at the n positions sel_j[] of the sorted list are needed: position of an
+    // entry = number of smaller keys (keys are distinct), found by counting - one barrier, no sort
+    for (int e = tid; e < ln; e += VOTE_THREADS) {
+      const unsigned long long key = list[e];
+      int pos = 0;
+      for (int f = 0; f < ln; ++f) pos += (list[f] < key);
+      for (int k = 0; k < n; ++k) {
+        if (sel_j[k] == pos) {
+          const int q = (int)(key & 0xffffffffu);
+          d.d_cand_wave[(size_t)u * d.top_n + k] = d.d_pair_y[q0 + q];
+          d.d_cand_pair[(size_t)u * d.top_n + k] = q0 + q;
+        }
+      }
+    }
+    return;
   }
   int np2 = 1;
   while (np2 < ln) np2 <<= 1;
