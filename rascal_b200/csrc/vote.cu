@@ -55,16 +55,12 @@ __device__ __forceinline__ double gauss_weight(double z) {
   return exp(z);
 }
 
-// Enumerate the hit bins of one pair; f(gi, j, pred) is called for every hit in
-// ascending flat bin index.
-template <class F>
-__device__ __forceinline__ void for_each_hit(const VoteCtx& c, double lam, F&& f) {
-  // Rows that can hold a hit: g*x + c_j within tol of lam for some bin centre c_j in [c_first, c_last]
-  // <=> g*x in [lam - c_last - tol, lam - c_first + tol].  The centres gc[] are equally spaced and
-  // increasing, so that is ONE contiguous row range, located arithmetically with a row of slack on
-  // each side (the exact window test below decides; skipped rows have no hits, the visiting order
-  // of the others is unchanged).
-  int g_begin = 0, g_end = c.xb;
+// Rows that can hold a hit of one pair: g*x + c_j within tol of lam for some bin centre c_j in
+// [c_first, c_last] <=> g*x in [lam - c_last - tol, lam - c_first + tol].  The centres gc[] are equally
+// spaced and increasing, so that is ONE contiguous row range, located arithmetically with a row of
+// slack on each side (the exact window test in row_hits decides; skipped rows have no hits).
+__device__ __forceinline__ void row_range(const VoteCtx& c, double lam, int& g_begin, int& g_end) {
+  g_begin = 0; g_end = c.xb;
   if (c.xb > 2 && c.x != 0.0 && c.inv_dg > 0.0) {
     const double lo_t = lam - c.c_last - c.tol, hi_t = lam - c.c_first + c.tol;
     double ga = lo_t / c.x, gb = hi_t / c.x;
@@ -74,29 +70,57 @@ __device__ __forceinline__ void for_each_hit(const VoteCtx& c, double lam, F&& f
     if (ra == ra && rb == rb) {  // NaN / inf inputs keep the full range
       g_begin = (int)fmax(0.0, fmin((double)c.xb, floor(ra) - 1.0));
       g_end = (int)fmax(0.0, fmin((double)c.xb, ceil(rb) + 2.0));
-    }
-  }
-  for (int gi = g_begin; gi < g_end; ++gi) {
-    const double gx = mul(c.gc[gi], c.x);
-    // first j whose centre line is within reach: (gx + c_j) - lam >= -tol
-    int j = (int)floor(((lam - gx) - c.tol - c.c_first) * c.inv_wy) - 1;
-    j = max(0, min(c.yb, j));
-    while (j > 0) {  // guess too high: step back while the previous bin is not below the window
-      const double df = sub(add(gx, add(c.ye[j - 1], c.hy)), lam);
-      if (df < -c.tol) break;
-      --j;
-    }
-    for (; j < c.yb; ++j) {
-      const double pred = add(gx, add(c.ye[j], c.hy));
-      const double df = sub(pred, lam);
-      if (df > c.tol) break;
-      if (fabs(df) <= c.tol) f(gi, j, pred);
+      if (g_end < g_begin) g_end = g_begin;
     }
   }
 }
 
+// The hit bins of one pair in gradient row gi; f(gi, j, pred) for every hit, ascending j.
+template <class F>
+__device__ __forceinline__ void row_hits(const VoteCtx& c, double lam, int gi, F&& f) {
+  const double gx = mul(c.gc[gi], c.x);
+  // first j whose centre line is within reach: (gx + c_j) - lam >= -tol
+  int j = (int)floor(((lam - gx) - c.tol - c.c_first) * c.inv_wy) - 1;
+  j = max(0, min(c.yb, j));
+  while (j > 0) {  // guess too high: step back while the previous bin is not below the window
+    const double df = sub(add(gx, add(c.ye[j - 1], c.hy)), lam);
+    if (df < -c.tol) break;
+    --j;
+  }
+  for (; j < c.yb; ++j) {
+    const double pred = add(gx, add(c.ye[j], c.hy));
+    const double df = sub(pred, lam);
+    if (df > c.tol) break;
+    if (fabs(df) <= c.tol) f(gi, j, pred);
+  }
+}
+
+// Work units (pair, row) of one peak, flattened: pair q owns units [uoff[q], uoff[q+1]) = its rows
+// ubeg[q].. in ascending order; thread t takes the contiguous slice [t*chunk, (t+1)*chunk).  Calls
+// body(q, gi) for every unit of the slice in order and edge(q, first_of_pair, last_of_pair) before /
+// after the run of units of pair q inside the slice.
+template <class Begin, class Body, class End>
+__device__ __forceinline__ void for_my_units(const int* uoff, const int* ubeg, int m, int tid, Begin&& begin, Body&& body,
+                                             End&& end) {
+  const int U = uoff[m];
+  const int chunk = (U + VOTE_THREADS - 1) / VOTE_THREADS;
+  const int u0 = tid * chunk, u1 = min(U, u0 + chunk);
+  if (u0 >= u1) return;
+  int lo = 0, hi = m - 1;  // pair that contains unit u0: last q with uoff[q] <= u0
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (uoff[mid] <= u0) lo = mid; else hi = mid - 1; }
+  int q = lo;
+  int uu = u0;
+  while (uu < u1) {
+    while (uoff[q + 1] <= uu) ++q;  // skip pairs without rows
+    const int pe = min(u1, uoff[q + 1]);
+    begin(q);
+    for (; uu < pe; ++uu) body(q, ubeg[q] + (uu - uoff[q]));
+    end(q, /*starts_here=*/uoff[q] >= u0, /*ends_here=*/uoff[q + 1] <= u1);
+  }
+}
+
 __global__ void __launch_bounds__(VOTE_THREADS)
-vote_kernel(const rb2_vote_desc* __restrict__ descs) {
+vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const rb2_vote_desc d = descs[blockIdx.y];
   const int u = blockIdx.x;
@@ -111,6 +135,10 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   unsigned long long* list = reinterpret_cast<unsigned long long*>(wagg + nw);
   int* wcnt = reinterpret_cast<int*>(list + VOTE_CAP);
   unsigned* rb_hist = reinterpret_cast<unsigned*>(wcnt + nw);
+  int* ubeg = reinterpret_cast<int*>(rb_hist + VOTE_NB);   // [ucap] first candidate row of pair q
+  int* uoff = ubeg + ucap;                                 // [ucap + 1] exclusive prefix of the row counts
+  __shared__ double pf_agg[VOTE_THREADS];                  // partial of a pair that began in an earlier thread
+  __shared__ int pf_q[VOTE_THREADS], pf_cnt[VOTE_THREADS];
   __shared__ int sel_wid[RB2_MAX_TOPN];
   __shared__ int sel_j[RB2_MAX_TOPN];
   __shared__ unsigned scan_s[VOTE_THREADS / 32];
@@ -140,22 +168,76 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   const int m = d.d_pair_off[u + 1] - q0;
   const int* __restrict__ rankpos = d.d_rankpos;
 
+  // ---- phase 0: candidate row range of every pair, flattened into (pair, row) work units ----
+  // (pairs whose line never crosses the histogram's intercept range have no units: without this
+  //  a CTA waits at the barrier for the few threads whose pairs span all rows)
+  const bool flat = m <= ucap;
+  if (flat) {
+    for (int q = tid; q < m; q += VOTE_THREADS) {
+      int gb, ge;
+      row_range(c, d.d_pair_y[q0 + q], gb, ge);
+      ubeg[q] = gb; uoff[q + 1] = ge - gb;
+    }
+    pf_q[tid] = -1;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan, 32 pairs per step
+      int run = 0;
+      for (int base = 0; base < m; base += 32) {
+        const int q = base + lane;
+        const int v = (q < m) ? uoff[q + 1] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (q < m) uoff[q + 1] = run + incl;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) uoff[0] = 0;
+    }
+    __syncthreads();
+  }
+
   // ---- phase 1: aggregate weights and counts, rank-bucket histogram ----------
-  for (int q = tid; q < m; q += VOTE_THREADS) {
-    const double lam = d.d_pair_y[q0 + q];
-    double agg = 0.0;
-    int cnt = 0;
-    for_each_hit(c, lam, [&](int gi, int j, double pred) {
-      const double t = sub(lam, pred);
-      const double w = gauss_weight(-mul(t, t) / d.gauss_denom);  // util.py:447, a = 1.0
-      agg = add(agg, w);
-      ++cnt;
-      atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
-    });
+  auto vote_hit = [&](double lam, double& agg, int& cnt, int gi, int j, double pred) {
+    const double t = sub(lam, pred);
+    const double w = gauss_weight(-mul(t, t) / d.gauss_denom);  // util.py:447, a = 1.0
+    agg = add(agg, w);
+    ++cnt;
+    atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
+  };
+  auto commit = [&](int q, double agg, int cnt) {
     if (cnt) {
       const int wid = d.d_pair_wid[q0 + q];
       atomicAdd(&wagg[wid], d.weighted ? agg : (double)cnt);
       atomicAdd(&wcnt[wid], cnt);
+    }
+  };
+  if (flat) {
+    double lam = 0.0, agg = 0.0;
+    int cnt = 0;
+    int own_q = -1, own_cnt = 0;  // a pair that starts in this slice and continues in the next threads
+    double own_agg = 0.0;
+    for_my_units(uoff, ubeg, m, tid,
+                 [&](int q) { lam = d.d_pair_y[q0 + q]; agg = 0.0; cnt = 0; },
+                 [&](int q, int gi) { row_hits(c, lam, gi, [&](int g, int j, double pred) { vote_hit(lam, agg, cnt, g, j, pred); }); },
+                 [&](int q, bool starts_here, bool ends_here) {
+                   if (starts_here && ends_here) commit(q, agg, cnt);
+                   else if (starts_here) { own_q = q; own_agg = agg; own_cnt = cnt; }
+                   else { pf_q[tid] = q; pf_agg[tid] = agg; pf_cnt[tid] = cnt; }  // continuation of an earlier thread's pair
+                 });
+    __syncthreads();
+    if (own_q >= 0) {  // add the continuations in thread order: the sum does not depend on timing
+      for (int t = tid + 1; t < VOTE_THREADS && pf_q[t] == own_q; ++t) { own_agg = add(own_agg, pf_agg[t]); own_cnt += pf_cnt[t]; }
+      commit(own_q, own_agg, own_cnt);
+    }
+  } else {
+    for (int q = tid; q < m; q += VOTE_THREADS) {
+      const double lam = d.d_pair_y[q0 + q];
+      double agg = 0.0;
+      int cnt = 0;
+      int gb, ge;
+      row_range(c, lam, gb, ge);
+      for (int gi = gb; gi < ge; ++gi) row_hits(c, lam, gi, [&](int g, int j, double pred) { vote_hit(lam, agg, cnt, g, j, pred); });
+      commit(q, agg, cnt);
     }
   }
   __syncthreads();
@@ -253,15 +335,25 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs) {
   const int tb = s_tb;
 
   // ---- phase 4: collect hits up to the threshold bucket, sort, pick W[j] ------
-  for (int q = tid; q < m; q += VOTE_THREADS) {
-    const double lam = d.d_pair_y[q0 + q];
-    for_each_hit(c, lam, [&](int gi, int j, double) {
-      const unsigned r = (unsigned)rankpos[gi * yb + j];
-      if ((int)(r >> shift) <= tb) {
-        const int pos = atomicAdd(&s_list_n, 1);
-        if (pos < VOTE_CAP) list[pos] = ((unsigned long long)r << 32) | (unsigned)q;
-      }
-    });
+  auto collect = [&](int q, int gi, int j) {
+    const unsigned r = (unsigned)rankpos[gi * yb + j];
+    if ((int)(r >> shift) <= tb) {
+      const int pos = atomicAdd(&s_list_n, 1);
+      if (pos < VOTE_CAP) list[pos] = ((unsigned long long)r << 32) | (unsigned)q;
+    }
+  };
+  if (flat) {
+    double lam = 0.0;
+    for_my_units(uoff, ubeg, m, tid, [&](int q) { lam = d.d_pair_y[q0 + q]; },
+                 [&](int q, int gi) { row_hits(c, lam, gi, [&](int g, int j, double) { collect(q, g, j); }); },
+                 [&](int, bool, bool) {});
+  } else {
+    for (int q = tid; q < m; q += VOTE_THREADS) {
+      const double lam = d.d_pair_y[q0 + q];
+      int gb, ge;
+      row_range(c, lam, gb, ge);
+      for (int gi = gb; gi < ge; ++gi) row_hits(c, lam, gi, [&](int g, int j, double) { collect(q, g, j); });
+    }
   }
   __syncthreads();
   int ln = s_list_n;
@@ -317,21 +409,26 @@ extern "C" int rb2_candidate_vote(int n_problems, const rb2_vote_desc* d_desc, c
   using namespace rb2;
   if (n_problems <= 0 || !d_desc || !h_desc) return RB2_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
-  int max_up = 0;
+  int max_up = 0, max_nw = 0;
   size_t smem = 0;
   for (int i = 0; i < n_problems; ++i) {
     const rb2_vote_desc& h = h_desc[i];
     if (h.top_n < 1 || h.top_n > RB2_MAX_TOPN || h.xbins < 1 || h.ybins < 1) return RB2_ERR_ARG;
     max_up = max(max_up, h.n_upeaks);
+    max_nw = max(max_nw, h.n_uwaves);
     size_t s = (size_t)(h.ybins + 1) * 8 + (size_t)h.xbins * 8 + (size_t)h.n_uwaves * 8 + (size_t)VOTE_CAP * 8 +
                (size_t)h.n_uwaves * 4 + (size_t)VOTE_NB * 4;
     smem = max(smem, s);
   }
   if (max_up == 0) return RB2_OK;
+  // flattened work units: room for the row tables of max_nw + 64 pairs per peak (a peak with more pairs,
+  // i.e. duplicated atlas lines beyond that, takes the pair-per-thread path)
+  const int ucap = max_nw + 64;
+  smem += (size_t)(2 * ucap + 1) * 4 + 16;
   if (smem > 200 * 1024) return RB2_ERR_ARG;
   RB2_CHECK(cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(max_up, n_problems);
-  vote_kernel<<<grid, VOTE_THREADS, smem, stream>>>(d_desc);
+  vote_kernel<<<grid, VOTE_THREADS, smem, stream>>>(d_desc, ucap);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }
