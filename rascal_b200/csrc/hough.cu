@@ -24,6 +24,7 @@
 //
 // Lazy: hough_points materialisation in the reference's exact row order.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace rb2 {
 
@@ -160,7 +161,7 @@ hough_edges_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __
 // are flushed with one shared atomicAdd(count).
 __global__ void __launch_bounds__(512)
 hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats* __restrict__ stats,
-                 int spc, int sub_cap_words) {
+                 int spc, int sub_cap_words, int crossing) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const rb2_hough_desc d = descs[blockIdx.z];
   const rb2_hough_stats st = stats[blockIdx.z];
@@ -206,9 +207,64 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
     const int words = (w1 - w0 + 1) * yb;
     for (int i = threadIdx.x; i < words; i += blockDim.x) subh[i] = 0u;
     __syncthreads();
+    if (crossing && lin_fast) {
+      // CROSSING MODE (many slopes per intercept bin): for a fixed pair the intercept is monotone in
+      // the slope index, so inside a gradient row the slopes that fall into one intercept bin are ONE
+      // run; its end is where c(i) crosses the bin edge - solved arithmetically (one division) and fixed
+      // up with the reference's own arithmetic at the neighbouring indices - instead of walking the
+      // run slope by slope: one step and one atomicAdd(count) per visited bin.
+      const double inv_step = 1.0 / sg.ls.step;
+      auto cval = [&](int i, double x, double y) {
+        const double g = (i == S - 1) ? sg.ls.stop : add(mul((double)i, sg.ls.step), sg.ls.start);
+        return sub(y, mul(g, x));
+      };
+      for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        const int a = max(d.d_lo[p], s0), b = min(d.d_hi[p], s1 - 1);
+        if (a > b) continue;
+        const double x = d.d_pair_x[p], y = d.d_pair_y[p];
+        const bool dec = x > 0.0;
+        int i = a;
+        while (i <= b) {
+          const int row = row_s[i - s0];
+          const int iend = min(b, row_last[row]);
+          if (row < w0 || row > w1) { i = iend + 1; continue; }
+          const int key_row = (row - w0) * yb;
+          double c = cval(i, x, y);
+          int k = fix_bin(ye, yb, c, (int)((c - ye0) * inv_wy));
+          while (i <= iend) {
+            int inext = iend + 1;
+            if (x != 0.0 && !(dec ? k == 0 : k == yb - 1)) {
+              const double e = dec ? ye[k] : ye[k + 1];  // the edge c crosses when it leaves bin k
+              const double gi = (((y - e) / x) - sg.ls.start) * inv_step;
+              int j = (gi < (double)iend) ? (int)fmax(gi, (double)i) + 1 : iend + 1;
+              j = max(i + 1, min(iend + 1, j));
+              // left(j): c(j) is past the edge (dec: c < e; inc: c >= e), monotone in j
+              while (j > i + 1) {
+                const double cj = cval(j - 1, x, y);
+                if (!(dec ? (cj < e) : !(cj < e))) break;
+                --j;
+              }
+              while (j <= iend) {
+                const double cj = cval(j, x, y);
+                if (dec ? (cj < e) : !(cj < e)) break;
+                ++j;
+              }
+              inext = j;
+            }
+            atomicAdd(&subh[key_row + k], (unsigned)(inext - i));
+            i = inext;
+            if (i <= iend) {
+              c = cval(i, x, y);
+              k = fix_bin(ye, yb, c, dec ? k - 1 : k + 1);
+            }
+          }
+        }
+      }
+    } else
     // A warp takes 32 consecutive pairs (one peak, neighbouring atlas lines: heavily overlapping
     // slope intervals) and walks the slope index in LOCKSTEP: slope, gradient row and row boundary
     // are warp-uniform, a lane is active while the index is inside its pair's interval.
+    {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int pb = p0 + warp * 32; pb < p1; pb += n_warps * 32) {
       const int p = pb + lane;
@@ -258,6 +314,7 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
         }
       }
       if (run) atomicAdd(&subh[cur], run);
+    }
     }
     __syncthreads();
     unsigned* gh = d.d_hist + (size_t)w0 * yb;
@@ -531,7 +588,11 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
     size_t smem = fixed + sub_words * 4;
     RB2_CHECK(cudaFuncSetAttribute(hough_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g3(n_chunks, pair_splits, n_problems);
-    hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words);
+    // crossing mode pays when a pair's ~0.2 S surviving slopes sweep the ybins intercept bins several
+    // slopes at a time; finer binnings keep the slope-by-slope walk
+    static const int force = getenv("RB2_HOUGH_CROSSING") ? atoi(getenv("RB2_HOUGH_CROSSING")) : -1;
+    const int crossing = force >= 0 ? force : (max_slopes >= 8 * max_yb);
+    hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words, crossing);
   }
   hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
   RB2_CHECK(cudaGetLastError());
