@@ -22,6 +22,7 @@
 //   mode 1: the exact Huber optimum (Householder QR least squares + IRLS when a
 //       normalised residual leaves the quadratic zone).
 #include "common.cuh"
+#include <stdio.h>
 
 namespace rb2 {
 
@@ -142,12 +143,31 @@ __device__ double trf_linearise(const double* a, int n, int m, const double* xn,
   return 0.5 * warp_sum(c);
 }
 
-// one-sided Jacobi SVD of w.J (copied to w.U): U columns normalised in place, s descending, V (n x n)
-__device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF]) {
+// one-sided Jacobi SVD of w.J (copied to w.U): U columns normalised in place, s descending, V (n x n,
+// shared memory).  A pair step is latency-bound on one warp, so it is kept short: the three inner
+// products share one interleaved butterfly, the rotation comes from one sqrt, one division and one
+// rsqrt (t = sign * |h| / (|d| + sqrt(d^2 + h^2)), d = be - al, h = 2 ga), lanes update the rows of U
+// and lane k row k of V.
+#ifdef RB2_K4_PROFILE
+__device__ int g_k4_rot = 0, g_k4_sweeps = 0;
+#endif
+// `warm`: V holds the right singular vectors of the previous Jacobian of the same problem; the
+// iteration then starts from U = J V (columns already nearly orthogonal: the Jacobian changes little
+// between trust-region steps), which saves most sweeps.  U S V^T is the same decomposition either way.
+__device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF], bool warm) {
   const int lane = lane_id();
-  for (int i = lane; i < m * n; i += 32) w.U[i] = w.J[i];
-  for (int a = 0; a < n; ++a)
-    for (int b = 0; b < n; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
+  if (!warm) {
+    for (int i = lane; i < m * n; i += 32) w.U[i] = w.J[i];
+    for (int i = lane; i < n * n; i += 32) V[i / n][i % n] = (i / n == i % n) ? 1.0 : 0.0;
+  } else {
+    for (int i = lane; i < m; i += 32) {
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc = fma(w.J[k * m + i], V[k][j], acc);
+        w.U[j * m + i] = acc;
+      }
+    }
+  }
   __syncwarp();
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
@@ -158,25 +178,38 @@ __device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF]) {
           const double up = w.U[p * m + i], uq = w.U[q * m + i];
           al = fma(up, up, al); be = fma(uq, uq, be); ga = fma(up, uq, ga);
         }
-        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-        if (fabs(ga) <= 1e-300 || fabs(ga) <= TRF_EPS * sqrt(al * be)) continue;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        // converged pair: |ga| <= eps * sqrt(al * be), tested on the squares
+        if (fabs(ga) <= 1e-300 || ga * ga <= (TRF_EPS * TRF_EPS) * (al * be)) continue;
         rotated = true;
-        const double zeta = (be - al) / (2.0 * ga);
-        const double t = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#ifdef RB2_K4_PROFILE
+        ++g_k4_rot;
+#endif
+        const double dd = be - al, hh = 2.0 * ga;
+        const double t = copysign(fabs(hh) / (fabs(dd) + sqrt(fma(dd, dd, hh * hh))),
+                                  (dd == 0.0 || (dd > 0.0) == (hh > 0.0)) ? 1.0 : -1.0);
+        const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
         for (int i = lane; i < m; i += 32) {
           const double up = w.U[p * m + i], uq = w.U[q * m + i];
           w.U[p * m + i] = c * up - sn * uq;
           w.U[q * m + i] = sn * up + c * uq;
         }
-        for (int k = 0; k < n; ++k) {
-          const double vp = V[k][p], vq = V[k][q];
-          V[k][p] = c * vp - sn * vq;
-          V[k][q] = sn * vp + c * vq;
+        if (lane < n) {
+          const double vp = V[lane][p], vq = V[lane][q];
+          V[lane][p] = c * vp - sn * vq;
+          V[lane][q] = sn * vp + c * vq;
         }
         __syncwarp();
       }
     }
+#ifdef RB2_K4_PROFILE
+    ++g_k4_sweeps;
+#endif
     if (!rotated) break;
   }
   for (int j = 0; j < n; ++j) {
@@ -191,7 +224,7 @@ __device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF]) {
     if (b != a) {
       const double ts = s[a]; s[a] = s[b]; s[b] = ts;
       for (int i = lane; i < m; i += 32) { const double tu = w.U[a * m + i]; w.U[a * m + i] = w.U[b * m + i]; w.U[b * m + i] = tu; }
-      for (int k = 0; k < n; ++k) { const double tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = tv; }
+      if (lane < n) { const double tv = V[lane][a]; V[lane][a] = V[lane][b]; V[lane][b] = tv; }
     }
   }
   __syncwarp();
@@ -215,11 +248,14 @@ __device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, co
   for (int i = 0; i < n; ++i) suf[i] = s[i] * uf[i];
   auto phi_and_derivative = [&](double al, double& phi, double& phi_prime) {
     double pn = 0.0, sm = 0.0;
-    for (int i = 0; i < n; ++i) {
-      const double den = s[i] * s[i] + al;
-      const double q = suf[i] / den;
-      pn = fma(q, q, pn);
-      sm += suf[i] * suf[i] / (den * den * den);
+#pragma unroll
+    for (int i = 0; i < NCF; ++i) {
+      if (i < n) {
+        const double r = 1.0 / (s[i] * s[i] + al);  // one division per term: q = suf / den, suf^2 / den^3 = q^2 / den
+        const double q = suf[i] * r;
+        pn = fma(q, q, pn);
+        sm = fma(q * q, r, sm);
+      }
     }
     pn = sqrt(pn);
     phi = pn - Delta;
@@ -277,18 +313,34 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
   double alpha = 0.0;
   int status = -1;
   double s[NCF], uf[NCF], step[NCF], a_new[NCF];
-  double V[NCF][NCF];
+  int svd_count = 0;
+  __shared__ double V[NCF][NCF];  // one warp per CTA in every kernel that runs the solver
+#ifdef RB2_K4_PROFILE
+  long long t_svd = 0, t_lin = 0, t_inner = 0, t0c = 0;
+  int n_outer = 0, n_inner = 0;
+#define K4_TIC() t0c = clock64()
+#define K4_TOC(acc) acc += clock64() - t0c
+#else
+#define K4_TIC()
+#define K4_TOC(acc)
+#endif
   for (;;) {
     double g_norm = 0.0;
     for (int k = 0; k < n; ++k) g_norm = fmax(g_norm, fabs(g[k]));
     if (g_norm < gtol) status = 1;
     if (status >= 0 || nfev == max_nfev) break;
-    trf_svd(n, m, w, s, V);
+    K4_TIC();
+    trf_svd(n, m, w, s, V, svd_count++ > 0);
     for (int j = 0; j < n; ++j) {
       double acc = 0.0;
       for (int i = lane; i < m; i += 32) acc = fma(w.U[j * m + i], w.f[i], acc);
       uf[j] = warp_sum(acc);
     }
+    K4_TOC(t_svd);
+#ifdef RB2_K4_PROFILE
+    ++n_outer;
+#endif
+    K4_TIC();
     double actual_reduction = -1.0, cost_new = cost;
     while (actual_reduction <= 0.0 && nfev < max_nfev) {
       trf_solve_tr(n, m, uf, s, V, Delta, alpha, step);
@@ -332,15 +384,21 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
       alpha *= Delta / Delta_new;
       Delta = Delta_new;
     }
+    K4_TOC(t_inner);
     if (actual_reduction > 0.0) {
       for (int k = 0; k < n; ++k) a[k] = a_new[k];
       __syncwarp();
       for (int i = lane; i < m; i += 32) w.f_true[i] = w.f_new[i];
       __syncwarp();
       cost = cost_new;
+      K4_TIC();
       trf_linearise(a, n, m, xn, yn, w, g);
+      K4_TOC(t_lin);
     }
   }
+#ifdef RB2_K4_PROFILE
+  if (lane == 0) printf("K4 profile: m %d n %d nfev %d outer %d  cycles svd %lld inner %lld linearise %lld  sweeps %d rotations %d (all lanes x32)\n", m, n, nfev, n_outer, t_svd, t_inner, t_lin, g_k4_sweeps, g_k4_rot);
+#endif
   nfev_out = nfev;
   status_out = status < 0 ? 0 : status;
 }
