@@ -263,9 +263,11 @@ __device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, co
   };
   const bool full_rank = (m >= n) && (s[n - 1] > TRF_EPS * m * s[0]);
   if (full_rank) {
+    double gn[NCF];  // Gauss-Newton step in the singular basis
+    for (int i = 0; i < n; ++i) gn[i] = uf[i] / s[i];
     for (int k = 0; k < n; ++k) {
       double acc = 0.0;
-      for (int i = 0; i < n; ++i) acc = fma(V[k][i], uf[i] / s[i], acc);
+      for (int i = 0; i < n; ++i) acc = fma(V[k][i], gn[i], acc);
       p[k] = -acc;
     }
     if (vnorm(p, n) <= Delta) { alpha = 0.0; return; }
@@ -287,9 +289,11 @@ __device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, co
     alpha -= (phi + Delta) * ratio / Delta;
     if (fabs(phi) < 0.01 * Delta) break;
   }
+  double lm[NCF];  // Levenberg-Marquardt step in the singular basis
+  for (int i = 0; i < n; ++i) lm[i] = suf[i] / (s[i] * s[i] + alpha);
   for (int k = 0; k < n; ++k) {
     double acc = 0.0;
-    for (int i = 0; i < n; ++i) acc = fma(V[k][i], suf[i] / (s[i] * s[i] + alpha), acc);
+    for (int i = 0; i < n; ++i) acc = fma(V[k][i], lm[i], acc);
     p[k] = -acc;
   }
   const double sc = Delta / vnorm(p, n);
