@@ -231,7 +231,11 @@ typedef struct {
   uint64_t counters[8];                 /* drawn, aborted, intercept, monotonic, empty, scored, eligible, unsupported */
 } rb2_ransac_result;
 
-/* blocks_per_problem = 0 lets the library choose (a multiple of the SM count
+/* Chunks of 2^22 hypothesis ids alternate over internal stream lanes that fork
+ * from and join back into `stream` (events; capturable); everything the call
+ * enqueues is ordered after prior work on `stream` and before later work on it.
+ * One host thread per device drives this entry point.
+ * blocks_per_problem = 0 lets the library choose (a multiple of the SM count
  * for one problem).  d_block_scratch must hold rb2_ransac_scratch_bytes(). */
 size_t rb2_ransac_scratch_bytes(int n_problems, int blocks_per_problem);
 int rb2_ransac_batch(int n_problems, const rb2_ransac_desc *d_desc,

@@ -75,7 +75,8 @@ class Calibrator:
         self.atlas = None
         self.pix_known = None
         self.wave_known = None
-        self.hough_lines = None
+        self._hough_done = False
+        self._hough_lines_override = None
         self.hough_points = None
         self.ht = HoughTransform()
         self.pairs = []
@@ -237,9 +238,30 @@ class Calibrator:
             self.ht.generate_hough_points_brute_force(self.pairs[:, 0], self.pairs[:, 1])
         else:
             self.ht.generate_hough_points(self.pairs[:, 0], self.pairs[:, 1], num_slopes=self.num_slopes)
-        self.ht.bin_hough_points(self.xbins, self.ybins)
+        self.ht.bin_hough_points(self.xbins, self.ybins)  # runs on the device when its results are first read
         self.hough_points = _LazyPoints(self.ht)
-        self.hough_lines = self.ht.hough_lines
+        self._hough_lines_override = None
+        self._hough_done = True
+
+    def save_hough_transform(self, filename="hough_transform", fileformat="npy", delimiter="+", to_disk=True):
+        """calibrator.py:1454-1481."""
+        self.ht.save(filename=filename, fileformat=fileformat, delimiter=delimiter, to_disk=to_disk)
+
+    def load_hough_transform(self, filename="hough_transform", filetype="npy"):
+        """calibrator.py:1483-1505: the loaded points are re-binned by the next do_hough_transform-less fit
+        through HoughTransform.bin_hough_points (explicit-points path)."""
+        self.ht.load(filename=filename, filetype=filetype)
+
+    @property
+    def hough_lines(self):
+        """Bin-centre lines in rank order (calibrator.py:1450-1452), from the HoughTransform on first use."""
+        if self._hough_lines_override is not None:
+            return self._hough_lines_override
+        return self.ht.hough_lines if self._hough_done else None
+
+    @hough_lines.setter
+    def hough_lines(self, value):
+        self._hough_lines_override = value
 
     # ------------------------------------------------------------------ fit
     def fit(self, max_tries=500, fit_deg=4, fit_coeff=None, fit_tolerance=5.0, fit_type="poly",
@@ -277,7 +299,7 @@ class Calibrator:
             self.sample_size = len(self.atlas)
         if self.sample_size <= self.fit_deg:
             self.sample_size = self.fit_deg + 1
-        if (self.hough_lines is None) or (self.hough_points is None):
+        if not self._hough_done:
             self.do_hough_transform()
         if self.minimum_matches > len(self.atlas):
             self.logger.warning("Requested minimum matches is greater than the atlas size, setting the minimum "
@@ -359,6 +381,91 @@ class Calibrator:
         return (self.fit_coeff, self.matched_peaks, self.matched_atlas, self.rms, self.residuals,
                 self.peak_utilisation, self.atlas_utilisation)
 
+    # candidate_peak / candidate_arc (calibrator.py:432-439): plain lists after the staged path; after the
+    # device-resident path they are read back from K3's tables when somebody asks
+    def _candidates(self, which):
+        out = self.__dict__.get("_lazy_candidates")
+        if out is not None:
+            t = out.k3_tables(0)
+            counts = np.diff(t["cand_off"])
+            self.__dict__["_candidate_peak"] = list(np.repeat(t["peaks"], counts))
+            self.__dict__["_candidate_arc"] = list(t["cand_wave"])
+            self.__dict__["_lazy_candidates"] = None
+        return self.__dict__.get(which)
+
+    @property
+    def candidate_peak(self):
+        return self._candidates("_candidate_peak")
+
+    @candidate_peak.setter
+    def candidate_peak(self, v):
+        self.__dict__["_lazy_candidates"] = None
+        self.__dict__["_candidate_peak"] = v
+
+    @property
+    def candidate_arc(self):
+        return self._candidates("_candidate_arc")
+
+    @candidate_arc.setter
+    def candidate_arc(self, v):
+        self.__dict__["_lazy_candidates"] = None
+        self.__dict__["_candidate_arc"] = v
+
+    def _solve_device_resident(self, fit_deg, candidate_tolerance, n_hypotheses):
+        """fit(n_hypotheses=N) without a host round trip between the stages: pairs -> K1 -> K2 ->
+        rb2_ransac_prepare -> K3 (this rank's shard) -> all-gather + merge -> K4 in one chain
+        (rascal_b200.pipeline), one H2D of peaks / lines / descriptors and one D2H of the result.
+        Returns None when the problem does not qualify (known pairs, filter_close, polygon constraint,
+        non-standard pixel list, ...) or the winner fails the refit-dependent acceptance - the staged
+        path with its fall-through then takes over."""
+        from . import batch, parallel, pipeline
+
+        if (self.pix_known is not None or self.constrain_poly or self.filter_close or not self.linear
+                or self.ht._external or self.sample_size != fit_deg + 1):
+            return None
+        pl = np.asarray(self.pixel_list, dtype=np.float64)
+        # K1 / K2 / K3 work on the ascending distinct peaks whatever the caller's order (the staged path
+        # reaches the same set through np.unique); duplicated peaks or unsorted atlas lines stay staged
+        peaks = np.sort(np.asarray(self.peaks, dtype=np.float64))
+        lines = np.asarray(self.atlas.get_lines(), dtype=np.float64)
+        if not (len(pl) and pl[0] == 0 and pl[-1] == len(pl) - 1 and np.all(np.diff(pl) == 1)):
+            return None
+        spec = dict(peaks=peaks, lines=lines, pixel_list=pl, pix_is_arange=True, sample_size=self.sample_size,
+                    limits=(self.min_slope, self.max_slope, self.min_intercept, self.max_intercept),
+                    hough=dict(num_slopes=self.num_slopes, xbins=self.xbins, ybins=self.ybins,
+                               range_tolerance=self.range_tolerance, linearity_tolerance=self.linearity_tolerance),
+                    ransac=dict(top_n_candidate=self.top_n_candidate, candidate_weighted=self.candidate_weighted,
+                                filter_close=False, ransac_tolerance=self.ransac_tolerance, hough_weight=self.hough_weight,
+                                minimum_matches=self.minimum_matches,
+                                minimum_peak_utilisation=self.minimum_peak_utilisation,
+                                minimum_fit_error=self.minimum_fit_error),
+                    fit=dict(fit_deg=fit_deg, candidate_tolerance=candidate_tolerance))
+        if not pipeline.eligible([spec]):
+            return None
+        rank, world = parallel.rank_world(self.dist_group)
+        key = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+        key = parallel.broadcast_int(key, self.dist_group)
+        lo, hi = parallel.shard_range(n_hypotheses, rank, world)
+        exchange = None
+        if world > 1:
+            def exchange(d_result, n):
+                parallel.exchange_device(d_result, n, self.dist_group)
+        out = pipeline.run([spec], hi - lo, seed=key, hyp_begin=lo, exchange=exchange)
+        if not out.enough[0] or not out.ok[0]:
+            return None  # nothing eligible, or the winner failed K4's acceptance: the staged path decides
+        self._lazy_candidates = out  # candidate_peak / candidate_arc are fetched from the device on first use
+        m = int(out.n_inliers[0])
+        self.matched_peaks, self.matched_atlas = list(out.mx[0, :m]), list(out.my[0, :m])
+        assert len(self.matched_atlas) == len(set(self.matched_atlas))
+        self.ransac_counters = {k: int(out.counters[0, j]) for j, k in enumerate(engine.N.COUNTER_NAMES)}
+        if self.ransac_counters["unsupported"]:
+            self.logger.warning("%d hypotheses left the corner-clamped Hough-weight regime and were skipped",
+                                self.ransac_counters["unsupported"])
+        self.best_cost = float(out.cost[0])
+        self.best_hypothesis = (int(out.hyp_id[0]), np.array(out.hyp_coeffs[0, :fit_deg + 1]))
+        self.refit_nfev = int(out.refit_nfev[0])
+        return (np.array(out.coeffs[0, :fit_deg + 1]), float(out.rms[0]), out.rs[0, :m].copy(), m, m > fit_deg + 1)
+
     def _vote(self, candidate_tolerance):
         """K2: _get_candidate_points_linear + _get_most_common_candidates (calibrator.py:154-261)."""
         sigma = (self.range_tolerance + self.linearity_tolerance) * 1.1775  # :256
@@ -377,8 +484,12 @@ class Calibrator:
         number of GPUs."""
         from . import parallel
 
-        if self.ht._batch is None:
+        if not self.ht.binned:
             raise NotImplementedError("fit() needs a Hough transform computed by do_hough_transform()")
+        if n_hypotheses is not None and fit_coeff is None:
+            fast = self._solve_device_resident(fit_deg, candidate_tolerance, int(n_hypotheses))
+            if fast is not None:
+                return fast
         self._vote(candidate_tolerance)
         best = (None, 1e50, None, 0, False)
         setup = engine.RansacSetup(

@@ -1201,14 +1201,20 @@ static PipeLayout pipe_layout(int n_problems) {
   return L;
 }
 
-// extra streams + fork / join events, created once per process
+// extra streams + fork / join events, created once per device (one host thread per device drives
+// rb2_ransac_batch: the lanes of concurrent calls on the same device would share these)
 struct LaneStreams {
   cudaStream_t aux[PIPE_MAX_LANES - 1] = {};
   cudaEvent_t fork = nullptr, join[PIPE_MAX_LANES - 1] = {};
   bool ok = false;
 };
 static LaneStreams& lane_streams() {
-  static LaneStreams ls;
+  constexpr int MAX_DEV = 64;
+  static LaneStreams per_dev[MAX_DEV];
+  static LaneStreams none;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return none;
+  LaneStreams& ls = per_dev[dev];
   if (!ls.ok) {
     bool good = cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int l = 0; l < PIPE_MAX_LANES - 1 && good; ++l)

@@ -22,17 +22,38 @@ class HoughTransform:
     def __init__(self):
         self._points = None          # materialised / externally supplied points
         self._pending = None         # (x, y, num_slopes) of a generate call not yet binned
-        self._batch = None           # engine.HoughBatch holding the device results
         self._external = False       # points came from add_hough_points / load / brute force
-        self.hough_lines = None
-        self.hist = None
-        self.xedges = None
-        self.yedges = None
-        self.hist_sorted_arg = None
+        self._lazy_bins = None       # (xbins, ybins) of a bin_hough_points call not yet run on the device
+        self._res = dict(hough_lines=None, hist=None, xedges=None, yedges=None, hist_sorted_arg=None, batch=None)
         self.min_slope = None
         self.max_slope = None
         self.min_intercept = None
         self.max_intercept = None
+
+    # Results of bin_hough_points are produced on first use: a fit that runs device-resident end to end
+    # (Calibrator.fit(n_hypotheses=...)) never needs the histogram on the host, and K1 then runs once,
+    # inside that chain, instead of twice.
+    def _get(self, name):
+        if self._lazy_bins is not None:
+            xb, yb = self._lazy_bins
+            self._lazy_bins = None
+            self._bin_now(xb, yb)
+        return self._res[name]
+
+    def _set(self, name, value):
+        self._res[name] = value
+
+    hough_lines = property(lambda self: self._get("hough_lines"), lambda self, v: self._set("hough_lines", v))
+    hist = property(lambda self: self._get("hist"), lambda self, v: self._set("hist", v))
+    xedges = property(lambda self: self._get("xedges"), lambda self, v: self._set("xedges", v))
+    yedges = property(lambda self: self._get("yedges"), lambda self, v: self._set("yedges", v))
+    hist_sorted_arg = property(lambda self: self._get("hist_sorted_arg"), lambda self, v: self._set("hist_sorted_arg", v))
+    _batch = property(lambda self: self._get("batch"), lambda self, v: self._set("batch", v))
+
+    @property
+    def binned(self):
+        """True once bin_hough_points has been called (its device pass may still be pending)."""
+        return self._lazy_bins is not None or self._res["batch"] is not None or self._res["hist"] is not None
 
     # ---- reference: houghtransform.py:22-58 --------------------------------
     def set_constraints(self, min_slope, max_slope, min_intercept, max_intercept):
@@ -54,6 +75,7 @@ class HoughTransform:
         y = np.asarray(y, dtype=np.float64).reshape(-1)
         self._pending = (x, y, int(num_slopes))
         self._points = None
+        self._lazy_bins = None
         self._batch = None
         self._external = False
 
@@ -103,6 +125,9 @@ class HoughTransform:
     def bin_hough_points(self, xbins, ybins):
         assert (self._pending is not None) or (self._points is not None), \
             "Please load an hough_points or create an hough_points with hough_points() first."
+        self._lazy_bins = (int(xbins), int(ybins))
+
+    def _bin_now(self, xbins, ybins):
         if self._external or self._pending is None:  # brute force / add_hough_points / load: explicit points
             batch = engine.PointsHoughBatch([dict(points=self._points, xbins=int(xbins), ybins=int(ybins))]).run()
         else:

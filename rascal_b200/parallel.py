@@ -102,3 +102,30 @@ def allgather_winners(local, group=False, device=None):
         recs = [N.RansacResult.from_buffer_copy(raw[w, i].tobytes()) for w in range(world)]
         merged.append(merge_winners(recs))
     return merged
+
+
+_GATHER = {}
+
+
+def exchange_device(d_result, n, group=None):
+    """The ONE collective of a sharded fit on device-resident winner records: all-gather the `n`
+    per-rank records (NCCL, device to device) and merge them in place (rb2_merge_winners: lower cost,
+    later hypothesis id on ties, counters add).  `d_result`: contiguous uint8 CUDA tensor of the records."""
+    import torch
+    import torch.distributed as dist
+
+    from . import engine
+
+    if group is False or not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    need = world * d_result.numel()
+    buf = _GATHER.get("buf")
+    if buf is None or buf.numel() < need:
+        buf = _GATHER["buf"] = torch.empty(need, dtype=torch.uint8, device=d_result.device)
+    gathered = buf[:need]
+    dist.all_gather_into_tensor(gathered, d_result, group=group)
+    rc = N.load().rb2_merge_winners(int(n), world, gathered.data_ptr(), d_result.data_ptr(), engine.current_stream_ptr())
+    N.check(rc, "rb2_merge_winners")

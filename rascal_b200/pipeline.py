@@ -27,8 +27,15 @@ _ALIGN = 16
 _CACHE = {}  # device-resident constants and scratch reused across calls
 
 
+_DT = {}
+
+
 def _dt(struct):
-    return np.dtype(struct)
+    """np.dtype with the C ABI's layout (from the ctypes struct), cached."""
+    dt = _DT.get(struct)
+    if dt is None:
+        dt = _DT[struct] = np.dtype(struct)
+    return dt
 
 
 def spline_operator(xb):
@@ -87,7 +94,7 @@ class BatchResults:
             nb = np.dtype(dtype).itemsize * count
             return b[int(off):int(off) + nb].cpu().numpy().view(dtype)
 
-        d = rd(t["desc"] + i * np.dtype(N.RansacDesc).itemsize, np.dtype(N.RansacDesc), 1)[0]
+        d = rd(t["desc"] + i * _dt(N.RansacDesc).itemsize, _dt(N.RansacDesc), 1)[0]
         nu, nc = int(d["n_upeaks"]), int(d["n_cand"])
         return dict(desc=d, peaks=rd(t["up"][i], np.float64, nu), cand_off=rd(t["coff"][i], np.int32, nu + 1),
                     cand_wave=rd(t["cwave"][i], np.float64, nc), cand_wid=rd(t["cwid"][i], np.int32, nc),
@@ -145,8 +152,12 @@ def eligible(specs):
     return True
 
 
-def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None):
-    """The whole path for `specs` (normalised, eligible) in batched device calls."""
+def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None):
+    """The whole path for `specs` (normalised, eligible) in batched device calls.
+
+    hyp_begin / n_hypotheses: the hypothesis-id range this process evaluates (a rank's shard of a
+    sharded fit); exchange(result_tensor, n): called between K3 and K4 with the device tensor of the
+    n winner records (the one collective of a multi-GPU fit: all-gather + rb2_merge_winners in place)."""
     import time
 
     torch = engine._torch()
@@ -266,7 +277,7 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     dk["n_pix"], dk["d_pix"] = n_pix, 0
     dk["min_inliers"] = np.maximum(deg + 1, np.minimum(np.minimum(mm, n_a), n_p))
     dk["min_inliers_frac"], dk["cost_ceiling"], dk["floor_cost"], dk["floor_id"] = mpu * n_p, 1e50, 0.0, -1
-    dk["hyp_begin"], dk["n_hyp"], dk["seed"] = 0, int(n_hypotheses), int(seed)
+    dk["hyp_begin"], dk["n_hyp"], dk["seed"] = int(hyp_begin), int(n_hypotheses), int(seed)
 
     if match_tolerance is not None:
         dm["d_peaks"], dm["d_atlas"], dm["n_peaks"], dm["n_atlas"] = u(o_peaks), u(o_lines), n_p, n_a
@@ -291,6 +302,8 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
         _CACHE["scratch"] = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + o_res, _CACHE["scratch"].data_ptr(), 0, stream),
             "rb2_ransac_batch")
+    if exchange is not None:
+        exchange(buf[o_res:o_res + rsz * n], n)
     N.check(lib.rb2_refit_winners(n, dptr("ransac"), hptr("ransac"), base + o_res, mfe, int(refit_mode), base + o_fit,
                                   base + o_mx, base + o_my, base + o_rs, max_p, stream), "rb2_refit_winners")
     if match_tolerance is not None:
@@ -318,6 +331,8 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     out.deg, out.n_p, out.n_a = deg, n_p, n_a
     out.enough = region(o_enough, 4 * n).view(np.int32) != 0
     out.counters, out.cost = win["counters"], win["cost"]
+    out.hyp_id, out.hyp_coeffs = win["hyp_id"], win["coeffs"]
+    out.refit_nfev, out.accepted = fit["huber_iters"], fit["accepted"]
     out.ok = out.enough & (win["hyp_id"] >= 0) & (fit["accepted"] != 0)
     out.coeffs, out.rms, out.n_inliers = fit["coeffs"], fit["rms"], fit["n_inliers"]
     shp = (n, max_p)

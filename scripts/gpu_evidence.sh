@@ -11,7 +11,7 @@ timeout 600 $CMD > gpurun_out/plain_$TAG.log 2>&1 && timeout 900 ncu --metrics g
 timeout 600 $CMD > gpurun_out/plain2_$TAG.log 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'ransac_(draw_fit|monotonic|match|cost|record)_kernel' -s 10 -c 5 -f -o gpurun_out/prof_k3_$TAG $CMD > gpurun_out/ncu_full_k3_$TAG.log 2>&1
 # K1 / K2 / K4 / K5 kernels of the many-spectra leg (64 spectra per launch)
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'hough_interval_kernel|hough_bin_kernel|hough_rank_kernel|vote_kernel|refit_kernel|match_peaks_kernel' -s 12 -c 6 -f -o gpurun_out/prof_k1245_$TAG $CMD > gpurun_out/ncu_full_k1245_$TAG.log 2>&1
-tail -1 gpurun_out/ncu_full_k3_$TAG.log gpurun_out/ncu_full_k1245_$TAG.log
+tail -n 1 gpurun_out/ncu_full_k3_$TAG.log; tail -n 1 gpurun_out/ncu_full_k1245_$TAG.log
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_$TAG.json").read().strip().splitlines()[-1])

@@ -122,3 +122,35 @@ def test_fit_with_prior_coefficients():
             c2.fit(progress=False, fit_coeff=g["fit_coeff"], **f)
     finally:
         engine.RansacSetup.prior_cost = orig
+
+
+@pytest.mark.parametrize("case", ["c3_deg4", "c5_deimos"])
+def test_device_resident_fit_equals_staged_fit(case):
+    """fit(n_hypotheses=N) runs pairs -> K1 -> K2 -> prepare -> K3 -> K4 without a host round trip when the
+    problem qualifies; the staged path (host set-up between K2 and K3) must give the same winner for the
+    same Philox key.  c5_deimos uses filter_close and therefore always takes the staged path."""
+    from rascal_b200.calibrator import Calibrator
+
+    g = load_golden(case)
+    f = {k: v for k, v in g["config"]["fit"].items() if k != "max_tries"}
+    a = make_calibrator(g)
+    a.do_hough_transform()
+    assert a.ht._lazy_bins is not None  # K1 has not run yet: its results are produced on first use
+    ra = a.fit(progress=False, n_hypotheses=300_000, **f)
+    took_fast = a.ht._lazy_bins is not None  # still pending => the device-resident chain did everything
+    assert took_fast == (case == "c3_deg4")
+    b = make_calibrator(g)
+    b.do_hough_transform()
+    orig = Calibrator._solve_device_resident
+    Calibrator._solve_device_resident = lambda self, *args, **kw: None
+    try:
+        rb = b.fit(progress=False, n_hypotheses=300_000, **f)
+    finally:
+        Calibrator._solve_device_resident = orig
+    assert a.best_hypothesis[0] == b.best_hypothesis[0] and np.isclose(a.best_cost, b.best_cost, rtol=1e-12)
+    assert np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2])
+    assert np.allclose(ra[0], rb[0], rtol=1e-6) and abs(ra[3] - rb[3]) < 1e-9
+    assert a.ransac_counters == b.ransac_counters
+    assert np.array_equal(np.array(a.candidate_peak), np.array(b.candidate_peak))
+    assert np.array_equal(np.array(a.candidate_arc), np.array(b.candidate_arc))
+    assert np.array_equal(a.ht.hist, g["hist"].astype(float))  # the lazy Hough pass still delivers the reference's histogram
