@@ -213,14 +213,19 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def k3_traffic():
-    """DRAM bytes (read + write) of the K3 stage kernels per 2^22-hypothesis chunk from the committed
-    `ncu --set full` capture (profiles/k3_traffic.json, written by scripts/ncu_summary.py); None if absent."""
+def k3_profile(key):
+    """Figures of the K3 stage kernels from the committed `ncu --set full` capture (profiles/k3_traffic.json):
+    "dram_bytes_per_chunk" = DRAM read + write bytes per 2^22-hypothesis chunk, "issue_slots_busy_pct" = issue-slot
+    utilisation per stage kernel; None if the file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_chunk"]
+            return json.load(f)[key]
     except Exception:
         return None
+
+
+def k3_traffic():
+    return k3_profile("dram_bytes_per_chunk")
 
 
 WORKLOAD_NAME = "C3: synthetic 60-peak/300-atlas-line arc, degree 4, sample 5, top-5 candidates (BASELINE configs[2])"
@@ -421,7 +426,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d" % world,
+        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d, chunks of 2^22 ids over 3 stream lanes per GPU" % world,
                    "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
         "clocks": clocks.summary(),
         "e2e": e2e,
@@ -432,6 +437,7 @@ def main():
                      "frac": achieved / fp64_peak, "traffic": k3_traffic(),
                      "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant, ~60 % of K3 time) + "
                                "monotonic + match + cost + record, timed together per step",
+                     "issue_slots_busy_pct": k3_profile("issue_slots_busy_pct"),
                      "flops_per_hypothesis": F, "f_intercept_pass": f_i,
                      "f_scored": f_m, "peak_source": "DFMA microbenchmark in this run (rb2_dfma_burn); FP64 is not in MEASURED_PEAKS.json",
                      "kernel_ms_per_step": kern_ms / args.steps},
