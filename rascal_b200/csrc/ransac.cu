@@ -509,13 +509,18 @@ struct TablesA {  // shared-memory views of one problem (stage A)
 };
 
 // first i with r < cdf32[i] (== searchsorted(cdf, u, 'right')), clamped: LUT over the top
-// LUT_BITS bits + scan (almost always zero or one step)
-constexpr int LUT_BITS = 10;
+// LUT_BITS bits.  A cell stores the index of its first value; bit 15 marks the few cells (about
+// n_u of 2^LUT_BITS) that a CDF boundary may cross - only those compare against the CDF, so a warp
+// usually takes the one-load path with all lanes.
+constexpr int LUT_BITS = 12;
+constexpr unsigned short LUT_CHECK = 0x8000u;
 __device__ __forceinline__ int draw_peak_lut(const TablesA& t, unsigned r) {
-  int i = t.lut[r >> (32 - LUT_BITS)];
-  const int last = t.n_u - 1;
-  i += (i < last && r >= t.cdf32[i]);  // at most one boundary per LUT cell unless a peak is rarer than 2^-LUT_BITS
-  while (i < last && r >= t.cdf32[i]) ++i;
+  const unsigned short e = t.lut[r >> (32 - LUT_BITS)];
+  int i = e & 0x7fff;
+  if (e & LUT_CHECK) {
+    const int last = t.n_u - 1;
+    while (i < last && r >= t.cdf32[i]) ++i;
+  }
   return i;
 }
 
@@ -746,11 +751,27 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   for (int i = tid; i <= n_u; i += RS_THREADS) s_coff[i] = d.d_cand_off[i];
   for (int i = tid; i < n_c; i += RS_THREADS) { s_cwave[i] = d.d_cand_wave[i]; s_cwid[i] = d.d_cand_wid[i]; }
   __syncthreads();
-  for (int b = tid; b < (1 << LUT_BITS); b += RS_THREADS) {  // lut[b] = #{i : cdf32[i] <= b << (32 - LUT_BITS)}, clamped
-    const unsigned r = (unsigned)b << (32 - LUT_BITS);
+  {
+    // lut[b] = #{i : cdf32[i] <= b << (32 - LUT_BITS)}, clamped: a thread fills a run of consecutive cells
+    // (one binary search, then a monotone walk); a cell is marked for checking when the next cell
+    // starts at another index (or the table cannot hold the index in 15 bits)
+    constexpr int NC = 1 << LUT_BITS, PER = NC / RS_THREADS;
+    const int b0 = tid * PER;
     int lo = 0, hi = n_u - 1;
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (r < s_cdf[m]) hi = m; else lo = m + 1; }
-    s_lut[b] = (unsigned short)lo;
+    const unsigned r0 = (unsigned)b0 << (32 - LUT_BITS);
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (r0 < s_cdf[m]) hi = m; else lo = m + 1; }
+    for (int b = b0; b < b0 + PER; ++b) {
+      const unsigned r = (unsigned)b << (32 - LUT_BITS);
+      while (lo < n_u - 1 && s_cdf[lo] <= r) ++lo;
+      s_lut[b] = (unsigned short)min(lo, 0x7fff);
+    }
+    __syncthreads();
+    const bool wide = n_u > 0x7fff;
+    for (int b = b0; b < b0 + PER; ++b) {
+      const int here = s_lut[b] & 0x7fff;
+      const int next = (b + 1 < NC) ? (s_lut[b + 1] & 0x7fff) : (n_u - 1);
+      if (wide || next != here) s_lut[b] = (unsigned short)(here | LUT_CHECK);
+    }
   }
   __syncthreads();
   TablesA tb;
