@@ -27,11 +27,10 @@ RANSAC_DEFAULTS = dict(sample_size=5, top_n_candidate=5, filter_close=False, ran
 FIT_DEFAULTS = dict(fit_deg=4, candidate_tolerance=2.0)
 
 
-def _limits(h, pixel_list):
-    """calibrator.py:1088-1116."""
+def _limits(h, span):
+    """calibrator.py:1088-1116; span = np.ptp(pixel_list)."""
     min_i = h["min_wavelength"] - h["range_tolerance"]
     max_i = h["min_wavelength"] + h["range_tolerance"]
-    span = np.ptp(pixel_list)
     lo = ((h["max_wavelength"] - h["range_tolerance"] - h["linearity_tolerance"])
           - (min_i + h["range_tolerance"] + h["linearity_tolerance"])) / span
     hi = ((h["max_wavelength"] + h["range_tolerance"] + h["linearity_tolerance"])
@@ -115,7 +114,7 @@ def ransac_setups(specs, hough, vote):
         s.pix_max = float(peaks[-1] + ptp * 0.2) if len(peaks) else 0.0
         s.hough_weight = float(r["hough_weight"])
         s.gc_min, s.gc_max, s.ic_min, s.h_lo, s.h_hi, s.pp_breaks, s.pp_coef = tables[i]
-        pl = sp["pixel_list"]
+        pl = sp["pixel_list"] if sp["pixel_list"] is not None else np.arange(sp["n_pix"], dtype=np.float64)
         s.n_pix = len(pl)
         s.pixel_list = pl
         s.pix_is_arange = sp["pix_is_arange"]
@@ -136,18 +135,19 @@ def normalise_spec(sp):
     if "pixel_list" in sp and sp["pixel_list"] is not None:
         pl = np.asarray(sp["pixel_list"], dtype=np.float64)
         is_ar = bool(len(pl) and pl[0] == 0 and pl[-1] == len(pl) - 1 and np.all(np.diff(pl) == 1))
-    else:
+        n_pix, span = len(pl), (float(np.ptp(pl)) if len(pl) else 0.0)
+    else:  # pixel_list = np.arange(num_pix) (calibrator.py:914-937), materialised only where it is read
         npix = sp.get("num_pix")
-        pl = np.arange(npix if npix is not None else 1.1 * max(peaks), dtype=np.float64)
-        is_ar = True
+        n_pix = int(np.ceil(npix if npix is not None else 1.1 * max(peaks)))
+        pl, is_ar, span = None, True, float(n_pix - 1)
     h = dict(HOUGH_DEFAULTS, **sp.get("hough", {}))
     r = dict(RANSAC_DEFAULTS, **sp.get("ransac", {}))
     f = dict(FIT_DEFAULTS, **sp.get("fit", {}))
     s = min(int(r["sample_size"]), len(lines))
     if s <= f["fit_deg"]:
         s = f["fit_deg"] + 1
-    return dict(peaks=peaks, lines=lines, pixel_list=pl, pix_is_arange=is_ar, hough=h, ransac=r, fit=f,
-                sample_size=s, limits=_limits(h, pl))
+    return dict(peaks=peaks, lines=lines, pixel_list=pl, n_pix=n_pix, pix_is_arange=is_ar, hough=h, ransac=r, fit=f,
+                sample_size=s, limits=_limits(h, span))
 
 
 class BatchResult(types.SimpleNamespace):

@@ -430,7 +430,7 @@ class Calibrator:
         lines = np.asarray(self.atlas.get_lines(), dtype=np.float64)
         if not (len(pl) and pl[0] == 0 and pl[-1] == len(pl) - 1 and np.all(np.diff(pl) == 1)):
             return None
-        spec = dict(peaks=peaks, lines=lines, pixel_list=pl, pix_is_arange=True, sample_size=self.sample_size,
+        spec = dict(peaks=peaks, lines=lines, pixel_list=pl, n_pix=len(pl), pix_is_arange=True, sample_size=self.sample_size,
                     limits=(self.min_slope, self.max_slope, self.min_intercept, self.max_intercept),
                     hough=dict(num_slopes=self.num_slopes, xbins=self.xbins, ybins=self.ybins,
                                range_tolerance=self.range_tolerance, linearity_tolerance=self.linearity_tolerance),

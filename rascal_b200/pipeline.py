@@ -143,13 +143,23 @@ def eligible(specs):
                 or bool(sp["ransac"]["candidate_weighted"]) != bool(s0["ransac"]["candidate_weighted"])
                 or sp["fit"]["fit_deg"] != s0["fit"]["fit_deg"] or sp["sample_size"] != s0["sample_size"]):
             return False
-        p, a = sp["peaks"], sp["lines"]
-        if len(p) < 1 or len(a) < 1 or (len(p) > 1 and not np.all(p[1:] > p[:-1])) or \
-                (len(a) > 1 and not np.all(a[1:] > a[:-1])):
+        if len(sp["peaks"]) < 1 or len(sp["lines"]) < 1:
             return False
     if int(s0["hough"]["xbins"]) < 8 or s0["sample_size"] != s0["fit"]["fit_deg"] + 1:
         return False
-    return True
+    return _strictly_increasing([sp["peaks"] for sp in specs]) and _strictly_increasing([sp["lines"] for sp in specs])
+
+
+def _strictly_increasing(arrays):
+    """Every array strictly increasing (vectorised over the batch: one diff over the concatenation,
+    the steps across array boundaries are ignored)."""
+    cat = np.concatenate(arrays)
+    if len(cat) < 2:
+        return True
+    ok = cat[1:] > cat[:-1]
+    ends = np.cumsum(np.fromiter((len(a) for a in arrays), dtype=np.int64, count=len(arrays)))[:-1]
+    ok[ends - 1] = True
+    return bool(ok.all())
 
 
 def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None):
@@ -181,7 +191,7 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     mm = np.fromiter((sp["ransac"]["minimum_matches"] for sp in specs), dtype=np.int64, count=n)
     mpu = np.fromiter((sp["ransac"]["minimum_peak_utilisation"] for sp in specs), dtype=np.float64, count=n)
     mfe = float(s0["ransac"]["minimum_fit_error"])
-    n_pix = np.fromiter((len(sp["pixel_list"]) for sp in specs), dtype=np.int64, count=n)
+    n_pix = np.fromiter((sp["n_pix"] for sp in specs), dtype=np.int64, count=n)
     sigma = (rtol + ltol) * 1.1775
 
     key = ("spline", xb)

@@ -28,7 +28,7 @@ def test_batch_equals_single_spectrum_pipeline():
                                         gauss_denom=2 * sigma ** 2 + 1e-9)]).run()
         cp, ca = vb.candidates(0)
         s = engine.RansacSetup(cp, ca, fit_deg=4, sample_size=5, ransac_tolerance=5, min_intercept=mi,
-                               max_intercept=ma, pixel_list=ns["pixel_list"], hist=hb.hist(0).astype(float),
+                               max_intercept=ma, pixel_list=np.arange(ns["n_pix"], dtype=float), hist=hb.hist(0).astype(float),
                                xedges=hb.xedges(0), yedges=hb.yedges(0), n_peaks_total=len(ns["peaks"]))
         rb = engine.RansacBatch([s])
         rb.run(0, n_hyp, seed=seed)
