@@ -31,6 +31,7 @@ constexpr int VOTE_NB = 4096;    // rank buckets
 constexpr int VOTE_CAP = 4096;   // collected (rank, pair) keys
 
 struct VoteCtx {
+  const double* cc;   // smem [yb] intercept-bin centres fl(ye[j] + hy) (houghtransform.py:205-208)
   const double* ye;   // smem [yb+1]
   const double* gc;   // smem [xb] gradient-bin centres
   double hy, x, tol, inv_wy, c_first, c_last, inv_dg;
@@ -80,15 +81,15 @@ template <class F>
 __device__ __forceinline__ void row_hits(const VoteCtx& c, double lam, int gi, F&& f) {
   const double gx = mul(c.gc[gi], c.x);
   // first j whose centre line is within reach: (gx + c_j) - lam >= -tol
-  int j = (int)floor(((lam - gx) - c.tol - c.c_first) * c.inv_wy) - 1;
+  int j = (int)floor(((lam - gx) - c.tol - c.c_first) * c.inv_wy);  // the step-back loop below repairs a high guess
   j = max(0, min(c.yb, j));
   while (j > 0) {  // guess too high: step back while the previous bin is not below the window
-    const double df = sub(add(gx, add(c.ye[j - 1], c.hy)), lam);
+    const double df = sub(add(gx, c.cc[j - 1]), lam);
     if (df < -c.tol) break;
     --j;
   }
   for (; j < c.yb; ++j) {
-    const double pred = add(gx, add(c.ye[j], c.hy));
+    const double pred = add(gx, c.cc[j]);
     const double df = sub(pred, lam);
     if (df > c.tol) break;
     if (fabs(df) <= c.tol) f(gi, j, pred);
@@ -131,7 +132,8 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
 
   double* ye = reinterpret_cast<double*>(smem_raw);
   double* gc = ye + (yb + 1);
-  double* wagg = gc + xb;
+  double* cc = gc + xb;
+  double* wagg = cc + yb;
   unsigned long long* list = reinterpret_cast<unsigned long long*>(wagg + nw);
   int* wcnt = reinterpret_cast<int*>(list + VOTE_CAP);
   unsigned* rb_hist = reinterpret_cast<unsigned*>(wcnt + nw);
@@ -148,6 +150,7 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   const double hy = (d.d_yedges[1] - d.d_yedges[0]) / 2;  // houghtransform.py:198
   for (int i = tid; i <= yb; i += VOTE_THREADS) ye[i] = d.d_yedges[i];
   for (int i = tid; i < xb; i += VOTE_THREADS) gc[i] = add(d.d_xedges[i], hx);
+  for (int i = tid; i < yb; i += VOTE_THREADS) cc[i] = add(d.d_yedges[i], hy);
   for (int i = tid; i < nw; i += VOTE_THREADS) { wagg[i] = 0.0; wcnt[i] = 0; }
   for (int i = tid; i < VOTE_NB; i += VOTE_THREADS) rb_hist[i] = 0u;
   if (tid == 0) { s_list_n = 0; s_L = 0; }
@@ -157,7 +160,7 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   while ((B >> shift) > VOTE_NB) ++shift;
 
   VoteCtx c;
-  c.ye = ye; c.gc = gc; c.hy = hy; c.x = d.d_upeak_x[u]; c.tol = d.tol;
+  c.ye = ye; c.gc = gc; c.cc = cc; c.hy = hy; c.x = d.d_upeak_x[u]; c.tol = d.tol;
   c.xb = xb; c.yb = yb;
   c.c_first = ye[0] + hy;
   c.c_last = ye[yb - 1] + hy;
@@ -197,9 +200,10 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   }
 
   // ---- phase 1: aggregate weights and counts, rank-bucket histogram ----------
+  const double inv_denom = 1.0 / d.gauss_denom;
   auto vote_hit = [&](double lam, double& agg, int& cnt, int gi, int j, double pred) {
     const double t = sub(lam, pred);
-    const double w = gauss_weight(-mul(t, t) / d.gauss_denom);  // util.py:447, a = 1.0
+    const double w = gauss_weight(-mul(t, t) * inv_denom);  // util.py:447, a = 1.0 (z to 1 ulp: w to 1e-20)
     agg = add(agg, w);
     ++cnt;
     atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
@@ -416,7 +420,7 @@ extern "C" int rb2_candidate_vote(int n_problems, const rb2_vote_desc* d_desc, c
     if (h.top_n < 1 || h.top_n > RB2_MAX_TOPN || h.xbins < 1 || h.ybins < 1) return RB2_ERR_ARG;
     max_up = max(max_up, h.n_upeaks);
     max_nw = max(max_nw, h.n_uwaves);
-    size_t s = (size_t)(h.ybins + 1) * 8 + (size_t)h.xbins * 8 + (size_t)h.n_uwaves * 8 + (size_t)VOTE_CAP * 8 +
+    size_t s = (size_t)(2 * h.ybins + 1) * 8 + (size_t)h.xbins * 8 + (size_t)h.n_uwaves * 8 + (size_t)VOTE_CAP * 8 +
                (size_t)h.n_uwaves * 4 + (size_t)VOTE_NB * 4;
     smem = max(smem, s);
   }
