@@ -190,15 +190,30 @@ def test_vote_batched_ragged():
 def test_vote_random_vs_oracle(seed, weighted):
     """Small random spectra: device vote == oracle's literal B*P loop, incl. aggregated
     weights (to rounding) and hit counts (exact)."""
+    _vote_random_case(seed, weighted, triple=False)
+
+
+def test_vote_heavily_duplicated_atlas():
+    """Every atlas line three times: more pairs per peak than the flattened work-unit tables hold
+    (distinct wavelengths + 64), so the kernel takes its pair-per-thread path; same answers."""
+    _vote_random_case(7, True, triple=True)
+
+
+def _vote_random_case(seed, weighted, triple):
     from rascal_b200 import engine
 
     rng = np.random.default_rng(100 + seed)
     n_p, n_a = int(rng.integers(5, 25)), int(rng.integers(8, 60))
+    if triple:
+        n_a = 45
     peaks = np.sort(rng.uniform(10, 1000, n_p))
     truth = 4000 + 2.0 * peaks + 1e-4 * peaks ** 2
     lines = np.sort(np.concatenate((truth[: n_p * 2 // 3], rng.uniform(3800, 6400, n_a))))
     if seed == 1:
         lines = np.concatenate((lines, lines[:3]))  # duplicated atlas wavelengths
+    if triple:
+        lines = np.concatenate((lines, lines, lines))
+        assert len(lines) > len(np.unique(lines)) + 64
     pairs = O.make_pairs(peaks, lines)
     lo, hi, mi, ma = O.hough_limits(4000.0, 6100.0, 200, 50, np.arange(1024))
     xb, yb = int(rng.integers(10, 50)), int(rng.integers(10, 50))
