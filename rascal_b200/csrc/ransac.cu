@@ -398,6 +398,69 @@ __device__ void lsq_polyfit(const double* xs, const double* ys, int m, int deg, 
     for (int j = n - 2; j >= i; --j) coef[j] = fma(-xc, coef[j + 1], coef[j]);
 }
 
+// Over-determined fit (sample_size > deg + 1 and / or known pairs, calibrator.py:569-575) with the degree
+// known at compile time: QR least squares by Givens rotations, one sample point at a time, on the
+// Vandermonde in the centred, scaled pixel - the (deg+1)^2/2 entries of R and Q^T y live in registers,
+// a rotation costs one rsqrt.  Backward stable like the Householder QR of the generic path (normal
+// equations or an orthogonal-polynomial recurrence lose digits the parity tests can see), whose
+// m x n matrix sits in local memory and makes it ~3x slower.
+template <int DEG>
+__device__ __forceinline__ void lsq_polyfit_givens(const double* xs, const double* ys, int m, double xc, double xsc,
+                                                   double* coef) {
+  constexpr int N = DEG + 1;
+  double R[N][N], q[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    q[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) R[j][k] = 0.0;
+  }
+  for (int i = 0; i < m; ++i) {
+    const double t = (xs[i] - xc) * xsc;
+    double row[N], y = ys[i];
+    row[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j < N; ++j) row[j] = row[j - 1] * t;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double ra = R[j][j], rb = row[j];
+      const double h2 = fma(ra, ra, rb * rb);
+      if (h2 > 0.0 && rb != 0.0) {
+        const double rinv = rsqrt(h2);
+        const double c = ra * rinv, sn = rb * rinv;
+        R[j][j] = h2 * rinv;
+#pragma unroll
+        for (int k = j + 1; k < N; ++k) {
+          const double rk = R[j][k], wk = row[k];
+          R[j][k] = fma(c, rk, sn * wk);
+          row[k] = fma(c, wk, -sn * rk);
+        }
+        const double qj = q[j];
+        q[j] = fma(c, qj, sn * y);
+        y = fma(c, y, -sn * qj);
+      }
+    }
+  }
+  double c[N];
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    double sk = q[k];
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) sk = fma(-R[k][j], c[j], sk);
+    c[k] = sk / R[k][k];
+  }
+  // t = (x - xc) * xsc  ->  monomials in x
+  double sc = 1.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) { c[j] *= sc; sc *= xsc; }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = N - 2; j >= i; --j) c[j] = fma(-xc, c[j + 1], c[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) coef[j] = c[j];
+}
+
 // exact interpolation through DEG+1 points: Newton divided differences with a
 // single FP64 division (all pairwise reciprocals from one product inverse).
 template <int DEG>
@@ -720,8 +783,10 @@ __device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigne
 #ifndef RB2_A_CTAS
 #define RB2_A_CTAS 4
 #endif
-template <int DEG_T>
-__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 ? RB2_A_CTAS : 2)
+// LSQ = false: sample_size == deg + 1, exact interpolation (newton_fit); LSQ = true (DEG_T > 0): run-time
+// sample size and known pairs, least squares with the compile-time degree (lsq_polyfit_givens)
+template <int DEG_T, bool LSQ = false>
+__global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 && !LSQ ? RB2_A_CTAS : 2)
 ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
                        rb2_ransac_result* __restrict__ result) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -778,7 +843,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   tb.peaks = s_peaks; tb.cwave = s_cwave; tb.coff = s_coff; tb.cwid = s_cwid; tb.cdf32 = s_cdf; tb.lut = s_lut; tb.n_u = n_u;
 
   const bool replay = d.d_replay_x != nullptr;
-  const int s = DEG_T > 0 ? DEG_T + 1 : d.sample_size;
+  const int s = (DEG_T > 0 && !LSQ) ? DEG_T + 1 : d.sample_size;
   const double min_i = d.min_intercept, max_i = d.max_intercept;
   const long long n_hyp = d.n_hyp;
   const double lsq_xc = 0.5 * (d.pix_min + d.pix_max);
@@ -796,7 +861,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
 #pragma unroll
     for (int i = 0; i < NCOEF; ++i) cf[i] = 0.0;
     if (active) {
-      if constexpr (DEG_T > 0) {
+      if constexpr (DEG_T > 0 && !LSQ) {
         int pi[DEG_T + 1], ci[DEG_T + 1];
         if (replay) {
 #pragma unroll
@@ -830,7 +895,11 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
           int m = 0;
           for (int k = 0; k < s; ++k) { xs[m] = tb.peaks[pi[k]]; ys[m] = tb.cwave[ci[k]]; ++m; }
           for (int k = 0; k < d.n_known && m < RB2_MAX_SAMPLE; ++k) { xs[m] = d.d_known_x[k]; ys[m] = d.d_known_y[k]; ++m; }
-          lsq_polyfit(xs, ys, m, deg, lsq_xc, lsq_xsc, cf);
+          if constexpr (LSQ) {
+            lsq_polyfit_givens<DEG_T>(xs, ys, m, lsq_xc, lsq_xsc, cf);
+          } else {
+            lsq_polyfit(xs, ys, m, deg, lsq_xc, lsq_xsc, cf);
+          }
         }
       }
       if (!aborted) pass = !((cf[0] < min_i) || (cf[0] > max_i));  // :578-582
@@ -1251,13 +1320,13 @@ static size_t stage_a_smem(const rb2_ransac_desc& h) {
          (size_t)h.n_upeaks * 4 + (size_t)(1 << LUT_BITS) * 2 + 16;
 }
 
-template <int DEG_T>
+template <int DEG_T, bool LSQ = false>
 static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int max_up, int single, int sms, cudaStream_t stream,
                         const rb2_ransac_desc* d_desc, const Pipe& pipe, long long chunk_begin, long long chunk_len,
                         rb2_ransac_result* d_result) {
   static bool configured = false;
   if (!configured || true) {
-    RB2_CHECK(cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)));
     RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     configured = true;
   }
@@ -1269,7 +1338,7 @@ static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids,
     return true;
   };
   pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(pipe);
-  ransac_draw_fit_kernel<DEG_T><<<grid_a, RS_THREADS, smem_a, stream>>>(d_desc, pipe, chunk_begin, chunk_len, d_result);
+  ransac_draw_fit_kernel<DEG_T, LSQ><<<grid_a, RS_THREADS, smem_a, stream>>>(d_desc, pipe, chunk_begin, chunk_len, d_result);
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
   ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(d_desc, pipe, d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
@@ -1372,6 +1441,12 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
     else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
     else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    // over-determined samples / known pairs: compile-time degree everywhere, least squares in stage A
+    else if (deg == 1) rc = launch_chunk<1, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (deg == 2) rc = launch_chunk<2, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (deg == 3) rc = launch_chunk<3, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (deg == 4) rc = launch_chunk<4, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    else if (deg == 5) rc = launch_chunk<5, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
     else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
     if (rc != RB2_OK) return rc;
   }
