@@ -414,6 +414,46 @@ def main():
                    "fitted_rank0": sum(r.fit_coeff is not None for r in bres), "within_1A_of_truth_rank0": good,
                    "stage_s_rank0": {k: round(v, 4) for k, v in tm.items()}}
 
+    # ---- K1 / K2 alone on resident inputs (rank 0): the Hough pass against SURVEY 8d's FP64-pipe roof ----
+    hough_roof = None
+    if args.spectra > 0 and rank == 0:
+        from rascal_b200 import batch as _b
+
+        ns = [_b.normalise_spec(sp) for sp in specs[:512]]
+        hp, vs = [], []
+        for sp in ns:
+            lo_, hi_, mi_, ma_ = sp["limits"]
+            h_ = sp["hough"]
+            hp.append(dict(pair_x=np.repeat(sp["peaks"], len(sp["lines"])), pair_y=np.tile(sp["lines"], len(sp["peaks"])),
+                           min_slope=lo_, max_slope=hi_, min_intercept=mi_, max_intercept=ma_,
+                           n_slopes=int(h_["num_slopes"]), xbins=int(h_["xbins"]), ybins=int(h_["ybins"])))
+            sg = (h_["range_tolerance"] + h_["linearity_tolerance"]) * 1.1775
+            vs.append(dict(pairs=None, peaks=sp["peaks"], lines=sp["lines"], top_n=sp["ransac"]["top_n_candidate"],
+                           weighted=sp["ransac"]["candidate_weighted"], tol=sp["fit"]["candidate_tolerance"],
+                           gauss_denom=2 * sg ** 2 + 1e-9))
+        hb = engine.HoughBatch(hp)
+        hb.run()
+        vb = engine.VoteBatch(hb, vs)
+        vb.run()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        hb.run()
+        e1.record()
+        vb.run()
+        e2.record()
+        torch.cuda.synchronize()
+        evals = float(sum(int(h_["n_slopes"]) * len(h_["pair_x"]) for h_ in hp))
+        points = float(sum(int(st.n_points) for st in hb.stats))
+        t1, t2 = e0.elapsed_time(e1) * 1e-3, e1.elapsed_time(e2) * 1e-3
+        roof = fp64_peak * 1e12 / 2.0 / 4.0  # 4 FP64-pipe instructions per (slope, pair) evaluation
+        hough_roof = {"kernel": "K1 rb2_hough_accumulate (interval + edges + bin + rank), 512 C4 spectra resident",
+                      "evaluations_per_s": evals / t1, "surviving_points_per_s": points / t1,
+                      "bound": "fp64", "peak_evaluations_per_s": roof, "frac": evals / t1 / roof, "ms": t1 * 1e3,
+                      "algorithmic_bytes": int(sum(16 * len(h_["pair_x"]) + 8 * int(h_["n_slopes"]) + 8 * 202 + 8 * 10000 for h_ in hp)),
+                      "k2_vote_ms": t2 * 1e3,
+                      "k2_bin_pair_tests_per_s": float(sum(10000 * len(h_["pair_x"]) for h_ in hp)) / t2}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -446,6 +486,8 @@ def main():
     }
     if spectra is not None:
         line["spectra_per_sec"] = spectra
+    if hough_roof is not None:
+        line["hough_roofline"] = hough_roof
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
