@@ -48,7 +48,7 @@ const char *rb2_last_cuda_error(void);
 /* Number of SMs of the current device (grid sizing is a multiple of this). */
 int rb2_sm_count(int *out);
 /* sizeof() of the structs below, in declaration order (0 = rb2_hough_desc ...
- * 5 = rb2_refit_result); lets a binding verify its layout. */
+ * 5 = rb2_refit_result ... 11 = rb2_refine_desc); lets a binding verify its layout. */
 int rb2_struct_size(int which);
 /* Roofline denominator for the FP64-bound kernels (not in
  * MEASURED_PEAKS.json): launches `blocks` CTAs of 256 threads doing 8*iters
@@ -377,6 +377,79 @@ typedef struct {
 int rb2_ransac_prepare(int n_problems, const rb2_prepare_desc *d_desc,
                        const rb2_prepare_desc *h_desc,
                        rb2_ransac_desc *d_ransac_desc, void *stream);
+
+/* ======================================================================= *
+ * K6  peak finding and sub-pixel refinement: the step BEFORE the path
+ *     (SURVEY.md 8f rank 2), batched over spectra.
+ * ======================================================================= */
+/* rb2_find_peaks replaces scipy.signal.find_peaks(spectrum, height=h,
+ * distance=d, prominence=p, threshold=None) as every reference example and
+ * test calls it before refine_peaks (test/test_xe_calibration.py:69,
+ * test/test_lt_sprat_manual_atlas.py:36, examples/example_*.py): strict local
+ * maxima with flat tops reported at their middle sample, then - in SciPy's
+ * order - the height, distance (highest first; among equal heights the later
+ * sample first) and prominence (wlen=None) conditions.  A condition is
+ * switched off with NaN.  One CTA per spectrum, candidates in shared memory:
+ * n_pix <= RB2_FIND_MAX_PIX, else RB2_ERR_CAPACITY. */
+#define RB2_FIND_MAX_PIX 16382
+typedef struct {
+  const double *d_spectrum;             /* [n_pix]                           */
+  int32_t n_pix;
+  int32_t max_peaks;                    /* capacity of the outputs           */
+  double height, distance, prominence;  /* minima; NaN = not asked           */
+  int32_t *d_peaks;                     /* out: [max_peaks] sample indices, ascending */
+  double *d_peaks_f64;                  /* out or NULL: the same as doubles (input of rb2_refine_peaks) */
+  double *d_heights;                    /* out or NULL: spectrum[peak]       */
+  double *d_prominences;                /* out or NULL (needs prominence)    */
+  int32_t *d_n_peaks;                   /* out: [1] number found; only the first max_peaks are stored */
+} rb2_findpeaks_desc;
+
+int rb2_find_peaks(int n_spectra, const rb2_findpeaks_desc *d_desc,
+                   const rb2_findpeaks_desc *h_desc, void *stream);
+
+/* rb2_refine_peaks replaces rascal.util.refine_peaks (util.py:450-523) with
+ * util.gauss (:425-447): per peak the window [int(peak)-w, int(peak)+w) is
+ * divided by its maximum IN the working copy of the spectrum (:478 - a later,
+ * overlapping window sees the divided values; d_work is that copy), and a
+ * Gaussian a*exp(-(x-x0)^2/(2 sigma^2+1e-9)) is fitted from p0 = [1, mean,
+ * sigma] (:487-488) by MINPACK's lmdif exactly as scipy.optimize.curve_fit runs
+ * it (ftol = xtol = 1.49012e-8, gtol = 0, maxfev = 800, factor 100, forward
+ * differences with step sqrt(eps)*|p|); a peak is dropped when the fit fails
+ * (ier not in 1..4), the height is negative or the centre leaves [0, n_pix]
+ * (:491-502); the survivors peak - w + centre are filtered to (0, n_pix) and
+ * de-duplicated against their predecessor with np.isclose (:509-517).
+ * Three launches: windows (one CTA per spectrum), fits (one thread per peak),
+ * collection (one thread per spectrum). */
+typedef enum {
+  RB2_PEAK_OK = 0,          /* fitted and appended (it may still fall to the final range / isclose filter) */
+  RB2_PEAK_NO_DATA = 1,     /* no finite sample in the window (:484-485)      */
+  RB2_PEAK_NOT_FINITE = 2,  /* some sample not finite: curve_fit returns NaN, removed by the final mask */
+  RB2_PEAK_FIT_FAILED = 3,  /* lmdif ier not in 1..4: RuntimeError in the reference (:504) */
+  RB2_PEAK_NEGATIVE = 4,    /* fitted height < 0 (:493)                       */
+  RB2_PEAK_OUTSIDE = 5,     /* fitted centre outside [0, n_pix] (:496)        */
+  RB2_PEAK_EMPTY_WINDOW = 6,/* window empty: the reference raises ValueError (nanmax of nothing) */
+  RB2_PEAK_TOO_FEW = 7      /* fewer than 3 samples: the reference raises TypeError (curve_fit) */
+} rb2_peak_status;
+
+#define RB2_REFINE_MAX_WINDOW 32        /* largest window_width              */
+
+typedef struct {
+  const double *d_spectrum;             /* [n_pix]                           */
+  double *d_work;                       /* scratch: [n_pix]                  */
+  int32_t n_pix;
+  int32_t n_peaks;                      /* number of peaks, or their capacity if d_n_peaks is given */
+  const double *d_peaks;                /* [n_peaks] initial estimates (pixels) */
+  const int32_t *d_n_peaks;             /* NULL, or [1] on the device (rb2_find_peaks output), clamped to n_peaks */
+  int32_t window_width, pad;
+  double *d_window;                     /* scratch: [n_peaks * 2*window_width] */
+  double *d_fit;                        /* out: [n_peaks][4] height, centre, sigma, (double)nfev */
+  int32_t *d_status;                    /* out: [n_peaks] rb2_peak_status; lmdif's ier in bits 8.. */
+  double *d_refined;                    /* out: [n_peaks] the refined peaks, compacted */
+  int32_t *d_n_refined;                 /* out: [1]                          */
+} rb2_refine_desc;
+
+int rb2_refine_peaks(int n_spectra, const rb2_refine_desc *d_desc,
+                     const rb2_refine_desc *h_desc, void *stream);
 
 #ifdef __cplusplus
 }

@@ -119,8 +119,27 @@ class PrepareDesc(C.Structure):
     ]
 
 
+class FindPeaksDesc(C.Structure):
+    _fields_ = [
+        ("d_spectrum", _vp), ("n_pix", C.c_int32), ("max_peaks", C.c_int32),
+        ("height", C.c_double), ("distance", C.c_double), ("prominence", C.c_double),
+        ("d_peaks", _vp), ("d_peaks_f64", _vp), ("d_heights", _vp), ("d_prominences", _vp), ("d_n_peaks", _vp),
+    ]
+
+
+class RefineDesc(C.Structure):
+    _fields_ = [
+        ("d_spectrum", _vp), ("d_work", _vp), ("n_pix", C.c_int32), ("n_peaks", C.c_int32),
+        ("d_peaks", _vp), ("d_n_peaks", _vp), ("window_width", C.c_int32), ("pad", C.c_int32),
+        ("d_window", _vp), ("d_fit", _vp), ("d_status", _vp), ("d_refined", _vp), ("d_n_refined", _vp),
+    ]
+
+
+PEAK_STATUS = ("ok", "no_data", "not_finite", "fit_failed", "negative", "outside", "empty_window", "too_few")
+REFINE_MAX_WINDOW = 32
+
 STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult, MatchDesc, MatchResult,
-           PairsDesc, PrepareDesc]
+           PairsDesc, PrepareDesc, FindPeaksDesc, RefineDesc]
 COUNTER_NAMES = ("drawn", "aborted", "intercept", "monotonic", "empty", "scored", "eligible", "unsupported")
 
 # every symbol include/rascal_b200.h declares
@@ -144,6 +163,8 @@ EXPORTS = {
     "rb2_ransac_prepare": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
     "rb2_match_peaks": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_refit_winners": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_double, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "rb2_find_peaks": (C.c_int, [C.c_int, _vp, _vp, _vp]),
+    "rb2_refine_peaks": (C.c_int, [C.c_int, _vp, _vp, _vp]),
 }
 
 _lib = None

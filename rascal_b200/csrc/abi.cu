@@ -6,6 +6,7 @@ static thread_local char g_last_cuda_error[256] = "";
 
 int rb2_set_cuda_error(cudaError_t e) {
   strncpy(g_last_cuda_error, cudaGetErrorString(e), sizeof(g_last_cuda_error) - 1);
+  cudaGetLastError();  // reported through the return value; do not leave it for the caller's next CUDA call
   return RB2_ERR_CUDA;
 }
 
@@ -49,6 +50,8 @@ extern "C" int rb2_struct_size(int which) {
     case 7: return (int)sizeof(rb2_match_result);
     case 8: return (int)sizeof(rb2_pairs_desc);
     case 9: return (int)sizeof(rb2_prepare_desc);
+    case 10: return (int)sizeof(rb2_findpeaks_desc);
+    case 11: return (int)sizeof(rb2_refine_desc);
     default: return -1;
   }
 }

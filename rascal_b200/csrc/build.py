@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "librascal_b200.so")
-SOURCES = ["abi.cu", "hough.cu", "vote.cu", "ransac.cu", "refit.cu", "batch.cu"]
+SOURCES = ["abi.cu", "hough.cu", "vote.cu", "ransac.cu", "refit.cu", "batch.cu", "peaks.cu"]
 HEADERS = ["common.cuh", os.path.join(PKG, "..", "include", "rascal_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
