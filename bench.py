@@ -86,6 +86,19 @@ def c4_input(i):
                 fit=dict(fit_deg=4, candidate_tolerance=10.0))
 
 
+def c4_arc(sp, i):
+    """The arc spectrum whose peaks spectrum i of the C4 batch has: Gaussian lines (sigma 1.1-1.8 px,
+    200-20000 counts) at sp["peaks"] on a sloping baseline with read noise.  Input of the K6 leg."""
+    rng = np.random.default_rng(20_000 + i)
+    n = int(sp["num_pix"])
+    s = 40.0 + 0.005 * np.arange(n) + rng.normal(0, 3.0, n)
+    for c, a, w in zip(sp["peaks"], rng.uniform(200, 20000, len(sp["peaks"])), rng.uniform(1.1, 1.8, len(sp["peaks"]))):
+        lo, hi = max(0, int(c) - 12), min(n, int(c) + 13)
+        x = np.arange(lo, hi)
+        s[lo:hi] += a * np.exp(-0.5 * ((x - c) / w) ** 2)
+    return s
+
+
 def flops_per_hypothesis(c, deg=4, s=5, n=60, k=5):
     """F = F_fit + f_i*F_mono + f_m*F_score (FP64 flops, algorithmic)."""
     d = deg
@@ -454,6 +467,54 @@ def main():
                       "k2_vote_ms": t2 * 1e3,
                       "k2_bin_pair_tests_per_s": float(sum(10000 * len(h_["pair_x"]) for h_ in hp)) / t2}
 
+    # ---- K6 (the step before the path): find_peaks + refine_peaks for 512 rendered C4 arcs (rank 0) ----
+    peak_leg = None
+    if args.spectra > 0 and rank == 0:
+        from rascal_b200 import util as rutil
+
+        n_arc = min(512, args.spectra)
+        arcs = [c4_arc(specs[i], i) for i in range(n_arc)]
+        recipe = dict(height=150.0, distance=3, prominence=100.0)
+        rutil.find_and_refine(arcs, window_width=5, max_peaks=256, **recipe)  # warm
+        pbatch = rutil.PeakBatch(arcs)
+        pbatch.find(max_peaks=256, **recipe).refine(5)
+        torch.cuda.synchronize()
+        reps = []
+        for _ in range(5):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            pbatch.find(max_peaks=256, **recipe)
+            e1.record()
+            pbatch.refine(5)
+            e2.record()
+            torch.cuda.synchronize()
+            reps.append((e0.elapsed_time(e2), e0.elapsed_time(e1), e1.elapsed_time(e2)))
+        t_all, t_find, t_refine = sorted(reps)[2]  # median repetition
+        refined = pbatch.fetch_refined()
+        t0 = time.perf_counter()
+        rutil.find_and_refine(arcs, window_width=5, max_peaks=256, **recipe)
+        t_pk = time.perf_counter() - t0
+        n_ref = sum(len(r) for r in refined)
+        off_px = np.concatenate([np.min(np.abs(r[:, None] - specs[i]["peaks"][None, :]), axis=1) for i, r in enumerate(refined) if len(r)])
+        peak_leg = {"kernel": "K6 rb2_find_peaks (1 launch) + rb2_refine_peaks (3 launches), %d C4 arcs resident" % n_arc,
+                    "find_ms": t_find, "refine_ms": t_refine, "refined_peaks": n_ref, "timing": "median of 5 repetitions, CUDA events",
+                    "peaks_per_s": n_ref / (t_all * 1e-3), "spectra_per_s": n_arc / (t_all * 1e-3),
+                    "e2e_spectra_per_s": n_arc / t_pk, "median_offset_from_true_centre_px": float(np.median(off_px)),
+                    "algorithmic_bytes": int(sum(8 * len(a) for a in arcs) + 8 * n_ref)}
+        if not args.no_cpu:
+            from scipy.signal import find_peaks as sp_find
+
+            from oracle import peaks as opeaks
+
+            t0 = time.perf_counter()
+            n_cpu = 0
+            for a in arcs[:16]:
+                pk, _ = sp_find(a, **recipe)
+                n_cpu += len(opeaks.refine_peaks(a, pk, window_width=5, fitter="scipy"))
+            t_cpu = time.perf_counter() - t0
+            peak_leg["cpu_baseline"] = {"spectra_per_s": 16 / t_cpu, "peaks_per_s": n_cpu / t_cpu, "cores": 1, "kind": "port",
+                                        "sample": "16 of the arcs: scipy.signal.find_peaks + util.refine_peaks restated over scipy.optimize.curve_fit"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -488,6 +549,8 @@ def main():
         line["spectra_per_sec"] = spectra
     if hough_roof is not None:
         line["hough_roofline"] = hough_roof
+    if peak_leg is not None:
+        line["peak_finding"] = peak_leg
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

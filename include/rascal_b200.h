@@ -418,8 +418,8 @@ int rb2_find_peaks(int n_spectra, const rb2_findpeaks_desc *d_desc,
  * (ier not in 1..4), the height is negative or the centre leaves [0, n_pix]
  * (:491-502); the survivors peak - w + centre are filtered to (0, n_pix) and
  * de-duplicated against their predecessor with np.isclose (:509-517).
- * Three launches: windows (one CTA per spectrum), fits (one thread per peak),
- * collection (one thread per spectrum). */
+ * Three launches: windows (one CTA per spectrum), fits (one warp per spectrum,
+ * one peak per lane at a time), collection (one thread per spectrum). */
 typedef enum {
   RB2_PEAK_OK = 0,          /* fitted and appended (it may still fall to the final range / isclose filter) */
   RB2_PEAK_NO_DATA = 1,     /* no finite sample in the window (:484-485)      */

@@ -154,6 +154,31 @@ class BatchResult(types.SimpleNamespace):
     pass
 
 
+def peaks_from_spectra(spectra):
+    """The step before the path for a batch: entries that carry an arc `spectrum`
+    instead of `peaks` get them from K6 - scipy.signal.find_peaks(**entry["find_peaks"]) followed by
+    rascal.util.refine_peaks(window_width=entry.get("window_width", 10)), as the reference's examples
+    do (examples/example_lt_sprat_xe.py:27-28) - in one device batch per distinct recipe; `num_pix`
+    defaults to len(spectrum).  Entries that already have `peaks` pass through untouched."""
+    from . import util
+
+    out = list(spectra)
+    groups = {}
+    for i, sp in enumerate(out):
+        if sp.get("peaks") is None and sp.get("spectrum") is not None:
+            fp = sp.get("find_peaks", {})
+            key = (fp.get("height"), fp.get("distance"), fp.get("prominence"), int(sp.get("window_width", 10)),
+                   sp.get("max_peaks"))
+            groups.setdefault(key, []).append(i)
+    for (h, d, p, ww, cap), idx in groups.items():
+        found = util.find_and_refine([out[i]["spectrum"] for i in idx], height=h, distance=d, prominence=p,
+                                     window_width=ww, max_peaks=cap)
+        for i, pk in zip(idx, found):
+            out[i] = dict(out[i], peaks=pk)
+            out[i].setdefault("num_pix", len(out[i]["spectrum"]))
+    return out
+
+
 def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=None, match_tolerance=None,
                     device_pipeline=True):
     """do_hough_transform() + fit() for every spectrum of `spectra` in batched device calls.
@@ -167,6 +192,9 @@ def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=
     peaks and lines, pixel_list = arange) run device-resident end to end (rascal_b200.pipeline: one
     H2D, one D2H, K3's tables built by rb2_ransac_prepare); others take the staged path below.
 
+    An entry may carry an arc `spectrum` (+ `find_peaks` = dict(height=, distance=, prominence=),
+    `window_width`) instead of `peaks`: peaks_from_spectra() finds and refines them on the device first.
+
     match_tolerance: if set, Calibrator.match_peaks(tolerance=match_tolerance) follows every fit
     (K5), reading the refit coefficients straight from K4's device records; the result gains
     `match` = BatchResult(fit_coeff, matched_peaks, matched_atlas, rms, residuals, n_ambiguous)."""
@@ -174,7 +202,7 @@ def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=
 
     torch = engine._torch()
     t0 = time.perf_counter()
-    specs = [normalise_spec(sp) for sp in spectra]
+    specs = [normalise_spec(sp) for sp in peaks_from_spectra(spectra)]
     if device_pipeline and pipeline.eligible(specs):
         return pipeline.run(specs, n_hypotheses, seed=seed, refit_mode=refit_mode, match_tolerance=match_tolerance,
                             timings=timings)

@@ -7,9 +7,11 @@
 //   refine_windows_kernel / refine_fit_kernel / refine_collect_kernel
 //                        rascal util.refine_peaks (util.py:450-523): the in-place window
 //                        normalisation is sequential per spectrum (one warp walks the peaks),
-//                        the Gaussian fits are independent (one thread per peak runs MINPACK's
-//                        lmdif, n = 3, as scipy.optimize.curve_fit does), the final range /
-//                        np.isclose filter is sequential again.
+//                        the Gaussian fits are independent (MINPACK's lmdif, n = 3, as
+//                        scipy.optimize.curve_fit runs it: one warp per spectrum, one peak per lane,
+//                        lanes refilled from the spectrum's remaining peaks and kept in step at
+//                        every outer iteration), the final range / np.isclose filter is
+//                        sequential again.
 //
 // The Levenberg-Marquardt code below is written from the published MINPACK-1 algorithm (More,
 // Garbow, Hillstrom 1980: lmdif, lmpar, qrfac, qrsolv, enorm, fdjac2) specialised to three
@@ -154,15 +156,33 @@ __global__ void __launch_bounds__(FP_THREADS) find_peaks_kernel(const rb2_findpe
   // (3) prominence (wlen = None): walk outwards to the next strictly higher sample on each
   //     side, remembering the lowest sample passed.
   if (has_p) {
-    for (int k = tid; k < nc; k += FP_THREADS) {
+    // one warp per peak, 32 samples per step: the first lane that sees a higher sample ends the walk
+    const int lane = tid & 31;
+    for (int k = tid >> 5; k < nc; k += FP_THREADS / 32) {
       const int p = idx[k];
       const double xp = x[p];
-      double lmin = xp, rmin = xp;
-      for (int i = p; i >= 0 && x[i] <= xp; --i) lmin = x[i] < lmin ? x[i] : lmin;
-      for (int i = p; i < n && x[i] <= xp; ++i) rmin = x[i] < rmin ? x[i] : rmin;
-      const double prom = xp - fmax(lmin, rmin);
-      val[k] = prom;  // carried through the compaction (heights are re-read from the spectrum)
-      keep[k] = prom >= d.prominence;
+      double side_min[2];
+      for (int dir = 0; dir < 2; ++dir) {
+        double mn = xp;
+        for (int base = p;; base += dir ? 32 : -32) {
+          const int i = dir ? base + lane : base - lane;
+          const bool valid = i >= 0 && i < n;
+          const double v = valid ? x[i] : xp;
+          const unsigned stop = __ballot_sync(0xffffffffu, !valid || !(v <= xp));
+          const int first = stop ? __ffs(stop) - 1 : 32;
+          double c = lane < first ? v : xp;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) c = fmin(c, __shfl_xor_sync(0xffffffffu, c, o));
+          mn = fmin(mn, c);
+          if (stop) break;
+        }
+        side_min[dir] = mn;
+      }
+      if (lane == 0) {
+        const double prom = xp - fmax(side_min[0], side_min[1]);
+        val[k] = prom;  // carried through the compaction (heights are re-read from the spectrum)
+        keep[k] = prom >= d.prominence;
+      }
     }
     __syncthreads();
     nc = block_compact(nc, idx, val, keep, ord, key, s_warp);
@@ -189,7 +209,7 @@ constexpr double LM_TOL = 1.49012e-8;  // scipy.optimize.leastsq: ftol = xtol
 constexpr int LM_MAXFEV = 200 * (LM_N + 1);
 
 // Euclidean norm with MINPACK's three accumulators (small / intermediate / large components)
-__device__ double enorm(int n, const double* v) {
+__device__ __noinline__ double enorm(int n, const double* v) {
   const double rdwarf = 3.834e-20, rgiant = 1.304e19;
   double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
   const double agiant = rgiant / (double)n;
@@ -226,7 +246,7 @@ __device__ double enorm(int n, const double* v) {
 }
 
 // residuals of util.gauss (util.py:447) on x = 0..m-1, each NumPy ufunc rounded on its own
-__device__ void gauss_residuals(const double* p, const double* __restrict__ y, int m, double* __restrict__ f) {
+__device__ __noinline__ void gauss_residuals(const double* p, const double* __restrict__ y, int m, double* __restrict__ f) {
   const double den = add(mul(2.0, mul(p[2], p[2])), 1e-9);
   for (int i = 0; i < m; ++i) {
     const double dx = sub((double)i, p[1]);
@@ -236,7 +256,7 @@ __device__ void gauss_residuals(const double* p, const double* __restrict__ y, i
 
 // Solve R z = Q^T b augmented by the diagonal `diag` (Givens eliminations); r: upper triangle
 // in, strict lower triangle used as work space, diagonal restored.
-__device__ void qrsolv3(double r[LM_N][LM_N], const int* ipvt, const double* diag, const double* qtb, double* x,
+__device__ __noinline__ void qrsolv3(double r[LM_N][LM_N], const int* ipvt, const double* diag, const double* qtb, double* x,
                         double* sdiag) {
   double wa[LM_N];
   for (int j = 0; j < LM_N; ++j) {
@@ -290,7 +310,7 @@ __device__ void qrsolv3(double r[LM_N][LM_N], const int* ipvt, const double* dia
 }
 
 // Levenberg-Marquardt parameter for the trust region ||D x|| <= delta
-__device__ double lmpar3(double r[LM_N][LM_N], const int* ipvt, const double* diag, const double* qtb, double delta,
+__device__ __noinline__ double lmpar3(double r[LM_N][LM_N], const int* ipvt, const double* diag, const double* qtb, double delta,
                          double par, double* x, double* sdiag) {
   double wa1[LM_N], wa2[LM_N];
   int nsing = LM_N;
@@ -362,177 +382,203 @@ __device__ double lmpar3(double r[LM_N][LM_N], const int* ipvt, const double* di
   return par;
 }
 
-// lmdif, mode 1, n = 3.  x: start in, solution out.  Returns MINPACK's info; *nfev_out = function evaluations.
-__device__ int lmdif_gauss(const double* __restrict__ y, int m, double* x, int* nfev_out) {
-  double fvec[LM_WMAX], wa4[LM_WMAX];
+// lmdif, mode 1, n = 3, cut at its outer loop so that the lanes of a warp can walk it in step:
+// lm_start() evaluates the start, lm_iterate() runs ONE outer iteration (Jacobian, QR, the inner
+// trust-region loop) and returns MINPACK's info (0 = not finished).
+struct LMState {
+  double y[LM_WMAX], fvec[LM_WMAX], wa4[LM_WMAX];
   double fj[LM_N][LM_WMAX];  // Jacobian by columns; after qrfac: R above the diagonal, Householder vectors below
-  double diag[LM_N], qtf[LM_N], wa1[LM_N], wa2[LM_N], wa3[LM_N], acn[LM_N], rdiag[LM_N], wq[LM_N], sdiag[LM_N];
+  double x[LM_N], diag[LM_N];
+  double fnorm, par, xnorm, delta;
+  int m, nfev, iter;
+};
+
+__device__ __noinline__ void lm_start(LMState& S) {
+  gauss_residuals(S.x, S.y, S.m, S.fvec);
+  S.nfev = 1;
+  S.iter = 1;
+  S.fnorm = enorm(S.m, S.fvec);
+  S.par = S.xnorm = S.delta = 0.0;
+}
+
+__device__ __noinline__ int lm_iterate(LMState& S) {
+  double qtf[LM_N], wa1[LM_N], wa2[LM_N], wa3[LM_N], acn[LM_N], rdiag[LM_N], wq[LM_N], sdiag[LM_N];
   double r[LM_N][LM_N];
   int ipvt[LM_N];
-  gauss_residuals(x, y, m, fvec);
-  int nfev = 1, info = 0, iter = 1;
-  double fnorm = enorm(m, fvec), par = 0.0, xnorm = 0.0, delta = 0.0;
+  const int m = S.m;
+  double* x = S.x;
+  double* diag = S.diag;
+  double* fvec = S.fvec;
+  double* wa4 = S.wa4;
+  double(*fj)[LM_WMAX] = S.fj;
   const double eps = sqrt(LM_EPSMCH);
-  for (;;) {
-    // forward-difference Jacobian
-    for (int j = 0; j < LM_N; ++j) {
-      const double t = x[j];
-      double h = eps * fabs(t);
-      if (h == 0.0) h = eps;
-      x[j] = t + h;
-      gauss_residuals(x, y, m, wa4);
-      x[j] = t;
-      for (int i = 0; i < m; ++i) fj[j][i] = (wa4[i] - fvec[i]) / h;
-    }
-    nfev += LM_N;
-    // Householder QR with column pivoting
-    for (int j = 0; j < LM_N; ++j) {
-      acn[j] = enorm(m, fj[j]);
-      rdiag[j] = acn[j];
-      wq[j] = rdiag[j];
-      ipvt[j] = j;
-    }
-    const int minmn = m < LM_N ? m : LM_N;
-    for (int j = 0; j < minmn; ++j) {
-      int kmax = j;
-      for (int k = j; k < LM_N; ++k)
-        if (rdiag[k] > rdiag[kmax]) kmax = k;
-      if (kmax != j) {
-        for (int i = 0; i < m; ++i) {
-          const double t = fj[j][i];
-          fj[j][i] = fj[kmax][i];
-          fj[kmax][i] = t;
-        }
-        rdiag[kmax] = rdiag[j];
-        wq[kmax] = wq[j];
-        const int t = ipvt[j];
-        ipvt[j] = ipvt[kmax];
-        ipvt[kmax] = t;
+  int info = 0;
+  // forward-difference Jacobian
+  for (int j = 0; j < LM_N; ++j) {
+    const double t = x[j];
+    double h = eps * fabs(t);
+    if (h == 0.0) h = eps;
+    x[j] = t + h;
+    gauss_residuals(x, S.y, m, wa4);
+    x[j] = t;
+#pragma unroll 1
+    for (int i = 0; i < m; ++i) fj[j][i] = (wa4[i] - fvec[i]) / h;
+  }
+  S.nfev += LM_N;
+  // Householder QR with column pivoting
+  for (int j = 0; j < LM_N; ++j) {
+    acn[j] = enorm(m, fj[j]);
+    rdiag[j] = acn[j];
+    wq[j] = rdiag[j];
+    ipvt[j] = j;
+  }
+  const int minmn = m < LM_N ? m : LM_N;
+#pragma unroll 1
+  for (int j = 0; j < minmn; ++j) {
+    int kmax = j;
+    for (int k = j; k < LM_N; ++k)
+      if (rdiag[k] > rdiag[kmax]) kmax = k;
+    if (kmax != j) {
+#pragma unroll 1
+      for (int i = 0; i < m; ++i) {
+        const double t = fj[j][i];
+        fj[j][i] = fj[kmax][i];
+        fj[kmax][i] = t;
       }
-      double ajnorm = enorm(m - j, fj[j] + j);
-      if (ajnorm != 0.0) {
-        if (fj[j][j] < 0.0) ajnorm = -ajnorm;
-        for (int i = j; i < m; ++i) fj[j][i] /= ajnorm;
-        fj[j][j] += 1.0;
-        for (int k = j + 1; k < LM_N; ++k) {
-          double s = 0.0;
-          for (int i = j; i < m; ++i) s += fj[j][i] * fj[k][i];
-          const double t = s / fj[j][j];
-          for (int i = j; i < m; ++i) fj[k][i] -= t * fj[j][i];
-          if (rdiag[k] != 0.0) {
-            const double u = fj[k][j] / rdiag[k];
-            rdiag[k] *= sqrt(fmax(0.0, 1.0 - u * u));
-            const double q = rdiag[k] / wq[k];
-            if (0.05 * q * q <= LM_EPSMCH) {
-              rdiag[k] = enorm(m - j - 1, fj[k] + j + 1);
-              wq[k] = rdiag[k];
-            }
+      rdiag[kmax] = rdiag[j];
+      wq[kmax] = wq[j];
+      const int t = ipvt[j];
+      ipvt[j] = ipvt[kmax];
+      ipvt[kmax] = t;
+    }
+    double ajnorm = enorm(m - j, fj[j] + j);
+    if (ajnorm != 0.0) {
+      if (fj[j][j] < 0.0) ajnorm = -ajnorm;
+#pragma unroll 1
+      for (int i = j; i < m; ++i) fj[j][i] /= ajnorm;
+      fj[j][j] += 1.0;
+#pragma unroll 1
+      for (int k = j + 1; k < LM_N; ++k) {
+        double s = 0.0;
+#pragma unroll 1
+        for (int i = j; i < m; ++i) s += fj[j][i] * fj[k][i];
+        const double t = s / fj[j][j];
+#pragma unroll 1
+        for (int i = j; i < m; ++i) fj[k][i] -= t * fj[j][i];
+        if (rdiag[k] != 0.0) {
+          const double u = fj[k][j] / rdiag[k];
+          rdiag[k] *= sqrt(fmax(0.0, 1.0 - u * u));
+          const double q = rdiag[k] / wq[k];
+          if (0.05 * q * q <= LM_EPSMCH) {
+            rdiag[k] = enorm(m - j - 1, fj[k] + j + 1);
+            wq[k] = rdiag[k];
           }
         }
       }
-      rdiag[j] = -ajnorm;
     }
-    if (iter == 1) {
-      for (int j = 0; j < LM_N; ++j) {
-        diag[j] = acn[j] == 0.0 ? 1.0 : acn[j];
-        wa3[j] = diag[j] * x[j];
-      }
-      xnorm = enorm(LM_N, wa3);
-      delta = 100.0 * xnorm;
-      if (delta == 0.0) delta = 100.0;
-    }
-    // first n components of Q^T fvec
-    for (int i = 0; i < m; ++i) wa4[i] = fvec[i];
-    for (int j = 0; j < LM_N; ++j) {
-      if (j < m && fj[j][j] != 0.0) {
-        double s = 0.0;
-        for (int i = j; i < m; ++i) s += fj[j][i] * wa4[i];
-        const double t = -s / fj[j][j];
-        for (int i = j; i < m; ++i) wa4[i] += fj[j][i] * t;
-      }
-      if (j < m) fj[j][j] = rdiag[j];
-      qtf[j] = j < m ? wa4[j] : 0.0;
-    }
-    for (int j = 0; j < LM_N; ++j)
-      for (int i = 0; i < LM_N; ++i) r[i][j] = (i <= j && i < m) ? fj[j][i] : 0.0;
-    // norm of the scaled gradient
-    double gnorm = 0.0;
-    if (fnorm != 0.0) {
-      for (int j = 0; j < LM_N; ++j) {
-        const int l = ipvt[j];
-        if (acn[l] != 0.0) {
-          double s = 0.0;
-          for (int i = 0; i <= j; ++i) s += r[i][j] * (qtf[i] / fnorm);
-          const double g = fabs(s / acn[l]);
-          if (g > gnorm) gnorm = g;  // max(gnorm, NaN) keeps gnorm, as the Fortran does
-        }
-      }
-    }
-    if (gnorm <= 0.0) {  // gtol = 0
-      info = 4;
-      break;
-    }
-    for (int j = 0; j < LM_N; ++j) diag[j] = fmax(diag[j], acn[j]);
-    for (;;) {
-      par = lmpar3(r, ipvt, diag, qtf, delta, par, wa1, sdiag);
-      for (int j = 0; j < LM_N; ++j) {
-        wa1[j] = -wa1[j];
-        wa2[j] = x[j] + wa1[j];
-        wa3[j] = diag[j] * wa1[j];
-      }
-      const double pnorm = enorm(LM_N, wa3);
-      if (iter == 1) delta = fmin(delta, pnorm);
-      gauss_residuals(wa2, y, m, wa4);
-      ++nfev;
-      const double fnorm1 = enorm(m, wa4);
-      double actred = -1.0;
-      if (0.1 * fnorm1 < fnorm) {
-        const double q = fnorm1 / fnorm;
-        actred = 1.0 - q * q;
-      }
-      for (int j = 0; j < LM_N; ++j) wa3[j] = 0.0;
-      for (int j = 0; j < LM_N; ++j) {
-        const double t = wa1[ipvt[j]];
-        for (int i = 0; i <= j; ++i) wa3[i] += r[i][j] * t;
-      }
-      const double temp1 = enorm(LM_N, wa3) / fnorm, temp2 = (sqrt(par) * pnorm) / fnorm;
-      const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
-      const double dirder = -(temp1 * temp1 + temp2 * temp2);
-      const double ratio = prered != 0.0 ? actred / prered : 0.0;
-      if (ratio <= 0.25) {
-        double t = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
-        if (0.1 * fnorm1 >= fnorm || t < 0.1) t = 0.1;
-        delta = t * fmin(delta, pnorm / 0.1);
-        par /= t;
-      } else if (par == 0.0 || ratio >= 0.75) {
-        delta = pnorm / 0.5;
-        par *= 0.5;
-      }
-      if (ratio >= 1e-4) {
-        for (int j = 0; j < LM_N; ++j) {
-          x[j] = wa2[j];
-          wa2[j] = diag[j] * x[j];
-        }
-        for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
-        xnorm = enorm(LM_N, wa2);
-        fnorm = fnorm1;
-        ++iter;
-      }
-      const bool fconv = fabs(actred) <= LM_TOL && prered <= LM_TOL && 0.5 * ratio <= 1.0;
-      if (fconv) info = 1;
-      if (delta <= LM_TOL * xnorm) info = 2;
-      if (fconv && info == 2) info = 3;
-      if (info != 0) break;
-      if (nfev >= LM_MAXFEV) info = 5;
-      if (fabs(actred) <= LM_EPSMCH && prered <= LM_EPSMCH && 0.5 * ratio <= 1.0) info = 6;
-      if (delta <= LM_EPSMCH * xnorm) info = 7;
-      if (gnorm <= LM_EPSMCH) info = 8;
-      if (info != 0) break;
-      if (ratio >= 1e-4) break;
-    }
-    if (info != 0) break;
+    rdiag[j] = -ajnorm;
   }
-  *nfev_out = nfev;
+  if (S.iter == 1) {
+    for (int j = 0; j < LM_N; ++j) {
+      diag[j] = acn[j] == 0.0 ? 1.0 : acn[j];
+      wa3[j] = diag[j] * x[j];
+    }
+    S.xnorm = enorm(LM_N, wa3);
+    S.delta = 100.0 * S.xnorm;
+    if (S.delta == 0.0) S.delta = 100.0;
+  }
+  // first n components of Q^T fvec
+#pragma unroll 1
+  for (int i = 0; i < m; ++i) wa4[i] = fvec[i];
+#pragma unroll 1
+  for (int j = 0; j < LM_N; ++j) {
+    if (j < m && fj[j][j] != 0.0) {
+      double s = 0.0;
+#pragma unroll 1
+      for (int i = j; i < m; ++i) s += fj[j][i] * wa4[i];
+      const double t = -s / fj[j][j];
+#pragma unroll 1
+      for (int i = j; i < m; ++i) wa4[i] += fj[j][i] * t;
+    }
+    if (j < m) fj[j][j] = rdiag[j];
+    qtf[j] = j < m ? wa4[j] : 0.0;
+  }
+  for (int j = 0; j < LM_N; ++j)
+    for (int i = 0; i < LM_N; ++i) r[i][j] = (i <= j && i < m) ? fj[j][i] : 0.0;
+  // norm of the scaled gradient
+  double gnorm = 0.0;
+  if (S.fnorm != 0.0) {
+    for (int j = 0; j < LM_N; ++j) {
+      const int l = ipvt[j];
+      if (acn[l] != 0.0) {
+        double s = 0.0;
+        for (int i = 0; i <= j; ++i) s += r[i][j] * (qtf[i] / S.fnorm);
+        const double g = fabs(s / acn[l]);
+        if (g > gnorm) gnorm = g;  // max(gnorm, NaN) keeps gnorm, as the Fortran does
+      }
+    }
+  }
+  if (gnorm <= 0.0) return 4;  // gtol = 0
+  for (int j = 0; j < LM_N; ++j) diag[j] = fmax(diag[j], acn[j]);
+#pragma unroll 1
+  for (;;) {
+    S.par = lmpar3(r, ipvt, diag, qtf, S.delta, S.par, wa1, sdiag);
+    for (int j = 0; j < LM_N; ++j) {
+      wa1[j] = -wa1[j];
+      wa2[j] = x[j] + wa1[j];
+      wa3[j] = diag[j] * wa1[j];
+    }
+    const double pnorm = enorm(LM_N, wa3);
+    if (S.iter == 1) S.delta = fmin(S.delta, pnorm);
+    gauss_residuals(wa2, S.y, m, wa4);
+    ++S.nfev;
+    const double fnorm1 = enorm(m, wa4);
+    double actred = -1.0;
+    if (0.1 * fnorm1 < S.fnorm) {
+      const double q = fnorm1 / S.fnorm;
+      actred = 1.0 - q * q;
+    }
+    for (int j = 0; j < LM_N; ++j) wa3[j] = 0.0;
+    for (int j = 0; j < LM_N; ++j) {
+      const double t = wa1[ipvt[j]];
+      for (int i = 0; i <= j; ++i) wa3[i] += r[i][j] * t;
+    }
+    const double temp1 = enorm(LM_N, wa3) / S.fnorm, temp2 = (sqrt(S.par) * pnorm) / S.fnorm;
+    const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+    const double dirder = -(temp1 * temp1 + temp2 * temp2);
+    const double ratio = prered != 0.0 ? actred / prered : 0.0;
+    if (ratio <= 0.25) {
+      double t = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+      if (0.1 * fnorm1 >= S.fnorm || t < 0.1) t = 0.1;
+      S.delta = t * fmin(S.delta, pnorm / 0.1);
+      S.par /= t;
+    } else if (S.par == 0.0 || ratio >= 0.75) {
+      S.delta = pnorm / 0.5;
+      S.par *= 0.5;
+    }
+    if (ratio >= 1e-4) {
+      for (int j = 0; j < LM_N; ++j) {
+        x[j] = wa2[j];
+        wa2[j] = diag[j] * x[j];
+      }
+#pragma unroll 1
+      for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
+      S.xnorm = enorm(LM_N, wa2);
+      S.fnorm = fnorm1;
+      ++S.iter;
+    }
+    const bool fconv = fabs(actred) <= LM_TOL && prered <= LM_TOL && 0.5 * ratio <= 1.0;
+    if (fconv) info = 1;
+    if (S.delta <= LM_TOL * S.xnorm) info = 2;
+    if (fconv && info == 2) info = 3;
+    if (info != 0) break;
+    if (S.nfev >= LM_MAXFEV) info = 5;
+    if (fabs(actred) <= LM_EPSMCH && prered <= LM_EPSMCH && 0.5 * ratio <= 1.0) info = 6;
+    if (S.delta <= LM_EPSMCH * S.xnorm) info = 7;
+    if (gnorm <= LM_EPSMCH) info = 8;
+    if (info != 0) break;
+    if (ratio >= 1e-4) break;
+  }
   return info;
 }
 
@@ -600,20 +646,21 @@ __device__ double numpy_sum(int n, F term) {
   return s;
 }
 
-// util.py:487-502: start values, the fit, the per-peak rejections.  One thread per peak.
-__global__ void __launch_bounds__(64) refine_fit_kernel(const rb2_refine_desc* __restrict__ descs) {
-  const rb2_refine_desc d = descs[blockIdx.y];  // the host offsets `descs` when the batch exceeds gridDim.y
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= refine_count(d)) return;
+// util.py:487-502: start values, the fit, the per-peak rejections.  One WARP per spectrum: every lane
+// fits one peak at a time and takes the spectrum's next unfitted peak when it is done; the lanes meet at
+// every outer Levenberg-Marquardt iteration (the __any_sync below), so a warp executes the iteration's
+// code once for all its lanes instead of once per straggler.
+__device__ __noinline__ bool refine_fit_begin(const rb2_refine_desc& d, int k, LMState& S) {
   double* fit = d.d_fit + (size_t)k * 4;
   fit[0] = fit[1] = fit[2] = CUDART_NAN;
   fit[3] = 0.0;
-  if (d.d_status[k] != RB2_PEAK_OK) return;
-  const int ww = d.window_width, n = d.n_pix;
+  if (d.d_status[k] != RB2_PEAK_OK) return false;
+  const int ww = d.window_width;
   const int ip = (int)d.d_peaks[k];
-  const int lo = max(0, ip - ww), hi = min(ip + ww, n), m = hi - lo;
-  double y[LM_WMAX];
+  const int lo = max(0, ip - ww), hi = min(ip + ww, d.n_pix), m = hi - lo;
   const double* __restrict__ w = d.d_window + (size_t)k * 2 * ww;
+  double* y = S.y;
+#pragma unroll 1
   for (int i = 0; i < m; ++i) y[i] = w[i];
   const double cnt = (double)m;
   const double mean = numpy_sum(m, [&](int i) { return mul((double)i, y[i]); }) / cnt;
@@ -621,18 +668,57 @@ __global__ void __launch_bounds__(64) refine_fit_kernel(const rb2_refine_desc* _
                          const double dx = sub((double)i, mean);
                          return mul(y[i], mul(dx, dx));
                        }) / cnt;
-  double p[LM_N] = {1.0, mean, sigma};
-  int nfev = 0;
-  const int ier = lmdif_gauss(y, m, p, &nfev);
-  fit[0] = p[0];
-  fit[1] = p[1];
-  fit[2] = p[2];
-  fit[3] = (double)nfev;
+  S.m = m;
+  S.x[0] = 1.0;
+  S.x[1] = mean;
+  S.x[2] = sigma;
+  lm_start(S);
+  return true;
+}
+
+__device__ __noinline__ void refine_fit_end(const rb2_refine_desc& d, int k, const LMState& S, int ier) {
+  double* fit = d.d_fit + (size_t)k * 4;
+  fit[0] = S.x[0];
+  fit[1] = S.x[1];
+  fit[2] = S.x[2];
+  fit[3] = (double)S.nfev;
   int status = RB2_PEAK_OK;
   if (ier < 1 || ier > 4) status = RB2_PEAK_FIT_FAILED;
-  else if (p[0] < 0.0) status = RB2_PEAK_NEGATIVE;
-  else if (p[1] > (double)n || p[1] < 0.0) status = RB2_PEAK_OUTSIDE;
+  else if (S.x[0] < 0.0) status = RB2_PEAK_NEGATIVE;
+  else if (S.x[1] > (double)d.n_pix || S.x[1] < 0.0) status = RB2_PEAK_OUTSIDE;
   d.d_status[k] = status | (ier << 8);
+}
+
+constexpr int FIT_WARPS = 2;
+
+__global__ void __launch_bounds__(32 * FIT_WARPS) refine_fit_kernel(const rb2_refine_desc* __restrict__ descs, int n_spectra) {
+  const int s = blockIdx.x * FIT_WARPS + (threadIdx.x >> 5);
+  if (s >= n_spectra) return;  // whole warp
+  const rb2_refine_desc d = descs[s];
+  const int np = refine_count(d);
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  LMState S;
+  int next = 0, k = -1;  // next: warp-uniform
+  bool run = false;
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xffffffffu, !run);
+    if (!run) {
+      k = next + __popc(idle & lt);
+      if (k < np) run = refine_fit_begin(d, k, S);
+    }
+    next += __popc(idle);
+    if (!__any_sync(0xffffffffu, run)) {
+      if (next >= np) break;
+      continue;
+    }
+    if (run) {
+      const int ier = lm_iterate(S);
+      if (ier != 0) {
+        refine_fit_end(d, k, S, ier);
+        run = false;
+      }
+    }
+  }
 }
 
 // util.py:499, 509-517: peak - window_width + centre, the (0, n_pix) mask and the np.isclose
@@ -700,8 +786,8 @@ extern "C" int rb2_refine_peaks(int n_spectra, const rb2_refine_desc* d_desc, co
   cudaStream_t st = (cudaStream_t)stream_;
   refine_windows_kernel<<<n_spectra, 128, 0, st>>>(d_desc);
   RB2_CHECK(cudaGetLastError());
-  for (int base = 0; max_peaks > 0 && base < n_spectra; base += 65535) {
-    refine_fit_kernel<<<dim3((max_peaks + 63) / 64, min(65535, n_spectra - base)), 64, 0, st>>>(d_desc + base);
+  if (max_peaks > 0) {
+    refine_fit_kernel<<<(n_spectra + FIT_WARPS - 1) / FIT_WARPS, 32 * FIT_WARPS, 0, st>>>(d_desc, n_spectra);
     RB2_CHECK(cudaGetLastError());
   }
   refine_collect_kernel<<<(n_spectra + 63) / 64, 64, 0, st>>>(d_desc, n_spectra);

@@ -31,6 +31,35 @@ from .engine import TRANSFER, _torch, current_stream_ptr
 _UNSUPPORTED = ("threshold", "width", "wlen", "rel_height", "plateau_size")
 
 
+class _Staging:
+    """Grow-only pinned staging buffers, one per purpose, reused across calls (cudaHostAlloc costs
+    milliseconds); an event guards the previous copy out of the buffer before it is overwritten."""
+
+    def __init__(self):
+        self.buf, self.evt = {}, {}
+
+    def upload(self, key, arr):
+        """Copy a contiguous numpy array to a new device tensor through the pinned buffer `key`."""
+        torch = _torch()
+        a = np.ascontiguousarray(arr).reshape(-1).view(np.uint8)
+        n = max(a.nbytes, 8)
+        buf = self.buf.get(key)
+        if buf is None or buf.numel() < n:
+            buf = self.buf[key] = torch.empty(max(n, 1 << 16) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+        elif key in self.evt:
+            self.evt[key].synchronize()
+        buf.numpy()[:a.nbytes] = a
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dev[:a.nbytes].copy_(buf[:a.nbytes], non_blocking=True)
+        ev = self.evt[key] = torch.cuda.Event()
+        ev.record()
+        TRANSFER["h2d"] += a.nbytes
+        return dev
+
+
+_STAGE = _Staging()
+
+
 def _scalar_min(name, v):
     if v is None:
         return float("nan")
@@ -54,13 +83,8 @@ class PeakBatch:
         self.n_pix = np.array([len(s) for s in self.spectra], dtype=np.int64)
         self.pix_off = np.concatenate(([0], np.cumsum(self.n_pix)))
         total = int(self.pix_off[-1])
-        host = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
-        hv = host.numpy()
-        for o, s in zip(self.pix_off[:-1], self.spectra):
-            hv[o:o + len(s)] = s
-        self.d_spec = host.cuda(non_blocking=True)
-        self._host = host
-        TRANSFER["h2d"] += total * 8
+        flat = np.concatenate(self.spectra) if total else np.zeros(1)
+        self.d_spec = _STAGE.upload("spectra", flat).view(torch.float64)
         self._found = None
         self._refined = None
 
@@ -138,12 +162,8 @@ class PeakBatch:
             pl = [np.asarray(p, dtype=np.float64).reshape(-1) for p in peaks]
             cap = np.array([len(p) for p in pl], dtype=np.int64)
             off = np.concatenate(([0], np.cumsum(cap)))
-            host = torch.empty(max(int(off[-1]), 1), dtype=torch.float64, pin_memory=True)
-            if off[-1]:
-                host.numpy()[:off[-1]] = np.concatenate(pl)
-            d_peaks, d_cnt = host.cuda(non_blocking=True), None
-            self._peaks_host = host
-            TRANSFER["h2d"] += int(off[-1]) * 8
+            flat = np.concatenate(pl) if off[-1] else np.zeros(1)
+            d_peaks, d_cnt = _STAGE.upload("peaks", flat).view(torch.float64), None
         tot = max(int(off[-1]), 1)
         r = dict(cap=cap, off=off, ww=ww, d_peaks=d_peaks,
                  work=torch.empty(max(int(self.pix_off[-1]), 1), dtype=torch.float64, device="cuda"),
@@ -204,12 +224,7 @@ class PeakBatch:
         return (out, det) if details else out
 
     def _upload(self, desc):
-        torch = _torch()
-        host = torch.empty(max(desc.nbytes, 1), dtype=torch.uint8, pin_memory=True)
-        host.numpy()[:desc.nbytes] = desc.view(np.uint8).reshape(-1)
-        TRANSFER["h2d"] += desc.nbytes
-        self._desc_host = host
-        return host.cuda(non_blocking=True)
+        return _STAGE.upload("desc", desc.view(np.uint8))
 
 
 def find_peaks(x, height=None, threshold=None, distance=None, prominence=None, **kwargs):

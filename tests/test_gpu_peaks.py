@@ -262,6 +262,10 @@ def test_found_peaks_feed_the_calibrator_batch():
                 fit=dict(fit_deg=2, candidate_tolerance=5.0))
     res = calibrate_batch([spec], n_hypotheses=4096, seed=1)
     r = res[0]
+    # the same through the batch entry point, from the spectrum itself
+    spec2 = dict(spec, peaks=None, spectrum=spectrum, find_peaks=dict(height=200, distance=5), window_width=5)
+    r2 = calibrate_batch([spec2], n_hypotheses=4096, seed=1)[0]
+    assert np.array_equal(np.asarray(r2.fit_coeff), np.asarray(r.fit_coeff))
     assert r.fit_coeff is not None
     fit = np.polynomial.polynomial.polyval(centres, np.asarray(r.fit_coeff))
     assert np.median(np.abs(fit - lines)) < 1.0
