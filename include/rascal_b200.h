@@ -418,8 +418,10 @@ int rb2_find_peaks(int n_spectra, const rb2_findpeaks_desc *d_desc,
  * (ier not in 1..4), the height is negative or the centre leaves [0, n_pix]
  * (:491-502); the survivors peak - w + centre are filtered to (0, n_pix) and
  * de-duplicated against their predecessor with np.isclose (:509-517).
- * Three launches: windows (one CTA per spectrum), fits (one warp per spectrum,
- * one peak per lane at a time), collection (one thread per spectrum). */
+ * Four launches: windows (one CTA per spectrum), the scan that turns the peak
+ * counts into one work queue, fits (persistent one-warp CTAs; an idle lane
+ * takes the batch's next peak), collection (one thread per spectrum).
+ * d_scratch: rb2_refine_scratch_bytes(n_spectra) bytes. */
 typedef enum {
   RB2_PEAK_OK = 0,          /* fitted and appended (it may still fall to the final range / isclose filter) */
   RB2_PEAK_NO_DATA = 1,     /* no finite sample in the window (:484-485)      */
@@ -448,8 +450,10 @@ typedef struct {
   int32_t *d_n_refined;                 /* out: [1]                          */
 } rb2_refine_desc;
 
+size_t rb2_refine_scratch_bytes(int n_spectra);
 int rb2_refine_peaks(int n_spectra, const rb2_refine_desc *d_desc,
-                     const rb2_refine_desc *h_desc, void *stream);
+                     const rb2_refine_desc *h_desc, void *d_scratch,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -164,7 +164,8 @@ EXPORTS = {
     "rb2_match_peaks": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_refit_winners": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_double, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_find_peaks": (C.c_int, [C.c_int, _vp, _vp, _vp]),
-    "rb2_refine_peaks": (C.c_int, [C.c_int, _vp, _vp, _vp]),
+    "rb2_refine_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "rb2_refine_peaks": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -8,10 +8,10 @@
 //                        rascal util.refine_peaks (util.py:450-523): the in-place window
 //                        normalisation is sequential per spectrum (one warp walks the peaks),
 //                        the Gaussian fits are independent (MINPACK's lmdif, n = 3, as
-//                        scipy.optimize.curve_fit runs it: one warp per spectrum, one peak per lane,
-//                        lanes refilled from the spectrum's remaining peaks and kept in step at
-//                        every outer iteration), the final range / np.isclose filter is
-//                        sequential again.
+//                        scipy.optimize.curve_fit runs it: persistent one-warp CTAs, one peak per
+//                        lane, idle lanes refilled from a queue over the whole batch, the lanes of
+//                        a warp kept in step at every outer iteration), the final range /
+//                        np.isclose filter is sequential again.
 //
 // The Levenberg-Marquardt code below is written from the published MINPACK-1 algorithm (More,
 // Garbow, Hillstrom 1980: lmdif, lmpar, qrfac, qrsolv, enorm, fdjac2) specialised to three
@@ -207,6 +207,10 @@ constexpr double LM_EPSMCH = DBL_EPSILON;
 constexpr double LM_DWARF = DBL_MIN;
 constexpr double LM_TOL = 1.49012e-8;  // scipy.optimize.leastsq: ftol = xtol
 constexpr int LM_MAXFEV = 200 * (LM_N + 1);
+#ifndef RB2_LM_UNROLL
+#define RB2_LM_UNROLL 1
+#endif
+constexpr int LM_UNROLL = RB2_LM_UNROLL;  // unrolling of the loops over the independent points of a window
 
 // Euclidean norm with MINPACK's three accumulators (small / intermediate / large components)
 __device__ __noinline__ double enorm(int n, const double* v) {
@@ -248,7 +252,8 @@ __device__ __noinline__ double enorm(int n, const double* v) {
 // residuals of util.gauss (util.py:447) on x = 0..m-1, each NumPy ufunc rounded on its own
 __device__ __noinline__ void gauss_residuals(const double* p, const double* __restrict__ y, int m, double* __restrict__ f) {
   const double den = add(mul(2.0, mul(p[2], p[2])), 1e-9);
-  for (int i = 0; i < m; ++i) {
+#pragma unroll LM_UNROLL
+  for (int i = 0; i < m; ++i) {  // independent points: unrolled so that one lane overlaps their div / exp chains
     const double dx = sub((double)i, p[1]);
     f[i] = sub(mul(p[0], exp(-mul(dx, dx) / den)), y[i]);
   }
@@ -421,7 +426,7 @@ __device__ __noinline__ int lm_iterate(LMState& S) {
     x[j] = t + h;
     gauss_residuals(x, S.y, m, wa4);
     x[j] = t;
-#pragma unroll 1
+#pragma unroll LM_UNROLL
     for (int i = 0; i < m; ++i) fj[j][i] = (wa4[i] - fvec[i]) / h;
   }
   S.nfev += LM_N;
@@ -454,7 +459,7 @@ __device__ __noinline__ int lm_iterate(LMState& S) {
     double ajnorm = enorm(m - j, fj[j] + j);
     if (ajnorm != 0.0) {
       if (fj[j][j] < 0.0) ajnorm = -ajnorm;
-#pragma unroll 1
+#pragma unroll LM_UNROLL
       for (int i = j; i < m; ++i) fj[j][i] /= ajnorm;
       fj[j][j] += 1.0;
 #pragma unroll 1
@@ -463,7 +468,7 @@ __device__ __noinline__ int lm_iterate(LMState& S) {
 #pragma unroll 1
         for (int i = j; i < m; ++i) s += fj[j][i] * fj[k][i];
         const double t = s / fj[j][j];
-#pragma unroll 1
+#pragma unroll LM_UNROLL
         for (int i = j; i < m; ++i) fj[k][i] -= t * fj[j][i];
         if (rdiag[k] != 0.0) {
           const double u = fj[k][j] / rdiag[k];
@@ -497,7 +502,7 @@ __device__ __noinline__ int lm_iterate(LMState& S) {
 #pragma unroll 1
       for (int i = j; i < m; ++i) s += fj[j][i] * wa4[i];
       const double t = -s / fj[j][j];
-#pragma unroll 1
+#pragma unroll LM_UNROLL
       for (int i = j; i < m; ++i) wa4[i] += fj[j][i] * t;
     }
     if (j < m) fj[j][j] = rdiag[j];
@@ -592,9 +597,11 @@ __device__ __forceinline__ int refine_count(const rb2_refine_desc& d) {
 }
 
 // util.py:471-485: working copy, then per peak (in order) the window divided by its nanmax in place.
-__global__ void __launch_bounds__(128) refine_windows_kernel(const rb2_refine_desc* __restrict__ descs) {
+__global__ void __launch_bounds__(128) refine_windows_kernel(const rb2_refine_desc* __restrict__ descs,
+                                                             int* __restrict__ item_off) {
   const rb2_refine_desc d = descs[blockIdx.x];
   const int n = d.n_pix;
+  if (threadIdx.x == 0) item_off[blockIdx.x] = refine_count(d);  // scanned by refine_queue_kernel
   for (int i = threadIdx.x; i < n; i += blockDim.x) d.d_work[i] = d.d_spectrum[i];
   __syncthreads();
   if (threadIdx.x >= 32) return;
@@ -646,10 +653,11 @@ __device__ double numpy_sum(int n, F term) {
   return s;
 }
 
-// util.py:487-502: start values, the fit, the per-peak rejections.  One WARP per spectrum: every lane
-// fits one peak at a time and takes the spectrum's next unfitted peak when it is done; the lanes meet at
-// every outer Levenberg-Marquardt iteration (the __any_sync below), so a warp executes the iteration's
-// code once for all its lanes instead of once per straggler.
+// util.py:487-502: start values, the fit, the per-peak rejections.  Every lane fits one peak at a time
+// and takes the batch's next unfitted peak when it is done (most fits need ~10 outer iterations, one in
+// a hundred needs 50-200: a fixed peak-to-lane map leaves 26 of 32 lanes idle); the lanes of a warp meet
+// at every outer Levenberg-Marquardt iteration (the __any_sync), so the iteration's code runs once for
+// all of them.
 __device__ __noinline__ bool refine_fit_begin(const rb2_refine_desc& d, int k, LMState& S) {
   double* fit = d.d_fit + (size_t)k * 4;
   fit[0] = fit[1] = fit[2] = CUDART_NAN;
@@ -689,32 +697,71 @@ __device__ __noinline__ void refine_fit_end(const rb2_refine_desc& d, int k, con
   d.d_status[k] = status | (ier << 8);
 }
 
-constexpr int FIT_WARPS = 2;
+// Work queue of the fits: item_off[0..n] = exclusive prefix of the per-spectrum peak counts (in
+// place over the counts refine_windows_kernel left), item_off[n + 1] = the queue head.
+__global__ void __launch_bounds__(1024) refine_queue_kernel(int* __restrict__ item_off, int n) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, chunk = (n + 1023) / 1024;
+  const int b = min(n, t * chunk), e = min(n, b + chunk);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += item_off[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = t >= o ? s_part[t - o] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = s_part[t] - sum;
+  for (int i = b; i < e; ++i) {
+    const int c = item_off[i];
+    item_off[i] = run;
+    run += c;
+  }
+  if (t == 1023) {
+    item_off[n] = s_part[1023];
+    item_off[n + 1] = 0;
+  }
+}
 
-__global__ void __launch_bounds__(32 * FIT_WARPS) refine_fit_kernel(const rb2_refine_desc* __restrict__ descs, int n_spectra) {
-  const int s = blockIdx.x * FIT_WARPS + (threadIdx.x >> 5);
-  if (s >= n_spectra) return;  // whole warp
-  const rb2_refine_desc d = descs[s];
-  const int np = refine_count(d);
-  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+// One-warp CTAs, persistent: an idle lane takes the next (spectrum, peak) item of the whole batch.
+__global__ void __launch_bounds__(32) refine_fit_kernel(const rb2_refine_desc* __restrict__ descs, int n_spectra,
+                                                        int* __restrict__ item_off) {
+  const int total = item_off[n_spectra];
+  const unsigned lane = threadIdx.x, lt = (1u << lane) - 1u;
   LMState S;
-  int next = 0, k = -1;  // next: warp-uniform
-  bool run = false;
+  const rb2_refine_desc* dp = nullptr;
+  int k = -1;
+  bool run = false, drained = false;  // drained: warp-uniform
   for (;;) {
     const unsigned idle = __ballot_sync(0xffffffffu, !run);
-    if (!run) {
-      k = next + __popc(idle & lt);
-      if (k < np) run = refine_fit_begin(d, k, S);
+    if (idle && !drained) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&item_off[n_spectra + 1], __popc(idle));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      drained = base + __popc(idle) >= total;
+      const int item = base + __popc(idle & lt);
+      if (!run && item < total) {
+        int lo = 0, hi = n_spectra - 1;  // last s with item_off[s] <= item
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (item_off[mid] <= item) lo = mid;
+          else hi = mid - 1;
+        }
+        dp = descs + lo;
+        k = item - item_off[lo];
+        run = refine_fit_begin(*dp, k, S);
+      }
     }
-    next += __popc(idle);
     if (!__any_sync(0xffffffffu, run)) {
-      if (next >= np) break;
+      if (drained) break;
       continue;
     }
     if (run) {
       const int ier = lm_iterate(S);
       if (ier != 0) {
-        refine_fit_end(d, k, S, ier);
+        refine_fit_end(*dp, k, S, ier);
         run = false;
       }
     }
@@ -771,23 +818,34 @@ extern "C" int rb2_find_peaks(int n_spectra, const rb2_findpeaks_desc* d_desc, c
   return RB2_OK;
 }
 
+extern "C" size_t rb2_refine_scratch_bytes(int n_spectra) { return sizeof(int) * ((size_t)max(n_spectra, 0) + 2); }
+
 extern "C" int rb2_refine_peaks(int n_spectra, const rb2_refine_desc* d_desc, const rb2_refine_desc* h_desc,
-                                void* stream_) {
+                                void* d_scratch, void* stream_) {
   using namespace rb2;
-  if (n_spectra <= 0 || !d_desc || !h_desc) return RB2_ERR_ARG;
-  int max_peaks = 0;
+  if (n_spectra <= 0 || !d_desc || !h_desc || !d_scratch) return RB2_ERR_ARG;
+  long long items = 0;
   for (int i = 0; i < n_spectra; ++i) {
     const rb2_refine_desc& h = h_desc[i];
     if (h.n_pix < 0 || h.n_peaks < 0 || h.window_width < 1 || h.window_width > RB2_REFINE_MAX_WINDOW) return RB2_ERR_ARG;
     if ((h.n_pix && (!h.d_spectrum || !h.d_work)) || !h.d_n_refined) return RB2_ERR_ARG;
     if (h.n_peaks && (!h.d_peaks || !h.d_window || !h.d_fit || !h.d_status || !h.d_refined)) return RB2_ERR_ARG;
-    max_peaks = max(max_peaks, h.n_peaks);
+    items += h.n_peaks;
   }
+  if (items > 0x7fffffffLL) return RB2_ERR_CAPACITY;
   cudaStream_t st = (cudaStream_t)stream_;
-  refine_windows_kernel<<<n_spectra, 128, 0, st>>>(d_desc);
+  int* item_off = (int*)d_scratch;
+  refine_windows_kernel<<<n_spectra, 128, 0, st>>>(d_desc, item_off);
   RB2_CHECK(cudaGetLastError());
-  if (max_peaks > 0) {
-    refine_fit_kernel<<<(n_spectra + FIT_WARPS - 1) / FIT_WARPS, 32 * FIT_WARPS, 0, st>>>(d_desc, n_spectra);
+  if (items > 0) {
+    int sms = 0;
+    const int rc = rb2_sm_count(&sms);
+    if (rc != RB2_OK) return rc;
+    refine_queue_kernel<<<1, 1024, 0, st>>>(item_off, n_spectra);
+    RB2_CHECK(cudaGetLastError());
+    // ~116 registers per thread: 16-17 one-warp CTAs fit an SM; `items` is an upper bound of the queue length
+    const int warps = (int)min((long long)sms * 16, (items + 31) / 32);
+    refine_fit_kernel<<<warps, 32, 0, st>>>(d_desc, n_spectra, item_off);
     RB2_CHECK(cudaGetLastError());
   }
   refine_collect_kernel<<<(n_spectra + 63) / 64, 64, 0, st>>>(d_desc, n_spectra);

@@ -184,7 +184,9 @@ class PeakBatch:
         desc["d_refined"] = r["refined"].data_ptr() + 8 * off[:-1]
         desc["d_n_refined"] = r["count"].data_ptr() + 4 * np.arange(self.n)
         d_desc = self._upload(desc)
-        rc = self.lib.rb2_refine_peaks(self.n, d_desc.data_ptr(), desc.ctypes.data, current_stream_ptr())
+        r["queue"] = torch.empty(int(self.lib.rb2_refine_scratch_bytes(self.n)), dtype=torch.uint8, device="cuda")
+        rc = self.lib.rb2_refine_peaks(self.n, d_desc.data_ptr(), desc.ctypes.data, r["queue"].data_ptr(),
+                                       current_stream_ptr())
         N.check(rc, "rb2_refine_peaks")
         r["desc"] = (desc, d_desc)
         r["d_cnt_in"] = d_cnt
