@@ -501,6 +501,17 @@ def main():
                     "peaks_per_s": n_ref / (t_all * 1e-3), "spectra_per_s": n_arc / (t_all * 1e-3),
                     "e2e_spectra_per_s": n_arc / t_pk, "median_offset_from_true_centre_px": float(np.median(off_px)),
                     "algorithmic_bytes": int(sum(8 * len(a) for a in arcs) + 8 * n_ref)}
+        # the whole chain from the arcs: K6 -> K1..K5 through calibrate_batch(spectrum=...)
+        arc_specs = [dict(specs[i], peaks=None, spectrum=arcs[i], find_peaks=recipe, window_width=5, max_peaks=256)
+                     for i in range(n_arc)]
+        batch.calibrate_batch(arc_specs, n_hypotheses=10_000, seed=1, match_tolerance=5.0)  # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ares = batch.calibrate_batch(arc_specs, n_hypotheses=10_000, seed=1, match_tolerance=5.0)
+        torch.cuda.synchronize()
+        t_arc = time.perf_counter() - t0
+        peak_leg["arcs_to_solutions_per_s"] = n_arc / t_arc
+        peak_leg["arcs_fitted"] = sum(r.fit_coeff is not None for r in ares)
         if not args.no_cpu:
             from scipy.signal import find_peaks as sp_find
 

@@ -174,7 +174,7 @@ def peaks_from_spectra(spectra):
         found = util.find_and_refine([out[i]["spectrum"] for i in idx], height=h, distance=d, prominence=p,
                                      window_width=ww, max_peaks=cap)
         for i, pk in zip(idx, found):
-            out[i] = dict(out[i], peaks=pk)
+            out[i] = dict(out[i], peaks=np.sort(pk))  # refined blends can cross; the path wants ascending peaks
             out[i].setdefault("num_pix", len(out[i]["spectrum"]))
     return out
 
