@@ -496,7 +496,7 @@ def main():
         t_pk = time.perf_counter() - t0
         n_ref = sum(len(r) for r in refined)
         off_px = np.concatenate([np.min(np.abs(r[:, None] - specs[i]["peaks"][None, :]), axis=1) for i, r in enumerate(refined) if len(r)])
-        peak_leg = {"kernel": "K6 rb2_find_peaks (1 launch) + rb2_refine_peaks (3 launches), %d C4 arcs resident" % n_arc,
+        peak_leg = {"kernel": "K6 rb2_find_peaks (1 launch) + rb2_refine_peaks (4 launches: windows, queue, fits, collect), %d C4 arcs resident" % n_arc,
                     "find_ms": t_find, "refine_ms": t_refine, "refined_peaks": n_ref, "timing": "median of 5 repetitions, CUDA events",
                     "peaks_per_s": n_ref / (t_all * 1e-3), "spectra_per_s": n_arc / (t_all * 1e-3),
                     "e2e_spectra_per_s": n_arc / t_pk, "median_offset_from_true_centre_px": float(np.median(off_px)),
