@@ -418,7 +418,7 @@ class Calibrator:
         Returns None when the problem does not qualify (known pairs, filter_close, polygon constraint,
         non-standard pixel list, ...) or the winner fails the refit-dependent acceptance - the staged
         path with its fall-through then takes over."""
-        from . import batch, parallel, pipeline
+        from . import parallel, pipeline
 
         if (self.pix_known is not None or self.constrain_poly or self.filter_close or not self.linear
                 or self.ht._external or self.sample_size != fit_deg + 1):

@@ -21,7 +21,6 @@ rb2_refine_peaks, include/rascal_b200.h); there is no CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 

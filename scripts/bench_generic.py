@@ -1,7 +1,6 @@
 """Throughput of K3's generic path (sample_size > deg + 1: Householder least squares per hypothesis)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 from rascal_b200 import engine
 from tests.conftest import load_golden
