@@ -203,6 +203,37 @@ def test_find_peaks_large_noise_spectrum_and_capacity():
         util.find_peaks(x, width=3)
 
 
+def test_degenerate_spectra_in_a_batch():
+    """Empty, one- and two-sample, constant and NaN-ridden spectra next to a normal one."""
+    from scipy.signal import find_peaks
+
+    from rascal_b200 import util
+
+    g = np.load(GOLD[2])
+    x = np.arange(50, dtype=np.float64)
+    with_nan = np.sin(x / 3.0)
+    with_nan[[7, 20, 21]] = np.nan
+    specs = [np.zeros(0), np.array([1.0]), np.array([1.0, 2.0]), np.full(40, 3.0), with_nan, g["spectrum"],
+             np.array([0.0, 1.0, 0.0]), np.array([0.0, 2.0, 2.0, 2.0, 2.0, 0.0])]
+    pb = util.PeakBatch(specs)
+    for kw in (dict(), dict(distance=2), dict(height=0.5, prominence=0.1), dict(prominence=0.0, distance=1)):
+        got = pb.find(**kw).fetch_found()
+        for sp, (pk, props) in zip(specs, got):
+            with np.errstate(invalid="ignore"):
+                ref, rprops = find_peaks(sp, **kw)
+            assert np.array_equal(pk, ref), (len(sp), kw)
+            if "prominences" in rprops:
+                assert np.array_equal(props["prominences"], rprops["prominences"])
+    # refine after find on the same batch: spectra without peaks simply give empty lists
+    out = pb.find(height=0.5, distance=2).refine(3).fetch_refined()
+    assert [len(o) for o in out[:4]] == [0, 0, 0, 0]
+    single = util.refine_peaks(g["spectrum"], util.find_peaks(g["spectrum"], height=0.5, distance=2)[0], window_width=3)
+    assert np.array_equal(out[5], single)
+    # and caller-supplied empty peak lists
+    out = pb.refine(5, [[] for _ in specs]).fetch_refined()
+    assert all(len(o) == 0 for o in out)
+
+
 def test_refine_edge_cases_follow_the_reference():
     from rascal_b200 import util
 
