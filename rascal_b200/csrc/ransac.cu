@@ -630,12 +630,15 @@ __device__ __forceinline__ bool draw_sample(const TablesA& t, unsigned long long
     w[4 * b] = o[0]; w[4 * b + 1] = o[1]; w[4 * b + 2] = o[2]; w[4 * b + 3] = o[3];
   }
   unsigned n_retry = 0;
-  auto retry_word = [&]() -> unsigned {
-    unsigned r = 0;
-    bool got = false;
+  auto retry_word = [&]() -> unsigned {  // spare words in stream order: a shift register, no indexed select
+    unsigned r;
+    if (n_retry < (unsigned)NSP) {
+      r = w[SP0];
 #pragma unroll
-    for (int j = 0; j < NSP; ++j) if (n_retry == (unsigned)j) { r = w[SP0 + j]; got = true; }
-    if (!got) r = philox_word(k0, k1, c0, c1, (unsigned)NW + (n_retry - (unsigned)NSP));
+      for (int j = 0; j + 1 < NSP; ++j) w[SP0 + j] = w[SP0 + j + 1];
+    } else {
+      r = philox_word(k0, k1, c0, c1, (unsigned)NW + (n_retry - (unsigned)NSP));
+    }
     ++n_retry;
     return r;
   };
