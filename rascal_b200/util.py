@@ -230,7 +230,9 @@ class PeakBatch:
 
 def find_peaks(x, height=None, threshold=None, distance=None, prominence=None, **kwargs):
     """``scipy.signal.find_peaks`` (height / distance / prominence) on the device:
-    returns ``(peaks, properties)`` with ``peak_heights`` and, if asked, ``prominences``."""
+    returns ``(peaks, properties)`` with ``peak_heights`` and, if asked, ``prominences``
+    (SciPy's ``left_bases`` / ``right_bases`` are not reported; the reference's recipes
+    discard the properties)."""
     if threshold is not None or any(kwargs.get(k) is not None for k in _UNSUPPORTED):
         raise NotImplementedError("find_peaks: only height, distance and prominence are implemented on the device")
     bad = set(kwargs) - set(_UNSUPPORTED)
