@@ -159,7 +159,7 @@ def peaks_from_spectra(spectra):
     instead of `peaks` get them from K6 - scipy.signal.find_peaks(**entry["find_peaks"]) followed by
     rascal.util.refine_peaks(window_width=entry.get("window_width", 10)), as the reference's examples
     do (examples/example_lt_sprat_xe.py:27-28) - in one device batch per distinct recipe; `num_pix`
-    defaults to len(spectrum).  Entries that already have `peaks` pass through untouched."""
+    defaults to len(spectrum), `max_peaks` (capacity per spectrum) to 1024.  Entries that already have `peaks` pass through untouched."""
     from . import util
 
     out = list(spectra)
@@ -168,7 +168,7 @@ def peaks_from_spectra(spectra):
         if sp.get("peaks") is None and sp.get("spectrum") is not None:
             fp = sp.get("find_peaks", {})
             key = (fp.get("height"), fp.get("distance"), fp.get("prominence"), int(sp.get("window_width", 10)),
-                   sp.get("max_peaks"))
+                   sp.get("max_peaks", 1024))  # output capacity per spectrum; exceeding it raises
             groups.setdefault(key, []).append(i)
     for (h, d, p, ww, cap), idx in groups.items():
         found = util.find_and_refine([out[i]["spectrum"] for i in idx], height=h, distance=d, prominence=p,
