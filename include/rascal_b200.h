@@ -148,6 +148,9 @@ typedef struct {
   double *d_agg;                        /* out: [n_upeaks*n_uwaves] aggregated weight (diagnostic / plotting) */
   int32_t *d_cnt;                       /* out: [n_upeaks*n_uwaves] hit counts */
   int32_t *d_status;                    /* out: [1] 0 or RB2_ERR_CAPACITY    */
+  const int32_t *d_rank;                /* from K1 (bins in rank order), or NULL: with it and ascending pair
+                                           wavelengths inside each peak the ordered hit list is read off the
+                                           bins in rank order instead of being enumerated a second time */
 } rb2_vote_desc;
 
 int rb2_candidate_vote(int n_problems, const rb2_vote_desc *d_desc,

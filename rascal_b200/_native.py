@@ -47,7 +47,7 @@ class VoteDesc(C.Structure):
         ("d_upeak_x", _vp), ("d_pair_off", _vp), ("d_pair_y", _vp), ("d_pair_wid", _vp),
         ("d_xedges", _vp), ("d_yedges", _vp), ("d_rankpos", _vp),
         ("d_cand_wave", _vp), ("d_cand_pair", _vp), ("d_cand_n", _vp),
-        ("d_agg", _vp), ("d_cnt", _vp), ("d_status", _vp),
+        ("d_agg", _vp), ("d_cnt", _vp), ("d_status", _vp), ("d_rank", _vp),
     ]
 
 

@@ -121,7 +121,7 @@ __device__ __forceinline__ void for_my_units(const int* uoff, const int* ubeg, i
 }
 
 __global__ void __launch_bounds__(VOTE_THREADS)
-vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
+vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap, int lam_off) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const rb2_vote_desc d = descs[blockIdx.y];
   const int u = blockIdx.x;
@@ -139,6 +139,7 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   unsigned* rb_hist = reinterpret_cast<unsigned*>(wcnt + nw);
   int* ubeg = reinterpret_cast<int*>(rb_hist + VOTE_NB);   // [ucap] first candidate row of pair q
   int* uoff = ubeg + ucap;                                 // [ucap + 1] exclusive prefix of the row counts
+  double* lam_s = reinterpret_cast<double*>(smem_raw + lam_off);  // [ucap] this peak's pair wavelengths
   __shared__ double pf_agg[VOTE_THREADS];                  // partial of a pair that began in an earlier thread
   __shared__ int pf_q[VOTE_THREADS], pf_cnt[VOTE_THREADS];
   __shared__ int sel_wid[RB2_MAX_TOPN];
@@ -175,14 +176,19 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   // (pairs whose line never crosses the histogram's intercept range have no units: without this
   //  a CTA waits at the barrier for the few threads whose pairs span all rows)
   const bool flat = m <= ucap;
+  bool inv = false;  // ordered hit list from the bins in rank order (phase 3'): needs ascending pair wavelengths
   if (flat) {
+    int ascending = 1;
     for (int q = tid; q < m; q += VOTE_THREADS) {
+      const double lam = d.d_pair_y[q0 + q];
       int gb, ge;
-      row_range(c, d.d_pair_y[q0 + q], gb, ge);
+      row_range(c, lam, gb, ge);
       ubeg[q] = gb; uoff[q + 1] = ge - gb;
+      lam_s[q] = lam;
+      if (q > 0 && !(lam >= d.d_pair_y[q0 + q - 1])) ascending = 0;
     }
     pf_q[tid] = -1;
-    __syncthreads();
+    inv = __syncthreads_and(ascending) && d.d_rank != nullptr;
     if (warp == 0) {  // exclusive scan, 32 pairs per step
       int run = 0;
       for (int base = 0; base < m; base += 32) {
@@ -206,7 +212,7 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
     const double w = gauss_weight(-mul(t, t) * inv_denom);  // util.py:447, a = 1.0 (z to 1 ulp: w to 1e-20)
     agg = add(agg, w);
     ++cnt;
-    atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
+    if (!inv) atomicAdd(&rb_hist[rankpos[gi * yb + j] >> shift], 1u);
   };
   auto commit = [&](int q, double agg, int cnt) {
     if (cnt) {
@@ -308,6 +314,53 @@ vote_kernel(const rb2_vote_desc* __restrict__ descs, int ucap) {
   }
   __syncthreads();
   const unsigned need = (unsigned)s_need;
+
+  // ---- phase 3': the first `need` entries of W straight from the bins in rank order ----------
+  // A bin (g, j) is hit by the pairs whose wavelength lies within tol of its line at this peak:
+  // with ascending wavelengths that is one contiguous run of pairs, found by bisection with the
+  // very test row_hits applies.  256 bins per step, a block scan places their hits; W is complete
+  // after the few hundred best bins - no second enumeration of the windows, no sort.
+  if (inv) {
+    int* W = reinterpret_cast<int*>(list);
+    const int* __restrict__ rank = d.d_rank;
+    unsigned running = 0;
+    for (int base = 0; base < B && running < need; base += VOTE_THREADS) {
+      const int r = base + tid;
+      int qa = 0, nh = 0;
+      if (r < B) {
+        const int b = rank[r];
+        const int g = b / yb, j = b - g * yb;
+        const double pred = add(mul(gc[g], c.x), cc[j]);
+        int lo = 0, hi = m;  // first pair that is not below the window: pred - lam <= tol
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sub(pred, lam_s[mid]) > c.tol) lo = mid + 1; else hi = mid;
+        }
+        qa = lo;
+        while (qa + nh < m && fabs(sub(pred, lam_s[qa + nh])) <= c.tol) ++nh;
+      }
+      unsigned incl = (unsigned)nh;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) scan_s[warp] = incl;
+      __syncthreads();
+      unsigned wpre = 0, total = 0;
+      for (int w = 0; w < VOTE_THREADS / 32; ++w) { if (w < warp) wpre += scan_s[w]; total += scan_s[w]; }
+      const unsigned pos = running + wpre + incl - (unsigned)nh;
+      for (int t = 0; t < nh; ++t) if (pos + t < need) W[pos + t] = qa + t;
+      running += total;
+      __syncthreads();
+    }
+    for (int k = tid; k < n; k += VOTE_THREADS) {
+      const int q = W[sel_j[k]];
+      d.d_cand_wave[(size_t)u * d.top_n + k] = d.d_pair_y[q0 + q];
+      d.d_cand_pair[(size_t)u * d.top_n + k] = q0 + q;
+    }
+    return;
+  }
 
   // ---- phase 3: rank threshold that covers the first `need` entries of W -----
   {
@@ -429,10 +482,12 @@ extern "C" int rb2_candidate_vote(int n_problems, const rb2_vote_desc* d_desc, c
   // i.e. duplicated atlas lines beyond that, takes the pair-per-thread path)
   const int ucap = max_nw + 64;
   smem += (size_t)(2 * ucap + 1) * 4 + 16;
+  const int lam_off = (int)((smem + 7) & ~(size_t)7);  // this peak's pair wavelengths, after the row tables
+  smem = (size_t)lam_off + (size_t)ucap * 8;
   if (smem > 200 * 1024) return RB2_ERR_ARG;
   RB2_CHECK(cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(max_up, n_problems);
-  vote_kernel<<<grid, VOTE_THREADS, smem, stream>>>(d_desc, ucap);
+  vote_kernel<<<grid, VOTE_THREADS, smem, stream>>>(d_desc, ucap, lam_off);
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }

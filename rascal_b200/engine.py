@@ -397,6 +397,7 @@ class VoteBatch:
             d.d_upeak_x, d.d_pair_off = base + o["ux"], base + o["off"]
             d.d_pair_y, d.d_pair_wid = base + o["y"], base + o["wid"]
             d.d_xedges, d.d_yedges, d.d_rankpos = hd.d_xedges, hd.d_yedges, hd.d_rankpos
+            d.d_rank = hd.d_rank
             d.d_cand_wave, d.d_cand_pair, d.d_cand_n = obase + o["cw"], obase + o["cp"], obase + o["cn"]
             d.d_agg = obase + o["agg"] if diagnostics else None
             d.d_cnt = obase + o["cnt"] if diagnostics else None

@@ -270,6 +270,7 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     dv["top_n"], dv["weighted"], dv["tol"], dv["gauss_denom"] = top_n, weighted, ctol, 2 * sigma ** 2 + 1e-9
     dv["d_upeak_x"], dv["d_pair_off"], dv["d_pair_y"], dv["d_pair_wid"] = u(o_peaks), u(o_poff), u(o_py), u(o_pwid)
     dv["d_xedges"], dv["d_yedges"], dv["d_rankpos"] = u(o_xe), u(o_ye), u(o_rpos)
+    dv["d_rank"] = u(o_rank)
     dv["d_cand_wave"], dv["d_cand_pair"], dv["d_cand_n"] = u(o_cw), u(o_cp), u(o_cn)
     dv["d_agg"], dv["d_cnt"], dv["d_status"] = 0, 0, u(o_vstat + 4 * np.arange(n))
 
