@@ -161,7 +161,7 @@ hough_edges_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __
 // are flushed with one shared atomicAdd(count).
 __global__ void __launch_bounds__(512)
 hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats* __restrict__ stats,
-                 int spc, int sub_cap_words, int crossing) {
+                 int spc, int sub_cap_words, int crossing, int pairs_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const rb2_hough_desc d = descs[blockIdx.z];
   const rb2_hough_stats st = stats[blockIdx.z];
@@ -172,6 +172,13 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
   s0 = max(s0, st.slope_lo);
   s1 = min(s1, st.slope_hi + 1);
   if (s0 >= s1) return;
+  // contiguous pair range of this CTA
+  const int np = d.n_pairs;
+  // pairs_per_cta > 0: fixed-size pair ranges (a batch of unequal problems: CTAs of equal work, the
+  // surplus CTAs of a small problem leave at once); 0: this problem's pairs in gridDim.y equal parts
+  const int per = pairs_per_cta > 0 ? pairs_per_cta : (np + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(np, p0 + per);
+  if (p0 >= p1) return;
 
   double* ye = reinterpret_cast<double*>(smem_raw);
   int* row_s = reinterpret_cast<int*>(ye + (yb + 1));
@@ -197,10 +204,6 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
   const double ye0 = ye[0];
   const double inv_wy = (double)yb / (ye[yb] - ye0);
 
-  // contiguous pair range of this split
-  const int np = d.n_pairs;
-  const int per = (np + gridDim.y - 1) / gridDim.y;
-  const int p0 = blockIdx.y * per, p1 = min(np, p0 + per);
 
   for (int w0 = row_lo; w0 <= row_hi; w0 += rows_cap) {
     const int w1 = min(row_hi, w0 + rows_cap - 1);
@@ -568,6 +571,17 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
       pair_splits = min(pair_splits, max(1, max_pairs / 2048));
       target_chunks = max_slopes;
     }
+    // a batch that already fills the GPU with one CTA per problem: problems differ a lot in size (C4:
+    // 2 k ... 38 k pairs), so the kernel would end on its few largest CTAs; cut them to equal pair ranges
+    int pairs_per_cta = 0;
+    {
+      static int ppc_env = -1;
+      if (ppc_env < 0) { const char* e = getenv("RB2_HOUGH_PAIRS_PER_CTA"); ppc_env = e ? max(0, atoi(e)) : 4096; }
+      if (target_chunks == 1 && pair_splits == 1 && ppc_env > 0 && max_pairs > ppc_env) {
+        pairs_per_cta = ppc_env;
+        pair_splits = (max_pairs + pairs_per_cta - 1) / pairs_per_cta;
+      }
+    }
     int spc = slopes_per_cta > 0 ? slopes_per_cta : (max_slopes + target_chunks - 1) / target_chunks;
     spc = max(1, spc);
     int n_chunks = (max_slopes + spc - 1) / spc;
@@ -592,7 +606,7 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
     // slopes at a time; finer binnings keep the slope-by-slope walk
     static const int force = getenv("RB2_HOUGH_CROSSING") ? atoi(getenv("RB2_HOUGH_CROSSING")) : -1;
     const int crossing = force >= 0 ? force : (max_slopes >= 8 * max_yb);
-    hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words, crossing);
+    hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words, crossing, pairs_per_cta);
   }
   hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
   RB2_CHECK(cudaGetLastError());
