@@ -571,15 +571,19 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
       pair_splits = min(pair_splits, max(1, max_pairs / 2048));
       target_chunks = max_slopes;
     }
-    // a batch that already fills the GPU with one CTA per problem: problems differ a lot in size (C4:
-    // 2 k ... 38 k pairs), so the kernel would end on its few largest CTAs; cut them to equal pair ranges
+    // batches: problems differ a lot in size (C4: 2 k ... 38 k pairs), and a grid of (slope chunks) x
+    // (problems) ends on its few largest CTAs; cut every problem into pair ranges of equal size
+    // instead and use only as many slope chunks as it then takes to fill the GPU
     int pairs_per_cta = 0;
     {
       static int ppc_env = -1;
       if (ppc_env < 0) { const char* e = getenv("RB2_HOUGH_PAIRS_PER_CTA"); ppc_env = e ? max(0, atoi(e)) : 4096; }
-      if (target_chunks == 1 && pair_splits == 1 && ppc_env > 0 && max_pairs > ppc_env) {
+      if (n_problems > 1 && pair_splits == 1 && ppc_env > 0 && max_pairs > ppc_env) {
         pairs_per_cta = ppc_env;
+        long long units = 0;
+        for (int i = 0; i < n_problems; ++i) units += (h_desc[i].n_pairs + pairs_per_cta - 1) / pairs_per_cta;
         pair_splits = (max_pairs + pairs_per_cta - 1) / pairs_per_cta;
+        target_chunks = (int)max(1LL, min((long long)max_slopes, (4LL * sms + units - 1) / max(1LL, units)));
       }
     }
     int spc = slopes_per_cta > 0 ? slopes_per_cta : (max_slopes + target_chunks - 1) / target_chunks;
