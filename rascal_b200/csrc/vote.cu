@@ -109,15 +109,21 @@ __device__ __forceinline__ void for_my_units(const int* uoff, const int* ubeg, i
   if (u0 >= u1) return;
   int lo = 0, hi = m - 1;  // pair that contains unit u0: last q with uoff[q] <= u0
   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (uoff[mid] <= u0) lo = mid; else hi = mid - 1; }
+  // ONE loop over the units, the change of pair handled inside it: every lane of a warp reaches body()
+  // (the window search) at the same point of every iteration instead of each lane nesting its own
+  // per-pair loops
   int q = lo;
-  int uu = u0;
-  while (uu < u1) {
-    while (uoff[q + 1] <= uu) ++q;  // skip pairs without rows
-    const int pe = min(u1, uoff[q + 1]);
-    begin(q);
-    for (; uu < pe; ++uu) body(q, ubeg[q] + (uu - uoff[q]));
-    end(q, /*starts_here=*/uoff[q] >= u0, /*ends_here=*/uoff[q + 1] <= u1);
+  bool open = false;
+  for (int uu = u0; uu < u1; ++uu) {
+    if (!open || uu >= uoff[q + 1]) {
+      if (open) end(q, /*starts_here=*/uoff[q] >= u0, /*ends_here=*/true);
+      while (uoff[q + 1] <= uu) ++q;  // skip pairs without rows
+      begin(q);
+      open = true;
+    }
+    body(q, ubeg[q] + (uu - uoff[q]));
   }
+  if (open) end(q, /*starts_here=*/uoff[q] >= u0, /*ends_here=*/uoff[q + 1] <= u1);
 }
 
 __global__ void __launch_bounds__(VOTE_THREADS)
