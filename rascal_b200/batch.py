@@ -154,6 +154,18 @@ class BatchResult(types.SimpleNamespace):
     pass
 
 
+def _batch_parts(n):
+    """Parts a device-pipeline batch of n spectra is cut into (RB2_BATCH_PARTS overrides; 1 below 512)."""
+    import os
+
+    if n < 512:
+        return 1
+    try:
+        return max(1, min(16, int(os.environ.get("RB2_BATCH_PARTS", "2"))))
+    except ValueError:
+        return 2
+
+
 def peaks_from_spectra(spectra):
     """The step before the path for a batch: entries that carry an arc `spectrum`
     instead of `peaks` get them from K6 - scipy.signal.find_peaks(**entry["find_peaks"]) followed by
@@ -198,14 +210,43 @@ def calibrate_batch(spectra, n_hypotheses=10_000, seed=0, refit_mode=0, timings=
     match_tolerance: if set, Calibrator.match_peaks(tolerance=match_tolerance) follows every fit
     (K5), reading the refit coefficients straight from K4's device records; the result gains
     `match` = BatchResult(fit_coeff, matched_peaks, matched_atlas, rms, residuals, n_ambiguous)."""
+    import functools
+    import time
+
+    t0 = time.perf_counter()
+    raw_specs = peaks_from_spectra(spectra)
+    parts = _batch_parts(len(raw_specs)) if device_pipeline else 1
+    kw = dict(seed=seed, refit_mode=refit_mode, match_tolerance=match_tolerance)
+    if parts > 1:
+        # large batch: consecutive parts, each normalised, packed and launched without waiting for the
+        # device, so the host prepares part k+1 (and unpacks part k-1) while the device works on part k;
+        # a part the device pipeline cannot take goes through the staged path when its turn comes
+        cut = [len(raw_specs) * k // parts for k in range(parts + 1)]
+        tms = [{} for _ in range(parts)]
+        pending = []
+        for k in range(parts):
+            sk = [normalise_spec(sp) for sp in raw_specs[cut[k]:cut[k + 1]]]
+            if pipeline.eligible(sk):
+                pending.append(pipeline.run_async(sk, n_hypotheses, timings=tms[k], slot=k, **kw))
+            else:
+                pending.append(functools.partial(_calibrate_staged, sk, n_hypotheses, timings=tms[k], **kw))
+        out = pipeline.ChainedResults([finish() for finish in pending])
+        if timings is not None:
+            timings.update(pack=sum(t.get("pack", 0.0) for t in tms), unpack=sum(t.get("unpack", 0.0) for t in tms),
+                           parts=parts, total=time.perf_counter() - t0)
+        return out
+    specs = [normalise_spec(sp) for sp in raw_specs]
+    if device_pipeline and pipeline.eligible(specs):
+        return pipeline.run(specs, n_hypotheses, timings=timings, **kw)
+    return _calibrate_staged(specs, n_hypotheses, timings=timings, **kw)
+
+
+def _calibrate_staged(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None):
+    """calibrate_batch for normalised specs through the staged engine classes (host RANSAC set-up)."""
     import time
 
     torch = engine._torch()
     t0 = time.perf_counter()
-    specs = [normalise_spec(sp) for sp in peaks_from_spectra(spectra)]
-    if device_pipeline and pipeline.eligible(specs):
-        return pipeline.run(specs, n_hypotheses, seed=seed, refit_mode=refit_mode, match_tolerance=match_tolerance,
-                            timings=timings)
     hp, vs = [], []
     for sp in specs:
         n_p, n_a = len(sp["peaks"]), len(sp["lines"])

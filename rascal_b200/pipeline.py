@@ -163,7 +163,46 @@ def _strictly_increasing(arrays):
 
 
 def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None):
-    """The whole path for `specs` (normalised, eligible) in batched device calls.
+    """run_async(...) followed by its finish(): the whole path for `specs`, results on the host."""
+    return run_async(specs, n_hypotheses, seed=seed, refit_mode=refit_mode, match_tolerance=match_tolerance,
+                     timings=timings, hyp_begin=hyp_begin, exchange=exchange)()
+
+
+class ChainedResults:
+    """Results of a batch that ran as several consecutive pipeline parts, indexed as one sequence."""
+
+    def __init__(self, parts):
+        self.parts = parts
+        self.starts = np.concatenate(([0], np.cumsum([len(p) for p in parts])))
+        self.n = int(self.starts[-1])
+
+    def __len__(self):
+        return self.n
+
+    def _locate(self, i):
+        if i < 0:
+            i += self.n
+        k = int(np.searchsorted(self.starts, i, side="right")) - 1
+        return self.parts[k], i - int(self.starts[k])
+
+    def __getitem__(self, i):
+        part, j = self._locate(i)
+        return part[j]
+
+    def __iter__(self):
+        return (r for part in self.parts for r in part)
+
+    def k3_tables(self, i):
+        part, j = self._locate(i)
+        return part.k3_tables(j)
+
+
+def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None,
+              slot=0):
+    """The whole path for `specs` (normalised, eligible) in batched device calls, without waiting for
+    the device: returns finish(), which waits for this call's results and unpacks them.  Calls with
+    different `slot`s use different device arenas / staging buffers, so the host can pack the next part
+    of a large batch while the device works on this one (batch.calibrate_batch does).
 
     hyp_begin / n_hypotheses: the hypothesis-id range this process evaluates (a rank's shard of a
     sharded fit); exchange(result_tensor, n): called between K3 and K4 with the device tensor of the
@@ -231,6 +270,7 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     # grow-only device arena and pinned staging buffers, reused across calls (cudaHostAlloc of tens of MB
     # costs more than the whole batch); results own their memory, only k3_tables() reads the arena later
     def cached(name, nbytes, **kw):
+        name = "%s/%d" % (name, slot)
         t = _CACHE.get(name)
         if t is None or t.numel() < nbytes:
             t = _CACHE[name] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, **kw)
@@ -308,10 +348,8 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
     N.check(lib.rb2_hough_accumulate(n, dptr("hough"), hptr("hough"), base + o_hstat, 0, stream), "rb2_hough_accumulate")
     N.check(lib.rb2_candidate_vote(n, dptr("vote"), hptr("vote"), stream), "rb2_candidate_vote")
     N.check(lib.rb2_ransac_prepare(n, dptr("prep"), hptr("prep"), dptr("ransac"), stream), "rb2_ransac_prepare")
-    nbytes = lib.rb2_ransac_scratch_bytes(n, 0)
-    if _CACHE.get("scratch") is None or _CACHE["scratch"].numel() < nbytes:
-        _CACHE["scratch"] = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + o_res, _CACHE["scratch"].data_ptr(), 0, stream),
+    scratch = cached("scratch", lib.rb2_ransac_scratch_bytes(n, 0), device="cuda")
+    N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + o_res, scratch.data_ptr(), 0, stream),
             "rb2_ransac_batch")
     if exchange is not None:
         exchange(buf[o_res:o_res + rsz * n], n)
@@ -322,45 +360,54 @@ def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings
                                     base + o_mmy, base + o_mrs, max_p, stream), "rb2_match_peaks")
     raw = cached("stage_out", res_end - res_begin, pin_memory=True)[:res_end - res_begin]
     raw.copy_(buf[res_begin:res_end], non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    done = torch.cuda.Event()
+    done.record()
     engine.TRANSFER["d2h"] += raw.numel()
-    t2 = time.perf_counter()
-    r = raw.numpy().copy()
+    t_launch = time.perf_counter()
 
-    def region(off, nbytes):
-        return r[off - res_begin:off - res_begin + nbytes]
+    def finish():
+        done.synchronize()
+        t2 = time.perf_counter()
+        return unpack(raw.numpy().copy(), t2)
 
-    hstat = region(o_hstat, C.sizeof(N.HoughStats) * n).view(_dt(N.HoughStats))
-    vstat = region(o_vstat, 4 * n).view(np.int32)
-    for st, what in ((hstat["status"], "rb2_hough_accumulate"), (vstat, "rb2_candidate_vote")):
-        bad = np.flatnonzero(st != 0)
-        if len(bad):
-            N.check(int(st[bad[0]]), what + " (device status)")
-    win = region(o_res, rsz * n).view(_dt(N.RansacResult))
-    fit = region(o_fit, fsz * n).view(_dt(N.RefitResult))
-    out = BatchResults(n)
-    out.deg, out.n_p, out.n_a = deg, n_p, n_a
-    out.enough = region(o_enough, 4 * n).view(np.int32) != 0
-    out.counters, out.cost = win["counters"], win["cost"]
-    out.hyp_id, out.hyp_coeffs = win["hyp_id"], win["coeffs"]
-    out.refit_nfev, out.accepted = fit["huber_iters"], fit["accepted"]
-    out.ok = out.enough & (win["hyp_id"] >= 0) & (fit["accepted"] != 0)
-    out.coeffs, out.rms, out.n_inliers = fit["coeffs"], fit["rms"], fit["n_inliers"]
-    shp = (n, max_p)
-    out.mx = region(o_mx, 8 * n * max_p).view(np.float64).reshape(shp)
-    out.my = region(o_my, 8 * n * max_p).view(np.float64).reshape(shp)
-    out.rs = region(o_rs, 8 * n * max_p).view(np.float64).reshape(shp)
-    out.match_ok = None
-    if match_tolerance is not None:
-        mres = region(o_mres, msz * n).view(_dt(N.MatchResult))
-        out.match_ok = out.ok & (mres["refit"]["accepted"] != 0)
-        out.m_n, out.m_amb = mres["n_matched"], mres["n_ambiguous"]
-        out.m_coeffs, out.m_rms = mres["refit"]["coeffs"], mres["refit"]["rms"]
-        out.mmx = region(o_mmx, 8 * n * max_p).view(np.float64).reshape(shp)
-        out.mmy = region(o_mmy, 8 * n * max_p).view(np.float64).reshape(shp)
-        out.mrs = region(o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
-    out._tables = dict(buf=buf, up=o_up, coff=o_coff, cwave=o_cwave, cwid=o_cwid, cdf=o_cdf, ppb=o_ppb, ppc=o_ppc,
-                       npp=npp, desc=o_desc["ransac"], top_n=top_n)
-    if timings is not None:
-        timings.update(pack=t1 - t0, device=t2 - t1, unpack=time.perf_counter() - t2)
-    return out
+    def unpack(r, t2):
+        def region(off, nbytes):
+            return r[off - res_begin:off - res_begin + nbytes]
+
+        hstat = region(o_hstat, C.sizeof(N.HoughStats) * n).view(_dt(N.HoughStats))
+        vstat = region(o_vstat, 4 * n).view(np.int32)
+        for st, what in ((hstat["status"], "rb2_hough_accumulate"), (vstat, "rb2_candidate_vote")):
+            bad = np.flatnonzero(st != 0)
+            if len(bad):
+                N.check(int(st[bad[0]]), what + " (device status)")
+        win = region(o_res, rsz * n).view(_dt(N.RansacResult))
+        fit = region(o_fit, fsz * n).view(_dt(N.RefitResult))
+        out = BatchResults(n)
+        out.deg, out.n_p, out.n_a = deg, n_p, n_a
+        out.enough = region(o_enough, 4 * n).view(np.int32) != 0
+        out.counters, out.cost = win["counters"], win["cost"]
+        out.hyp_id, out.hyp_coeffs = win["hyp_id"], win["coeffs"]
+        out.refit_nfev, out.accepted = fit["huber_iters"], fit["accepted"]
+        out.ok = out.enough & (win["hyp_id"] >= 0) & (fit["accepted"] != 0)
+        out.coeffs, out.rms, out.n_inliers = fit["coeffs"], fit["rms"], fit["n_inliers"]
+        shp = (n, max_p)
+        out.mx = region(o_mx, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.my = region(o_my, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.rs = region(o_rs, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.match_ok = None
+        if match_tolerance is not None:
+            mres = region(o_mres, msz * n).view(_dt(N.MatchResult))
+            out.match_ok = out.ok & (mres["refit"]["accepted"] != 0)
+            out.m_n, out.m_amb = mres["n_matched"], mres["n_ambiguous"]
+            out.m_coeffs, out.m_rms = mres["refit"]["coeffs"], mres["refit"]["rms"]
+            out.mmx = region(o_mmx, 8 * n * max_p).view(np.float64).reshape(shp)
+            out.mmy = region(o_mmy, 8 * n * max_p).view(np.float64).reshape(shp)
+            out.mrs = region(o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
+        out._tables = dict(buf=buf, up=o_up, coff=o_coff, cwave=o_cwave, cwid=o_cwid, cdf=o_cdf, ppb=o_ppb, ppc=o_ppc,
+                           npp=npp, desc=o_desc["ransac"], top_n=top_n)
+        if timings is not None:
+            timings.update(pack=t1 - t0, launch=t_launch - t1, device=t2 - t1, unpack=time.perf_counter() - t2)
+        return out
+
+    return finish
+

@@ -110,3 +110,29 @@ def test_ineligible_batches_take_the_staged_path():
     raw[1] = dict(raw[1], ransac=dict(raw[1]["ransac"], filter_close=True))
     res = batch.calibrate_batch(raw, n_hypotheses=5000, seed=1)
     assert isinstance(res, list) and len(res) == 4
+
+
+def test_large_batch_in_parts_equals_one_part(monkeypatch):
+    """calibrate_batch cuts batches of >= 512 spectra into consecutively launched parts (host packing
+    overlaps the device); every spectrum gets exactly what the undivided batch gives it."""
+    from bench import c4_input
+    from rascal_b200 import batch
+
+    specs = [c4_input(i) for i in range(520)]
+    monkeypatch.setenv("RB2_BATCH_PARTS", "1")
+    one = batch.calibrate_batch(specs, n_hypotheses=2000, seed=3, match_tolerance=5.0)
+    monkeypatch.setenv("RB2_BATCH_PARTS", "3")
+    tm = {}
+    many = batch.calibrate_batch(specs, n_hypotheses=2000, seed=3, match_tolerance=5.0, timings=tm)
+    assert tm["parts"] == 3 and len(many) == len(one) == 520
+    for i, (a, b) in enumerate(zip(one, many)):
+        assert (a.fit_coeff is None) == (b.fit_coeff is None), i
+        assert a.cost == b.cost and a.counters == b.counters, i
+        if a.fit_coeff is not None:
+            assert np.array_equal(a.fit_coeff, b.fit_coeff) and np.array_equal(a.matched_atlas, b.matched_atlas), i
+            assert (a.match is None) == (b.match is None)
+            if a.match is not None:
+                assert np.array_equal(a.match.fit_coeff, b.match.fit_coeff)
+    t = many.k3_tables(519)
+    assert t["peaks"].shape[0] == int(t["desc"]["n_upeaks"])
+    assert many[-1].cost == one[-1].cost
