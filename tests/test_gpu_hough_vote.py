@@ -199,7 +199,15 @@ def test_vote_heavily_duplicated_atlas():
     _vote_random_case(7, True, triple=True)
 
 
-def _vote_random_case(seed, weighted, triple):
+def test_vote_unsorted_atlas_takes_the_enumeration_path():
+    """Atlas lines in random order: pair wavelengths are not ascending inside a peak, so the ordered hit
+    list cannot be read off the rank order by bisection and the kernel falls back to the second window
+    enumeration; the answers (which depend on the pair order, App. A.3) still equal the oracle's."""
+    for seed in (0, 2):
+        _vote_random_case(seed, True, triple=False, shuffle=True)
+
+
+def _vote_random_case(seed, weighted, triple, shuffle=False):
     from rascal_b200 import engine
 
     rng = np.random.default_rng(100 + seed)
@@ -214,6 +222,8 @@ def _vote_random_case(seed, weighted, triple):
     if triple:
         lines = np.concatenate((lines, lines, lines))
         assert len(lines) > len(np.unique(lines)) + 64
+    if shuffle:
+        lines = rng.permutation(lines)
     pairs = O.make_pairs(peaks, lines)
     lo, hi, mi, ma = O.hough_limits(4000.0, 6100.0, 200, 50, np.arange(1024))
     xb, yb = int(rng.integers(10, 50)), int(rng.integers(10, 50))
