@@ -216,8 +216,19 @@ constexpr int LM_UNROLL = RB2_LM_UNROLL;  // unrolling of the loops over the ind
 // Euclidean norm with MINPACK's three accumulators (small / intermediate / large components)
 __device__ __noinline__ double enorm(int n, const double* v) {
   const double rdwarf = 3.834e-20, rgiant = 1.304e19;
-  double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
   const double agiant = rgiant / (double)n;
+  {  // every component zero or of intermediate size (the normal case): MINPACK's result is sqrt(sum x^2)
+    double q = 0.0;
+    bool mid = true;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const double xabs = fabs(v[i]);
+      mid &= (xabs > rdwarf && xabs < agiant) || xabs == 0.0;
+      q += xabs * xabs;
+    }
+    if (mid) return sqrt(q);
+  }
+  double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
   for (int i = 0; i < n; ++i) {
     const double xabs = fabs(v[i]);
     if (xabs > rdwarf && xabs < agiant) {
