@@ -438,8 +438,9 @@ __device__ __noinline__ int lm_iterate(LMState& S) {
     x[j] = t + h;
     gauss_residuals(x, S.y, m, wa4);
     x[j] = t;
+    const double rh = 1.0 / h;  // one division per column: the differences carry ~1e-8 of rounding noise anyway
 #pragma unroll LM_UNROLL
-    for (int i = 0; i < m; ++i) fj[j][i] = (wa4[i] - fvec[i]) / h;
+    for (int i = 0; i < m; ++i) fj[j][i] = (wa4[i] - fvec[i]) * rh;
   }
   S.nfev += LM_N;
   // Householder QR with column pivoting
@@ -471,8 +472,9 @@ __device__ __noinline__ int lm_iterate(LMState& S) {
     double ajnorm = enorm(m - j, fj[j] + j);
     if (ajnorm != 0.0) {
       if (fj[j][j] < 0.0) ajnorm = -ajnorm;
+      const double rn = 1.0 / ajnorm;
 #pragma unroll LM_UNROLL
-      for (int i = j; i < m; ++i) fj[j][i] /= ajnorm;
+      for (int i = j; i < m; ++i) fj[j][i] *= rn;
       fj[j][j] += 1.0;
 #pragma unroll 1
       for (int k = j + 1; k < LM_N; ++k) {
