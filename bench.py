@@ -13,7 +13,12 @@ block-best), ONE all-gather of the per-rank winner records, and K4 (winner refit
 Hough + candidate vote (K1, K2) run once per spectrum and are part of the e2e leg,
 which goes through the public Calibrator API with host buffers every step.
 
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  Beyond the contract's keys it carries three auxiliary legs
+(skipped with --spectra 0): `spectra_per_sec` = a bounded sample of BASELINE configs[3] (C4
+spectra through rascal_b200.batch.calibrate_batch, K1..K5 each, host arrays in / results out),
+`hough_roofline` = K1 and K2 alone on 512 resident C4 spectra against the FP64-pipe roof, and
+`peak_finding` = K6 (find_peaks + refine_peaks) on 512 rendered C4 arcs, resident and from the
+raw arcs to wavelength solutions, with the reference's recipe timed on one host core beside it.
 """
 import argparse
 import json
