@@ -55,3 +55,29 @@ def test_eligibility_rules():
     bad[3] = dict(bad[3], hough=dict(bad[3]["hough"], xbins=50))
     assert not pipeline.eligible(bad)
     assert not pipeline.eligible([])
+
+
+def test_chained_results_index_like_one_sequence():
+    from rascal_b200 import pipeline
+
+    class Part(list):
+        def k3_tables(self, i):
+            return ("tables", self[i])
+
+    parts = [Part(["a0", "a1", "a2"]), Part([]), Part(["c0"]), Part(["d0", "d1"])]
+    ch = pipeline.ChainedResults(parts)
+    flat = ["a0", "a1", "a2", "c0", "d0", "d1"]
+    assert len(ch) == 6 and list(ch) == flat
+    assert [ch[i] for i in range(6)] == flat and ch[-1] == "d1" and ch[-6] == "a0"
+    assert ch.k3_tables(3) == ("tables", "c0") and ch.k3_tables(5) == ("tables", "d1")
+
+
+def test_batch_parts_policy(monkeypatch):
+    from rascal_b200 import batch
+
+    monkeypatch.delenv("RB2_BATCH_PARTS", raising=False)
+    assert batch._batch_parts(100) == 1 and batch._batch_parts(511) == 1 and batch._batch_parts(512) == 2
+    monkeypatch.setenv("RB2_BATCH_PARTS", "5")
+    assert batch._batch_parts(4096) == 5 and batch._batch_parts(10) == 1
+    monkeypatch.setenv("RB2_BATCH_PARTS", "junk")
+    assert batch._batch_parts(4096) == 2
