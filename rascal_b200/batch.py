@@ -13,6 +13,7 @@ Spectra are independent: with torch.distributed, rank r takes spectra r, r+world
 """
 from __future__ import annotations
 
+import math
 import types
 
 import numpy as np
@@ -25,16 +26,16 @@ RANSAC_DEFAULTS = dict(sample_size=5, top_n_candidate=5, filter_close=False, ran
                        candidate_weighted=True, hough_weight=1.0, minimum_matches=0,
                        minimum_peak_utilisation=0.0, minimum_fit_error=1e-4)
 FIT_DEFAULTS = dict(fit_deg=4, candidate_tolerance=2.0)
+_EMPTY = {}
 
 
 def _limits(h, span):
     """calibrator.py:1088-1116; span = np.ptp(pixel_list)."""
-    min_i = h["min_wavelength"] - h["range_tolerance"]
-    max_i = h["min_wavelength"] + h["range_tolerance"]
-    lo = ((h["max_wavelength"] - h["range_tolerance"] - h["linearity_tolerance"])
-          - (min_i + h["range_tolerance"] + h["linearity_tolerance"])) / span
-    hi = ((h["max_wavelength"] + h["range_tolerance"] + h["linearity_tolerance"])
-          - (min_i - h["range_tolerance"] - h["linearity_tolerance"])) / span
+    wmin, wmax, rt, lt = h["min_wavelength"], h["max_wavelength"], h["range_tolerance"], h["linearity_tolerance"]
+    min_i = wmin - rt
+    max_i = wmin + rt
+    lo = ((wmax - rt - lt) - (min_i + rt + lt)) / span
+    hi = ((wmax + rt + lt) - (min_i - rt - lt)) / span
     return lo, hi, min_i, max_i
 
 
@@ -132,17 +133,18 @@ def normalise_spec(sp):
     """Fill defaults, derive limits / pairs; mirrors Calibrator.__init__ + the three setters."""
     peaks = np.asarray(sp["peaks"], dtype=np.float64)
     lines = np.asarray(sp["lines"], dtype=np.float64)
-    if "pixel_list" in sp and sp["pixel_list"] is not None:
-        pl = np.asarray(sp["pixel_list"], dtype=np.float64)
+    pl = sp.get("pixel_list")
+    if pl is not None:
+        pl = np.asarray(pl, dtype=np.float64)
         is_ar = bool(len(pl) and pl[0] == 0 and pl[-1] == len(pl) - 1 and np.all(np.diff(pl) == 1))
         n_pix, span = len(pl), (float(np.ptp(pl)) if len(pl) else 0.0)
     else:  # pixel_list = np.arange(num_pix) (calibrator.py:914-937), materialised only where it is read
         npix = sp.get("num_pix")
-        n_pix = int(np.ceil(npix if npix is not None else 1.1 * max(peaks)))
-        pl, is_ar, span = None, True, float(n_pix - 1)
-    h = dict(HOUGH_DEFAULTS, **sp.get("hough", {}))
-    r = dict(RANSAC_DEFAULTS, **sp.get("ransac", {}))
-    f = dict(FIT_DEFAULTS, **sp.get("fit", {}))
+        n_pix = math.ceil(npix if npix is not None else 1.1 * peaks.max())
+        is_ar, span = True, float(n_pix - 1)
+    h = {**HOUGH_DEFAULTS, **sp.get("hough", _EMPTY)}
+    r = {**RANSAC_DEFAULTS, **sp.get("ransac", _EMPTY)}
+    f = {**FIT_DEFAULTS, **sp.get("fit", _EMPTY)}
     s = min(int(r["sample_size"]), len(lines))
     if s <= f["fit_deg"]:
         s = f["fit_deg"] + 1

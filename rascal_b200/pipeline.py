@@ -133,17 +133,15 @@ def eligible(specs):
     if not specs:
         return False
     s0 = specs[0]
-    keys_h = ("num_slopes", "xbins", "ybins")
+    h0, r0 = s0["hough"], s0["ransac"]
+    ns0, xb0, yb0 = h0["num_slopes"], h0["xbins"], h0["ybins"]
+    top0, wt0, deg0, ss0 = r0["top_n_candidate"], bool(r0["candidate_weighted"]), s0["fit"]["fit_deg"], s0["sample_size"]
     for sp in specs:
-        if not sp["pix_is_arange"] or sp["ransac"]["filter_close"]:
-            return False
-        if any(sp["hough"][k] != s0["hough"][k] for k in keys_h):
-            return False
-        if (sp["ransac"]["top_n_candidate"] != s0["ransac"]["top_n_candidate"]
-                or bool(sp["ransac"]["candidate_weighted"]) != bool(s0["ransac"]["candidate_weighted"])
-                or sp["fit"]["fit_deg"] != s0["fit"]["fit_deg"] or sp["sample_size"] != s0["sample_size"]):
-            return False
-        if len(sp["peaks"]) < 1 or len(sp["lines"]) < 1:
+        h, r = sp["hough"], sp["ransac"]
+        if (not sp["pix_is_arange"] or r["filter_close"] or h["num_slopes"] != ns0 or h["xbins"] != xb0
+                or h["ybins"] != yb0 or r["top_n_candidate"] != top0 or bool(r["candidate_weighted"]) != wt0
+                or sp["fit"]["fit_deg"] != deg0 or sp["sample_size"] != ss0 or len(sp["peaks"]) < 1
+                or len(sp["lines"]) < 1):
             return False
     if int(s0["hough"]["xbins"]) < 8 or s0["sample_size"] != s0["fit"]["fit_deg"] + 1:
         return False
