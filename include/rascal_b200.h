@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RB2_ABI_VERSION 1
+#define RB2_ABI_VERSION 2
 #define RB2_MAX_DEG 7       /* polynomial degree of a hypothesis            */
 #define RB2_MAX_SAMPLE 16   /* sample_size + known pairs                    */
 #define RB2_MAX_TOPN 32     /* top_n_candidate                              */
@@ -215,6 +215,15 @@ typedef struct {
   double *d_out_weight;                 /* [n_hyp]                           */
   double *d_out_coeffs;                 /* [n_hyp*(deg+1)]                   */
   int32_t *d_out_counts;                /* [n_hyp*2] n_match, n_inliers      */
+  int32_t *d_out_sample;                /* [n_hyp*sample_size*2] the draw itself: (peak index, candidate index
+                                           inside that peak's list) per sampled point, in draw order; -1 for an
+                                           aborted draw.  Lets a test check the sampler's law (App. A.8) on the
+                                           device                                                                */
+  const double *d_replay_coeffs;        /* with d_replay_x: [n_hyp*(deg+1)] hypothesis coefficients used INSTEAD
+                                           of fitting the replayed sample (parity: the reference's own polyfit
+                                           output, so that every later decision is checked on identical input)  */
+  double min_fit_error;                 /* K4: the winner is accepted iff rms >= this (calibrator.py:673-679);
+                                           used when rb2_refit_winners is called with minimum_fit_error = NaN   */
 } rb2_ransac_desc;
 
 typedef enum {
@@ -239,7 +248,8 @@ typedef struct {
  * enqueues is ordered after prior work on `stream` and before later work on it.
  * One host thread per device drives this entry point.
  * blocks_per_problem = 0 lets the library choose (a multiple of the SM count
- * for one problem).  d_block_scratch must hold rb2_ransac_scratch_bytes(). */
+ * for one problem).  d_block_scratch must hold rb2_ransac_scratch_bytes().
+ * All problems of one call share deg, sample_size and seed (else RB2_ERR_ARG). */
 size_t rb2_ransac_scratch_bytes(int n_problems, int blocks_per_problem);
 int rb2_ransac_batch(int n_problems, const rb2_ransac_desc *d_desc,
                      const rb2_ransac_desc *h_desc, rb2_ransac_result *d_result,
@@ -271,7 +281,9 @@ typedef struct {
 } rb2_refit_result;
 
 /* d_matched_x / d_matched_y / d_residual: [n_problems * max_upeaks] outputs
- * (inliers sorted by wavelength, first n_inliers entries valid). */
+ * (inliers sorted by wavelength, first n_inliers entries valid).
+ * minimum_fit_error: one threshold for every problem, or NaN = each problem's
+ * own rb2_ransac_desc.min_fit_error. */
 int rb2_refit_winners(int n_problems, const rb2_ransac_desc *d_desc,
                       const rb2_ransac_desc *h_desc,
                       const rb2_ransac_result *d_winner, double minimum_fit_error,
@@ -360,7 +372,10 @@ int rb2_expand_pairs(int n_problems, const rb2_pairs_desc *d_desc,
  * n_peaks*top_n (x2), n_peaks, n_pp+1, 4*n_pp); the kernel fills those tables
  * and the data-dependent scalars (n_upeaks, n_cand, n_wids, pix_min/max,
  * gc_min/max, ic_min, h_lo/h_hi, w_upper) and sets n_hyp = 0 where the
- * reference would return before the loop (:468-469; d_enough[0] = 0). */
+ * reference would return before the loop (:468-469; d_enough[0] = 0) and where
+ * its sampling weights are not finite (a peak on an interior edge of the 10-bin
+ * histogram next to an empty bin: np.random.choice raises "probabilities contain
+ * NaN", :521-540; d_enough[0] = -1). */
 typedef struct {
   const double *d_upeak_x;              /* [n_peaks] ascending (K2's input)  */
   const double *d_cand_wave;            /* [n_peaks*top_n] K2 output         */

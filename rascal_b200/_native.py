@@ -9,8 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librascal_b200.so")
+LIB_PATH = os.environ.get("RB2_LIB") or os.path.join(_HERE, "librascal_b200.so")  # RB2_LIB: a tuning variant (csrc/build.py)
 
+ABI_VERSION = 2
 RB2_MAX_DEG = 7
 RB2_MAX_SAMPLE = 16
 RB2_MAX_TOPN = 32
@@ -68,7 +69,8 @@ class RansacDesc(C.Structure):
         ("hyp_begin", C.c_int64), ("n_hyp", C.c_int64), ("seed", C.c_uint64),
         ("d_replay_x", _vp), ("d_replay_y", _vp),
         ("d_out_status", _vp), ("d_out_cost", _vp), ("d_out_weight", _vp),
-        ("d_out_coeffs", _vp), ("d_out_counts", _vp),
+        ("d_out_coeffs", _vp), ("d_out_counts", _vp), ("d_out_sample", _vp), ("d_replay_coeffs", _vp),
+        ("min_fit_error", C.c_double),
     ]
 
 
@@ -189,7 +191,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rb2_abi_version() != 1:
+    if lib.rb2_abi_version() != ABI_VERSION:
         raise NativeError("ABI version mismatch")
     for i, s in enumerate(STRUCTS):
         if lib.rb2_struct_size(i) != C.sizeof(s):

@@ -106,7 +106,11 @@ def ransac_setups(specs, hough, vote):
         s.cand_wid = wid.astype(np.int32)
         s.deg, s.sample_size = int(f["fit_deg"]), int(sp["sample_size"])
         s.enough = len(peaks) > s.deg and len(peaks) > s.sample_size
-        s.cdf32 = _sampling_cdf(peaks) if s.enough else np.zeros(len(peaks), dtype=np.uint32)
+        s.error = None
+        try:
+            s.cdf32 = _sampling_cdf(peaks) if s.enough else np.zeros(len(peaks), dtype=np.uint32)
+        except ValueError as e:  # "probabilities contain NaN": this spectrum fails, the batch goes on
+            s.enough, s.error, s.cdf32 = False, e, np.zeros(len(peaks), dtype=np.uint32)
         s.known_x = s.known_y = np.zeros(0)
         s.tol = float(r["ransac_tolerance"])
         s.min_intercept, s.max_intercept = float(sp["limits"][2]), float(sp["limits"][3])
@@ -272,7 +276,7 @@ def _calibrate_staged(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance
     live = [i for i, s in enumerate(setups) if s.enough]
     results = [BatchResult(fit_coeff=None, matched_peaks=[], matched_atlas=[], rms=1e50, residual=None,
                            peak_utilisation=0.0, atlas_utilisation=0.0, valid=False, cost=float("inf"),
-                           counters=None, match=None) for _ in specs]
+                           counters=None, match=None, error=s.error) for s in setups]
     if live:
         rb = engine.RansacBatch([setups[i] for i in live])
         rb.run(0, int(n_hypotheses), seed=seed)

@@ -450,10 +450,12 @@ class Calibrator:
         if world > 1:
             def exchange(d_result, n):
                 parallel.exchange_device(d_result, n, self.dist_group)
-        out = pipeline.run([spec], hi - lo, seed=key, hyp_begin=lo, exchange=exchange)
+        out = pipeline.run([spec], hi - lo, seed=key, hyp_begin=lo, exchange=exchange, keep_tables=True)
+        if out.law_error[0]:
+            raise ValueError("probabilities contain NaN")  # np.random.choice in the reference's loop (:538)
         if not out.enough[0] or not out.ok[0]:
             return None  # nothing eligible, or the winner failed K4's acceptance: the staged path decides
-        self._lazy_candidates = out  # candidate_peak / candidate_arc are fetched from the device on first use
+        self._lazy_candidates = out  # candidate_peak / candidate_arc: unpacked on first use from tables `out` owns
         m = int(out.n_inliers[0])
         self.matched_peaks, self.matched_atlas = list(out.mx[0, :m]), list(out.my[0, :m])
         assert len(self.matched_atlas) == len(set(self.matched_atlas))
@@ -549,8 +551,10 @@ class Calibrator:
         if self.ransac_counters["unsupported"]:
             self.logger.warning("%d hypotheses left the corner-clamped Hough-weight regime and were skipped",
                                 self.ransac_counters["unsupported"])
-        # refit-dependent acceptance (:652-679); fall through to the next best on failure
-        for _ in range(16):
+        # refit-dependent acceptance (:652-679); fall through to the next best on failure.  The reference keeps
+        # drawing until a hypothesis passes; here every rejected winner costs one more pass over the spans
+        # (noise-free data with a large minimum_fit_error rejects one perfect fit after the other)
+        for _ in range(256):
             if winner.hyp_id < 0:
                 return best
             o = fit[0]

@@ -131,6 +131,7 @@ ransac_prepare_kernel(const rb2_prepare_desc* __restrict__ descs, rb2_ransac_des
     }
     if (!enough) o.n_hyp = 0;
     if (d.d_enough) d.d_enough[0] = enough ? 1 : 0;
+    bool law_ok = true;
     if (enough) {
       double lo = peaks[0], hi = peaks[nu - 1];
       if (lo == hi) { lo -= 0.5; hi += 0.5; }
@@ -149,7 +150,14 @@ ransac_prepare_kernel(const rb2_prepare_desc* __restrict__ descs, rb2_ransac_des
         int k = 0;
         while (k < 11 && e[k] < peaks[i]) ++k;
         const int dig = (k - 1 < 0) ? 9 : min(k - 1, 9);
+        // a peak exactly on an interior edge whose left bin is empty: weight 1/0, prob = NaN - the reference's
+        // np.random.choice raises "probabilities contain NaN" on the first draw (calibrator.py:538)
+        if (counts[dig] == 0) law_ok = false;
         total = add(total, 1.0 / (double)counts[dig]);
+      }
+      if (!law_ok) {
+        o.n_hyp = 0;
+        if (d.d_enough) d.d_enough[0] = -1;
       }
       double run = 0.0;
       // two passes: cdf = cumsum(prob / total); cdf /= cdf[-1]
@@ -170,6 +178,8 @@ ransac_prepare_kernel(const rb2_prepare_desc* __restrict__ descs, rb2_ransac_des
         cdf32[i] = (c >= 4294967295.0) ? 0xFFFFFFFFu : (unsigned)c;
       }
       cdf32[nu - 1] = 0xFFFFFFFFu;
+      if (!law_ok)
+        for (int i = 0; i < nu; ++i) cdf32[i] = 0u;
     } else {
       for (int i = 0; i < nu; ++i) cdf32[i] = 0u;
     }

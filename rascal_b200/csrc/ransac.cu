@@ -565,24 +565,32 @@ struct Rng {  // 32-bit words for the peak draws, 16-bit halves for the candidat
   }
 };
 
+// ---- stage-A tables: packed 16-byte records, one LDS.128 each --------------------------------
+// PeakRec: the peak's interval [lo, lo + wd) of the 32-bit sampling CDF (calibrator.py:521-523; the last
+// interval ends at 2^32, all arithmetic is mod 2^32), the start of its candidate list and kt = K | thr << 16
+// with K = number of candidates and thr = 65536 mod K (Lemire's rejection threshold for a 16-bit pick).
+struct alignas(16) PeakRec { unsigned lo, wd, off, kt; };
+struct alignas(16) CandRec { double wave; int wid; int pad; };
+
 struct TablesA {  // shared-memory views of one problem (stage A)
-  const double* peaks; const double* cwave; const int* coff; const int* cwid;
-  const unsigned* cdf32; const unsigned short* lut;
+  const PeakRec* prec; const CandRec* crec; const double* peaks;
+  const unsigned short* lut;
   int n_u;
 };
 
-// first i with r < cdf32[i] (== searchsorted(cdf, u, 'right')), clamped: LUT over the top
-// LUT_BITS bits.  A cell stores the index of its first value; bit 15 marks the few cells (about
-// n_u of 2^LUT_BITS) that a CDF boundary may cross - only those compare against the CDF, so a warp
-// usually takes the one-load path with all lanes.
+// index i of the interval that holds u (== searchsorted(cdf, u, 'right'), clamped) and its record: LUT over
+// the top LUT_BITS bits.  A cell stores the index of its first value; bit 15 marks the few cells (about n_u
+// of 2^LUT_BITS) that a CDF boundary may cross - only those walk the records, so a warp usually takes the
+// two-load path with all lanes.
 constexpr int LUT_BITS = 12;
 constexpr unsigned short LUT_CHECK = 0x8000u;
-__device__ __forceinline__ int draw_peak_lut(const TablesA& t, unsigned r) {
-  const unsigned short e = t.lut[r >> (32 - LUT_BITS)];
+__device__ __forceinline__ int find_peak(const TablesA& t, unsigned u, PeakRec& r) {
+  const unsigned short e = t.lut[u >> (32 - LUT_BITS)];
   int i = e & 0x7fff;
+  r = t.prec[i];
   if (e & LUT_CHECK) {
     const int last = t.n_u - 1;
-    while (i < last && r >= t.cdf32[i]) ++i;
+    while (i < last && (u - r.lo) >= r.wd) { ++i; r = t.prec[i]; }
   }
   return i;
 }
@@ -601,6 +609,27 @@ __device__ __forceinline__ void philox_block(unsigned k0, unsigned k1, unsigned 
   }
   out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
 }
+// The round keys depend on the seed only; as a kernel parameter they sit in the constant bank and the
+// key XOR of every round takes them as an immediate operand (no per-thread key schedule).
+struct PhiloxKey { unsigned a[10], b[10]; };
+static PhiloxKey philox_key(unsigned long long seed) {
+  PhiloxKey k;
+  unsigned a = (unsigned)seed, b = (unsigned)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { k.a[r] = a; k.b[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+  return k;
+}
+__device__ __forceinline__ void philox_block(const PhiloxKey& key, unsigned c0, unsigned c1, unsigned blk,
+                                             unsigned (&out)[4]) {
+  unsigned x0 = c0, x1 = c1, x2 = blk, x3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * x0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * x2;
+    const unsigned y0 = (unsigned)(p1 >> 32) ^ x1 ^ key.a[r], y2 = (unsigned)(p0 >> 32) ^ x3 ^ key.b[r];
+    x0 = y0; x1 = (unsigned)p1; x2 = y2; x3 = (unsigned)p0;
+  }
+  out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+}
 // word `n` of the stream beyond the eager blocks (rare path; one copy of the code)
 __device__ __noinline__ unsigned philox_word(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned n) {
   unsigned w[4];
@@ -609,119 +638,178 @@ __device__ __noinline__ unsigned philox_word(unsigned k0, unsigned k1, unsigned 
   return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
 }
 
-// Fast-path sampler (sample size S = deg + 1 known at compile time).  All lanes generate the
-// same number of Philox blocks up front (no divergence in the generator): word k is the first
-// try of peak k, half-word k of the following words the first try of candidate k, the rest
-// are spares for the retries (duplicate peak / duplicate wavelength / Lemire rejection); only
-// a hypothesis that exhausts the spares continues with philox_word().  Same law as
-// draw_sample_dyn; the streams differ.
+// Sampler of the exactly determined path (sample size S = deg + 1 known at compile time), SURVEY.md
+// App. A.8.  Every lane generates the same NB Philox blocks (no divergence in the generator): word k
+// draws peak k, half-word k of the following words is the first try of candidate k.
+//
+// Peaks - np.random.choice(peaks, S, replace=False, p=prob) (:538-540) is successive sampling: the next
+// peak is drawn from the law renormalised over the peaks not yet chosen.  No rejection loop: word k is
+// scaled onto the REMAINING mass (u = mulhi(w, 2^32 - chosen mass): a monotone map, so every interval keeps
+// its probability to 2^-32, the CDF's own resolution) and then shifted past the chosen intervals in
+// ascending order (<= S-1 compare+add, the chosen list is kept sorted in registers).
+//
+// Candidates - uniform over the peak's candidate ARRAY (duplicates count, App. A.3), redrawn while the
+// wavelength is already used (:544-566).  The fast path takes the first try of every pick (Lemire's
+// multiply-shift on 16 bits); a hypothesis that needs a redraw (a Lemire rejection or a repeated
+// wavelength, ~5 %) is reported back and finished by draw_candidates_slow() in a warp-wide round of
+// such hypotheses (stage A's deferred queue), which continues with the Philox blocks after the eager
+// ones; an impossible draw aborts there (the try is consumed, :557-566).
 template <int S>
-__device__ __forceinline__ bool draw_sample(const TablesA& t, unsigned long long seed, unsigned long long gid,
-                                            int (&pi)[S], int (&ci)[S]) {
-  constexpr int NWC = (S + 1) / 2;           // words holding the candidate half-words
-  constexpr int NB = (S + NWC + 2 + 3) / 4;  // eager blocks: at least two spare words
-  constexpr int NW = 4 * NB, SP0 = S + NWC, NSP = NW - SP0;
-  const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), c0 = (unsigned)gid, c1 = (unsigned)(gid >> 32);
-  unsigned w[NW];
+struct SamplerDims {
+  static constexpr int NWC = (S + 1) / 2;       // words holding the candidate half-words
+  static constexpr int NB = (S + NWC + 3) / 4;  // eager blocks
+  static constexpr int NW = 4 * NB;
+};
+
+template <int S>
+__device__ __forceinline__ void draw_peaks(const TablesA& t, const unsigned (&w)[SamplerDims<S>::NW], int (&pi)[S],
+                                           unsigned (&off)[S], unsigned (&kt)[S]) {
+  unsigned lo_s[S > 1 ? S - 1 : 1], wd_s[S > 1 ? S - 1 : 1];  // chosen intervals, ascending lo
+  unsigned mass = 0u;                                         // their total width (mod 2^32)
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
+  for (int k = 0; k < S; ++k) {
+    unsigned u = (k == 0) ? w[0] : __umulhi(w[k], 0u - mass);
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j)
+      if (j < k) u += (u >= lo_s[j]) ? wd_s[j] : 0u;
+    PeakRec r;
+    pi[k] = find_peak(t, u, r);
+    off[k] = r.off; kt[k] = r.kt;
+    if (k < S - 1) {
+      unsigned cl = r.lo, cw = r.wd;
+#pragma unroll
+      for (int j = 0; j < S - 1; ++j) {
+        if (j < k) {
+          const bool sw = cl < lo_s[j];
+          const unsigned tl = sw ? lo_s[j] : cl, tw = sw ? wd_s[j] : cw;
+          lo_s[j] = sw ? cl : lo_s[j]; wd_s[j] = sw ? cw : wd_s[j];
+          cl = tl; cw = tw;
+        }
+      }
+      lo_s[k] = cl; wd_s[k] = cw;
+      mass += r.wd;
+    }
+  }
+}
+
+template <int S, class KEY>
+__device__ __forceinline__ void philox_eager(const KEY& key, unsigned c0, unsigned c1, unsigned (&w)[SamplerDims<S>::NW]) {
+#pragma unroll
+  for (int b = 0; b < SamplerDims<S>::NB; ++b) {
     unsigned o[4];
-    philox_block(k0, k1, c0, c1, (unsigned)b, o);
+    if constexpr (sizeof(KEY) == sizeof(PhiloxKey)) philox_block(key, c0, c1, (unsigned)b, o);
+    else philox_block((unsigned)key, (unsigned)(key >> 32), c0, c1, (unsigned)b, o);
     w[4 * b] = o[0]; w[4 * b + 1] = o[1]; w[4 * b + 2] = o[2]; w[4 * b + 3] = o[3];
   }
-  unsigned n_retry = 0;
-  auto retry_word = [&]() -> unsigned {  // spare words in stream order: a shift register, no indexed select
-    unsigned r;
-    if (n_retry < (unsigned)NSP) {
-      r = w[SP0];
-#pragma unroll
-      for (int j = 0; j + 1 < NSP; ++j) w[SP0 + j] = w[SP0 + j + 1];
-    } else {
-      r = philox_word(k0, k1, c0, c1, (unsigned)NW + (n_retry - (unsigned)NSP));
-    }
-    ++n_retry;
-    return r;
-  };
-  // peaks: weighted, without replacement (np.random.choice(..., replace=False, p=prob), :538-540)
-#pragma unroll
-  for (int k = 0; k < S; ++k) {
-    int idx = draw_peak_lut(t, w[k]);
-    for (;;) {
-      bool dup = false;
-#pragma unroll
-      for (int j = 0; j < S; ++j) if (j < k) dup |= (pi[j] == idx);
-      if (!dup) break;
-      idx = draw_peak_lut(t, retry_word());
-    }
-    pi[k] = idx;
-  }
-  // one candidate wavelength per peak, no wavelength twice (:544-566); exactly uniform in [0, K)
-  // from 16 bits by Lemire's multiply-shift with the rare rejection that removes the bias
+}
+
+// returns false when a candidate pick needs a redraw (-> slow round); pi / ci / ys are complete when true
+template <int S>
+__device__ __forceinline__ bool draw_sample_fast(const TablesA& t, const PhiloxKey& key, unsigned long long gid,
+                                                 int (&pi)[S], int (&ci)[S], double (&ys)[S]) {
+  unsigned w[SamplerDims<S>::NW];
+  philox_eager<S>(key, (unsigned)gid, (unsigned)(gid >> 32), w);
+  unsigned off[S], kt[S];
+  draw_peaks<S>(t, w, pi, off, kt);
   int wi[S];
+  bool ok = true;
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    const int o0 = t.coff[pi[k]], K = t.coff[pi[k] + 1] - o0;
+    const unsigned K = kt[k] & 0xffffu, thr = kt[k] >> 16;
+    const unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
+    const unsigned x = h * K;
+    ok &= (x & 0xffffu) >= thr;
+    const int c = (int)(off[k] + (x >> 16));
+    const CandRec cr = t.crec[c];
+#pragma unroll
+    for (int q = 0; q < S; ++q) if (q < k) ok &= (wi[q] != cr.wid);
+    wi[k] = cr.wid; ci[k] = c; ys[k] = cr.wave;
+  }
+  return ok;
+}
+
+constexpr int DRAW_MAX_TRIES = 1 << 14;  // per pick; a draw that still fails then is counted as aborted
+
+// the same hypothesis with the redraw loops; false = impossible draw (aborted)
+template <int S>
+__device__ __noinline__ bool draw_sample_slow(const TablesA& t, unsigned long long seed, unsigned long long gid,
+                                              int (&pi)[S], int (&ci)[S], double (&ys)[S]) {
+  constexpr int NW = SamplerDims<S>::NW;
+  const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), c0 = (unsigned)gid, c1 = (unsigned)(gid >> 32);
+  unsigned w[NW];
+  philox_eager<S>(seed, c0, c1, w);
+  unsigned off[S], kt[S];
+  draw_peaks<S>(t, w, pi, off, kt);
+  int wi[S];
+  unsigned n_half = 0u, cur = 0u;  // 16-bit halves of the words after the eager blocks, in stream order
+  for (int k = 0; k < S; ++k) {
+    const unsigned K = kt[k] & 0xffffu, thr = kt[k] >> 16;
     unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
     bool checked = false;
     int n_dup = 0;
-    for (;;) {
-      unsigned x = h * (unsigned)K;
-      bool redraw = false;
-      if ((x & 0xffffu) < (unsigned)K) redraw = (x & 0xffffu) < (65536u % (unsigned)K);
-      if (!redraw) {
-        const int j = (int)(x >> 16);
-        const int wv = t.cwid[o0 + j];
+    for (int tries = 0;; ++tries) {
+      if (tries >= DRAW_MAX_TRIES) return false;
+      const unsigned x = h * K;
+      if ((x & 0xffffu) >= thr) {
+        const int c = (int)(off[k] + (x >> 16));
+        const CandRec cr = t.crec[c];
         bool dup = false;
-#pragma unroll
-        for (int q = 0; q < S; ++q) if (q < k) dup |= (wi[q] == wv);
-        if (!dup) { wi[k] = wv; ci[k] = o0 + j; break; }
+        for (int q = 0; q < k; ++q) dup |= (wi[q] == cr.wid);
+        if (!dup) { wi[k] = cr.wid; ci[k] = c; ys[k] = cr.wave; break; }
         if (!checked && ++n_dup >= 3) {  // after a few duplicates: is any unused wavelength left for this peak?
           bool possible = false;
-          for (int jj = 0; jj < K; ++jj) {
-            const int ww = t.cwid[o0 + jj];
+          for (unsigned jj = 0; jj < K; ++jj) {
+            const int ww = t.crec[off[k] + jj].wid;
             bool used = false;
-#pragma unroll
-            for (int q = 0; q < S; ++q) if (q < k) used |= (wi[q] == ww);
+            for (int q = 0; q < k; ++q) used |= (wi[q] == ww);
             possible |= !used;
           }
           if (!possible) return false;  // impossible draw: the try is consumed (:557-566)
           checked = true;
         }
       }
-      h = retry_word() & 0xffffu;
+      if (n_half & 1u) h = cur >> 16;
+      else { cur = philox_word(k0, k1, c0, c1, (unsigned)NW + (n_half >> 1)); h = cur & 0xffffu; }
+      ++n_half;
     }
   }
   return true;
 }
 
-// generic (run-time sample size) variant for the least-squares path
+// generic (run-time sample size) variant for the least-squares path: rejection sampling with the
+// sequential Philox stream (same law; the streams differ)
 __device__ bool draw_sample_dyn(const TablesA& t, unsigned long long seed, unsigned long long gid, int s, int* pi, int* ci) {
   Rng rng;
   rng.init(seed, gid);
   int wi[RB2_MAX_SAMPLE];
+  unsigned off[RB2_MAX_SAMPLE], kt[RB2_MAX_SAMPLE];
   for (int k = 0; k < s; ++k) {
     int idx;
     bool dup;
+    int tries = 0;
+    PeakRec r;
     do {
-      idx = draw_peak_lut(t, rng.next32());
+      if (++tries > DRAW_MAX_TRIES) return false;  // degenerate sampling law: never spin
+      idx = find_peak(t, rng.next32(), r);
       dup = false;
       for (int j = 0; j < k; ++j) dup |= (pi[j] == idx);
     } while (dup);
-    pi[k] = idx;
+    pi[k] = idx; off[k] = r.off; kt[k] = r.kt;
   }
   for (int k = 0; k < s; ++k) {
-    const int o0 = t.coff[pi[k]], K = t.coff[pi[k] + 1] - o0;
+    const int o0 = (int)off[k], K = (int)(kt[k] & 0xffffu);
     bool checked = false;
-    for (;;) {
+    for (int tries = 0;; ++tries) {
+      if (tries >= DRAW_MAX_TRIES) return false;
       const int j = rng.uniform(K);
-      const int w = t.cwid[o0 + j];
+      const int w = t.crec[o0 + j].wid;
       bool dup = false;
       for (int q = 0; q < k; ++q) dup |= (wi[q] == w);
       if (!dup) { wi[k] = w; ci[k] = o0 + j; break; }
       if (!checked) {
         bool possible = false;
         for (int jj = 0; jj < K; ++jj) {
-          const int ww = t.cwid[o0 + jj];
+          const int ww = t.crec[o0 + jj].wid;
           bool used = false;
           for (int q = 0; q < k; ++q) used |= (wi[q] == ww);
           possible |= !used;
@@ -737,11 +825,18 @@ __device__ bool draw_sample_dyn(const TablesA& t, unsigned long long seed, unsig
 struct Pipe {  // device pointers of the staged pipeline (one per rb2_ransac_batch call)
   double* qa; double* qb;           // queues, `cap` entries of qs doubles
   unsigned* counts;                 // [0] = |queue A|, [1] = |queue B|
-  BestKey* best;                    // [n_problems]
+  BestKey* best;                    // [n_problems] running best over the stage-C2 costs (tree-summed errors)
+  BestKey* best_exact;              // [n_problems] running best over the exact costs of the contenders (stage C3)
   double* res_cost; double* res_esum; int2* res_cnt;  // per queue-B entry
+  double* res_w;                    // per queue-B entry: Hough-density weight (when the cost was evaluated)
+  unsigned char* res_flag;          // per queue-B entry: RES_* bits
   rb2_ransac_result* win;           // [n_problems] winner records written by THIS lane's stage D
   unsigned cap; int qs;
 };
+enum : unsigned char { RES_ELIGIBLE = 1, RES_NEAR_FLOOR = 2, RES_EXACT = 4 };
+// two costs computed from the same coefficients differ only by the summation order of <= n_peaks clipped
+// errors (a few ulp); anything within this relative margin of the running best is re-summed exactly
+constexpr double COST_MARGIN = 1e-12;
 
 constexpr int PIPE_MAX_LANES = 4;
 struct PipeSet { Pipe p[PIPE_MAX_LANES]; int n; };
@@ -750,7 +845,8 @@ __global__ void pipe_init_kernel(PipeSet ps, rb2_ransac_result* __restrict__ res
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 2) for (int l = 0; l < ps.n; ++l) ps.p[l].counts[i] = 0u;
   if (i >= n_problems) return;
-  ps.p[0].best[i].hi = ~0ull; ps.p[0].best[i].lo = ~0ull;  // the running best is shared by all lanes
+  ps.p[0].best[i].hi = ~0ull; ps.p[0].best[i].lo = ~0ull;  // the running bests are shared by all lanes
+  ps.p[0].best_exact[i].hi = ~0ull; ps.p[0].best_exact[i].lo = ~0ull;
   rb2_ransac_result r;
   r.cost = CUDART_INF; r.hyp_id = -1; r.n_match = 0; r.n_inliers = 0;
   for (int k = 0; k < NCOEF; ++k) r.coeffs[k] = 0.0;
@@ -787,15 +883,21 @@ __device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigne
 #define RB2_A_CTAS 4
 #endif
 // LSQ = false: sample_size == deg + 1, exact interpolation (newton_fit); LSQ = true (DEG_T > 0): run-time
-// sample size and known pairs, least squares with the compile-time degree (lsq_polyfit_givens)
+// sample size and known pairs, least squares with the compile-time degree (lsq_polyfit_givens).
+//
+// Work items of a warp are either the next 32 hypothesis ids of its stream (fast sampler) or 32
+// hypotheses from its deferred queue (those whose fast draw needs a redraw: slow sampler, all lanes
+// busy again); draw, fit, intercept test and the queue push are the same code for both.
 template <int DEG_T, bool LSQ = false>
 __global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 && !LSQ ? RB2_A_CTAS : 2)
 ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
-                       rb2_ransac_result* __restrict__ result) {
+                       rb2_ransac_result* __restrict__ result, const PhiloxKey pkey) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ rb2_ransac_desc s_desc;
   __shared__ unsigned s_cnt[3];
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ unsigned s_defer[RS_WARPS][64];
+  constexpr bool FAST = DEG_T > 0 && !LSQ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int problem = blockIdx.y;
   {
     const unsigned* src = reinterpret_cast<const unsigned*>(descs + problem);
@@ -809,15 +911,26 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   const int ncoef = deg + 1;
   const int n_u = d.n_upeaks, n_c = d.n_cand;
 
-  double* s_peaks = reinterpret_cast<double*>(smem_raw);
-  double* s_cwave = s_peaks + n_u;
-  int* s_coff = reinterpret_cast<int*>(s_cwave + n_c);
-  int* s_cwid = s_coff + (n_u + 1);
-  unsigned* s_cdf = reinterpret_cast<unsigned*>(s_cwid + n_c);
+  PeakRec* s_prec = reinterpret_cast<PeakRec*>(smem_raw);
+  CandRec* s_crec = reinterpret_cast<CandRec*>(s_prec + n_u);
+  double* s_peaks = reinterpret_cast<double*>(s_crec + n_c);
+  unsigned* s_cdf = reinterpret_cast<unsigned*>(s_peaks + n_u);
   unsigned short* s_lut = reinterpret_cast<unsigned short*>(s_cdf + n_u);
-  for (int i = tid; i < n_u; i += RS_THREADS) { s_peaks[i] = d.d_peaks[i]; s_cdf[i] = d.d_cdf32 ? d.d_cdf32[i] : 0u; }
-  for (int i = tid; i <= n_u; i += RS_THREADS) s_coff[i] = d.d_cand_off[i];
-  for (int i = tid; i < n_c; i += RS_THREADS) { s_cwave[i] = d.d_cand_wave[i]; s_cwid[i] = d.d_cand_wid[i]; }
+  for (int i = tid; i < n_u; i += RS_THREADS) {
+    s_peaks[i] = d.d_peaks[i];
+    const unsigned hi = d.d_cdf32 ? d.d_cdf32[i] : 0u, lo = (i > 0 && d.d_cdf32) ? d.d_cdf32[i - 1] : 0u;
+    const int o0 = d.d_cand_off[i], K = d.d_cand_off[i + 1] - o0;
+    PeakRec r;
+    r.lo = lo; r.wd = (i == n_u - 1) ? 0u - lo : hi - lo;  // the last interval ends at 2^32
+    r.off = (unsigned)o0; r.kt = (unsigned)K | ((K > 0 ? 65536u % (unsigned)K : 0u) << 16);
+    s_prec[i] = r;
+    s_cdf[i] = hi;
+  }
+  for (int i = tid; i < n_c; i += RS_THREADS) {
+    CandRec c;
+    c.wave = d.d_cand_wave[i]; c.wid = d.d_cand_wid[i]; c.pad = 0;
+    s_crec[i] = c;
+  }
   __syncthreads();
   {
     // lut[b] = #{i : cdf32[i] <= b << (32 - LUT_BITS)}, clamped: a thread fills a run of consecutive cells
@@ -843,60 +956,113 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   }
   __syncthreads();
   TablesA tb;
-  tb.peaks = s_peaks; tb.cwave = s_cwave; tb.coff = s_coff; tb.cwid = s_cwid; tb.cdf32 = s_cdf; tb.lut = s_lut; tb.n_u = n_u;
+  tb.prec = s_prec; tb.crec = s_crec; tb.peaks = s_peaks; tb.lut = s_lut; tb.n_u = n_u;
 
   const bool replay = d.d_replay_x != nullptr;
-  const int s = (DEG_T > 0 && !LSQ) ? DEG_T + 1 : d.sample_size;
+  const int s = FAST ? DEG_T + 1 : d.sample_size;
   const double min_i = d.min_intercept, max_i = d.max_intercept;
   const long long n_hyp = d.n_hyp;
   const double lsq_xc = 0.5 * (d.pix_min + d.pix_max);
   const double lsq_xsc = (d.pix_max > d.pix_min) ? 2.0 / (d.pix_max - d.pix_min) : 1.0;
   const int qs = pipe.qs;
   unsigned c_drawn = 0, c_abort = 0, c_icpt = 0;
-  const bool diag = d.d_out_status != nullptr || d.d_out_coeffs != nullptr;  // parity / diagnostics launches only
+  const bool diag = d.d_out_status != nullptr || d.d_out_coeffs != nullptr || d.d_out_sample != nullptr;  // parity / diagnostics launches only
 
   const long long stride = (long long)gridDim.x * RS_THREADS;
-  for (long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane); base < chunk_len; base += stride) {
-    const long long id = chunk_begin + base + lane;  // index inside this call
-    const bool active = (base + lane < chunk_len) && (id < n_hyp);
-    bool pass = false, aborted = false;
+  long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane);
+  unsigned qn = 0u;  // hypotheses in this warp's deferred queue (warp-uniform)
+  unsigned* const s_q = s_defer[warp];
+  for (;;) {
+    const bool stream_left = base < chunk_len;
+    bool slow = false, active = false;
+    unsigned rel = 0u;  // hypothesis index inside the chunk
+    if (FAST && (qn >= 32u || (!stream_left && qn > 0u))) {
+      const unsigned take = min(qn, 32u);
+      slow = true;
+      active = (unsigned)lane < take;
+      if (active) rel = s_q[qn - take + lane];
+      qn -= take;
+      __syncwarp();
+    } else if (stream_left) {
+      rel = (unsigned)(base + lane);
+      active = (base + lane < chunk_len) && (chunk_begin + base + lane < n_hyp);
+      base += stride;
+    } else {
+      break;
+    }
+    const long long id = chunk_begin + (long long)rel;  // index inside this call
+    bool pass = false, aborted = false, deferred = false;
     double cf[NCOEF];
 #pragma unroll
     for (int i = 0; i < NCOEF; ++i) cf[i] = 0.0;
-    if (active) {
-      if constexpr (DEG_T > 0 && !LSQ) {
-        int pi[DEG_T + 1], ci[DEG_T + 1];
+    if constexpr (FAST) {
+      int pi[DEG_T + 1], ci[DEG_T + 1];
+      double ys[DEG_T + 1];
+      if (active) {
         if (replay) {
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) {
             pi[k] = d.d_replay_x[id * (DEG_T + 1) + k];
-            ci[k] = tb.coff[pi[k]] + d.d_replay_y[id * (DEG_T + 1) + k];
+            ci[k] = (int)tb.prec[pi[k]].off + d.d_replay_y[id * (DEG_T + 1) + k];
+            ys[k] = tb.crec[ci[k]].wave;
           }
+        } else if (!slow) {
+          deferred = !draw_sample_fast<DEG_T + 1>(tb, pkey, (unsigned long long)(d.hyp_begin + id), pi, ci, ys);
         } else {
-          aborted = !draw_sample<DEG_T + 1>(tb, d.seed, (unsigned long long)(d.hyp_begin + id), pi, ci);
-        }
-        if (!aborted) {
-          double xs[DEG_T + 1], ys[DEG_T + 1], cc[DEG_T + 1];
+          // own arrays: the call is not inlined, its outputs live in local memory - only here
+          int pi2[DEG_T + 1], ci2[DEG_T + 1];
+          double ys2[DEG_T + 1];
+          aborted = !draw_sample_slow<DEG_T + 1>(tb, d.seed, (unsigned long long)(d.hyp_begin + id), pi2, ci2, ys2);
 #pragma unroll
-          for (int k = 0; k <= DEG_T; ++k) { xs[k] = tb.peaks[pi[k]]; ys[k] = tb.cwave[ci[k]]; }
+          for (int k = 0; k <= DEG_T; ++k) { pi[k] = pi2[k]; ci[k] = ci2[k]; ys[k] = ys2[k]; }
+        }
+      }
+      if (!slow && !replay) {  // park the hypotheses that need a redraw
+        const unsigned dm = __ballot_sync(0xffffffffu, deferred);
+        if (dm) {
+          if (deferred) s_q[qn + __popc(dm & ((1u << lane) - 1u))] = rel;
+          qn += __popc(dm);
+          __syncwarp();
+        }
+        active = active && !deferred;
+      }
+      if (active && !aborted) {
+        if (replay && d.d_replay_coeffs) {
+#pragma unroll
+          for (int k = 0; k <= DEG_T; ++k) cf[k] = d.d_replay_coeffs[id * (DEG_T + 1) + k];
+        } else {
+          double xs[DEG_T + 1], cc[DEG_T + 1];
+#pragma unroll
+          for (int k = 0; k <= DEG_T; ++k) xs[k] = tb.peaks[pi[k]];
           newton_fit<DEG_T>(xs, ys, cc);
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) cf[k] = cc[k];
         }
-      } else {
-        int pi[RB2_MAX_SAMPLE], ci[RB2_MAX_SAMPLE];
-        if (replay) {
-          for (int k = 0; k < s; ++k) {
-            pi[k] = d.d_replay_x[id * s + k];
-            ci[k] = tb.coff[pi[k]] + d.d_replay_y[id * s + k];
-          }
-        } else {
-          aborted = !draw_sample_dyn(tb, d.seed, (unsigned long long)(d.hyp_begin + id), s, pi, ci);
+      }
+      if (active && d.d_out_sample) {
+#pragma unroll
+        for (int k = 0; k <= DEG_T; ++k) {
+          d.d_out_sample[(id * (DEG_T + 1) + k) * 2] = aborted ? -1 : pi[k];
+          d.d_out_sample[(id * (DEG_T + 1) + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)tb.prec[pi[k]].off;
         }
-        if (!aborted) {
+      }
+    } else if (active) {
+      int pi[RB2_MAX_SAMPLE], ci[RB2_MAX_SAMPLE];
+      if (replay) {
+        for (int k = 0; k < s; ++k) {
+          pi[k] = d.d_replay_x[id * s + k];
+          ci[k] = (int)tb.prec[pi[k]].off + d.d_replay_y[id * s + k];
+        }
+      } else {
+        aborted = !draw_sample_dyn(tb, d.seed, (unsigned long long)(d.hyp_begin + id), s, pi, ci);
+      }
+      if (!aborted) {
+        if (replay && d.d_replay_coeffs) {
+          for (int k = 0; k < ncoef; ++k) cf[k] = d.d_replay_coeffs[id * ncoef + k];
+        } else {
           double xs[RB2_MAX_SAMPLE], ys[RB2_MAX_SAMPLE];
           int m = 0;
-          for (int k = 0; k < s; ++k) { xs[m] = tb.peaks[pi[k]]; ys[m] = tb.cwave[ci[k]]; ++m; }
+          for (int k = 0; k < s; ++k) { xs[m] = tb.peaks[pi[k]]; ys[m] = tb.crec[ci[k]].wave; ++m; }
           for (int k = 0; k < d.n_known && m < RB2_MAX_SAMPLE; ++k) { xs[m] = d.d_known_x[k]; ys[m] = d.d_known_y[k]; ++m; }
           if constexpr (LSQ) {
             lsq_polyfit_givens<DEG_T>(xs, ys, m, lsq_xc, lsq_xsc, cf);
@@ -905,6 +1071,13 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
           }
         }
       }
+      if (d.d_out_sample)
+        for (int k = 0; k < s; ++k) {
+          d.d_out_sample[(id * s + k) * 2] = aborted ? -1 : pi[k];
+          d.d_out_sample[(id * s + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)tb.prec[pi[k]].off;
+        }
+    }
+    if (active) {
       if (!aborted) pass = !((cf[0] < min_i) || (cf[0] > max_i));  // :578-582
       if (diag) {
         if (!aborted) {
@@ -918,7 +1091,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
     }
     const unsigned pm = __ballot_sync(0xffffffffu, pass);
     c_drawn += active && !aborted;
-    c_abort += aborted;
+    c_abort += active && aborted;
     c_icpt += active && !aborted && !pass;
     if (pm) {  // warp-aggregated push
       unsigned slot0 = 0;
@@ -1109,6 +1282,23 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
 // problem's running best (or the hypothesis lacks the inliers to be eligible) the weight cannot
 // change the outcome and only its regime test is run.  Selection and counters are unaffected
 // (the `eligible` counter counts the inlier criteria only).
+// The cost here uses stage C1's tree-summed errors; it ranks the hypotheses up to COST_MARGIN.  The
+// final choice is made by stage C3 on exactly summed costs of the few that are that close to the best.
+__device__ __forceinline__ double key_cost(unsigned long long k) {  // inverse of cost_key
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ void best_update(BestKey* slot, const BestKey& mine) {
+  BestKey cur;
+  cur.hi = *reinterpret_cast<volatile unsigned long long*>(&slot->hi);
+  cur.lo = *reinterpret_cast<volatile unsigned long long*>(&slot->lo);
+  while (key_better(mine, cur)) {
+    const BestKey old = atomicCAS(slot, cur, mine);
+    if (old.hi == cur.hi && old.lo == cur.lo) break;
+    cur = old;
+  }
+}
+
 template <int DEG_T>
 __global__ void __launch_bounds__(128, 4)
 ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
@@ -1132,7 +1322,7 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
       const int2 cnt = pipe.res_cnt[e];
       const int nm = cnt.x, ni = cnt.y;
       const double esum = pipe.res_esum[e];
-      pipe.res_cost[e] = CUDART_NAN;
+      unsigned char flag = 0;
       if (nm == 0) {  // :607-608
         kind = 0;
         if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY;
@@ -1143,7 +1333,7 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
         bool need_value = wants_all || counts_ok;
         const double denom = (double)(nm - ncoef + 1);
         if (need_value && !wants_all && d.w_upper > 0.0) {
-          const double lb = esum / denom / (d.w_upper + 1e-9);
+          const double lb = esum / denom / (d.w_upper + 1e-9) * (1.0 - COST_MARGIN);
           const unsigned long long best_hi = *reinterpret_cast<volatile unsigned long long*>(&pipe.best[problem].hi);
           if (cost_key(lb) > best_hi || lb > d.cost_ceiling) need_value = false;
         }
@@ -1159,26 +1349,28 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
           if (need_value) {
             const double cost = esum / denom / (weight + 1e-9);  // :629-633
             bool elig = counts_ok && (cost <= d.cost_ceiling);
-            if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
+            bool near_floor = false;
+            if (elig && d.floor_id >= 0) {  // fall-through: only what ranks after (floor_cost, floor_id), decided exactly in C3
+              const double slack = COST_MARGIN * fabs(d.floor_cost);
+              near_floor = fabs(cost - d.floor_cost) <= slack;
+              elig = near_floor || cost > d.floor_cost;
+            }
             if (d.d_out_cost) d.d_out_cost[id] = cost;
             if (d.d_out_weight) d.d_out_weight[id] = weight;
             if (elig) {
               pipe.res_cost[e] = cost;
-              BestKey mine;
-              mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
-              BestKey* slot = pipe.best + problem;
-              BestKey cur;
-              cur.hi = *reinterpret_cast<volatile unsigned long long*>(&slot->hi);
-              cur.lo = *reinterpret_cast<volatile unsigned long long*>(&slot->lo);
-              while (key_better(mine, cur)) {
-                const BestKey old = atomicCAS(slot, cur, mine);
-                if (old.hi == cur.hi && old.lo == cur.lo) break;
-                cur = old;
+              pipe.res_w[e] = weight;
+              flag = near_floor ? RES_NEAR_FLOOR : RES_ELIGIBLE;
+              if (!near_floor) {
+                BestKey mine;
+                mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
+                best_update(pipe.best + problem, mine);
               }
             }
           }
         }
       }
+      pipe.res_flag[e] = flag;
     }
     // counters (empty, scored, eligible, unsupported), aggregated over the lanes of one problem
     const unsigned have = __ballot_sync(0xffffffffu, kind >= 0);
@@ -1194,19 +1386,119 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
   }
 }
 
+// ---- stage C3 --------------------------------------------------------------------------
+// The reference sums the clipped errors with Python's sequential sum() in ascending-wavelength order
+// (calibrator.py:629); stage C1 sums them per lane and by a butterfly.  The few
+// hypotheses whose C2 cost is within COST_MARGIN of the running best (or of the fall-through floor) are
+// re-matched here, one warp each, and their errors added one by one in that order; the exact costs feed
+// a second running best, which is the one stage D records.  Dynamic smem: u64 berr[max_wids] per warp.
+template <int DEG_T>
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_exact_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned n = pipe.counts[1];
+  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1;
+  unsigned long long* berr = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * max_wids;
+  for (int i = lane; i < max_wids; i += 32) berr[i] = INF_BITS;
+  __syncwarp();
+  const unsigned total_warps = gridDim.x * RS_WARPS;
+  for (unsigned g = blockIdx.x * RS_WARPS + warp; g * 32u < n; g += total_warps) {
+    const unsigned e = g * 32u + lane;
+    bool contender = false;
+    if (e < n) {
+      const unsigned char flag = pipe.res_flag[e];
+      if (flag & RES_NEAR_FLOOR) {
+        contender = true;
+      } else if (flag & RES_ELIGIBLE) {
+        const unsigned long long tag = (unsigned long long)__double_as_longlong(pipe.qb[(size_t)e * qs + ncoef]);
+        const unsigned long long bh = *reinterpret_cast<volatile unsigned long long*>(&pipe.best[(int)(tag >> 40)].hi);
+        const double best = key_cost(bh);
+        contender = pipe.res_cost[e] <= best + COST_MARGIN * fabs(best);
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, contender);
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned eb = g * 32u + b;
+      const double* q = pipe.qb + (size_t)eb * qs;
+      double cr[deg_cap(DEG_T) + 1];
+#pragma unroll
+      for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? q[k] : 0.0;
+      const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+      const int problem = (int)(tag >> 40);
+      const rb2_ransac_desc& d = descs[problem];
+      const int n_u = d.n_upeaks, n_w = d.n_wids;
+      const double tol = d.tol;
+      // nearest candidate per peak, best error per wavelength (calibrator.py:341-376)
+      for (int u = lane; u < n_u; u += 32) {
+        const double fit = horner_ref<deg_cap(DEG_T)>(cr, ncoef, d.d_peaks[u]);
+        const int o0 = d.d_cand_off[u], o1 = d.d_cand_off[u + 1];
+        double be = CUDART_INF;
+        int bk = -1;
+        for (int k = o0; k < o1; ++k) {
+          const double er = fabs(sub(fit, d.d_cand_wave[k]));
+          if (er < be) { be = er; bk = k; }
+        }
+        if (bk >= 0) atomicMin(&berr[d.d_cand_wid[bk]], (unsigned long long)__double_as_longlong(be));
+      }
+      __syncwarp();
+      // sum(err) in ascending wavelength (= ascending id) order, one addition after the other
+      double esum = 0.0;
+      int nm = 0;
+      for (int i0 = 0; i0 < n_w; i0 += 32) {
+        const int i = i0 + lane;
+        double er = 0.0;
+        bool has = false;
+        if (i < n_w) {
+          const unsigned long long bits = berr[i];
+          has = bits != INF_BITS;
+          er = __longlong_as_double((long long)bits);
+          if (er > tol) er = tol;  // M-SAC clip (:611)
+          berr[i] = INF_BITS;
+        }
+        unsigned hm = __ballot_sync(0xffffffffu, has);
+        nm += __popc(hm);
+        while (hm) {
+          const int src = __ffs(hm) - 1;
+          hm &= hm - 1;
+          esum = add(esum, __shfl_sync(0xffffffffu, er, src));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const double cost = esum / (double)(nm - ncoef + 1) / (pipe.res_w[eb] + 1e-9);  // :629-633
+        const long long gid = d.hyp_begin + (long long)(tag & TAG_ID_MASK);
+        bool elig = cost <= d.cost_ceiling;
+        if (elig && d.floor_id >= 0) elig = (cost > d.floor_cost) || (cost == d.floor_cost && gid < d.floor_id);
+        if (d.d_out_cost) d.d_out_cost[tag & TAG_ID_MASK] = cost;
+        if (elig) {
+          pipe.res_cost[eb] = cost;
+          pipe.res_flag[eb] = (unsigned char)(pipe.res_flag[eb] | RES_EXACT);
+          BestKey mine;
+          mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
+          best_update(pipe.best_exact + problem, mine);
+        }
+      }
+    }
+  }
+}
+
 // ---- stage D ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ransac_record_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe) {
   const unsigned n = pipe.counts[1];
   const int qs = pipe.qs, ncoef = qs - 1;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    if (!(pipe.res_flag[e] & RES_EXACT)) continue;
     const double cost = pipe.res_cost[e];
-    if (!(cost == cost)) continue;  // NaN = not eligible
     const double* q = pipe.qb + (size_t)e * qs;
     const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
     const int problem = (int)(tag >> 40);
     const long long gid = descs[problem].hyp_begin + (long long)(tag & TAG_ID_MASK);
-    const BestKey b = pipe.best[problem];
+    const BestKey b = pipe.best_exact[problem];
     if (b.hi != cost_key(cost) || b.lo != ~(unsigned long long)gid) continue;
     rb2_ransac_result* r = pipe.win + problem;
     r->cost = cost; r->hyp_id = gid;
@@ -1273,13 +1565,14 @@ static int pipe_lanes() {
   }();
   return n;
 }
-struct PipeLayout { size_t best, lane0, lane_bytes, counts, win, qa, qb, res_cost, res_esum, res_cnt, total; };
+struct PipeLayout { size_t best, best_exact, lane0, lane_bytes, counts, win, qa, qb, res_cost, res_esum, res_cnt, res_w, res_flag, total; };
 
 static PipeLayout pipe_layout(int n_problems) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   PipeLayout L;
   size_t o = 0;
   L.best = o; o = up(o + (size_t)n_problems * sizeof(BestKey));
+  L.best_exact = o; o = up(o + (size_t)n_problems * sizeof(BestKey));
   const size_t lane0 = o;
   L.lane0 = lane0;
   L.counts = o - lane0; o = up(o + 16);
@@ -1289,6 +1582,8 @@ static PipeLayout pipe_layout(int n_problems) {
   L.res_cost = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
   L.res_esum = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
   L.res_cnt = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.res_w = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
+  L.res_flag = o - lane0; o = up(o + (size_t)PIPE_CHUNK);
   L.lane_bytes = o - lane0;
   L.total = lane0 + (size_t)pipe_lanes() * L.lane_bytes;
   return L;
@@ -1319,37 +1614,57 @@ static LaneStreams& lane_streams() {
 }
 
 static size_t stage_a_smem(const rb2_ransac_desc& h) {
-  return (size_t)h.n_upeaks * 8 + (size_t)h.n_cand * 8 + (size_t)(h.n_upeaks + 1) * 4 + (size_t)h.n_cand * 4 +
-         (size_t)h.n_upeaks * 4 + (size_t)(1 << LUT_BITS) * 2 + 16;
+  return (size_t)h.n_upeaks * (sizeof(PeakRec) + 8 + 4) + (size_t)h.n_cand * sizeof(CandRec) +
+         (size_t)(1 << LUT_BITS) * 2 + 16;
 }
 
+struct ChunkArgs {
+  dim3 grid_a; size_t smem_a, smem_c, smem_x; int max_wids, max_up, single, sms; cudaStream_t stream;
+  const rb2_ransac_desc* d_desc; Pipe pipe; long long chunk_begin, chunk_len; rb2_ransac_result* d_result;
+  PhiloxKey key;
+};
+
 template <int DEG_T, bool LSQ = false>
-static int launch_chunk(dim3 grid_a, size_t smem_a, size_t smem_c, int max_wids, int max_up, int single, int sms, cudaStream_t stream,
-                        const rb2_ransac_desc* d_desc, const Pipe& pipe, long long chunk_begin, long long chunk_len,
-                        rb2_ransac_result* d_result) {
-  static bool configured = false;
-  if (!configured || true) {
-    RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)));
-    RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    configured = true;
+static int launch_chunk(const ChunkArgs& a) {
+  // the opt-in for dynamic shared memory is per function and per device and only grows
+  static size_t cfg_a[64] = {}, cfg_c[64] = {}, cfg_x[64] = {};
+  int dev = 0;
+  RB2_CHECK(cudaGetDevice(&dev));
+  dev = (dev >= 0 && dev < 64) ? dev : 0;
+  if (a.smem_a > cfg_a[dev]) {
+    RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_a)));
+    cfg_a[dev] = a.smem_a;
+  }
+  if (a.smem_c > cfg_c[dev]) {
+    RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_c));
+    cfg_c[dev] = a.smem_c;
+  }
+  if (a.smem_x > cfg_x[dev] && a.smem_x > 48 * 1024) {
+    RB2_CHECK(cudaFuncSetAttribute(ransac_exact_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_x));
+    cfg_x[dev] = a.smem_x;
   }
   static const bool dbg = getenv("RB2_DEBUG_SYNC") != nullptr;  // diagnostics: name the stage that faults
+  cudaStream_t stream = a.stream;
   auto stage_ok = [&](const char* name) {
     if (!dbg) return true;
     const cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { fprintf(stderr, "rb2: stage %s failed: %s\n", name, cudaGetErrorString(e)); return false; }
     return true;
   };
-  pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(pipe);
-  ransac_draw_fit_kernel<DEG_T, LSQ><<<grid_a, RS_THREADS, smem_a, stream>>>(d_desc, pipe, chunk_begin, chunk_len, d_result);
+  const int sms = a.sms;
+  pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(a.pipe);
+  ransac_draw_fit_kernel<DEG_T, LSQ><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(a.d_desc, a.pipe, a.chunk_begin, a.chunk_len,
+                                                                                 a.d_result, a.key);
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
-  ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(d_desc, pipe, d_result);
+  ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
-  ransac_match_kernel<DEG_T><<<sms * 4, RS_THREADS, smem_c, stream>>>(d_desc, pipe, max_wids, max_up, single);
+  ransac_match_kernel<DEG_T><<<sms * 4, RS_THREADS, a.smem_c, stream>>>(a.d_desc, a.pipe, a.max_wids, a.max_up, a.single);
   if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
-  ransac_cost_kernel<DEG_T><<<sms * 8, 128, 0, stream>>>(d_desc, pipe, d_result);
+  ransac_cost_kernel<DEG_T><<<sms * 8, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
-  ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(d_desc, pipe);
+  ransac_exact_kernel<DEG_T><<<sms * 2, RS_THREADS, a.smem_x, stream>>>(a.d_desc, a.pipe, a.max_wids);
+  if (!stage_ok("C3 exact")) return RB2_ERR_CUDA;
+  ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(a.d_desc, a.pipe);
   if (!stage_ok("D record")) return RB2_ERR_CUDA;
   return RB2_OK;
 }
@@ -1371,7 +1686,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   cudaStream_t stream = (cudaStream_t)stream_;
   int sms = 148;
   if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
-  // all problems of one call share degree / sample size (one kernel instantiation)
+  // all problems of one call share degree / sample size (one kernel instantiation) and the Philox key
   const int deg = h_desc[0].deg, s = h_desc[0].sample_size;
   bool fast = true;
   size_t smem_a = 0;
@@ -1379,7 +1694,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   long long max_hyp = 0;
   for (int i = 0; i < n_problems; ++i) {
     const rb2_ransac_desc& h = h_desc[i];
-    if (h.deg != deg || h.sample_size != s) return RB2_ERR_ARG;
+    if (h.deg != deg || h.sample_size != s || h.seed != h_desc[0].seed) return RB2_ERR_ARG;
     if (h.deg < 1 || h.deg > RB2_MAX_DEG || h.sample_size < h.deg + 1) return RB2_ERR_ARG;
     if (h.sample_size + h.n_known > RB2_MAX_SAMPLE) return RB2_ERR_ARG;
     if (h.n_upeaks < h.sample_size && !h.d_replay_x) return RB2_ERR_ARG;
@@ -1392,9 +1707,11 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     max_hyp = max(max_hyp, (long long)h.n_hyp);
   }
   const int single = (n_problems == 1);
+  const size_t smem_x = (size_t)RS_WARPS * max_wids * 8;
+  const PhiloxKey key = philox_key(h_desc[0].seed);
   size_t smem_c = (size_t)RS_WARPS * ((size_t)max_wids + max_up + (max_up + 1) / 2) * 8;
   if (single) smem_c += (size_t)h_desc[0].n_upeaks * 8 + (size_t)h_desc[0].n_cand * 12 + (size_t)(h_desc[0].n_upeaks + 1) * 4 + 16;
-  if (smem_a > 200 * 1024 || smem_c > 200 * 1024) return RB2_ERR_ARG;
+  if (smem_a > 200 * 1024 || smem_c > 200 * 1024 || smem_x > 200 * 1024) return RB2_ERR_ARG;
 
   const PipeLayout L = pipe_layout(n_problems);
   unsigned char* base = (unsigned char*)d_block_scratch;
@@ -1404,6 +1721,9 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     unsigned char* lb = base + L.lane0 + (size_t)l * L.lane_bytes;
     Pipe& pipe = ps.p[l];
     pipe.best = (BestKey*)(base + L.best);
+    pipe.best_exact = (BestKey*)(base + L.best_exact);
+    pipe.res_w = (double*)(lb + L.res_w);
+    pipe.res_flag = (unsigned char*)(lb + L.res_flag);
     pipe.counts = (unsigned*)(lb + L.counts);
     pipe.win = (rb2_ransac_result*)(lb + L.win);
     pipe.qa = (double*)(lb + L.qa);
@@ -1437,20 +1757,25 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
       const long long fill = max(1ll, (long long)(ctas_per_sm * sms) / n_problems);  // CTAs per SM overall
       bpp = (int)max(1ll, min(want, fill));
     }
-    dim3 grid_a(bpp, n_problems);
+    ChunkArgs ca;
+    ca.grid_a = dim3(bpp, n_problems); ca.smem_a = smem_a; ca.smem_c = smem_c; ca.smem_x = smem_x;
+    ca.max_wids = max_wids; ca.max_up = max_up; ca.single = single; ca.sms = sms; ca.stream = cstream;
+    ca.d_desc = d_desc; ca.pipe = pipe; ca.chunk_begin = c0; ca.chunk_len = len; ca.d_result = d_result; ca.key = key;
     int rc;
-    if (fast && deg == 1) rc = launch_chunk<1>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 2) rc = launch_chunk<2>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 3) rc = launch_chunk<3>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 4) rc = launch_chunk<4>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (fast && deg == 5) rc = launch_chunk<5>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    // over-determined samples / known pairs: compile-time degree everywhere, least squares in stage A
-    else if (deg == 1) rc = launch_chunk<1, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (deg == 2) rc = launch_chunk<2, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (deg == 3) rc = launch_chunk<3, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (deg == 4) rc = launch_chunk<4, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else if (deg == 5) rc = launch_chunk<5, true>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
-    else rc = launch_chunk<0>(grid_a, smem_a, smem_c, max_wids, max_up, single, sms, cstream, d_desc, pipe, c0, len, d_result);
+    switch ((fast ? 0 : 8) + (deg <= 5 ? deg : 0)) {
+      case 1: rc = launch_chunk<1>(ca); break;
+      case 2: rc = launch_chunk<2>(ca); break;
+      case 3: rc = launch_chunk<3>(ca); break;
+      case 4: rc = launch_chunk<4>(ca); break;
+      case 5: rc = launch_chunk<5>(ca); break;
+      // over-determined samples / known pairs: compile-time degree everywhere, least squares in stage A
+      case 9: rc = launch_chunk<1, true>(ca); break;
+      case 10: rc = launch_chunk<2, true>(ca); break;
+      case 11: rc = launch_chunk<3, true>(ca); break;
+      case 12: rc = launch_chunk<4, true>(ca); break;
+      case 13: rc = launch_chunk<5, true>(ca); break;
+      default: rc = launch_chunk<0>(ca); break;
+    }
     if (rc != RB2_OK) return rc;
   }
   for (int l = 1; l < n_lanes; ++l) {  // join: the caller's stream continues after every lane

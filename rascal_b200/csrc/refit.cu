@@ -557,7 +557,8 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
     res_out[(size_t)p * max_up + i] = res;
   }
   r.rms = sqrt(warp_sum(ss) / m);
-  r.accepted = (r.rms < min_fit_error) ? 0 : 1;
+  const double mfe = (min_fit_error == min_fit_error) ? min_fit_error : d.min_fit_error;  // NaN: per problem
+  r.accepted = (r.rms < mfe) ? 0 : 1;
   if (lane == 0) out[p] = r;
 }
 

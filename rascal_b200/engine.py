@@ -454,6 +454,10 @@ def sampling_cdf32(peaks):
     idx = np.minimum(np.searchsorted(edges, peaks, side="right") - 1, 9)
     counts = np.bincount(idx, minlength=10)
     dig = np.searchsorted(edges, peaks, side="left") - 1  # np.digitize(peaks, edges, right=True) - 1
+    if not np.all(counts[dig] > 0):
+        # a peak exactly on an interior histogram edge whose left bin is empty: the reference's weight is
+        # 1/0 = inf, prob = nan, and np.random.choice raises this on the first draw (calibrator.py:538)
+        raise ValueError("probabilities contain NaN")
     w = 1.0 / counts[dig]
     prob = w / np.cumsum(w)[-1]
     cdf = np.cumsum(prob)
@@ -634,6 +638,7 @@ class RansacBatch:
             d.min_inliers, d.min_inliers_frac = s.min_inliers, s.min_inliers_frac
             d.cost_ceiling = s.cost_ceiling
             d.floor_cost, d.floor_id = 0.0, -1
+            d.min_fit_error = float(s.minimum_fit_error)
         torch = _torch()
         sms = C.c_int(0)
         N.check(self.lib.rb2_sm_count(C.byref(sms)), "rb2_sm_count")
@@ -671,13 +676,17 @@ class RansacBatch:
         TRANSFER["h2d"] += nb
         self._desc_synced = True
 
-    def run(self, hyp_begin, n_hyp, seed=0, replay=None, per_hypothesis=False, floors=None):
+    def run(self, hyp_begin, n_hyp, seed=0, replay=None, per_hypothesis=False, floors=None, replay_coeffs=None,
+            samples=False):
         """Evaluate hypothesis ids [hyp_begin, hyp_begin + n_hyp) of every problem; the winner
         records stay on the device (results() / fetch() bring them back).
 
         replay: optional (x_idx[n_hyp, s], y_idx[n_hyp, s]) int arrays (parity
-        mode, one problem); per_hypothesis=True also returns status / cost /
-        weight / coefficients / counts of every hypothesis (one problem).
+        mode, one problem), replay_coeffs: with it, [n_hyp, deg+1] hypothesis coefficients used
+        instead of fitting (the reference's own polyfit output); per_hypothesis=True also returns
+        status / cost / weight / coefficients / counts of every hypothesis (one problem);
+        samples=True returns the draws themselves, "sample" [n_hyp, s, 2] = (peak index, candidate
+        index inside that peak's list), -1 where the draw was aborted (one problem).
         """
         torch = _torch()
         self._keep = []
@@ -687,6 +696,7 @@ class RansacBatch:
             d.hyp_begin, d.n_hyp, d.seed = int(hyp_begin), int(n_hyp), int(seed)
             d.d_replay_x = d.d_replay_y = None
             d.d_out_status = d.d_out_cost = d.d_out_weight = d.d_out_coeffs = d.d_out_counts = None
+            d.d_out_sample = d.d_replay_coeffs = None
             if floors is not None:
                 d.floor_cost, d.floor_id = float(floors[i][0]), int(floors[i][1])
             else:
@@ -698,6 +708,11 @@ class RansacBatch:
             assert rx.shape == (n_hyp, self.setups[0].sample_size)
             self._keep += [rx, ry]
             self.h_desc[0].d_replay_x, self.h_desc[0].d_replay_y = rx.data_ptr(), ry.data_ptr()
+            if replay_coeffs is not None:
+                rc_ = torch.from_numpy(np.ascontiguousarray(replay_coeffs, dtype=np.float64)).cuda()
+                assert rc_.shape == (n_hyp, self.setups[0].deg + 1)
+                self._keep.append(rc_)
+                self.h_desc[0].d_replay_coeffs = rc_.data_ptr()
         if per_hypothesis:
             assert self.n == 1
             nc = self.setups[0].deg + 1
@@ -710,6 +725,11 @@ class RansacBatch:
             d.d_out_status, d.d_out_cost = outs["status"].data_ptr(), outs["cost"].data_ptr()
             d.d_out_weight, d.d_out_coeffs = outs["weight"].data_ptr(), outs["coeffs"].data_ptr()
             d.d_out_counts = outs["counts"].data_ptr()
+        if samples:
+            assert self.n == 1
+            outs = outs if outs is not None else {}
+            outs["sample"] = torch.full((n_hyp, self.setups[0].sample_size, 2), -2, dtype=torch.int32, device="cuda")
+            self.h_desc[0].d_out_sample = outs["sample"].data_ptr()
         self._sync_desc()
         rc = self.lib.rb2_ransac_batch(self.n, self.d_desc.data_ptr(), C.addressof(self.h_desc),
                                        self.d_result.data_ptr(), self.scratch.data_ptr(), self.blocks_per_problem,
@@ -747,7 +767,7 @@ class RansacBatch:
 
     def refit_async(self, mode=0):
         """K4 on the winner records currently on the device; nothing is copied back."""
-        mfe = self.setups[0].minimum_fit_error
+        mfe = float("nan")  # every problem's own minimum_fit_error (rb2_ransac_desc.min_fit_error)
         if not self._desc_synced:
             self._sync_desc()
         base = self.d_out.data_ptr()

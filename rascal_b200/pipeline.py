@@ -85,13 +85,17 @@ class BatchResults:
         return (self[i] for i in range(self.n))
 
     def k3_tables(self, i):
-        """The K3 inputs rb2_ransac_prepare built for spectrum i (device -> host; tests / diagnostics).
-        Valid until the next pipeline.run() call (the device arena is reused)."""
+        """The K3 inputs rb2_ransac_prepare built for spectrum i.  After run(keep_tables=True) they are part of
+        this object (they came back with the results); otherwise they are read from the shared device arena
+        and are only valid until the next pipeline.run() call (tests / diagnostics)."""
         t = self._tables
         b = t["buf"]
 
         def rd(off, dtype, count):
             nb = np.dtype(dtype).itemsize * count
+            if "host" in t:
+                o = int(off) - t["host_base"]
+                return t["host"][o:o + nb].view(dtype)
             return b[int(off):int(off) + nb].cpu().numpy().view(dtype)
 
         d = rd(t["desc"] + i * _dt(N.RansacDesc).itemsize, _dt(N.RansacDesc), 1)[0]
@@ -106,7 +110,9 @@ class BatchResults:
             i += self.n
         r = types.SimpleNamespace(fit_coeff=None, matched_peaks=[], matched_atlas=[], rms=1e50, residual=None,
                                   peak_utilisation=0.0, atlas_utilisation=0.0, valid=False, cost=float("inf"),
-                                  counters=None, match=None)
+                                  counters=None, match=None, error=None)
+        if self.law_error[i]:
+            r.error = ValueError("probabilities contain NaN")
         if not self.enough[i]:
             return r
         r.counters = {k: int(self.counters[i, j]) for j, k in enumerate(N.COUNTER_NAMES)}
@@ -160,10 +166,11 @@ def _strictly_increasing(arrays):
     return bool(ok.all())
 
 
-def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None):
+def run(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None,
+        keep_tables=False):
     """run_async(...) followed by its finish(): the whole path for `specs`, results on the host."""
     return run_async(specs, n_hypotheses, seed=seed, refit_mode=refit_mode, match_tolerance=match_tolerance,
-                     timings=timings, hyp_begin=hyp_begin, exchange=exchange)()
+                     timings=timings, hyp_begin=hyp_begin, exchange=exchange, keep_tables=keep_tables)()
 
 
 class ChainedResults:
@@ -196,7 +203,7 @@ class ChainedResults:
 
 
 def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, timings=None, hyp_begin=0, exchange=None,
-              slot=0):
+              slot=0, keep_tables=False):
     """The whole path for `specs` (normalised, eligible) in batched device calls, without waiting for
     the device: returns finish(), which waits for this call's results and unpacks them.  Calls with
     different `slot`s use different device arenas / staging buffers, so the host can pack the next part
@@ -204,7 +211,11 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
 
     hyp_begin / n_hypotheses: the hypothesis-id range this process evaluates (a rank's shard of a
     sharded fit); exchange(result_tensor, n): called between K3 and K4 with the device tensor of the
-    n winner records (the one collective of a multi-GPU fit: all-gather + rb2_merge_winners in place)."""
+    n winner records (the one collective of a multi-GPU fit: all-gather + rb2_merge_winners in place).
+
+    keep_tables: the K3 tables rb2_ransac_prepare builds (peaks with candidates, candidate lists, sampling
+    CDF - a few KB per spectrum) travel back with the results, so that k3_tables() reads memory the result
+    object owns; without it k3_tables() reads the shared device arena and is only valid until the next run."""
     import time
 
     torch = engine._torch()
@@ -227,7 +238,7 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
     hw = np.fromiter((sp["ransac"]["hough_weight"] for sp in specs), dtype=np.float64, count=n)
     mm = np.fromiter((sp["ransac"]["minimum_matches"] for sp in specs), dtype=np.int64, count=n)
     mpu = np.fromiter((sp["ransac"]["minimum_peak_utilisation"] for sp in specs), dtype=np.float64, count=n)
-    mfe = float(s0["ransac"]["minimum_fit_error"])
+    mfe = np.fromiter((sp["ransac"]["minimum_fit_error"] for sp in specs), dtype=np.float64, count=n)
     n_pix = np.fromiter((sp["n_pix"] for sp in specs), dtype=np.int64, count=n)
     sigma = (rtol + ltol) * 1.1775
 
@@ -236,7 +247,7 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
         op, brk = spline_operator(xb)
         _CACHE[key] = (torch.from_numpy(op).cuda(), torch.from_numpy(brk).cuda(), len(brk) - 1)
     d_op, d_brk, npp = _CACHE[key]
-    max_p = int(n_p.max())
+    max_p = max(int(n_p.max()), ssz)  # stride of the per-spectrum outputs; K3's descriptors carry >= ssz peaks
 
     # ---- layout: [inputs | descriptors] (H2D)  [work] (device only)  [results] (D2H) ----
     L = _Layout()
@@ -252,10 +263,13 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
     zero_begin = L.size
     o_cw, o_cp, o_cn = L.many(8 * n_p * top_n), L.many(4 * n_p * top_n), L.many(4 * n_p)
     zero_end = L.size
+    res_begin = L.size  # with keep_tables the D2H region starts here and includes the K3 tables
     o_up, o_coff, o_cwave = L.many(8 * n_p), L.many(4 * (n_p + 1)), L.many(8 * n_p * top_n)
     o_cwid, o_cdf = L.many(4 * n_p * top_n), L.many(4 * n_p)
     o_ppb, o_ppc = L.one(8 * (npp + 1) * n) + 8 * (npp + 1) * np.arange(n), L.one(32 * npp * n) + 32 * npp * np.arange(n)
-    res_begin = L.size
+    o_kdesc = L.one(dts["ransac"].itemsize * n)  # the descriptors as rb2_ransac_prepare completed them
+    if not keep_tables:
+        res_begin = L.size
     rsz, fsz, msz = C.sizeof(N.RansacResult), C.sizeof(N.RefitResult), C.sizeof(N.MatchResult)
     o_res, o_fit = L.one(rsz * n), L.one(fsz * n)
     o_mx, o_my, o_rs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
@@ -327,6 +341,7 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
     dk["min_inliers"] = np.maximum(deg + 1, np.minimum(np.minimum(mm, n_a), n_p))
     dk["min_inliers_frac"], dk["cost_ceiling"], dk["floor_cost"], dk["floor_id"] = mpu * n_p, 1e50, 0.0, -1
     dk["hyp_begin"], dk["n_hyp"], dk["seed"] = int(hyp_begin), int(n_hypotheses), int(seed)
+    dk["min_fit_error"] = mfe
 
     if match_tolerance is not None:
         dm["d_peaks"], dm["d_atlas"], dm["n_peaks"], dm["n_atlas"] = u(o_peaks), u(o_lines), n_p, n_a
@@ -351,12 +366,15 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
             "rb2_ransac_batch")
     if exchange is not None:
         exchange(buf[o_res:o_res + rsz * n], n)
-    N.check(lib.rb2_refit_winners(n, dptr("ransac"), hptr("ransac"), base + o_res, mfe, int(refit_mode), base + o_fit,
+    N.check(lib.rb2_refit_winners(n, dptr("ransac"), hptr("ransac"), base + o_res, float("nan"), int(refit_mode), base + o_fit,
                                   base + o_mx, base + o_my, base + o_rs, max_p, stream), "rb2_refit_winners")
     if match_tolerance is not None:
         N.check(lib.rb2_match_peaks(n, dptr("match"), hptr("match"), int(refit_mode), base + o_mres, base + o_mmx,
                                     base + o_mmy, base + o_mrs, max_p, stream), "rb2_match_peaks")
     raw = cached("stage_out", res_end - res_begin, pin_memory=True)[:res_end - res_begin]
+    if keep_tables:
+        nb = dts["ransac"].itemsize * n
+        buf[o_kdesc:o_kdesc + nb].copy_(buf[o_desc["ransac"]:o_desc["ransac"] + nb], non_blocking=True)
     raw.copy_(buf[res_begin:res_end], non_blocking=True)
     done = torch.cuda.Event()
     done.record()
@@ -382,7 +400,9 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
         fit = region(o_fit, fsz * n).view(_dt(N.RefitResult))
         out = BatchResults(n)
         out.deg, out.n_p, out.n_a = deg, n_p, n_a
-        out.enough = region(o_enough, 4 * n).view(np.int32) != 0
+        enough = region(o_enough, 4 * n).view(np.int32)
+        out.enough = enough > 0
+        out.law_error = enough < 0  # the reference raises ValueError("probabilities contain NaN") for these
         out.counters, out.cost = win["counters"], win["cost"]
         out.hyp_id, out.hyp_coeffs = win["hyp_id"], win["coeffs"]
         out.refit_nfev, out.accepted = fit["huber_iters"], fit["accepted"]
@@ -403,6 +423,8 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
             out.mrs = region(o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
         out._tables = dict(buf=buf, up=o_up, coff=o_coff, cwave=o_cwave, cwid=o_cwid, cdf=o_cdf, ppb=o_ppb, ppc=o_ppc,
                            npp=npp, desc=o_desc["ransac"], top_n=top_n)
+        if keep_tables:  # own copy: later runs reuse the arena
+            out._tables.update(host=r, host_base=res_begin, desc=o_kdesc)
         if timings is not None:
             timings.update(pack=t1 - t0, launch=t_launch - t1, device=t2 - t1, unpack=time.perf_counter() - t2)
         return out

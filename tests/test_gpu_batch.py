@@ -66,3 +66,42 @@ def test_batch_quality_on_c4_sample():
         good += np.sqrt(np.mean((P.polyval(x, r.fit_coeff) - P.polyval(x, sp["truth"])) ** 2)) < 1.0
     print("within 1 A of truth: %d / %d" % (good, len(specs)))
     assert sum(r.fit_coeff is not None for r in res) >= 48
+
+
+def test_c4_batch_against_reference_recordings():
+    """The many-spectra path on ITS OWN inputs against the reference: three spectra of the C4 batch (one per
+    detector size; tests/golden/make_golden_c4.py recorded them from the unmodified reference) go through
+    calibrate_batch's device pipeline together with neighbours of the batch; the K3 tables the device
+    built from its own K1 / K2 outputs (peaks with candidates, candidate lists in order) are the
+    reference's, bit for bit, and replaying the reference's recorded draws on those tables gives its
+    decisions and its winner."""
+    from bench import c4_input
+    from rascal_b200 import batch, engine, pipeline
+    from tests.conftest import load_golden
+    from tests.test_gpu_ransac_refit import setup_from_golden
+
+    gold = [load_golden("c4_npix%d" % n) for n in (1024, 2048, 4096)]
+    idx = [int(g["c4_index"]) for g in gold]
+    others = [i for i in range(max(idx) + 4) if i not in idx][:9]
+    order = idx + others  # ragged batch of 12: the recorded three first
+    specs = [batch.normalise_spec(c4_input(i)) for i in order]
+    assert pipeline.eligible(specs)
+    out = pipeline.run(specs, 5_000, seed=3)
+    for k, g in enumerate(gold):
+        assert np.array_equal(specs[k]["peaks"], np.sort(g["peaks"])) and np.array_equal(specs[k]["lines"], g["lines"])
+        t = out.k3_tables(k)
+        assert np.array_equal(t["peaks"], g["tr_ransac_peaks"])
+        assert np.array_equal(np.diff(t["cand_off"]), g["tr_cand_len"])
+        assert np.array_equal(t["cand_wave"], g["tr_cand_flat"])
+        # the device-prepared sampling law / weight tables equal the host set-up's on the recorded inputs
+        s = setup_from_golden(g)
+        assert np.array_equal(t["cdf32"], s.cdf32)
+        d = t["desc"]
+        assert (float(d["pix_min"]), float(d["pix_max"])) == (s.pix_min, s.pix_max)
+        assert np.allclose(t["pp_coef"], s.pp_coef, rtol=1e-9, atol=1e-9 * np.abs(s.pp_coef).max())
+        # replay of the reference's draws on tables identical to the device's
+        rb = engine.RansacBatch([s])
+        n = len(g["tr_status"])
+        st = rb.run(0, n, replay=(g["tr_x_idx"], g["tr_y_idx"]), per_hypothesis=True)
+        assert np.array_equal(st["status"], g["tr_status"].astype(np.uint8))
+        assert rb.results()[0].hyp_id == int(np.flatnonzero(g["tr_accepted"])[-1])

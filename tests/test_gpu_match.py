@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import rascal_oracle as O
-from tests.conftest import GOLDEN_CASES, load_golden
+from tests.conftest import MATCH_CASES, load_golden
 from tests.test_oracle_match import lines_of, load_match, tol_of
 
 pytestmark = pytest.mark.gpu
@@ -43,7 +43,7 @@ def check_against_oracle(r, mx, my, rs, o, deg, mode):
             assert np.allclose(np.array(r.refit.coeffs[:deg + 1]), exact, rtol=1e-9, atol=0)
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("case", MATCH_CASES)
 @pytest.mark.parametrize("mode", [0, 1])
 def test_match_peaks_golden(case, mode):
     g = load_match(case)
@@ -106,7 +106,7 @@ def test_match_peaks_device_chained_coeffs():
     assert bytes(a[0]) == bytes(b[0]) and np.array_equal(a[3], b[3])
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("case", MATCH_CASES)
 def test_facade_match_peaks(case):
     from rascal_b200.calibrator import Calibrator, LineList
 

@@ -113,3 +113,14 @@ def test_prior_cost_is_the_reference_initial_cost(golden):
     for coeffs in (g["fit_coeff"], g["tr_coeffs"][0]):
         err, _, _ = O.match_bijective(p, coeffs)
         assert s.prior_cost(coeffs) == float(sum(err))
+
+
+def test_degenerate_sampling_law_raises_like_the_reference():
+    """A peak exactly on an interior edge of the 10-bin histogram whose left bin is empty: the reference's
+    weights hold 1/0, np.random.choice raises ValueError('probabilities contain NaN') (calibrator.py:521-540)."""
+    import pytest
+
+    from rascal_b200 import engine
+
+    with pytest.raises(ValueError, match="probabilities contain NaN"):
+        engine.sampling_cdf32(np.array([100.0, 150.0, 500.0, 700.0, 1100.0]))

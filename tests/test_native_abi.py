@@ -45,7 +45,7 @@ def test_struct_layouts(lib):
 
 
 def test_diagnostics(lib):
-    assert lib.rb2_abi_version() == 1
+    assert lib.rb2_abi_version() == 2
     assert lib.rb2_status_string(0) == b"ok"
     assert lib.rb2_status_string(-2) == b"bad argument"
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import rascal_oracle as O
-from tests.conftest import GOLDEN_CASES, GOLDEN_DIR
+from tests.conftest import GOLDEN_DIR, MATCH_CASES
 
 
 def load_match(case):
@@ -25,7 +25,7 @@ def lines_of(g, key):
     return g["lines_sep"] if key.endswith("_sep") else g["lines"]
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("case", MATCH_CASES)
 def test_oracle_match_peaks_reproduces_reference(case):
     g = load_match(case)
     n_ok = 0
