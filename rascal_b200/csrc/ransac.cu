@@ -565,18 +565,29 @@ struct Rng {  // 32-bit words for the peak draws, 16-bit halves for the candidat
   }
 };
 
-// ---- stage-A tables: packed 16-byte records, one LDS.128 each --------------------------------
-// PeakRec: the peak's interval [lo, lo + wd) of the 32-bit sampling CDF (calibrator.py:521-523; the last
-// interval ends at 2^32, all arithmetic is mod 2^32), the start of its candidate list and kt = K | thr << 16
-// with K = number of candidates and thr = 65536 mod K (Lemire's rejection threshold for a 16-bit pick).
-struct alignas(16) PeakRec { unsigned lo, wd, off, kt; };
-struct alignas(16) CandRec { double wave; int wid; int pad; };
+// ---- stage-A tables ---------------------------------------------------------------------------
+// Stage A is bound by shared-memory wavefronts (every lane reads its own random table entries: ~3 wavefronts
+// per 32-bit load, ~5.5 per 64-bit, ~9 per 128-bit), so the tables are as small as the draw allows:
+//   PeakRec  16 B, one LDS.128: the peak's interval [lo, lo + wd) of the 32-bit sampling CDF
+//            (calibrator.py:521-523; the last interval ends at 2^32, all arithmetic is mod 2^32) and its pixel;
+//   okt      4 B: start of the peak's candidate list | K << 16 | (65536 mod K) << 24 - only read when the
+//            peaks do not all have the same number K of candidates (then the three are warp-uniform constants
+//            and the list of peak i starts at i * K);
+//   cwave    8 B: the candidate wavelength.  "Already used" is tested on the wavelength itself (equal ids ==
+//            equal values), the ids are not needed here.
+struct alignas(16) PeakRec { unsigned lo, wd; double x; };
 
 struct TablesA {  // shared-memory views of one problem (stage A)
-  const PeakRec* prec; const CandRec* crec; const double* peaks;
+  const PeakRec* prec; const unsigned* okt; const double* cwave;
   const unsigned short* lut;
   int n_u;
+  unsigned uni;  // != 0: every peak has (uni & 0xff) candidates; uni = K | (65536 mod K) << 8
+  __device__ __forceinline__ void cand_list(int i, unsigned& off, unsigned& K, unsigned& thr) const {
+    if (uni) { K = uni & 0xffu; thr = uni >> 8; off = (unsigned)i * K; }
+    else { const unsigned v = okt[i]; off = v & 0xffffu; K = (v >> 16) & 0xffu; thr = v >> 24; }
+  }
 };
+constexpr int A_MAX_K = 255, A_MAX_CAND = 65535;  // limits of the packed okt word (else: RB2_ERR_ARG)
 
 // index i of the interval that holds u (== searchsorted(cdf, u, 'right'), clamped) and its record: LUT over
 // the top LUT_BITS bits.  A cell stores the index of its first value; bit 15 marks the few cells (about n_u
@@ -663,7 +674,7 @@ struct SamplerDims {
 
 template <int S>
 __device__ __forceinline__ void draw_peaks(const TablesA& t, const unsigned (&w)[SamplerDims<S>::NW], int (&pi)[S],
-                                           unsigned (&off)[S], unsigned (&kt)[S]) {
+                                           double (&xs)[S]) {
   unsigned lo_s[S > 1 ? S - 1 : 1], wd_s[S > 1 ? S - 1 : 1];  // chosen intervals, ascending lo
   unsigned mass = 0u;                                         // their total width (mod 2^32)
 #pragma unroll
@@ -674,7 +685,7 @@ __device__ __forceinline__ void draw_peaks(const TablesA& t, const unsigned (&w)
       if (j < k) u += (u >= lo_s[j]) ? wd_s[j] : 0u;
     PeakRec r;
     pi[k] = find_peak(t, u, r);
-    off[k] = r.off; kt[k] = r.kt;
+    xs[k] = r.x;
     if (k < S - 1) {
       unsigned cl = r.lo, cw = r.wd;
 #pragma unroll
@@ -703,27 +714,30 @@ __device__ __forceinline__ void philox_eager(const KEY& key, unsigned c0, unsign
   }
 }
 
-// returns false when a candidate pick needs a redraw (-> slow round); pi / ci / ys are complete when true
+__device__ __forceinline__ bool same_wave(double a, double b) {  // bit equality on the integer pipe
+  return __double_as_longlong(a) == __double_as_longlong(b);
+}
+
+// returns false when a candidate pick needs a redraw (-> slow round); pi / ci / xs / ys are complete when true
 template <int S>
 __device__ __forceinline__ bool draw_sample_fast(const TablesA& t, const PhiloxKey& key, unsigned long long gid,
-                                                 int (&pi)[S], int (&ci)[S], double (&ys)[S]) {
+                                                 int (&pi)[S], int (&ci)[S], double (&xs)[S], double (&ys)[S]) {
   unsigned w[SamplerDims<S>::NW];
   philox_eager<S>(key, (unsigned)gid, (unsigned)(gid >> 32), w);
-  unsigned off[S], kt[S];
-  draw_peaks<S>(t, w, pi, off, kt);
-  int wi[S];
+  draw_peaks<S>(t, w, pi, xs);
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < S; ++k) {
-    const unsigned K = kt[k] & 0xffffu, thr = kt[k] >> 16;
+    unsigned off, K, thr;
+    t.cand_list(pi[k], off, K, thr);
     const unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
     const unsigned x = h * K;
     ok &= (x & 0xffffu) >= thr;
-    const int c = (int)(off[k] + (x >> 16));
-    const CandRec cr = t.crec[c];
+    const int c = (int)(off + (x >> 16));
+    const double wv = t.cwave[c];
 #pragma unroll
-    for (int q = 0; q < S; ++q) if (q < k) ok &= (wi[q] != cr.wid);
-    wi[k] = cr.wid; ci[k] = c; ys[k] = cr.wave;
+    for (int q = 0; q < S; ++q) if (q < k) ok &= !same_wave(ys[q], wv);
+    ci[k] = c; ys[k] = wv;
   }
   return ok;
 }
@@ -733,17 +747,16 @@ constexpr int DRAW_MAX_TRIES = 1 << 14;  // per pick; a draw that still fails th
 // the same hypothesis with the redraw loops; false = impossible draw (aborted)
 template <int S>
 __device__ __noinline__ bool draw_sample_slow(const TablesA& t, unsigned long long seed, unsigned long long gid,
-                                              int (&pi)[S], int (&ci)[S], double (&ys)[S]) {
+                                              int (&pi)[S], int (&ci)[S], double (&xs)[S], double (&ys)[S]) {
   constexpr int NW = SamplerDims<S>::NW;
   const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), c0 = (unsigned)gid, c1 = (unsigned)(gid >> 32);
   unsigned w[NW];
   philox_eager<S>(seed, c0, c1, w);
-  unsigned off[S], kt[S];
-  draw_peaks<S>(t, w, pi, off, kt);
-  int wi[S];
+  draw_peaks<S>(t, w, pi, xs);
   unsigned n_half = 0u, cur = 0u;  // 16-bit halves of the words after the eager blocks, in stream order
   for (int k = 0; k < S; ++k) {
-    const unsigned K = kt[k] & 0xffffu, thr = kt[k] >> 16;
+    unsigned off, K, thr;
+    t.cand_list(pi[k], off, K, thr);
     unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
     bool checked = false;
     int n_dup = 0;
@@ -751,17 +764,17 @@ __device__ __noinline__ bool draw_sample_slow(const TablesA& t, unsigned long lo
       if (tries >= DRAW_MAX_TRIES) return false;
       const unsigned x = h * K;
       if ((x & 0xffffu) >= thr) {
-        const int c = (int)(off[k] + (x >> 16));
-        const CandRec cr = t.crec[c];
+        const int c = (int)(off + (x >> 16));
+        const double wv = t.cwave[c];
         bool dup = false;
-        for (int q = 0; q < k; ++q) dup |= (wi[q] == cr.wid);
-        if (!dup) { wi[k] = cr.wid; ci[k] = c; ys[k] = cr.wave; break; }
+        for (int q = 0; q < k; ++q) dup |= same_wave(ys[q], wv);
+        if (!dup) { ci[k] = c; ys[k] = wv; break; }
         if (!checked && ++n_dup >= 3) {  // after a few duplicates: is any unused wavelength left for this peak?
           bool possible = false;
           for (unsigned jj = 0; jj < K; ++jj) {
-            const int ww = t.crec[off[k] + jj].wid;
+            const double ww = t.cwave[off + jj];
             bool used = false;
-            for (int q = 0; q < k; ++q) used |= (wi[q] == ww);
+            for (int q = 0; q < k; ++q) used |= same_wave(ys[q], ww);
             possible |= !used;
           }
           if (!possible) return false;  // impossible draw: the try is consumed (:557-566)
@@ -778,11 +791,10 @@ __device__ __noinline__ bool draw_sample_slow(const TablesA& t, unsigned long lo
 
 // generic (run-time sample size) variant for the least-squares path: rejection sampling with the
 // sequential Philox stream (same law; the streams differ)
-__device__ bool draw_sample_dyn(const TablesA& t, unsigned long long seed, unsigned long long gid, int s, int* pi, int* ci) {
+__device__ bool draw_sample_dyn(const TablesA& t, unsigned long long seed, unsigned long long gid, int s, int* pi, int* ci,
+                                double* xs, double* ys) {
   Rng rng;
   rng.init(seed, gid);
-  int wi[RB2_MAX_SAMPLE];
-  unsigned off[RB2_MAX_SAMPLE], kt[RB2_MAX_SAMPLE];
   for (int k = 0; k < s; ++k) {
     int idx;
     bool dup;
@@ -794,24 +806,25 @@ __device__ bool draw_sample_dyn(const TablesA& t, unsigned long long seed, unsig
       dup = false;
       for (int j = 0; j < k; ++j) dup |= (pi[j] == idx);
     } while (dup);
-    pi[k] = idx; off[k] = r.off; kt[k] = r.kt;
+    pi[k] = idx; xs[k] = r.x;
   }
   for (int k = 0; k < s; ++k) {
-    const int o0 = (int)off[k], K = (int)(kt[k] & 0xffffu);
+    unsigned off, K, thr;
+    t.cand_list(pi[k], off, K, thr);
     bool checked = false;
     for (int tries = 0;; ++tries) {
       if (tries >= DRAW_MAX_TRIES) return false;
-      const int j = rng.uniform(K);
-      const int w = t.crec[o0 + j].wid;
+      const int j = rng.uniform((int)K);
+      const double wv = t.cwave[off + j];
       bool dup = false;
-      for (int q = 0; q < k; ++q) dup |= (wi[q] == w);
-      if (!dup) { wi[k] = w; ci[k] = o0 + j; break; }
+      for (int q = 0; q < k; ++q) dup |= same_wave(ys[q], wv);
+      if (!dup) { ys[k] = wv; ci[k] = (int)off + j; break; }
       if (!checked) {
         bool possible = false;
-        for (int jj = 0; jj < K; ++jj) {
-          const int ww = t.crec[o0 + jj].wid;
+        for (unsigned jj = 0; jj < K; ++jj) {
+          const double ww = t.cwave[off + jj];
           bool used = false;
-          for (int q = 0; q < k; ++q) used |= (wi[q] == ww);
+          for (int q = 0; q < k; ++q) used |= same_wave(ys[q], ww);
           possible |= !used;
         }
         if (!possible) return false;
@@ -911,26 +924,26 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   const int ncoef = deg + 1;
   const int n_u = d.n_upeaks, n_c = d.n_cand;
 
+  __shared__ int s_kmin, s_kmax;
   PeakRec* s_prec = reinterpret_cast<PeakRec*>(smem_raw);
-  CandRec* s_crec = reinterpret_cast<CandRec*>(s_prec + n_u);
-  double* s_peaks = reinterpret_cast<double*>(s_crec + n_c);
-  unsigned* s_cdf = reinterpret_cast<unsigned*>(s_peaks + n_u);
+  double* s_cwave = reinterpret_cast<double*>(s_prec + n_u);
+  unsigned* s_okt = reinterpret_cast<unsigned*>(s_cwave + n_c);
+  unsigned* s_cdf = s_okt + n_u;
   unsigned short* s_lut = reinterpret_cast<unsigned short*>(s_cdf + n_u);
+  if (tid == 0) { s_kmin = 0x7fffffff; s_kmax = 0; }
+  __syncthreads();
   for (int i = tid; i < n_u; i += RS_THREADS) {
-    s_peaks[i] = d.d_peaks[i];
     const unsigned hi = d.d_cdf32 ? d.d_cdf32[i] : 0u, lo = (i > 0 && d.d_cdf32) ? d.d_cdf32[i - 1] : 0u;
     const int o0 = d.d_cand_off[i], K = d.d_cand_off[i + 1] - o0;
     PeakRec r;
     r.lo = lo; r.wd = (i == n_u - 1) ? 0u - lo : hi - lo;  // the last interval ends at 2^32
-    r.off = (unsigned)o0; r.kt = (unsigned)K | ((K > 0 ? 65536u % (unsigned)K : 0u) << 16);
+    r.x = d.d_peaks[i];
     s_prec[i] = r;
+    s_okt[i] = (unsigned)o0 | ((unsigned)K << 16) | ((K > 0 ? 65536u % (unsigned)K : 0u) << 24);
     s_cdf[i] = hi;
+    atomicMin(&s_kmin, K); atomicMax(&s_kmax, K);
   }
-  for (int i = tid; i < n_c; i += RS_THREADS) {
-    CandRec c;
-    c.wave = d.d_cand_wave[i]; c.wid = d.d_cand_wid[i]; c.pad = 0;
-    s_crec[i] = c;
-  }
+  for (int i = tid; i < n_c; i += RS_THREADS) s_cwave[i] = d.d_cand_wave[i];
   __syncthreads();
   {
     // lut[b] = #{i : cdf32[i] <= b << (32 - LUT_BITS)}, clamped: a thread fills a run of consecutive cells
@@ -956,7 +969,8 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   }
   __syncthreads();
   TablesA tb;
-  tb.prec = s_prec; tb.crec = s_crec; tb.peaks = s_peaks; tb.lut = s_lut; tb.n_u = n_u;
+  tb.prec = s_prec; tb.okt = s_okt; tb.cwave = s_cwave; tb.lut = s_lut; tb.n_u = n_u;
+  tb.uni = (s_kmin == s_kmax && s_kmax > 0) ? ((unsigned)s_kmax | ((65536u % (unsigned)s_kmax) << 8)) : 0u;
 
   const bool replay = d.d_replay_x != nullptr;
   const int s = FAST ? DEG_T + 1 : d.sample_size;
@@ -997,24 +1011,24 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
     for (int i = 0; i < NCOEF; ++i) cf[i] = 0.0;
     if constexpr (FAST) {
       int pi[DEG_T + 1], ci[DEG_T + 1];
-      double ys[DEG_T + 1];
+      double xs[DEG_T + 1], ys[DEG_T + 1];
       if (active) {
         if (replay) {
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) {
             pi[k] = d.d_replay_x[id * (DEG_T + 1) + k];
-            ci[k] = (int)tb.prec[pi[k]].off + d.d_replay_y[id * (DEG_T + 1) + k];
-            ys[k] = tb.crec[ci[k]].wave;
+            ci[k] = (int)(tb.okt[pi[k]] & 0xffffu) + d.d_replay_y[id * (DEG_T + 1) + k];
+            xs[k] = tb.prec[pi[k]].x; ys[k] = tb.cwave[ci[k]];
           }
         } else if (!slow) {
-          deferred = !draw_sample_fast<DEG_T + 1>(tb, pkey, (unsigned long long)(d.hyp_begin + id), pi, ci, ys);
+          deferred = !draw_sample_fast<DEG_T + 1>(tb, pkey, (unsigned long long)(d.hyp_begin + id), pi, ci, xs, ys);
         } else {
           // own arrays: the call is not inlined, its outputs live in local memory - only here
           int pi2[DEG_T + 1], ci2[DEG_T + 1];
-          double ys2[DEG_T + 1];
-          aborted = !draw_sample_slow<DEG_T + 1>(tb, d.seed, (unsigned long long)(d.hyp_begin + id), pi2, ci2, ys2);
+          double xs2[DEG_T + 1], ys2[DEG_T + 1];
+          aborted = !draw_sample_slow<DEG_T + 1>(tb, d.seed, (unsigned long long)(d.hyp_begin + id), pi2, ci2, xs2, ys2);
 #pragma unroll
-          for (int k = 0; k <= DEG_T; ++k) { pi[k] = pi2[k]; ci[k] = ci2[k]; ys[k] = ys2[k]; }
+          for (int k = 0; k <= DEG_T; ++k) { pi[k] = pi2[k]; ci[k] = ci2[k]; xs[k] = xs2[k]; ys[k] = ys2[k]; }
         }
       }
       if (!slow && !replay) {  // park the hypotheses that need a redraw
@@ -1031,9 +1045,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) cf[k] = d.d_replay_coeffs[id * (DEG_T + 1) + k];
         } else {
-          double xs[DEG_T + 1], cc[DEG_T + 1];
-#pragma unroll
-          for (int k = 0; k <= DEG_T; ++k) xs[k] = tb.peaks[pi[k]];
+          double cc[DEG_T + 1];
           newton_fit<DEG_T>(xs, ys, cc);
 #pragma unroll
           for (int k = 0; k <= DEG_T; ++k) cf[k] = cc[k];
@@ -1043,26 +1055,26 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
 #pragma unroll
         for (int k = 0; k <= DEG_T; ++k) {
           d.d_out_sample[(id * (DEG_T + 1) + k) * 2] = aborted ? -1 : pi[k];
-          d.d_out_sample[(id * (DEG_T + 1) + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)tb.prec[pi[k]].off;
+          d.d_out_sample[(id * (DEG_T + 1) + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)(tb.okt[pi[k]] & 0xffffu);
         }
       }
     } else if (active) {
       int pi[RB2_MAX_SAMPLE], ci[RB2_MAX_SAMPLE];
+      double xs[RB2_MAX_SAMPLE], ys[RB2_MAX_SAMPLE];
       if (replay) {
         for (int k = 0; k < s; ++k) {
           pi[k] = d.d_replay_x[id * s + k];
-          ci[k] = (int)tb.prec[pi[k]].off + d.d_replay_y[id * s + k];
+          ci[k] = (int)(tb.okt[pi[k]] & 0xffffu) + d.d_replay_y[id * s + k];
+          xs[k] = tb.prec[pi[k]].x; ys[k] = tb.cwave[ci[k]];
         }
       } else {
-        aborted = !draw_sample_dyn(tb, d.seed, (unsigned long long)(d.hyp_begin + id), s, pi, ci);
+        aborted = !draw_sample_dyn(tb, d.seed, (unsigned long long)(d.hyp_begin + id), s, pi, ci, xs, ys);
       }
       if (!aborted) {
         if (replay && d.d_replay_coeffs) {
           for (int k = 0; k < ncoef; ++k) cf[k] = d.d_replay_coeffs[id * ncoef + k];
         } else {
-          double xs[RB2_MAX_SAMPLE], ys[RB2_MAX_SAMPLE];
-          int m = 0;
-          for (int k = 0; k < s; ++k) { xs[m] = tb.peaks[pi[k]]; ys[m] = tb.crec[ci[k]].wave; ++m; }
+          int m = s;
           for (int k = 0; k < d.n_known && m < RB2_MAX_SAMPLE; ++k) { xs[m] = d.d_known_x[k]; ys[m] = d.d_known_y[k]; ++m; }
           if constexpr (LSQ) {
             lsq_polyfit_givens<DEG_T>(xs, ys, m, lsq_xc, lsq_xsc, cf);
@@ -1074,7 +1086,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
       if (d.d_out_sample)
         for (int k = 0; k < s; ++k) {
           d.d_out_sample[(id * s + k) * 2] = aborted ? -1 : pi[k];
-          d.d_out_sample[(id * s + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)tb.prec[pi[k]].off;
+          d.d_out_sample[(id * s + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)(tb.okt[pi[k]] & 0xffffu);
         }
     }
     if (active) {
@@ -1614,8 +1626,13 @@ static LaneStreams& lane_streams() {
 }
 
 static size_t stage_a_smem(const rb2_ransac_desc& h) {
-  return (size_t)h.n_upeaks * (sizeof(PeakRec) + 8 + 4) + (size_t)h.n_cand * sizeof(CandRec) +
-         (size_t)(1 << LUT_BITS) * 2 + 16;
+  return (size_t)h.n_upeaks * (sizeof(PeakRec) + 4 + 4) + (size_t)h.n_cand * 8 + (size_t)(1 << LUT_BITS) * 2 + 16;
+}
+
+static int knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v < 1 ? dflt : v;
 }
 
 struct ChunkArgs {
@@ -1652,15 +1669,17 @@ static int launch_chunk(const ChunkArgs& a) {
     return true;
   };
   const int sms = a.sms;
+  // CTAs per SM of the small stages (tuning knobs; the defaults are the measured optimum)
+  static const int nb = knob("RB2_B_CTAS_PER_SM", 8), nc1 = knob("RB2_C1_CTAS_PER_SM", 4), nc2 = knob("RB2_C2_CTAS_PER_SM", 8);
   pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(a.pipe);
   ransac_draw_fit_kernel<DEG_T, LSQ><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(a.d_desc, a.pipe, a.chunk_begin, a.chunk_len,
                                                                                  a.d_result, a.key);
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
-  ransac_monotonic_kernel<DEG_T><<<sms * 8, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
+  ransac_monotonic_kernel<DEG_T><<<sms * nb, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
-  ransac_match_kernel<DEG_T><<<sms * 4, RS_THREADS, a.smem_c, stream>>>(a.d_desc, a.pipe, a.max_wids, a.max_up, a.single);
+  ransac_match_kernel<DEG_T><<<sms * nc1, RS_THREADS, a.smem_c, stream>>>(a.d_desc, a.pipe, a.max_wids, a.max_up, a.single);
   if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
-  ransac_cost_kernel<DEG_T><<<sms * 8, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
+  ransac_cost_kernel<DEG_T><<<sms * nc2, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
   ransac_exact_kernel<DEG_T><<<sms * 2, RS_THREADS, a.smem_x, stream>>>(a.d_desc, a.pipe, a.max_wids);
   if (!stage_ok("C3 exact")) return RB2_ERR_CUDA;
@@ -1699,7 +1718,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     if (h.sample_size + h.n_known > RB2_MAX_SAMPLE) return RB2_ERR_ARG;
     if (h.n_upeaks < h.sample_size && !h.d_replay_x) return RB2_ERR_ARG;
     if (h.sample_size != h.deg + 1 || h.n_known != 0) fast = false;
-    if (h.n_cand < h.n_upeaks || h.n_wids < 1 || h.n_upeaks > 65535) return RB2_ERR_ARG;
+    if (h.n_cand < h.n_upeaks || h.n_wids < 1 || h.n_upeaks > 65535 || h.n_cand > A_MAX_CAND) return RB2_ERR_ARG;
     if (h.n_hyp < 0 || h.n_hyp >= (1ll << 40)) return RB2_ERR_ARG;
     smem_a = max(smem_a, stage_a_smem(h));
     max_wids = max(max_wids, h.n_wids);

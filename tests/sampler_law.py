@@ -120,24 +120,39 @@ def check_sample_law(sample, setup, sim_seed=1):
     for k in range(s):
         chi2_two_sample(np.bincount(pk[:, k], minlength=n_u), np.bincount(spk[:, k], minlength=n_u), "peak position %d" % k)
     chi2_two_sample(np.bincount(pk.ravel(), minlength=n_u), np.bincount(spk.ravel(), minlength=n_u), "peak inclusion")
-    # --- candidates: the pick is uniform over the entries of the peak's ARRAY whose wavelength is unused
-    cells = {}
-    for k in range(s):
-        free, _ = free_entries(setup, pk[:, k], wid[:, :k])
-        rows = np.arange(len(pk))
-        assert free[rows, ck[:, k]].all(), "a used wavelength (or an entry outside the list) was picked"
-        n_free = free.sum(axis=1)
-        rank = (np.cumsum(free, axis=1) - 1)[rows, ck[:, k]]
-        for nf in np.unique(n_free):
-            sel = n_free == nf
-            cells.setdefault(int(nf), np.zeros(int(nf)))
-            cells[int(nf)] += np.bincount(rank[sel], minlength=int(nf))
-        if k == 0:  # per (peak, entry): duplicated entries must each get their share
-            first = np.zeros((n_u, int(K.max())))
-            np.add.at(first, (pk[:, 0], ck[:, 0]), 1)
-            n_first = np.bincount(pk[:, 0], minlength=n_u)
-            chi2_ok(first, (n_first / K)[:, None] * (np.arange(int(K.max()))[None, :] < K[:, None]), "first candidate")
-    for nf, cnt in cells.items():
-        if nf > 1:
-            chi2_ok(cnt, np.full(nf, cnt.sum() / nf), "candidate rank among %d free entries" % nf)
+    # --- candidates: the pick is uniform over the entries of the peak's ARRAY whose wavelength is unused.
+    #     Without impossible draws that is checked against the exact expectation; where draws can be
+    #     abandoned the COMPLETED draws are a biased subset (a first pick that leaves a later peak without a
+    #     free wavelength is under-represented), so the same statistics are compared with the simulation's.
+    def candidate_stats(pk_, ck_, wid_):
+        cells = {}
+        rows = np.arange(len(pk_))
+        for k in range(s):
+            free, _ = free_entries(setup, pk_[:, k], wid_[:, :k])
+            assert free[rows, ck_[:, k]].all(), "a used wavelength (or an entry outside the list) was picked"
+            n_free = free.sum(axis=1)
+            rank = (np.cumsum(free, axis=1) - 1)[rows, ck_[:, k]]
+            for nf in np.unique(n_free):
+                sel = n_free == nf
+                cells.setdefault(int(nf), np.zeros(int(nf)))
+                cells[int(nf)] += np.bincount(rank[sel], minlength=int(nf))
+        first = np.zeros((n_u, int(K.max())))  # per (peak, entry): duplicated entries must each get their share
+        np.add.at(first, (pk_[:, 0], ck_[:, 0]), 1)
+        return cells, first
+
+    cells, first = candidate_stats(pk, ck, wid)
+    if not aborted.any() and not sim_ab.any():
+        n_first = np.bincount(pk[:, 0], minlength=n_u)
+        chi2_ok(first, (n_first / K)[:, None] * (np.arange(int(K.max()))[None, :] < K[:, None]), "first candidate")
+        for nf, cnt in cells.items():
+            if nf > 1:
+                chi2_ok(cnt, np.full(nf, cnt.sum() / nf), "candidate rank among %d free entries" % nf)
+    else:
+        sck = sim[~sim_ab][:, :, 1].astype(np.int64)
+        swid = setup.cand_wid[setup.cand_off[spk] + sck]
+        scells, sfirst = candidate_stats(spk, sck, swid)
+        chi2_two_sample(first, sfirst, "first candidate")
+        for nf, cnt in cells.items():
+            if nf > 1 and nf in scells:
+                chi2_two_sample(cnt, scells[nf], "candidate rank among %d free entries" % nf)
     return float(aborted.mean())

@@ -90,7 +90,7 @@ def test_law_is_the_same_in_every_launch_split():
 def tiny_setup(cands, deg, **kw):
     from rascal_b200 import engine
 
-    x = np.concatenate([[float(100 * (i + 1))] * len(c) for i, c in enumerate(cands)])
+    x = np.concatenate([[float(100 * (i + 1) + 7 * i * i)] * len(c) for i, c in enumerate(cands)])  # off the histogram edges
     y = np.concatenate([np.asarray(c, dtype=float) for c in cands])
     e = np.linspace(1.0, 2.0, 5)
     return engine.RansacSetup(x, y, fit_deg=deg, sample_size=deg + 1, ransac_tolerance=5.0, min_intercept=-1e9,

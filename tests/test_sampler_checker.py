@@ -22,6 +22,17 @@ def test_checker_accepts_the_law():
     check_sample_law(simulate_law(s, N, np.random.default_rng(7)), s, sim_seed=8)
 
 
+def test_checker_accepts_the_law_with_abandoned_draws():
+    """A table where draws can be impossible: completed draws are a biased subset, the checker compares with
+    the simulation of the same law instead of the unconditional expectations."""
+    from tests.test_gpu_ransac_refit import setup_from_golden
+
+    s = setup_from_golden(load_golden("poly_quadratic_deg2"))
+    d = simulate_law(s, N, np.random.default_rng(17))
+    assert (d[:, 0, 0] < 0).any()
+    check_sample_law(d, s, sim_seed=18)
+
+
 def test_checker_rejects_a_biased_peak_law():
     s = _setup()
     p = s.prob.copy()
