@@ -80,45 +80,139 @@ ransac_prepare_kernel(const rb2_prepare_desc* __restrict__ descs, rb2_ransac_des
   __syncthreads();
   const int nu = s_nu, nc = s_nc;
 
-  // 2. wavelength ids = rank among the distinct candidate wavelengths (np.unique(..., return_inverse))
+  // 2. wavelength ids = rank among the distinct candidate wavelengths (np.unique(..., return_inverse));
+  //    the candidate wavelengths are staged in shared memory for the two all-pairs passes
+  double* s_w = reinterpret_cast<double*>(first + ((nc + 1) & ~1));
+  for (int i = tid; i < nc; i += PREP_THREADS) s_w[i] = cwave[i];
+  __syncthreads();
   for (int i = tid; i < nc; i += PREP_THREADS) {
-    const double v = cwave[i];
+    const double v = s_w[i];
     int f = 1;
-    for (int j = 0; j < i; ++j) if (cwave[j] == v) { f = 0; break; }
+    for (int j = 0; j < i; ++j) if (s_w[j] == v) { f = 0; break; }
     first[i] = f;
   }
   __syncthreads();
   for (int i = tid; i < nc; i += PREP_THREADS) {
-    const double v = cwave[i];
+    const double v = s_w[i];
     int r = 0;
-    for (int j = 0; j < nc; ++j) r += (first[j] && cwave[j] < v);
+    for (int j = 0; j < nc; ++j) r += (first[j] && s_w[j] < v);
     cwid[i] = r;
     if (first[i]) atomicAdd(&s_nw, 1);
   }
 
   // 3. Hough-density weight tables: the pp-form of the interpolating cubic spline of hist[:, 0] is a
   //    LINEAR map of that row (matrix d_spline_op, built once per xbins on the host from SciPy's
-  //    not-a-knot spline on the integer grid); scaled to the gradient-centre axis here
+  //    not-a-knot spline on the integer grid); scaled to the gradient-centre axis here.  The operator is
+  //    banded in practice but stored dense: 8 lanes share one row (coalesced 64-byte reads of the row,
+  //    the strided histogram column staged in shared memory first)
   const int xb = d.xbins, yb = d.ybins, npp = d.n_pp;
   const double hx = (d.d_xedges[1] - d.d_xedges[0]) / 2.0, hy = (d.d_yedges[1] - d.d_yedges[0]) / 2.0;
   const double gc0 = d.d_xedges[1] - hx, gcn = d.d_xedges[xb] - hx, ic0 = d.d_yedges[1] - hy;
   const double step = (gcn - gc0) / (double)(xb - 1);
-  for (int r = tid; r < npp * 4; r += PREP_THREADS) {
-    const double* row = d.d_spline_op + (size_t)r * xb;
-    double acc = 0.0;
-    for (int i = 0; i < xb; ++i) acc = fma(row[i], (double)d.d_hist[(size_t)i * yb], acc);
-    const int k = r & 3;
-    double sc = 1.0;
-    for (int q = 0; q < k; ++q) sc *= step;
-    ppc[r] = acc / sc;
+  double* s_h0 = s_w + nc;  // [xb] first intercept row of the histogram
+  __syncthreads();
+  for (int i = tid; i < xb; i += PREP_THREADS) s_h0[i] = (double)d.d_hist[(size_t)i * yb];
+  __syncthreads();
+  {
+    const int sub = tid & 7;
+    for (int r = tid >> 3; r < npp * 4; r += PREP_THREADS / 8) {
+      const double* row = d.d_spline_op + (size_t)r * xb;
+      double acc = 0.0;
+      // the partial sums are combined in a fixed order, so the table does not depend on the launch
+      for (int i = sub; i < xb; i += 8) acc = fma(row[i], s_h0[i], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (sub == 0) {
+        const int k = r & 3;
+        double sc = 1.0;
+        for (int q = 0; q < k; ++q) sc *= step;
+        ppc[r] = acc / sc;
+      }
+    }
   }
   for (int j = tid; j <= npp; j += PREP_THREADS) ppb[j] = (j == npp) ? gcn : gc0 + d.d_spline_brk[j] * step;
   __syncthreads();
 
-  // 4. scalars, sampling law (one thread: short sequential arithmetic, restated bit for bit from the
-  //    host's sampling_cdf32) and the weight's upper bound
+  // 4. scalars, sampling law and the weight's upper bound.  The law (calibrator.py:521-523) is restated bit
+  //    for bit from the host's sampling_cdf32: the three running sums are sequential there, so they are
+  //    sequential here (thread 0: additions only), everything around them runs over the peaks in parallel
+  const bool enough = (nu > o.deg) && (nu > o.sample_size);
+  __shared__ double s_edge[11];
+  __shared__ int s_count[10], s_lawbad;
+  __shared__ double s_total, s_last;
+  double* s_q = s_h0 + xb;  // [nu] weight / running sums per peak
+  if (tid < 10) s_count[tid] = 0;
+  if (tid == 0) s_lawbad = 0;
+  if (enough && tid < 11) {
+    double lo = peaks[0], hi = peaks[nu - 1];
+    if (lo == hi) { lo -= 0.5; hi += 0.5; }
+    const Linspace edges(lo, hi, 11);
+    s_edge[tid] = edges.at(tid);
+  }
+  __syncthreads();
+  if (enough) {
+    for (int i = tid; i < nu; i += PREP_THREADS) {  // np.histogram: searchsorted(edges, v, 'right') - 1, last edge inclusive
+      int k = 0;
+      while (k < 11 && s_edge[k] <= peaks[i]) ++k;
+      atomicAdd(&s_count[min(k - 1, 9)], 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < nu; i += PREP_THREADS) {  // np.digitize(v, edges, right=True) - 1; index -1 wraps to the last bin
+      int k = 0;
+      while (k < 11 && s_edge[k] < peaks[i]) ++k;
+      const int dig = (k - 1 < 0) ? 9 : min(k - 1, 9);
+      // a peak exactly on an interior edge whose left bin is empty: weight 1/0, prob = NaN - the reference's
+      // np.random.choice raises "probabilities contain NaN" on the first draw (calibrator.py:538)
+      if (s_count[dig] == 0) s_lawbad = 1;
+      s_q[i] = 1.0 / (double)s_count[dig];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double total = 0.0;
+      for (int i = 0; i < nu; ++i) total = add(total, s_q[i]);
+      s_total = total;
+    }
+    __syncthreads();
+    for (int i = tid; i < nu; i += PREP_THREADS) s_q[i] = s_q[i] / s_total;
+    __syncthreads();
+    if (tid == 0) {  // cdf = cumsum(prob); its last value normalises once more (cdf /= cdf[-1])
+      double run = 0.0;
+      for (int i = 0; i < nu; ++i) { run = add(run, s_q[i]); s_q[i] = run; }
+      s_last = run;
+    }
+    __syncthreads();
+    const bool law_ok = s_lawbad == 0;
+    for (int i = tid; i < nu; i += PREP_THREADS) {
+      const double c = floor(mul(s_q[i] / s_last, 4294967296.0));
+      unsigned v = (c >= 4294967295.0) ? 0xFFFFFFFFu : (unsigned)c;
+      if (i == nu - 1) v = 0xFFFFFFFFu;
+      cdf32[i] = law_ok ? v : 0u;
+    }
+  } else {
+    for (int i = tid; i < nu; i += PREP_THREADS) cdf32[i] = 0u;
+  }
+  // weight upper bound (engine.weight_upper_bound): Bernstein coefficients enclose each cubic piece
+  __shared__ double s_lo[PREP_THREADS / 32], s_hi[PREP_THREADS / 32];
+  {
+    double lo_v = CUDART_INF, hi_v = -CUDART_INF;
+    for (int j = tid; j < npp; j += PREP_THREADS) {
+      const double h = ppb[j + 1] - ppb[j];
+      const double c0 = ppc[4 * j], c1 = ppc[4 * j + 1], c2 = ppc[4 * j + 2], c3 = ppc[4 * j + 3];
+      const double b0 = c0, b1 = c0 + c1 * h / 3.0, b2 = c0 + 2.0 * c1 * h / 3.0 + c2 * h * h / 3.0,
+                   b3 = c0 + c1 * h + c2 * h * h + c3 * h * h * h;
+      lo_v = fmin(lo_v, fmin(fmin(b0, b1), fmin(b2, b3)));
+      hi_v = fmax(hi_v, fmax(fmax(b0, b1), fmax(b2, b3)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo_v = fmin(lo_v, __shfl_xor_sync(0xffffffffu, lo_v, off));
+      hi_v = fmax(hi_v, __shfl_xor_sync(0xffffffffu, hi_v, off));
+    }
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo_v; s_hi[tid >> 5] = hi_v; }
+  }
+  __syncthreads();
   if (tid == 0) {
-    const bool enough = (nu > o.deg) && (nu > o.sample_size);
     o.n_upeaks = nu; o.n_cand = nc; o.n_wids = max(s_nw, 1);
     o.gc_min = gc0; o.gc_max = gcn; o.ic_min = ic0;
     o.h_lo = (double)d.d_hist[0]; o.h_hi = (double)d.d_hist[(size_t)(xb - 1) * yb];
@@ -129,70 +223,11 @@ ransac_prepare_kernel(const rb2_prepare_desc* __restrict__ descs, rb2_ransac_des
     } else {
       o.pix_min = 0.0; o.pix_max = 0.0;
     }
-    if (!enough) o.n_hyp = 0;
-    if (d.d_enough) d.d_enough[0] = enough ? 1 : 0;
-    bool law_ok = true;
-    if (enough) {
-      double lo = peaks[0], hi = peaks[nu - 1];
-      if (lo == hi) { lo -= 0.5; hi += 0.5; }
-      const Linspace edges(lo, hi, 11);
-      double e[11];
-      for (int i = 0; i < 11; ++i) e[i] = edges.at(i);
-      int counts[10];
-      for (int b = 0; b < 10; ++b) counts[b] = 0;
-      for (int i = 0; i < nu; ++i) {  // np.histogram: searchsorted(edges, v, 'right') - 1, last edge inclusive
-        int k = 0;
-        while (k < 11 && e[k] <= peaks[i]) ++k;
-        ++counts[min(k - 1, 9)];
-      }
-      double total = 0.0;
-      for (int i = 0; i < nu; ++i) {  // np.digitize(v, edges, right=True) - 1; index -1 wraps to the last bin
-        int k = 0;
-        while (k < 11 && e[k] < peaks[i]) ++k;
-        const int dig = (k - 1 < 0) ? 9 : min(k - 1, 9);
-        // a peak exactly on an interior edge whose left bin is empty: weight 1/0, prob = NaN - the reference's
-        // np.random.choice raises "probabilities contain NaN" on the first draw (calibrator.py:538)
-        if (counts[dig] == 0) law_ok = false;
-        total = add(total, 1.0 / (double)counts[dig]);
-      }
-      if (!law_ok) {
-        o.n_hyp = 0;
-        if (d.d_enough) d.d_enough[0] = -1;
-      }
-      double run = 0.0;
-      // two passes: cdf = cumsum(prob / total); cdf /= cdf[-1]
-      for (int i = 0; i < nu; ++i) {
-        int k = 0;
-        while (k < 11 && e[k] < peaks[i]) ++k;
-        const int dig = (k - 1 < 0) ? 9 : min(k - 1, 9);
-        run = add(run, (1.0 / (double)counts[dig]) / total);
-      }
-      const double last = run;
-      run = 0.0;
-      for (int i = 0; i < nu; ++i) {
-        int k = 0;
-        while (k < 11 && e[k] < peaks[i]) ++k;
-        const int dig = (k - 1 < 0) ? 9 : min(k - 1, 9);
-        run = add(run, (1.0 / (double)counts[dig]) / total);
-        const double c = floor(mul(run / last, 4294967296.0));
-        cdf32[i] = (c >= 4294967295.0) ? 0xFFFFFFFFu : (unsigned)c;
-      }
-      cdf32[nu - 1] = 0xFFFFFFFFu;
-      if (!law_ok)
-        for (int i = 0; i < nu; ++i) cdf32[i] = 0u;
-    } else {
-      for (int i = 0; i < nu; ++i) cdf32[i] = 0u;
-    }
-    // weight upper bound (engine.weight_upper_bound): Bernstein coefficients enclose each cubic piece
+    const bool law_ok = s_lawbad == 0;
+    if (!enough || !law_ok) o.n_hyp = 0;
+    if (d.d_enough) d.d_enough[0] = !enough ? 0 : (law_ok ? 1 : -1);
     double lo_v = fmin(o.h_lo, o.h_hi), hi_v = fmax(o.h_lo, o.h_hi);
-    for (int j = 0; j < npp; ++j) {
-      const double h = ppb[j + 1] - ppb[j];
-      const double c0 = ppc[4 * j], c1 = ppc[4 * j + 1], c2 = ppc[4 * j + 2], c3 = ppc[4 * j + 3];
-      const double b0 = c0, b1 = c0 + c1 * h / 3.0, b2 = c0 + 2.0 * c1 * h / 3.0 + c2 * h * h / 3.0,
-                   b3 = c0 + c1 * h + c2 * h * h + c3 * h * h * h;
-      lo_v = fmin(lo_v, fmin(fmin(b0, b1), fmin(b2, b3)));
-      hi_v = fmax(hi_v, fmax(fmax(b0, b1), fmax(b2, b3)));
-    }
+    for (int w = 0; w < PREP_THREADS / 32; ++w) { lo_v = fmin(lo_v, s_lo[w]); hi_v = fmax(hi_v, s_hi[w]); }
     const bool bounded = (lo_v >= 0.0) && (hi_v > 0.0) && (o.hough_weight > 0.0) && isfinite(hi_v);
     o.w_upper = bounded ? o.hough_weight * (double)o.n_pix * hi_v * (1.0 + 1e-9) : -1.0;
   }
@@ -228,7 +263,9 @@ extern "C" int rb2_ransac_prepare(int n_problems, const rb2_prepare_desc* d_desc
     if (!h.d_cand_wave || !h.d_cand_n || !h.d_upeak_x || !h.d_xedges || !h.d_yedges || !h.d_hist || !h.d_spline_op ||
         !h.d_spline_brk)
       return RB2_ERR_ARG;
-    smem = max(smem, (size_t)h.n_peaks * h.top_n * 4 + 16);
+    // first[] (int per candidate) | candidate wavelengths | first histogram row | per-peak sums
+    smem = max(smem, (size_t)(h.n_peaks * h.top_n + 2) * 4 + (size_t)h.n_peaks * h.top_n * 8 + (size_t)h.xbins * 8 +
+                         (size_t)h.n_peaks * 8 + 32);
   }
   if (smem > 200 * 1024) return RB2_ERR_ARG;  // > 50k candidate entries: prepare those on the host
   RB2_CHECK(cudaFuncSetAttribute(ransac_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -333,16 +333,33 @@ hough_bin_kernel(const rb2_hough_desc* __restrict__ descs, const rb2_hough_stats
 // One CTA (1024 threads) per problem.  Stable LSD radix sort (8-bit digits) of
 // the bins visited in DESCENDING flat index, by DESCENDING count:
 //   == np.argsort(hist.ravel(), kind='stable')[::-1].
+// The sort is a chain of short dependent steps (per tile of 1024 bins: digit of hist[src[e]], rank inside the
+// tile, scatter), i.e. latency-bound on its loads: when the histogram and both index buffers fit in shared memory
+// (12 bytes per bin: every default shape, 100 x 100 ... 125 x 125) the whole sort runs there - 224 -> ~40 us for one
+// 100 x 100 spectrum, which is fixed cost of every single-spectrum fit; finer binnings sort in global memory.
+constexpr int RANK_SMEM_MAX_BINS = 16384;
 __global__ void __launch_bounds__(1024)
-hough_rank_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+hough_rank_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats, int smem_bins) {
+  extern __shared__ __align__(16) unsigned char rank_smem[];
   __shared__ unsigned base[256];
   __shared__ unsigned tile_tot[256];
   __shared__ __align__(16) unsigned short wcnt[32][256];
   __shared__ unsigned red[32];
   const rb2_hough_desc d = descs[blockIdx.x];
   const int B = d.xbins * d.ybins;
-  const unsigned* __restrict__ hist = d.d_hist;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool in_smem = B <= smem_bins;
+  const unsigned* hist = d.d_hist;
+  int* buf_a = d.d_rank;
+  int* buf_b = d.d_sort_tmp;
+  if (in_smem) {
+    unsigned* sh = reinterpret_cast<unsigned*>(rank_smem);
+    for (int i = tid; i < B; i += 1024) sh[i] = d.d_hist[i];
+    hist = sh;
+    buf_a = reinterpret_cast<int*>(sh + smem_bins);
+    buf_b = buf_a + smem_bins;
+    __syncthreads();
+  }
 
   // max count -> number of 8-bit passes
   unsigned mx = 0;
@@ -363,12 +380,12 @@ hough_rank_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __r
   while (passes < 4 && (mx >> (8 * passes)) != 0) ++passes;
 
   if (passes == 0) {
-    for (int e = tid; e < B; e += 1024) d.d_rank[e] = B - 1 - e;
+    for (int e = tid; e < B; e += 1024) buf_a[e] = B - 1 - e;
   }
   const int* src = nullptr;  // pass 0 reads the implicit reversed identity
   for (int ps = 0; ps < passes; ++ps) {
     const int sh = 8 * ps;
-    int* dst = (((passes - 1 - ps) & 1) == 0) ? d.d_rank : d.d_sort_tmp;  // last pass lands in d_rank
+    int* dst = (((passes - 1 - ps) & 1) == 0) ? buf_a : buf_b;  // the last pass lands in buf_a
     if (tid < 256) base[tid] = 0;
     __syncthreads();
     for (int e = tid; e < B; e += 1024) {
@@ -434,7 +451,11 @@ hough_rank_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __r
     src = dst;
   }
   __syncthreads();
-  for (int r = tid; r < B; r += 1024) d.d_rankpos[d.d_rank[r]] = r;
+  for (int r = tid; r < B; r += 1024) {
+    const int e = buf_a[r];
+    if (in_smem) d.d_rank[r] = e;
+    d.d_rankpos[e] = r;
+  }
 }
 
 // ---- lazy materialisation of hough_points -----------------------------------
@@ -534,6 +555,27 @@ hough_points_kernel(const rb2_hough_desc d, const long long* __restrict__ off, d
 }  // namespace rb2
 
 // ---- host entry points -------------------------------------------------------
+static cudaError_t launch_rank(int n_problems, const rb2_hough_desc* d_desc, const rb2_hough_desc* h_desc,
+                               rb2_hough_stats* d_stats, cudaStream_t stream) {
+  using namespace rb2;
+  int max_bins = 0;
+  for (int i = 0; i < n_problems; ++i) max_bins = max(max_bins, h_desc[i].xbins * h_desc[i].ybins);
+  const int smem_bins = (max_bins <= RANK_SMEM_MAX_BINS) ? max_bins : 0;  // 0: sort in global memory
+  const size_t smem = (size_t)smem_bins * 12;
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev = (dev >= 0 && dev < 64) ? dev : 0;
+  if (smem > configured[dev]) {
+    e = cudaFuncSetAttribute(hough_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = smem;
+  }
+  hough_rank_kernel<<<n_problems, 1024, smem, stream>>>(d_desc, d_stats, smem_bins);
+  return cudaGetLastError();
+}
+
 extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc, const rb2_hough_desc* h_desc,
                                     rb2_hough_stats* d_stats, int slopes_per_cta, void* stream_) {
   using namespace rb2;
@@ -612,7 +654,7 @@ extern "C" int rb2_hough_accumulate(int n_problems, const rb2_hough_desc* d_desc
     const int crossing = force >= 0 ? force : (max_slopes >= 8 * max_yb);
     hough_bin_kernel<<<g3, 512, smem, stream>>>(d_desc, d_stats, spc, (int)sub_words, crossing, pairs_per_cta);
   }
-  hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
+  RB2_CHECK(launch_rank(n_problems, d_desc, h_desc, d_stats, stream));
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }
@@ -796,7 +838,7 @@ extern "C" int rb2_hough_bin_points(int n_problems, const rb2_hough_desc* d_desc
   const int zb = max(1, min(64, (max_bins + 256 * 16 - 1) / (256 * 16)));
   points_edges_kernel<<<dim3(zb, n_problems), 256, 0, stream>>>(d_desc, d_stats);
   if (max_n > 0) points_bin_kernel<<<dim3(gx, n_problems), 256, 0, stream>>>(d_desc);
-  hough_rank_kernel<<<n_problems, 1024, 0, stream>>>(d_desc, d_stats);
+  RB2_CHECK(launch_rank(n_problems, d_desc, h_desc, d_stats, stream));
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }

@@ -718,25 +718,61 @@ __device__ __forceinline__ bool same_wave(double a, double b) {  // bit equality
   return __double_as_longlong(a) == __double_as_longlong(b);
 }
 
-// returns false when a candidate pick needs a redraw (-> slow round); pi / ci / xs / ys are complete when true
+// Candidate half-words: half j lives in word S + j / 2.  Halves 0..S-1 are the first tries of the S picks;
+// the halves after them - first the ones left in the eager words, then the words of the following Philox
+// blocks - form ONE retry stream that the picks consume in order.
+template <int S>
+struct CandStream {
+  static constexpr int NW = SamplerDims<S>::NW;
+  static constexpr int EAGER = 2 * (NW - S);                                  // halves held by the eager words
+  static constexpr int FAST_RETRIES = (EAGER - S) < 2 ? (EAGER - S) : 2;      // retries the fast path may take
+  __device__ static __forceinline__ unsigned eager_half(const unsigned (&w)[NW], int j) {
+    return (j & 1) ? (w[S + j / 2] >> 16) : (w[S + j / 2] & 0xffffu);
+  }
+};
+
+// returns false when the draw needs more retries than the eager words hold (-> slow round); pi / ci / xs / ys
+// are complete when true.  Most redraws (a repeated wavelength, ~7 % of the C3 hypotheses) are settled here
+// with the spare eager halves; the slow round sees ~1 %.
 template <int S>
 __device__ __forceinline__ bool draw_sample_fast(const TablesA& t, const PhiloxKey& key, unsigned long long gid,
                                                  int (&pi)[S], int (&ci)[S], double (&xs)[S], double (&ys)[S]) {
+  using CS = CandStream<S>;
   unsigned w[SamplerDims<S>::NW];
   philox_eager<S>(key, (unsigned)gid, (unsigned)(gid >> 32), w);
   draw_peaks<S>(t, w, pi, xs);
   bool ok = true;
+  int nr = 0;  // retry halves consumed
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     unsigned off, K, thr;
     t.cand_list(pi[k], off, K, thr);
-    const unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
-    const unsigned x = h * K;
-    ok &= (x & 0xffffu) >= thr;
-    const int c = (int)(off + (x >> 16));
-    const double wv = t.cwave[c];
+    unsigned h = CS::eager_half(w, k);
+    bool good;
+    int c;
+    double wv;
+    {
+      const unsigned x = h * K;
+      good = (x & 0xffffu) >= thr;
+      c = (int)(off + (x >> 16));
+      wv = t.cwave[c];
 #pragma unroll
-    for (int q = 0; q < S; ++q) if (q < k) ok &= !same_wave(ys[q], wv);
+      for (int q = 0; q < S; ++q) if (q < k) good &= !same_wave(ys[q], wv);
+    }
+#pragma unroll
+    for (int r = 0; r < CS::FAST_RETRIES; ++r) {
+      if (ok && !good && nr < CS::FAST_RETRIES) {
+        h = (nr == 0) ? CS::eager_half(w, S) : CS::eager_half(w, S + (CS::FAST_RETRIES > 1 ? 1 : 0));
+        ++nr;
+        const unsigned x = h * K;
+        good = (x & 0xffffu) >= thr;
+        c = (int)(off + (x >> 16));
+        wv = t.cwave[c];
+#pragma unroll
+        for (int q = 0; q < S; ++q) if (q < k) good &= !same_wave(ys[q], wv);
+      }
+    }
+    ok &= good;
     ci[k] = c; ys[k] = wv;
   }
   return ok;
@@ -744,20 +780,22 @@ __device__ __forceinline__ bool draw_sample_fast(const TablesA& t, const PhiloxK
 
 constexpr int DRAW_MAX_TRIES = 1 << 14;  // per pick; a draw that still fails then is counted as aborted
 
-// the same hypothesis with the redraw loops; false = impossible draw (aborted)
+// the same hypothesis with unbounded redraw loops over the same retry stream; false = impossible draw (aborted)
 template <int S>
 __device__ __noinline__ bool draw_sample_slow(const TablesA& t, unsigned long long seed, unsigned long long gid,
                                               int (&pi)[S], int (&ci)[S], double (&xs)[S], double (&ys)[S]) {
+  using CS = CandStream<S>;
   constexpr int NW = SamplerDims<S>::NW;
   const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32), c0 = (unsigned)gid, c1 = (unsigned)(gid >> 32);
   unsigned w[NW];
   philox_eager<S>(seed, c0, c1, w);
   draw_peaks<S>(t, w, pi, xs);
-  unsigned n_half = 0u, cur = 0u;  // 16-bit halves of the words after the eager blocks, in stream order
+  int n_retry = 0;     // position in the retry stream
+  unsigned cur = 0u;   // current word beyond the eager blocks
   for (int k = 0; k < S; ++k) {
     unsigned off, K, thr;
     t.cand_list(pi[k], off, K, thr);
-    unsigned h = (k & 1) ? (w[S + k / 2] >> 16) : (w[S + k / 2] & 0xffffu);
+    unsigned h = CS::eager_half(w, k);
     bool checked = false;
     int n_dup = 0;
     for (int tries = 0;; ++tries) {
@@ -781,9 +819,17 @@ __device__ __noinline__ bool draw_sample_slow(const TablesA& t, unsigned long lo
           checked = true;
         }
       }
-      if (n_half & 1u) h = cur >> 16;
-      else { cur = philox_word(k0, k1, c0, c1, (unsigned)NW + (n_half >> 1)); h = cur & 0xffffu; }
-      ++n_half;
+      const int j = S + n_retry;  // next half of the retry stream
+      ++n_retry;
+      if (j < CS::EAGER) {
+        h = 0u;
+#pragma unroll
+        for (int e = S; e < CS::EAGER; ++e) if (e == j) h = CS::eager_half(w, e);
+      } else {
+        const int z = j - CS::EAGER;
+        if ((z & 1) == 0) cur = philox_word(k0, k1, c0, c1, (unsigned)NW + (unsigned)(z >> 1));
+        h = (z & 1) ? (cur >> 16) : (cur & 0xffffu);
+      }
     }
   }
   return true;
@@ -1772,7 +1818,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     int bpp = blocks_per_problem;
     if (bpp <= 0) {
       const long long want = (len + RS_THREADS * 8 - 1) / (RS_THREADS * 8);   // >= 8 passes per CTA
-      static const int ctas_per_sm = getenv("RB2_A_CTAS_PER_SM") ? atoi(getenv("RB2_A_CTAS_PER_SM")) : 8;
+      static const int ctas_per_sm = knob("RB2_A_CTAS_PER_SM", 3);  // 3 resident CTAs leave registers for the small stages of the other lanes (measured: 2: 1.71, 3: 1.78, 4: 1.74, 8: 1.68 e10 hyp/s)
       const long long fill = max(1ll, (long long)(ctas_per_sm * sms) / n_problems);  // CTAs per SM overall
       bpp = (int)max(1ll, min(want, fill));
     }
