@@ -156,6 +156,16 @@ typedef struct {
 int rb2_candidate_vote(int n_problems, const rb2_vote_desc *d_desc,
                        const rb2_vote_desc *h_desc, void *stream);
 
+/* Calibrator.candidates (calibrator.py:239-261), the list the reference builds before the vote and its
+ * plotting code reads (plotting.py:309-349): for every Hough line in rank order the pairs with
+ * |gradient*x + intercept - wavelength| <= tol (in pair order) and their Gaussian weights.  Materialised on
+ * demand only (the vote itself never builds it).  h_hough: the problem's K1 descriptor (host copy; its
+ * d_xedges / d_yedges / d_rank / d_pair_x / d_pair_y are read).  Two calls: d_x == NULL writes the per-line
+ * counts to d_off[1..B] (the caller turns them into offsets d_off[0..B], d_off[0] = 0), then with d_x / d_y /
+ * d_w [d_off[B]] the entries of line r are written at d_off[r]. */
+int rb2_candidate_points(const rb2_hough_desc *h_hough, double tol, double gauss_denom,
+                         int64_t *d_off, double *d_x, double *d_y, double *d_w, void *stream);
+
 /* ======================================================================= *
  * K3  batched RANSAC hypothesis draw / fit / test / score / reduce
  *     replaces the loop body of Calibrator._solve_candidate_ransac
@@ -224,6 +234,17 @@ typedef struct {
                                            output, so that every later decision is checked on identical input)  */
   double min_fit_error;                 /* K4: the winner is accepted iff rms >= this (calibrator.py:673-679);
                                            used when rb2_refit_winners is called with minimum_fit_error = NaN   */
+  /* general Hough-density weight: the clamped bicubic spline
+     RectBivariateSpline(gradient centres, intercept centres, hist) itself, evaluated per pixel as the reference
+     does (calibrator.py:614-627, arguments swapped and clamped to the knot range) for the hypotheses that
+     leave the corner regime - nm-scale problems, where gradients and intercepts are of the same size.
+     d_bs_c == NULL: such hypotheses are counted `unsupported` instead. */
+  int32_t bs_nx, bs_ny;                 /* B-spline coefficients per axis (= xbins, ybins)               */
+  const double *d_bs_tx, *d_bs_ty;      /* knots [bs_nx+4], [bs_ny+4] (FITPACK regrid, k = 3, s = 0)     */
+  const double *d_bs_c;                 /* coefficients [bs_nx*bs_ny], row-major (x = gradient axis first) */
+  const double *d_bs_ppx, *d_bs_ppy;    /* per knot interval m = 0..n-4 the four non-zero cubic B-splines
+                                           N_m..N_m+3 as polynomials in (x - t[m+3]):
+                                           [(n-3)][4 basis][4 coefficients, ascending powers]             */
 } rb2_ransac_desc;
 
 typedef enum {
@@ -232,7 +253,7 @@ typedef enum {
   RB2_HYP_MONOTONIC = 2,
   RB2_HYP_EMPTY = 3,
   RB2_HYP_SCORED = 4,
-  RB2_HYP_UNSUPPORTED = 5   /* weight outside the corner-clamped regime      */
+  RB2_HYP_UNSUPPORTED = 5   /* weight outside the corner-clamped regime and no general spline tables given */
 } rb2_hyp_status;
 
 typedef struct {

@@ -71,6 +71,8 @@ class RansacDesc(C.Structure):
         ("d_out_status", _vp), ("d_out_cost", _vp), ("d_out_weight", _vp),
         ("d_out_coeffs", _vp), ("d_out_counts", _vp), ("d_out_sample", _vp), ("d_replay_coeffs", _vp),
         ("min_fit_error", C.c_double),
+        ("bs_nx", C.c_int32), ("bs_ny", C.c_int32), ("d_bs_tx", _vp), ("d_bs_ty", _vp), ("d_bs_c", _vp),
+        ("d_bs_ppx", _vp), ("d_bs_ppy", _vp),
     ]
 
 
@@ -155,6 +157,7 @@ EXPORTS = {
     "rb2_hough_accumulate": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_hough_points": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
     "rb2_candidate_vote": (C.c_int, [C.c_int, _vp, _vp, _vp]),
+    "rb2_candidate_points": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "rb2_ransac_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rb2_ransac_batch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_merge_winners": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),

@@ -411,6 +411,24 @@ class Calibrator:
         self.__dict__["_lazy_candidates"] = None
         self.__dict__["_candidate_arc"] = v
 
+    @property
+    def candidates(self):
+        """The reference's `self.candidates` (calibrator.py:239-261): one (pixels, wavelengths, weights) triple
+        per Hough line in rank order - read by its plotting code (plotting.py:309-349).  The vote (K2) never
+        builds this list; it is materialised from the device on first use after a fit."""
+        c = self.__dict__.get("_candidates")
+        if c is None and self.__dict__.get("_candidates_args") is not None:
+            tol = self._candidates_args
+            sigma = (self.range_tolerance + self.linearity_tolerance) * 1.1775  # :256
+            self.ht.hist  # noqa: B018  (runs the Hough transform if it is still pending)
+            off, x, y, w = engine.candidate_points(self.ht._batch, 0, tol, 2 * sigma ** 2 + 1e-9, pairs=self.pairs)
+            c = self.__dict__["_candidates"] = [(x[a:b], y[a:b], w[a:b]) for a, b in zip(off[:-1], off[1:])]
+        return c
+
+    @candidates.setter
+    def candidates(self, v):
+        self.__dict__["_candidates"] = v
+
     def _solve_device_resident(self, fit_deg, candidate_tolerance, n_hypotheses):
         """fit(n_hypotheses=N) without a host round trip between the stages: pairs -> K1 -> K2 ->
         rb2_ransac_prepare -> K3 (this rank's shard) -> all-gather + merge -> K4 in one chain
@@ -461,8 +479,9 @@ class Calibrator:
         assert len(self.matched_atlas) == len(set(self.matched_atlas))
         self.ransac_counters = {k: int(out.counters[0, j]) for j, k in enumerate(engine.N.COUNTER_NAMES)}
         if self.ransac_counters["unsupported"]:
-            self.logger.warning("%d hypotheses left the corner-clamped Hough-weight regime and were skipped",
-                                self.ransac_counters["unsupported"])
+            # hypotheses outside the corner-clamped Hough-weight regime (nm-scale problems): the staged path
+            # carries the spline tables of the general weight
+            return None
         self.best_cost = float(out.cost[0])
         self.best_hypothesis = (int(out.hyp_id[0]), np.array(out.hyp_coeffs[0, :fit_deg + 1]))
         self.refit_nfev = int(out.refit_nfev[0])
@@ -488,6 +507,7 @@ class Calibrator:
 
         if not self.ht.binned:
             raise NotImplementedError("fit() needs a Hough transform computed by do_hough_transform()")
+        self.__dict__["_candidates"], self.__dict__["_candidates_args"] = None, candidate_tolerance
         if n_hypotheses is not None and fit_coeff is None:
             fast = self._solve_device_resident(fit_deg, candidate_tolerance, int(n_hypotheses))
             if fast is not None:

@@ -388,9 +388,21 @@ hough_rank_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __r
     int* dst = (((passes - 1 - ps) & 1) == 0) ? buf_a : buf_b;  // the last pass lands in buf_a
     if (tid < 256) base[tid] = 0;
     __syncthreads();
-    for (int e = tid; e < B; e += 1024) {
-      const int idx = src ? src[e] : (B - 1 - e);
-      atomicAdd(&base[255u - ((hist[idx] >> sh) & 255u)], 1u);
+    // digit histogram: most bins share a few digits (in the high-byte pass nearly all of them share ONE), so a
+    // plain shared atomic per bin serialises on one address; lanes with equal digits are merged first
+    for (int e0 = 0; e0 < B; e0 += 1024) {
+      const int e = e0 + tid;
+      const bool valid = e < B;
+      unsigned dg = 0;
+      if (valid) {
+        const int idx = src ? src[e] : (B - 1 - e);
+        dg = 255u - ((hist[idx] >> sh) & 255u);
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const unsigned peers = __match_any_sync(act, dg);
+        if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&base[dg], (unsigned)__popc(peers));
+      }
     }
     __syncthreads();
     if (warp == 0) {  // exclusive scan of the 256 digit counters

@@ -892,7 +892,7 @@ struct Pipe {  // device pointers of the staged pipeline (one per rb2_ransac_bat
   rb2_ransac_result* win;           // [n_problems] winner records written by THIS lane's stage D
   unsigned cap; int qs;
 };
-enum : unsigned char { RES_ELIGIBLE = 1, RES_NEAR_FLOOR = 2, RES_EXACT = 4 };
+enum : unsigned char { RES_ELIGIBLE = 1, RES_NEAR_FLOOR = 2, RES_EXACT = 4, RES_GENERAL = 8 };
 // two costs computed from the same coefficients differ only by the summation order of <= n_peaks clipped
 // errors (a few ulp); anything within this relative margin of the running best is re-summed exactly
 constexpr double COST_MARGIN = 1e-12;
@@ -1357,6 +1357,121 @@ __device__ __forceinline__ void best_update(BestKey* slot, const BestKey& mine) 
   }
 }
 
+// status / counts of a scored hypothesis (parity outputs)
+__device__ __forceinline__ void cost_report(const rb2_ransac_desc& d, long long id, int nm, int ni) {
+  if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
+  if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
+}
+// cost of a scored hypothesis from its (tree-summed) errors and its weight, eligibility, running best;
+// returns the entry's RES_* flag
+__device__ __forceinline__ unsigned char cost_tail(const rb2_ransac_desc& d, Pipe& pipe, unsigned e, long long id,
+                                                   int problem, int nm, int ni, double esum, double weight,
+                                                   bool counts_ok, int ncoef) {
+  cost_report(d, id, nm, ni);
+  const long long gid = d.hyp_begin + id;
+  const double denom = (double)(nm - ncoef + 1);
+  const double cost = esum / denom / (weight + 1e-9);  // :629-633
+  bool elig = counts_ok && (cost <= d.cost_ceiling);
+  bool near_floor = false;
+  if (elig && d.floor_id >= 0) {  // fall-through: only what ranks after (floor_cost, floor_id), decided exactly in C3
+    const double slack = COST_MARGIN * fabs(d.floor_cost);
+    near_floor = fabs(cost - d.floor_cost) <= slack;
+    elig = near_floor || cost > d.floor_cost;
+  }
+  if (d.d_out_cost) d.d_out_cost[id] = cost;
+  if (d.d_out_weight) d.d_out_weight[id] = weight;
+  if (!elig) return 0;
+  pipe.res_cost[e] = cost;
+  pipe.res_w[e] = weight;
+  if (!near_floor) {
+    BestKey mine;
+    mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
+    best_update(pipe.best + problem, mine);
+  }
+  return near_floor ? RES_NEAR_FLOOR : RES_ELIGIBLE;
+}
+
+// ---- general Hough-density weight (calibrator.py:497-506, 614-627) -------------------
+// twoditp(intercept, gradient) of the reference: RectBivariateSpline(gradient centres, intercept centres, hist)
+// with both arguments clamped to its knot range (FITPACK bispev), evaluated at the tangent intercept and the
+// gradient of the hypothesis at one pixel.  B-spline form: 4 x 4 coefficients times the non-zero cubic
+// B-splines of either axis, each a stored polynomial on its knot interval.
+__device__ __forceinline__ int bs_interval(const double* __restrict__ t, int n, double x) {
+  int lo = 0, hi = n - 4;  // interval m: t[m + 3] <= x < t[m + 4]; the last one is closed
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (x >= t[mid + 3]) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ double bs_eval(const rb2_ransac_desc& d, double x, double y) {
+  const int nx = d.bs_nx, ny = d.bs_ny;
+  x = fmin(fmax(x, d.d_bs_tx[3]), d.d_bs_tx[nx]);
+  y = fmin(fmax(y, d.d_bs_ty[3]), d.d_bs_ty[ny]);
+  const int m = bs_interval(d.d_bs_tx, nx, x), l = bs_interval(d.d_bs_ty, ny, y);
+  const double u = x - d.d_bs_tx[m + 3], v = y - d.d_bs_ty[l + 3];
+  double by[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const double* k = d.d_bs_ppy + ((size_t)l * 4 + b) * 4;
+    by[b] = fma(fma(fma(k[3], v, k[2]), v, k[1]), v, k[0]);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double* k = d.d_bs_ppx + ((size_t)m * 4 + a) * 4;
+    const double bx = fma(fma(fma(k[3], u, k[2]), u, k[1]), u, k[0]);
+    const double* c = d.d_bs_c + (size_t)(m + a) * ny + l;
+    s = fma(bx, fma(c[0], by[0], fma(c[1], by[1], fma(c[2], by[2], c[3] * by[3]))), s);
+  }
+  return s;
+}
+
+// one warp per queue-B entry flagged RES_GENERAL by stage C2: weight = hough_weight * sum over the pixels
+template <int DEG_T>
+__global__ void __launch_bounds__(256)
+ransac_weight_general_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned n = pipe.counts[1];
+  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
+  const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
+  for (unsigned g = blockIdx.x * (blockDim.x >> 5) + warp; g * 32u < n; g += total_warps) {
+    const unsigned e = g * 32u + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, e < n && (pipe.res_flag[e] & RES_GENERAL));
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned eb = g * 32u + b;
+      const double* q = pipe.qb + (size_t)eb * qs;
+      WeightCtx<DEG_T> w;
+      constexpr int CAP = deg_cap(DEG_T);
+#pragma unroll
+      for (int k = 0; k <= CAP; ++k) w.c[k] = (k < ncoef) ? q[k] : 0.0;
+#pragma unroll
+      for (int k = 0; k <= CAP; ++k) w.dc[k] = (k < deg) ? mul((double)(k + 1), w.c[k + 1 <= CAP ? k + 1 : CAP]) : 0.0;
+      const unsigned long long tag = (unsigned long long)__double_as_longlong(q[ncoef]);
+      const int problem = (int)(tag >> 40);
+      const long long id = (long long)(tag & TAG_ID_MASK);
+      const rb2_ransac_desc& d = descs[problem];
+      w.deg = deg; w.pix = d.d_pix;
+      double acc = 0.0;
+      for (int i = lane; i < d.n_pix; i += 32) {
+        const double x = w.px(i);
+        const double grad = (deg >= 1) ? horner_ref<CAP>(w.dc, deg, x) : 0.0;
+        acc += bs_eval(d, w.t_at(i), grad);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        const int2 cnt = pipe.res_cnt[eb];
+        const bool counts_ok = (cnt.y >= d.min_inliers) && ((double)cnt.y >= d.min_inliers_frac);
+        pipe.res_flag[eb] = cost_tail(d, pipe, eb, id, problem, cnt.x, cnt.y, pipe.res_esum[eb], d.hough_weight * acc,
+                                      counts_ok, ncoef);
+      }
+    }
+  }
+}
+
 template <int DEG_T>
 __global__ void __launch_bounds__(128, 4)
 ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
@@ -1397,35 +1512,18 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
         }
         double weight;
         const bool ok = hough_weight_thread<DEG_T>(d, cr, deg, need_value, &weight);
-        if (!ok) {
+        if (!ok && d.d_bs_c) {
+          // outside the corner regime: the weight is the clamped bicubic spline summed over the pixels -
+          // warp-sized work, done by ransac_weight_general_kernel (which also finishes the cost)
+          kind = counts_ok ? 2 : 1;
+          flag = RES_GENERAL;
+        } else if (!ok) {
           kind = 3;
           if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED;
         } else {
           kind = counts_ok ? 2 : 1;
-          if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
-          if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
-          if (need_value) {
-            const double cost = esum / denom / (weight + 1e-9);  // :629-633
-            bool elig = counts_ok && (cost <= d.cost_ceiling);
-            bool near_floor = false;
-            if (elig && d.floor_id >= 0) {  // fall-through: only what ranks after (floor_cost, floor_id), decided exactly in C3
-              const double slack = COST_MARGIN * fabs(d.floor_cost);
-              near_floor = fabs(cost - d.floor_cost) <= slack;
-              elig = near_floor || cost > d.floor_cost;
-            }
-            if (d.d_out_cost) d.d_out_cost[id] = cost;
-            if (d.d_out_weight) d.d_out_weight[id] = weight;
-            if (elig) {
-              pipe.res_cost[e] = cost;
-              pipe.res_w[e] = weight;
-              flag = near_floor ? RES_NEAR_FLOOR : RES_ELIGIBLE;
-              if (!near_floor) {
-                BestKey mine;
-                mine.hi = cost_key(cost); mine.lo = ~(unsigned long long)gid;
-                best_update(pipe.best + problem, mine);
-              }
-            }
-          }
+          if (need_value) flag = cost_tail(d, pipe, e, id, problem, nm, ni, esum, weight, counts_ok, ncoef);
+          else cost_report(d, id, nm, ni);
         }
       }
       pipe.res_flag[e] = flag;
@@ -1610,7 +1708,16 @@ __global__ void ransac_finalize_kernel(const rb2_ransac_result* __restrict__ rec
 
 namespace rb2 {
 
-constexpr unsigned PIPE_CHUNK = 1u << 22;  // hypotheses per chunk == queue capacity (worst case: all survive)
+// hypotheses per chunk == queue capacity (worst case: all survive); RB2_PIPE_CHUNK_LOG2 overrides (tuning)
+static unsigned pipe_chunk() {
+  static const unsigned n = [] {
+    const char* e = getenv("RB2_PIPE_CHUNK_LOG2");
+    const int v = e ? atoi(e) : 22;
+    return 1u << (v < 12 ? 12 : (v > 26 ? 26 : v));
+  }();
+  return n;
+}
+#define PIPE_CHUNK (rb2::pipe_chunk())
 
 // Two LANES: consecutive chunks alternate between two independent sets of queues on two streams,
 // so that the issue-bound draw/fit stage of one chunk overlaps the latency-bound match / cost
@@ -1685,6 +1792,7 @@ struct ChunkArgs {
   dim3 grid_a; size_t smem_a, smem_c, smem_x; int max_wids, max_up, single, sms; cudaStream_t stream;
   const rb2_ransac_desc* d_desc; Pipe pipe; long long chunk_begin, chunk_len; rb2_ransac_result* d_result;
   PhiloxKey key;
+  bool general_weight;  // some problem carries the spline tables of the general Hough-density weight
 };
 
 template <int DEG_T, bool LSQ = false>
@@ -1727,6 +1835,10 @@ static int launch_chunk(const ChunkArgs& a) {
   if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
   ransac_cost_kernel<DEG_T><<<sms * nc2, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
+  if (a.general_weight) {
+    ransac_weight_general_kernel<DEG_T><<<sms * 4, 256, 0, stream>>>(a.d_desc, a.pipe);
+    if (!stage_ok("C2g general weight")) return RB2_ERR_CUDA;
+  }
   ransac_exact_kernel<DEG_T><<<sms * 2, RS_THREADS, a.smem_x, stream>>>(a.d_desc, a.pipe, a.max_wids);
   if (!stage_ok("C3 exact")) return RB2_ERR_CUDA;
   ransac_record_kernel<<<sms * 2, 256, 0, stream>>>(a.d_desc, a.pipe);
@@ -1753,7 +1865,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
   // all problems of one call share degree / sample size (one kernel instantiation) and the Philox key
   const int deg = h_desc[0].deg, s = h_desc[0].sample_size;
-  bool fast = true;
+  bool fast = true, general_weight = false;
   size_t smem_a = 0;
   int max_wids = 1, max_up = 1;
   long long max_hyp = 0;
@@ -1766,6 +1878,10 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     if (h.sample_size != h.deg + 1 || h.n_known != 0) fast = false;
     if (h.n_cand < h.n_upeaks || h.n_wids < 1 || h.n_upeaks > 65535 || h.n_cand > A_MAX_CAND) return RB2_ERR_ARG;
     if (h.n_hyp < 0 || h.n_hyp >= (1ll << 40)) return RB2_ERR_ARG;
+    if (h.d_bs_c) {
+      if (h.bs_nx < 4 || h.bs_ny < 4 || !h.d_bs_tx || !h.d_bs_ty || !h.d_bs_ppx || !h.d_bs_ppy) return RB2_ERR_ARG;
+      general_weight = true;
+    }
     smem_a = max(smem_a, stage_a_smem(h));
     max_wids = max(max_wids, h.n_wids);
     max_up = max(max_up, h.n_upeaks);
@@ -1825,7 +1941,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     ChunkArgs ca;
     ca.grid_a = dim3(bpp, n_problems); ca.smem_a = smem_a; ca.smem_c = smem_c; ca.smem_x = smem_x;
     ca.max_wids = max_wids; ca.max_up = max_up; ca.single = single; ca.sms = sms; ca.stream = cstream;
-    ca.d_desc = d_desc; ca.pipe = pipe; ca.chunk_begin = c0; ca.chunk_len = len; ca.d_result = d_result; ca.key = key;
+    ca.d_desc = d_desc; ca.pipe = pipe; ca.chunk_begin = c0; ca.chunk_len = len; ca.d_result = d_result; ca.key = key; ca.general_weight = general_weight;
     int rc;
     switch ((fast ? 0 : 8) + (deg <= 5 ? deg : 0)) {
       case 1: rc = launch_chunk<1>(ca); break;

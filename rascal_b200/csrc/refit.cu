@@ -143,97 +143,29 @@ __device__ double trf_linearise(const double* a, int n, int m, const double* xn,
   return 0.5 * warp_sum(c);
 }
 
-// Singular value decomposition of the scaled Jacobian for solve_lsq_trust_region, which only needs the
-// singular values s, the right singular vectors V and U^T f (SciPy: svd(J, full_matrices=False)):
-//   1. Householder QR of [J | f] (m x (n+1), column-major in w.U), rows spread over the lanes; the
-//      n-k+1 inner products of one reflection are accumulated together and share one interleaved
-//      butterfly -> R (n x n) and the first n entries of Q^T f;
-//   2. one-sided Jacobi on the n x n matrix A = R V0 (V0 = identity, or the previous step's V: the
-//      Jacobian changes little between trust-region steps, so the columns start nearly orthogonal and one
-//      or two sweeps suffice); lane r owns row r of A and of V, a pair step is three 8-lane reductions and
-//      four multiply-adds per lane - not a pass over m rows and a 32-lane butterfly as a Jacobi SVD of J
-//      itself would need (that was 69 % of K4's time);
-//   3. s_j = |A[:, j]|, U^T f = (A^T Q^T f)_j / s_j.
-// J = Q R, R V = U_r S  =>  J = (Q U_r) S V^T: the same decomposition (singular values are NOT sorted;
-// the callers use min / max and sums over all directions only).
+// one-sided Jacobi SVD of w.J (copied to w.U): U columns normalised in place, s descending, V (n x n,
+// shared memory).  A pair step is latency-bound on one warp, so it is kept short: the three inner
+// products share one interleaved butterfly, the rotation comes from one sqrt, one division and one
+// rsqrt (t = sign * |h| / (|d| + sqrt(d^2 + h^2)), d = be - al, h = 2 ga), lanes update the rows of U
+// and lane k row k of V.
 #ifdef RB2_K4_PROFILE
 __device__ int g_k4_rot = 0, g_k4_sweeps = 0;
 #endif
-struct SmallSvd {            // shared memory, one warp per CTA in every kernel that runs the solver
-  double A[NCF][NCF + 1];    // row r, column c (padded: lanes read one column in parallel)
-  double V[NCF][NCF];
-  double qtf[NCF], s[NCF], uf[NCF];
-};
-
-__device__ void trf_factor(int n, int m, TrfWs& w, SmallSvd& S, double* s, double* uf, bool warm) {
+// `warm`: V holds the right singular vectors of the previous Jacobian of the same problem; the
+// iteration then starts from U = J V (columns already nearly orthogonal: the Jacobian changes little
+// between trust-region steps), which saves most sweeps.  U S V^T is the same decomposition either way.
+__device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF], bool warm) {
   const int lane = lane_id();
-  // -- 1. Householder QR of [J | f] in w.U --
-  for (int i = lane; i < m * n; i += 32) w.U[i] = w.J[i];
-  for (int i = lane; i < m; i += 32) w.U[n * m + i] = w.f[i];
-  __syncwarp();
-  for (int k = 0; k < n; ++k) {
-    double acc[NCF + 1];
-#pragma unroll
-    for (int j = 0; j <= NCF; ++j) acc[j] = 0.0;
+  if (!warm) {
+    for (int i = lane; i < m * n; i += 32) w.U[i] = w.J[i];
+    for (int i = lane; i < n * n; i += 32) V[i / n][i % n] = (i / n == i % n) ? 1.0 : 0.0;
+  } else {
     for (int i = lane; i < m; i += 32) {
-      if (i < k) continue;
-      const double xk = w.U[k * m + i];
-#pragma unroll
-      for (int j = 0; j <= NCF; ++j)
-        if (j >= k && j <= n) acc[j] = fma(xk, w.U[j * m + i], acc[j]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int j = 0; j <= NCF; ++j)
-        if (j >= k && j <= n) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    }
-    double xx = 0.0;
-#pragma unroll
-    for (int j = 0; j <= NCF; ++j) if (j == k) xx = acc[j];
-    const double akk = w.U[k * m + k];
-    const double nrm = sqrt(xx);
-    if (nrm == 0.0) { __syncwarp(); continue; }
-    const double alpha = (akk > 0.0) ? -nrm : nrm;
-    const double den = xx - alpha * akk;  // v.v / 2, v = x - alpha e_k
-    if (den == 0.0) { __syncwarp(); continue; }
-    const double beta = 1.0 / den;
-    double sj[NCF + 1];
-#pragma unroll
-    for (int j = 0; j <= NCF; ++j)
-      sj[j] = (j > k && j <= n) ? (acc[j] - alpha * w.U[j * m + k]) * beta : 0.0;
-    __syncwarp();
-    for (int i = lane; i < m; i += 32) {
-      if (i < k) continue;
-      const double vi = w.U[k * m + i] - ((i == k) ? alpha : 0.0);
-#pragma unroll
-      for (int j = 0; j <= NCF; ++j)
-        if (j > k && j <= n) w.U[j * m + i] = fma(-sj[j], vi, w.U[j * m + i]);
-    }
-    __syncwarp();
-    if (lane == 0) w.U[k * m + k] = alpha;
-    __syncwarp();
-  }
-  // -- 2. A = R V0, one-sided Jacobi over the n x n matrix --
-  if (lane < n) {
-    const int r = lane;
-    S.qtf[r] = (r < m) ? w.U[n * m + r] : 0.0;
-    double row[NCF];
-#pragma unroll
-    for (int c = 0; c < NCF; ++c) row[c] = (c < n && c >= r && r < m) ? w.U[c * m + r] : 0.0;  // R[r][c]
-    if (warm) {
-#pragma unroll
-      for (int c = 0; c < NCF; ++c) {
-        if (c < n) {
-          double a = 0.0;
-#pragma unroll
-          for (int t = 0; t < NCF; ++t) if (t < n) a = fma(row[t], S.V[t][c], a);
-          S.A[r][c] = a;
-        }
+      for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc = fma(w.J[k * m + i], V[k][j], acc);
+        w.U[j * m + i] = acc;
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < NCF; ++c) if (c < n) { S.A[r][c] = row[c]; S.V[r][c] = (r == c) ? 1.0 : 0.0; }
     }
   }
   __syncwarp();
@@ -241,15 +173,17 @@ __device__ void trf_factor(int n, int m, TrfWs& w, SmallSvd& S, double* s, doubl
     bool rotated = false;
     for (int p = 0; p < n - 1; ++p) {
       for (int q = p + 1; q < n; ++q) {
-        const double ap = (lane < n) ? S.A[lane][p] : 0.0, aq = (lane < n) ? S.A[lane][q] : 0.0;
-        double al = ap * ap, be = aq * aq, ga = ap * aq;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int i = lane; i < m; i += 32) {
+          const double up = w.U[p * m + i], uq = w.U[q * m + i];
+          al = fma(up, up, al); be = fma(uq, uq, be); ga = fma(up, uq, ga);
+        }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = 16; o > 0; o >>= 1) {
           al += __shfl_xor_sync(0xffffffffu, al, o);
           be += __shfl_xor_sync(0xffffffffu, be, o);
           ga += __shfl_xor_sync(0xffffffffu, ga, o);
         }
-        al = __shfl_sync(0xffffffffu, al, 0); be = __shfl_sync(0xffffffffu, be, 0); ga = __shfl_sync(0xffffffffu, ga, 0);
         // converged pair: |ga| <= eps * sqrt(al * be), tested on the squares
         if (fabs(ga) <= 1e-300 || ga * ga <= (TRF_EPS * TRF_EPS) * (al * be)) continue;
         rotated = true;
@@ -260,13 +194,17 @@ __device__ void trf_factor(int n, int m, TrfWs& w, SmallSvd& S, double* s, doubl
         const double t = copysign(fabs(hh) / (fabs(dd) + sqrt(fma(dd, dd, hh * hh))),
                                   (dd == 0.0 || (dd > 0.0) == (hh > 0.0)) ? 1.0 : -1.0);
         const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
-        if (lane < n) {
-          S.A[lane][p] = c * ap - sn * aq;
-          S.A[lane][q] = sn * ap + c * aq;
-          const double vp = S.V[lane][p], vq = S.V[lane][q];
-          S.V[lane][p] = c * vp - sn * vq;
-          S.V[lane][q] = sn * vp + c * vq;
+        for (int i = lane; i < m; i += 32) {
+          const double up = w.U[p * m + i], uq = w.U[q * m + i];
+          w.U[p * m + i] = c * up - sn * uq;
+          w.U[q * m + i] = sn * up + c * uq;
         }
+        if (lane < n) {
+          const double vp = V[lane][p], vq = V[lane][q];
+          V[lane][p] = c * vp - sn * vq;
+          V[lane][q] = sn * vp + c * vq;
+        }
+        __syncwarp();
       }
     }
 #ifdef RB2_K4_PROFILE
@@ -274,21 +212,26 @@ __device__ void trf_factor(int n, int m, TrfWs& w, SmallSvd& S, double* s, doubl
 #endif
     if (!rotated) break;
   }
-  __syncwarp();
-  // -- 3. singular values and U^T f (lane j: direction j) --
-  if (lane < n) {
-    double ss = 0.0, dot = 0.0;
-    for (int r = 0; r < n; ++r) {
-      const double a = S.A[r][lane];
-      ss = fma(a, a, ss);
-      dot = fma(a, S.qtf[r], dot);
+  for (int j = 0; j < n; ++j) {
+    double ss = 0.0;
+    for (int i = lane; i < m; i += 32) ss = fma(w.U[j * m + i], w.U[j * m + i], ss);
+    s[j] = sqrt(warp_sum(ss));
+  }
+  // selection sort, descending (stable enough: n <= 8), permuting U columns and V columns
+  for (int a = 0; a < n - 1; ++a) {
+    int b = a;
+    for (int k = a + 1; k < n; ++k) if (s[k] > s[b]) b = k;
+    if (b != a) {
+      const double ts = s[a]; s[a] = s[b]; s[b] = ts;
+      for (int i = lane; i < m; i += 32) { const double tu = w.U[a * m + i]; w.U[a * m + i] = w.U[b * m + i]; w.U[b * m + i] = tu; }
+      if (lane < n) { const double tv = V[lane][a]; V[lane][a] = V[lane][b]; V[lane][b] = tv; }
     }
-    const double sv = sqrt(ss);
-    S.s[lane] = sv;
-    S.uf[lane] = (sv > 0.0) ? dot / sv : 0.0;
   }
   __syncwarp();
-  for (int j = 0; j < n; ++j) { s[j] = S.s[j]; uf[j] = S.uf[j]; }
+  for (int j = 0; j < n; ++j) {
+    const double inv = (s[j] > 0.0) ? 1.0 / s[j] : 0.0;
+    for (int i = lane; i < m; i += 32) w.U[j * m + i] *= inv;
+  }
   __syncwarp();
 }
 
@@ -318,9 +261,7 @@ __device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, co
     phi = pn - Delta;
     phi_prime = -sm / pn;
   };
-  double s_min = s[0], s_max = s[0];  // the singular values come unsorted (trf_factor)
-  for (int i = 1; i < n; ++i) { s_min = fmin(s_min, s[i]); s_max = fmax(s_max, s[i]); }
-  const bool full_rank = (m >= n) && (s_min > TRF_EPS * m * s_max);
+  const bool full_rank = (m >= n) && (s[n - 1] > TRF_EPS * m * s[0]);
   if (full_rank) {
     double gn[NCF];  // Gauss-Newton step in the singular basis
     for (int i = 0; i < n; ++i) gn[i] = uf[i] / s[i];
@@ -377,8 +318,7 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
   int status = -1;
   double s[NCF], uf[NCF], step[NCF], a_new[NCF];
   int svd_count = 0;
-  __shared__ SmallSvd S;  // one warp per CTA in every kernel that runs the solver
-  double (*V)[NCF] = S.V;
+  __shared__ double V[NCF][NCF];  // one warp per CTA in every kernel that runs the solver
 #ifdef RB2_K4_PROFILE
   long long t_svd = 0, t_lin = 0, t_inner = 0, t0c = 0;
   int n_outer = 0, n_inner = 0;
@@ -394,7 +334,12 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
     if (g_norm < gtol) status = 1;
     if (status >= 0 || nfev == max_nfev) break;
     K4_TIC();
-    trf_factor(n, m, w, S, s, uf, svd_count++ > 0);
+    trf_svd(n, m, w, s, V, svd_count++ > 0);
+    for (int j = 0; j < n; ++j) {
+      double acc = 0.0;
+      for (int i = lane; i < m; i += 32) acc = fma(w.U[j * m + i], w.f[i], acc);
+      uf[j] = warp_sum(acc);
+    }
     K4_TOC(t_svd);
 #ifdef RB2_K4_PROFILE
     ++n_outer;
@@ -463,7 +408,7 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
 }
 
 // models.robust_polyfit (models.py:70-123) on m points (ix, iy) in shared memory, one warp.
-// xn, yn, sw: [m] scratch; A: [(2n+4)*m] scratch.  Fills r.coeffs (low order first),
+// xn, yn, sw: [m] scratch; A: [(2n+3)*m] scratch.  Fills r.coeffs (low order first),
 // r.huber_iters (nfev / IRLS passes) and r.pad (SciPy status).
 __device__ void robust_polyfit_warp(int m, int n, const double* ix, const double* iy, double* xn, double* yn, double* sw,
                                     double* A, int mode, rb2_refit_result& r) {
@@ -486,7 +431,7 @@ __device__ void robust_polyfit_warp(int m, int n, const double* ix, const double
   r.pad = 0;
   if (mode == 0) {
     TrfWs ws;
-    ws.J = A; ws.U = A + (size_t)m * n; ws.f_true = A + (size_t)2 * m * n + m;  // U holds [J | f]: m x (n + 1)
+    ws.J = A; ws.U = A + (size_t)m * n; ws.f_true = A + (size_t)2 * m * n;
     ws.f = ws.f_true + m; ws.f_new = ws.f + m; ws.js = sw;
     double ah[NCF];
     int nfev = 0, status = 0;
@@ -545,8 +490,8 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
   double* xn = iy + n_u;                                                         // [n_u]
   double* yn = xn + n_u;                                                         // [n_u]
   double* sw = yn + n_u;                                                         // [n_u]
-  double* A = sw + n_u;                                                          // [n_u*(n+1)] (QR) / J, U = [J | f], f_true, f, f_new (TRF): n_u*(2n+4)
-  int* bpeak = reinterpret_cast<int*>(A + (size_t)n_u * (2 * n + 4));            // [n_w]
+  double* A = sw + n_u;                                                          // [n_u*(n+1)] (QR) / J, U, f_true, f, f_new (TRF)
+  int* bpeak = reinterpret_cast<int*>(A + (size_t)n_u * (2 * n + 3));            // [n_w]
 
   double c[NCF];
   for (int i = 0; i < NCF; ++i) c[i] = w.coeffs[i];
@@ -665,7 +610,7 @@ match_peaks_kernel(const rb2_match_desc* __restrict__ descs, int mode, int max_p
   double* xn = iy + max_p;
   double* yn = xn + max_p;
   double* sw = yn + max_p;
-  double* A = sw + max_p;  // (2 max_n + 4) * max_p
+  double* A = sw + max_p;  // (2 max_n + 3) * max_p
   (void)max_n;
   rb2_match_result r;
   r.n_matched = 0; r.n_ambiguous = 0; r.polyfit_err = 0.0; r.polyfit_rms = 0.0;
@@ -765,7 +710,7 @@ extern "C" int rb2_refit_winners(int n_problems, const rb2_ransac_desc* d_desc, 
     const rb2_ransac_desc& h = h_desc[i];
     if (h.n_upeaks > max_upeaks) return RB2_ERR_ARG;
     const size_t n = h.deg + 1;
-    size_t b = (size_t)h.n_wids * 16 + (size_t)h.n_upeaks * 8 * 5 + (size_t)h.n_upeaks * (2 * n + 4) * 8 + (size_t)h.n_wids * 4;
+    size_t b = (size_t)h.n_wids * 16 + (size_t)h.n_upeaks * 8 * 5 + (size_t)h.n_upeaks * (2 * n + 3) * 8 + (size_t)h.n_wids * 4;
     smem = max(smem, b);
   }
   if (smem > 200 * 1024) return RB2_ERR_ARG;
@@ -786,7 +731,7 @@ extern "C" int rb2_robust_polyfit(int n_problems, const int32_t* d_off, const in
     if (h_off[i + 1] < h_off[i]) return RB2_ERR_ARG;
     max_m = max(max_m, h_off[i + 1] - h_off[i]);
   }
-  const size_t smem = (size_t)max_m * 8 * (5 + 2 * (deg + 1) + 4);
+  const size_t smem = (size_t)max_m * 8 * (5 + 2 * (deg + 1) + 3);
   if (smem > 200 * 1024) return RB2_ERR_ARG;
   RB2_CHECK(cudaFuncSetAttribute(robust_polyfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   robust_polyfit_kernel<<<n_problems, 32, smem, (cudaStream_t)stream_>>>(d_off, d_x, d_y, deg, mode, max_m, d_out);
@@ -810,7 +755,7 @@ extern "C" int rb2_match_peaks(int n_problems, const rb2_match_desc* d_desc, con
     if ((h.n_peaks && !h.d_peaks) || (h.n_atlas && !h.d_atlas)) return RB2_ERR_ARG;
     max_n = max(max_n, h.fit_deg + 1);
   }
-  const size_t smem = (size_t)max_peaks * 8 * (5 + 2 * max_n + 4);
+  const size_t smem = (size_t)max_peaks * 8 * (5 + 2 * max_n + 3);
   if (smem > 200 * 1024) return RB2_ERR_ARG;
   RB2_CHECK(cudaFuncSetAttribute(match_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   match_peaks_kernel<<<n_problems, 32, smem, (cudaStream_t)stream_>>>(d_desc, mode, max_peaks, max_n, d_out, d_matched_x,

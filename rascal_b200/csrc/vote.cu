@@ -497,3 +497,65 @@ extern "C" int rb2_candidate_vote(int n_problems, const rb2_vote_desc* d_desc, c
   RB2_CHECK(cudaGetLastError());
   return RB2_OK;
 }
+
+// ---- Calibrator.candidates (calibrator.py:239-261), materialised on demand --------------------------------
+// For every Hough line in rank order: the pairs within candidate_tolerance of the line (mask `<=`, pairs in
+// the caller's order) and their Gaussian weights - the list the reference builds before the vote and that
+// its plotting code reads.  One warp per line; lanes sweep the pairs, ordered compaction by ballot.
+namespace rb2 {
+
+__global__ void __launch_bounds__(256)
+candidate_points_kernel(const double* __restrict__ xedges, const double* __restrict__ yedges, int ybins,
+                        const int* __restrict__ rank, int n_bins, const double* __restrict__ px,
+                        const double* __restrict__ py, int n_pairs, double tol, double gauss_denom,
+                        long long* __restrict__ off, double* __restrict__ out_x, double* __restrict__ out_y,
+                        double* __restrict__ out_w) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const double hx = (xedges[1] - xedges[0]) / 2, hy = (yedges[1] - yedges[0]) / 2;  // houghtransform.py:197-198
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_bins; r += warps) {
+    const int b = rank[r];
+    const double g = add(xedges[b / ybins], hx), c = add(yedges[b % ybins], hy);
+    long long run = out_x ? off[r] : 0;
+    for (int p0 = 0; p0 < n_pairs; p0 += 32) {
+      const int p = p0 + lane;
+      bool hit = false;
+      double x = 0.0, y = 0.0, pred = 0.0;
+      if (p < n_pairs) {
+        x = px[p]; y = py[p];
+        pred = add(mul(g, x), c);                       // gradient * pairs[:, 0] + intercept (:242)
+        hit = fabs(sub(pred, y)) <= tol;                // :244-245
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (out_x && hit) {
+        const long long o = run + __popc(m & ((1u << lane) - 1u));
+        const double dlt = sub(y, pred);
+        out_x[o] = x; out_y[o] = y;
+        out_w[o] = exp(-mul(dlt, dlt) / gauss_denom);  // util.gauss(actual, 1., predicted, sigma) (:250-257)
+      }
+      run += __popc(m);
+    }
+    if (!out_x && lane == 0) off[r + 1] = run;  // counts; the caller turns them into offsets
+  }
+}
+
+}  // namespace rb2
+
+extern "C" int rb2_candidate_points(const rb2_hough_desc* h_hough, double tol, double gauss_denom, int64_t* d_off,
+                                    double* d_x, double* d_y, double* d_w, void* stream_) {
+  using namespace rb2;
+  if (!h_hough || !d_off || !h_hough->d_xedges || !h_hough->d_yedges || !h_hough->d_rank) return RB2_ERR_ARG;
+  if ((d_x != nullptr) != (d_y != nullptr) || (d_x != nullptr) != (d_w != nullptr)) return RB2_ERR_ARG;
+  const rb2_hough_desc& h = *h_hough;
+  const long long B = (long long)h.xbins * h.ybins;
+  if (B <= 0 || B > 0x7fffffffll || h.n_pairs < 0 || (h.n_pairs && (!h.d_pair_x || !h.d_pair_y))) return RB2_ERR_ARG;
+  int sms = 148;
+  if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
+  const int blocks = (int)min((long long)sms * 8, (B + 7) / 8);
+  candidate_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(h.d_xedges, h.d_yedges, h.ybins, h.d_rank, (int)B,
+                                                                     h.d_pair_x, h.d_pair_y, h.n_pairs, tol, gauss_denom,
+                                                                     (long long*)d_off, d_x, d_y, d_w);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
+

@@ -240,6 +240,36 @@ class HoughBatch:
         return out[:n_points].cpu().numpy()
 
 
+def candidate_points(hough, i, tol, gauss_denom, pairs=None):
+    """Calibrator.candidates (calibrator.py:239-261) of problem i of a HoughBatch: (offsets[B + 1], x, y, w) -
+    line r in rank order owns entries offsets[r]:offsets[r + 1] (rb2_candidate_points; on demand only).
+    pairs: [P, 2] (pixel, wavelength) when the batch does not hold them (explicit-points transforms)."""
+    torch = _torch()
+    lib = N.load()
+    one = N.struct_array(N.HoughDesc, 1)
+    C.memmove(one, C.byref(hough.h_desc[i]), C.sizeof(N.HoughDesc))
+    keep = None
+    if pairs is not None:
+        pairs = np.asarray(pairs, dtype=np.float64).reshape(-1, 2)
+        keep = (torch.from_numpy(np.ascontiguousarray(pairs[:, 0])).cuda(), torch.from_numpy(np.ascontiguousarray(pairs[:, 1])).cuda())
+        TRANSFER["h2d"] += pairs.nbytes
+        one[0].d_pair_x, one[0].d_pair_y, one[0].n_pairs = keep[0].data_ptr(), keep[1].data_ptr(), len(pairs)
+    B = one[0].xbins * one[0].ybins
+    off = torch.zeros(B + 1, dtype=torch.int64, device="cuda")
+    args = (C.addressof(one), float(tol), float(gauss_denom), off.data_ptr())
+    N.check(lib.rb2_candidate_points(*args, None, None, None, current_stream_ptr()), "rb2_candidate_points")
+    torch.cumsum(off, 0, out=off)
+    total = int(off[B].item())
+    out = torch.empty((3, max(total, 1)), dtype=torch.float64, device="cuda")
+    if total:
+        N.check(lib.rb2_candidate_points(*args, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                         current_stream_ptr()), "rb2_candidate_points")
+    h = out[:, :total].cpu().numpy()
+    TRANSFER["d2h"] += h.nbytes + 8 * (B + 1)
+    del keep
+    return off.cpu().numpy(), h[0], h[1], h[2]
+
+
 class PointsHoughBatch(HoughBatch):
     """bin_hough_points for EXPLICIT Hough points (brute force / add_hough_points / load):
     rb2_hough_bin_points.  problems: dicts with points ([N, 2] gradient, intercept), xbins, ybins.
@@ -467,6 +497,23 @@ def sampling_cdf32(peaks):
     return prob, c32
 
 
+def bspline_basis_pp(t):
+    """The cubic B-spline basis on knots t (first / last four equal) as local polynomials: for every knot
+    interval m = 0..n-4 (n = len(t) - 4 basis functions) the four non-zero basis functions N_m..N_m+3 in
+    powers of (x - t[m+3]), ascending: array [n-3, 4, 4], flattened."""
+    from scipy.interpolate import BSpline
+
+    t = np.asarray(t, dtype=np.float64)
+    n = len(t) - 4
+    b = BSpline(t, np.eye(n), 3)
+    left = t[3:n]  # left end of interval m is t[m + 3] (evaluation there is right-continuous)
+    fact = (1.0, 1.0, 2.0, 6.0)
+    tay = np.stack([b(left, nu=p) / fact[p] for p in range(4)], axis=2)  # [interval, basis, power]
+    m = np.arange(n - 3)
+    out = np.stack([tay[m, m + a, :] for a in range(4)], axis=1)  # [interval, 4 non-zero basis functions, power]
+    return np.ascontiguousarray(out.reshape(-1))
+
+
 class RansacSetup:
     """Read-only inputs of the hypothesis loop, as the reference prepares them
     at the top of _solve_candidate_ransac (calibrator.py:441-523)."""
@@ -549,6 +596,11 @@ class RansacSetup:
         coef = np.linalg.solve(np.vander(u, 4, increasing=True), v.T).T / w[:, None] ** np.arange(4)[None, :]
         self.pp_breaks = brk.astype(np.float64)
         self.pp_coef = coef.reshape(-1)
+        # the spline itself for hypotheses outside the corner regime (general evaluation on the device)
+        ty = spl.get_knots()[1]
+        self.bs_tx, self.bs_ty = np.ascontiguousarray(tx, dtype=np.float64), np.ascontiguousarray(ty, dtype=np.float64)
+        self.bs_c = np.ascontiguousarray(spl.get_coeffs(), dtype=np.float64)  # [(len(tx)-4) * (len(ty)-4)], x first
+        self.bs_ppx, self.bs_ppy = bspline_basis_pp(self.bs_tx), bspline_basis_pp(self.bs_ty)
 
     def prior_cost(self, fit_coeff):
         """The initial cost of a pre-existing fit (calibrator.py:512-515): the plain sum of the
@@ -610,6 +662,9 @@ class RansacBatch:
             o = dict(peaks=ar.add(s.peaks), coff=ar.add(s.cand_off), cwave=ar.add(s.cand_wave),
                      cwid=ar.add(s.cand_wid), cdf=ar.add(s.cdf32), kx=ar.add(s.known_x), ky=ar.add(s.known_y),
                      ppb=ar.add(s.pp_breaks), ppc=ar.add(s.pp_coef))
+            if getattr(s, "bs_c", None) is not None:
+                o.update(btx=ar.add(s.bs_tx), bty=ar.add(s.bs_ty), bc=ar.add(s.bs_c), bpx=ar.add(s.bs_ppx),
+                         bpy=ar.add(s.bs_ppy))
             if not s.pix_is_arange:
                 if not s.pix_sorted:
                     raise NotImplementedError("pixel_list must be strictly increasing")
@@ -639,6 +694,10 @@ class RansacBatch:
             d.cost_ceiling = s.cost_ceiling
             d.floor_cost, d.floor_id = 0.0, -1
             d.min_fit_error = float(s.minimum_fit_error)
+            if "bc" in o:
+                d.bs_nx, d.bs_ny = len(s.bs_tx) - 4, len(s.bs_ty) - 4
+                d.d_bs_tx, d.d_bs_ty, d.d_bs_c = base + o["btx"], base + o["bty"], base + o["bc"]
+                d.d_bs_ppx, d.d_bs_ppy = base + o["bpx"], base + o["bpy"]
         torch = _torch()
         sms = C.c_int(0)
         N.check(self.lib.rb2_sm_count(C.byref(sms)), "rb2_sm_count")

@@ -154,3 +154,45 @@ def test_device_resident_fit_equals_staged_fit(case):
     assert np.array_equal(np.array(a.candidate_peak), np.array(b.candidate_peak))
     assert np.array_equal(np.array(a.candidate_arc), np.array(b.candidate_arc))
     assert np.array_equal(a.ht.hist, g["hist"].astype(float))  # the lazy Hough pass still delivers the reference's histogram
+
+
+@pytest.mark.parametrize("case", ["c3_deg4", "poly_quadratic_deg2", "c1_sprat_xe", "synth_nm_deg4"])
+def test_candidates_attribute_matches_reference(case):
+    """Calibrator.candidates (calibrator.py:239-261; read by plotting.py:309-349): one (pixels, wavelengths,
+    weights) triple per Hough line in rank order.  Materialised from the device on first use: entry counts per
+    line equal the recording, the entries equal the reference's own arithmetic."""
+    g = load_golden(case)
+    c = make_calibrator(g)
+    f = dict(g["config"]["fit"])
+    c.fit(progress=False, **f)
+    cand = c.candidates
+    assert len(cand) == g["hist"].size
+    assert np.array_equal([len(t[0]) for t in cand], g["n_cand_per_line"])
+    tol = f.get("candidate_tolerance", 2.0)
+    h = g["config"]["hough"]
+    sigma = (h.get("range_tolerance", 500) + h.get("linearity_tolerance", 100)) * 1.1775
+    lines = np.asarray(c.hough_lines)
+    for r in list(range(5)) + [len(cand) // 2, len(cand) - 1]:
+        grad, icpt = lines[r]
+        pred = grad * g["pairs"][:, 0] + icpt
+        m = np.abs(pred - g["pairs"][:, 1]) <= tol
+        assert np.array_equal(cand[r][0], g["pairs"][m, 0]) and np.array_equal(cand[r][1], g["pairs"][m, 1])
+        w = np.exp(-((g["pairs"][m, 1] - pred[m]) ** 2) / (2 * sigma ** 2 + 1e-9))
+        assert np.allclose(cand[r][2], w, rtol=1e-14, atol=0)
+    # the candidate_peak / candidate_arc the vote produced are what the reference derives from this list
+    assert np.array_equal(np.array(c.candidate_arc), g["candidate_arc"])
+
+
+def test_nm_scale_fit_scores_every_hypothesis():
+    """test/test_synthetic_calibration.py:8-62 (100 nm + 2 nm/px): gradients and intercepts are of the size of
+    the Hough bin centres, the Hough-density weight is a genuine bicubic-spline sum.
+    Nothing is skipped as unsupported; the reference's own assertions hold."""
+    g = load_golden("synth_nm_deg4")
+    c = make_calibrator(g)
+    coeff, mp, ma, rms, residual, pu, au = c.fit(max_tries=500, progress=False)
+    assert c.ransac_counters["unsupported"] == 0 and c.ransac_counters["scored"] >= 500
+    coeff, x_fit, y_fit, rms, residual, pu, au = c.match_peaks(coeff, refine=False, robust_refit=True)
+    fit_diff = c.polyval(x_fit, coeff) - y_fit
+    assert pu > 0.7 and au > 0.0 and np.sqrt(np.sum(fit_diff ** 2 / len(x_fit))) < 5.0
+    assert abs(coeff[0] - 100.0) < 1e-3 and abs(coeff[1] - 2.0) < 1e-5
+

@@ -20,7 +20,10 @@ def test_restated_trf_follows_scipy_on_golden_inlier_sets(golden):
     # C4 inlier sets (the last ftol test falls on the other side of its threshold: FD-Jacobian noise)
     assert abs(nfev - info["nfev"]) <= 1
     # the end point is reproducible only to TRF's own inexactness
-    assert np.allclose(p, ref, rtol=2e-5, atol=0)
+    # (a coefficient whose true value is zero - linear data fitted at degree 4 - has no relative scale: it is
+    #  held to what it contributes over the detector, 1e-5 A; the curves themselves are compared below)
+    atol = 1e-5 / np.max(np.abs(x)) ** np.arange(deg + 1)
+    assert np.allclose(p, ref, rtol=2e-5, atol=atol)
     assert np.max(np.abs(P.polyval(x, p) - P.polyval(x, ref))) < 1e-6
 
 
