@@ -416,18 +416,18 @@ class Calibrator:
         """The reference's `self.candidates` (calibrator.py:239-261): one (pixels, wavelengths, weights) triple
         per Hough line in rank order - read by its plotting code (plotting.py:309-349).  The vote (K2) never
         builds this list; it is materialised from the device on first use after a fit."""
-        c = self.__dict__.get("_candidates")
-        if c is None and self.__dict__.get("_candidates_args") is not None:
-            tol = self._candidates_args
+        c = self.__dict__.get("_cand_triples")
+        if c is None and self.__dict__.get("_cand_triples_tol") is not None:
+            tol = self.__dict__["_cand_triples_tol"]
             sigma = (self.range_tolerance + self.linearity_tolerance) * 1.1775  # :256
             self.ht.hist  # noqa: B018  (runs the Hough transform if it is still pending)
             off, x, y, w = engine.candidate_points(self.ht._batch, 0, tol, 2 * sigma ** 2 + 1e-9, pairs=self.pairs)
-            c = self.__dict__["_candidates"] = [(x[a:b], y[a:b], w[a:b]) for a, b in zip(off[:-1], off[1:])]
+            c = self.__dict__["_cand_triples"] = [(x[a:b], y[a:b], w[a:b]) for a, b in zip(off[:-1], off[1:])]
         return c
 
     @candidates.setter
     def candidates(self, v):
-        self.__dict__["_candidates"] = v
+        self.__dict__["_cand_triples"] = v
 
     def _solve_device_resident(self, fit_deg, candidate_tolerance, n_hypotheses):
         """fit(n_hypotheses=N) without a host round trip between the stages: pairs -> K1 -> K2 ->
@@ -507,7 +507,7 @@ class Calibrator:
 
         if not self.ht.binned:
             raise NotImplementedError("fit() needs a Hough transform computed by do_hough_transform()")
-        self.__dict__["_candidates"], self.__dict__["_candidates_args"] = None, candidate_tolerance
+        self.__dict__["_cand_triples"], self.__dict__["_cand_triples_tol"] = None, candidate_tolerance
         if n_hypotheses is not None and fit_coeff is None:
             fast = self._solve_device_resident(fit_deg, candidate_tolerance, int(n_hypotheses))
             if fast is not None:

@@ -567,11 +567,78 @@ hough_points_kernel(const rb2_hough_desc d, const long long* __restrict__ off, d
 }  // namespace rb2
 
 // ---- host entry points -------------------------------------------------------
+namespace rb2 {
+// Ranking of a FEW spectra by counting: rank(e) = #{e' : hist[e'] > hist[e]} + #{e' > e : hist[e'] == hist[e]}
+// is exactly the canonical order (count descending, ties by descending flat index) and needs no sort - B^2
+// comparisons spread over the whole GPU (B = 10^4: 10^8, a few microseconds) instead of a chain of dependent
+// radix tiles on one CTA (224 us for one 100 x 100 spectrum, fixed cost of every single-spectrum fit).
+constexpr int RANKP_T = 256;
+__global__ void __launch_bounds__(RANKP_T)
+hough_rank_zero_kernel(const rb2_hough_desc* __restrict__ descs) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  const int B = d.xbins * d.ybins;
+  for (int e = blockIdx.x * RANKP_T + threadIdx.x; e < B; e += gridDim.x * RANKP_T) d.d_rankpos[e] = 0;
+}
+__global__ void __launch_bounds__(RANKP_T)
+hough_rank_pairs_kernel(const rb2_hough_desc* __restrict__ descs, int src_chunk) {
+  __shared__ unsigned s_h[1024];
+  const rb2_hough_desc d = descs[blockIdx.z];
+  const int B = d.xbins * d.ybins;
+  const int e = blockIdx.x * RANKP_T + threadIdx.x;
+  if (blockIdx.x * RANKP_T >= B) return;
+  const unsigned he = (e < B) ? d.d_hist[e] : 0u;
+  const int s0 = blockIdx.y * src_chunk, s1 = min(B, s0 + src_chunk);
+  int cnt = 0;
+  for (int t0 = s0; t0 < s1; t0 += 1024) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += RANKP_T) s_h[i] = (t0 + i < s1) ? d.d_hist[t0 + i] : 0u;
+    __syncthreads();
+    const int n = min(1024, s1 - t0);
+    // sources before e only count when strictly larger, sources after e also when equal
+    const int split = max(0, min(n, e + 1 - t0));  // tile entries with index <= e
+    for (int i = 0; i < split; ++i) cnt += (s_h[i] > he);
+    for (int i = split; i < n; ++i) cnt += (s_h[i] >= he);
+  }
+  if (e < B && cnt) atomicAdd(&d.d_rankpos[e], cnt);
+}
+__global__ void __launch_bounds__(RANKP_T)
+hough_rank_scatter_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_stats* __restrict__ stats) {
+  const rb2_hough_desc d = descs[blockIdx.y];
+  const int B = d.xbins * d.ybins;
+  unsigned mx = 0;
+  for (int e = blockIdx.x * RANKP_T + threadIdx.x; e < B; e += gridDim.x * RANKP_T) {
+    d.d_rank[d.d_rankpos[e]] = e;
+    mx = max(mx, d.d_hist[e]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&stats[blockIdx.y].max_count, mx);
+}
+}  // namespace rb2
+
 static cudaError_t launch_rank(int n_problems, const rb2_hough_desc* d_desc, const rb2_hough_desc* h_desc,
                                rb2_hough_stats* d_stats, cudaStream_t stream) {
   using namespace rb2;
   int max_bins = 0;
-  for (int i = 0; i < n_problems; ++i) max_bins = max(max_bins, h_desc[i].xbins * h_desc[i].ybins);
+  double pair_work = 0.0;
+  for (int i = 0; i < n_problems; ++i) {
+    const int b = h_desc[i].xbins * h_desc[i].ybins;
+    max_bins = max(max_bins, b);
+    pair_work += (double)b * (double)b;
+  }
+  if (pair_work <= 4e9 && max_bins > 0) {  // a few spectra: rank by counting on the whole GPU
+    const int tiles = (max_bins + RANKP_T - 1) / RANKP_T;
+    int sms = 148;
+    rb2_sm_count(&sms);
+    int split = max(1, min(64, (4 * sms) / max(1, tiles * n_problems)));  // source chunks per target tile: fill the GPU
+    int src_chunk = (max_bins + split - 1) / split;
+    src_chunk = (src_chunk + 1023) / 1024 * 1024;
+    split = (max_bins + src_chunk - 1) / src_chunk;
+    hough_rank_zero_kernel<<<dim3(min(tiles, 64), n_problems), RANKP_T, 0, stream>>>(d_desc);
+    hough_rank_pairs_kernel<<<dim3(tiles, split, n_problems), RANKP_T, 0, stream>>>(d_desc, src_chunk);
+    hough_rank_scatter_kernel<<<dim3(min(tiles, 64), n_problems), RANKP_T, 0, stream>>>(d_desc, d_stats);
+    return cudaGetLastError();
+  }
   const int smem_bins = (max_bins <= RANK_SMEM_MAX_BINS) ? max_bins : 0;  // 0: sort in global memory
   const size_t smem = (size_t)smem_bins * 12;
   static size_t configured[64] = {};

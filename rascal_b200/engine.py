@@ -646,6 +646,22 @@ def weight_upper_bound(s):
     return float(s.hough_weight * s.n_pix * hi * (1.0 + 1e-9))
 
 
+_SCRATCH = {}
+
+
+def ransac_scratch(nbytes):
+    """K3's survivor queues (rb2_ransac_scratch_bytes: several GB at the default chunk of 2^24 hypotheses):
+    ONE grow-only buffer per device and process.  Every K3 call is ordered on the caller's stream, so calls
+    can share it; allocating it per call would cost more than most fits."""
+    torch = _torch()
+    dev = torch.cuda.current_device()
+    t = _SCRATCH.get(dev)
+    if t is None or t.numel() < nbytes:
+        _SCRATCH[dev] = None
+        t = _SCRATCH[dev] = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device="cuda")
+    return t
+
+
 class RansacBatch:
     """K3 + K4 for a batch of prepared problems (rb2_ransac_batch / rb2_refit_winners)."""
 
@@ -703,8 +719,7 @@ class RansacBatch:
         N.check(self.lib.rb2_sm_count(C.byref(sms)), "rb2_sm_count")
         self.sm_count = sms.value
         self.blocks_per_problem = max(0, int(blocks_per_problem))  # stage-A CTAs per problem per chunk; 0 = auto
-        nbytes = self.lib.rb2_ransac_scratch_bytes(self.n, self.blocks_per_problem)
-        self.scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
+        self.scratch = ransac_scratch(self.lib.rb2_ransac_scratch_bytes(self.n, self.blocks_per_problem))
         # every per-fit output lives in ONE device buffer so that a fit costs one D2H copy:
         # [winner records | refit results | matched_x | matched_y | residual]
         rsz, fsz = C.sizeof(N.RansacResult) * self.n, C.sizeof(N.RefitResult) * self.n

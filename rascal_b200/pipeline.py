@@ -361,7 +361,7 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
     N.check(lib.rb2_hough_accumulate(n, dptr("hough"), hptr("hough"), base + o_hstat, 0, stream), "rb2_hough_accumulate")
     N.check(lib.rb2_candidate_vote(n, dptr("vote"), hptr("vote"), stream), "rb2_candidate_vote")
     N.check(lib.rb2_ransac_prepare(n, dptr("prep"), hptr("prep"), dptr("ransac"), stream), "rb2_ransac_prepare")
-    scratch = cached("scratch", lib.rb2_ransac_scratch_bytes(n, 0), device="cuda")
+    scratch = engine.ransac_scratch(lib.rb2_ransac_scratch_bytes(n, 0))
     N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + o_res, scratch.data_ptr(), 0, stream),
             "rb2_ransac_batch")
     if exchange is not None:
