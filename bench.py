@@ -171,61 +171,168 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU legs (the oracle = a port of the reference's algorithm; test infrastructure)
+# CPU legs: the reference itself (baseline/_ref, scripts/make_baseline_ref.py) when the snapshot carries
+# it, else the oracle (a port of its algorithm; test infrastructure) - `kind` says which
 # ---------------------------------------------------------------------------
 
-
-def _cpu_worker(args):
-    seed, max_tries = args
-    from oracle import rascal_oracle as O
-
-    w = c3_input()
-    trace, tm = [], {}
-    O.run_path(w["peaks"], w["atlas"], num_pix=w["npix"], max_tries=max_tries, seed=seed, trace=trace,
-               timings=tm, **w["hough"], **w["ransac"], **w["fit"])
-    return len(trace), tm
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
-def cpu_baseline(max_tries=1200):
-    """Single-thread oracle port on a bounded sample of the same workload."""
-    n, tm = _cpu_worker((0, max_tries))
-    return {"value": n / tm["ransac"], "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "C3 spectrum, max_tries=%d (%d hypotheses drawn, %.1f s RANSAC loop; Hough %.2f s and "
-                      "candidate vote %.2f s not included)" % (max_tries, n, tm["ransac"], tm["hough"],
-                                                              tm["candidates"])}
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "rascal"))
+
+
+def config_input(name):
+    """Workload of a BASELINE config: dict(peaks, atlas, npix, hough, ransac, fit, tries).  c3 is synthetic;
+    c2 / c5 take peaks and atlas lines from the recordings of the real-data cases (tests/golden/*.npz: the
+    reference's own peak-finding recipe and NIST atlas, see tests/golden/make_golden_configs.py) with the
+    sizes BASELINE.json states."""
+    if name == "c3":
+        w = c3_input()
+        w["tries"] = None
+        return w
+    g = np.load(os.path.join(ROOT, "tests", "golden", {"c2": "c2_gmos_cuar", "c5": "c5_deimos"}[name] + ".npz"))
+    cfg = json.loads(str(g["config_json"]))
+    w = dict(peaks=g["peaks"], atlas=g["lines"], npix=len(g["pixel_list"]), truth=None, hough=dict(cfg["hough"]),
+             ransac=dict(cfg["ransac"]), fit={k: v for k, v in cfg["fit"].items() if k != "max_tries"})
+    if name == "c2":   # Gemini GMOS CuAr, degree 5, 1e5 RANSAC tries
+        w["fit"]["fit_deg"] = 5
+        w["tries"] = 100_000
+    else:              # Keck DEIMOS 830G, fine Hough binning 2000 x (1000 x 1000), 1e6 tries
+        w["hough"].update(num_slopes=2000, xbins=1000, ybins=1000)
+        w["tries"] = 1_000_000
+    w["fit"].setdefault("candidate_tolerance", 2.0)
+    return w
+
+
+WORKLOADS = {
+    "c3": "C3: synthetic 60-peak/300-atlas-line arc, degree 4, sample 5, top-5 candidates (BASELINE configs[2])",
+    "c2": "C2: Gemini GMOS CuAr arc (ground-truth spectrum of the reference), 67 peaks / 53 lines, Hough 5000 x (200 x 200), "
+          "degree 5, 1e5 RANSAC tries (BASELINE configs[1])",
+    "c5": "C5: Keck DEIMOS 830G Ne+Ar+Kr arc, 51 peaks / 100 lines, Hough 2000 x (1000 x 1000) = 1e6 lines, degree 4, "
+          "1e6 RANSAC tries (BASELINE configs[4])",
+}
+
+
+def _reference_worker(args):
+    """One process: do_hough_transform() + fit(max_tries) of the reference (or the oracle port) on `config`;
+    returns (polyfit calls = hypotheses, seconds: hough, candidates, ransac loop)."""
+    config, seed, max_tries, use_ref = args
+    w = config_input(config)
+    if not use_ref:
+        from oracle import rascal_oracle as O
+
+        trace, tm = [], {}
+        O.run_path(w["peaks"], w["atlas"], num_pix=w["npix"], max_tries=max_tries, seed=seed, trace=trace,
+                   timings=tm, **w["hough"], **w["ransac"], **w["fit"])
+        return len(trace), tm
+    import logging
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    logging.disable(logging.WARNING)
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    from rascal import calibrator as rc
+    from rascal.atlas import Atlas
+
+    n = [0]
+    tm = dict(hough=0.0, candidates=0.0, ransac=0.0)
+    orig_fit = np.polynomial.polynomial.polyfit
+
+    def counted(*a, **k):
+        n[0] += 1
+        return orig_fit(*a, **k)
+
+    def timed(fn):
+        def wrap(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                tm["candidates"] += time.perf_counter() - t0
+        return wrap
+
+    C = rc.Calibrator
+    saved = (C._get_candidate_points_linear, C._get_most_common_candidates)
+    C._get_candidate_points_linear, C._get_most_common_candidates = timed(saved[0]), timed(saved[1])
+    np.polynomial.polynomial.polyfit = counted
+    try:
+        c = C(w["peaks"], spectrum=np.zeros(w["npix"]))
+        c.set_calibrator_properties(seed=seed)
+        c.set_hough_properties(**w["hough"])
+        c.set_ransac_properties(**w["ransac"])
+        a = Atlas()
+        a.add_user_atlas(elements=["X"] * len(w["atlas"]), wavelengths=w["atlas"])
+        c.set_atlas(a, candidate_tolerance=10.0)
+        t0 = time.perf_counter()
+        c.do_hough_transform()
+        tm["hough"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        try:
+            c.fit(max_tries=max_tries, progress=False, **w["fit"])
+        except AssertionError:  # "Couldn't fit": the timing stands
+            pass
+        tm["ransac"] = time.perf_counter() - t0 - tm["candidates"]
+    finally:
+        np.polynomial.polynomial.polyfit = orig_fit
+        C._get_candidate_points_linear, C._get_most_common_candidates = saved
+    return n[0], tm
+
+
+REF_TRIES = {"c3": 600, "c2": 300, "c5": 150}   # bounded samples: ~10-30 s of RANSAC loop on one core
+
+
+def cpu_baseline(config="c3", max_tries=None):
+    """Single-thread reference (or port) on a bounded sample of the same workload."""
+    use_ref = reference_available()
+    max_tries = max_tries or REF_TRIES[config]
+    n, tm = _reference_worker((config, 0, max_tries, use_ref))
+    return {"value": n / tm["ransac"], "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
+            "sample": "%s spectrum, fit(max_tries=%d): %d hypotheses (polyfit calls) in %.1f s of RANSAC loop; Hough %.2f s "
+                      "and candidate collection %.2f s are not in the rate" % (config.upper(), max_tries, n, tm["ransac"],
+                                                                               tm["hough"], tm["candidates"]),
+            "hough_s": tm["hough"], "candidates_s": tm["candidates"], "ransac_loop_s": tm["ransac"], "hypotheses": n}
 
 
 def reference_arm(args):
-    """The reference's CPU algorithm (oracle port; the reference itself is pure Python and
-    cannot travel) on all host cores: independent worker processes, distinct seeds."""
+    """`--impl reference`: the reference's own CPU implementation (baseline/_ref; the oracle port if the
+    snapshot does not carry it) on all host cores: independent worker processes with distinct seeds, each a
+    bounded sample fit(max_tries=...) of the same workload."""
     import multiprocessing as mp
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_ref = reference_available()
     cores = os.cpu_count() or 1
-    max_tries = 150
+    config = args.config
+    max_tries = max(20, REF_TRIES[config] // 4)
     with mp.get_context("spawn").Pool(cores) as pool:
         for _ in range(args.warmup and 1):
-            pool.map(_cpu_worker, [(1000 + i, 20) for i in range(cores)])
-        times, hyps = [], []
+            pool.map(_reference_worker, [(config, 1000 + i, 5, use_ref) for i in range(cores)])
+        times, hyps, hough, cand = [], [], [], []
         for k in range(args.steps):
-            t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(k * cores + i, max_tries) for i in range(cores)])
-            dt = time.perf_counter() - t0
+            res = pool.map(_reference_worker, [(config, k * cores + i, max_tries, use_ref) for i in range(cores)])
             # hypotheses/s of the RANSAC loop itself: every worker's draws over the slowest loop
-            loop = max(tm["ransac"] for _, tm in res)
-            times.append(loop)
+            times.append(max(tm["ransac"] for _, tm in res))
             hyps.append(sum(n for n, _ in res))
-            del dt
+            hough.append(float(np.median([tm["hough"] for _, tm in res])))
+            cand.append(float(np.median([tm["candidates"] for _, tm in res])))
     value = sum(hyps) / sum(times)
+    kind = "reference" if use_ref else "port"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample": "max_tries=%d per worker" % max_tries},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d worker processes x max_tries=%d x %d steps of the C3 spectrum "
-                                       "(RANSAC loop time only)" % (cores, max_tries, args.steps)},
+            "data": "synthetic" if config == "c3" else "real arc (recorded peaks / NIST lines)",
+            "config": {"workload": WORKLOADS[config], "sample": "fit(max_tries=%d) per worker" % max_tries},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d worker processes x fit(max_tries=%d) x %d steps of the %s spectrum (RANSAC loop time "
+                                       "only; per worker the Hough transform takes %.2f s and candidate collection %.2f s on top)"
+                                       % (cores, max_tries, args.steps, config.upper(), float(np.median(hough)),
+                                          float(np.median(cand))),
+                             "hough_s_per_spectrum": float(np.median(hough)),
+                             "candidates_s_per_spectrum": float(np.median(cand))},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -246,7 +353,7 @@ def k3_traffic():
     return k3_profile("dram_bytes_per_chunk")
 
 
-WORKLOAD_NAME = "C3: synthetic 60-peak/300-atlas-line arc, degree 4, sample 5, top-5 candidates (BASELINE configs[2])"
+WORKLOAD_NAME = WORKLOADS["c3"]
 
 
 # ---------------------------------------------------------------------------
@@ -261,6 +368,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--hyp", type=float, default=1e8, help="hypotheses per step over all ranks")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"],
+                    help="BASELINE config: c3 (headline, default), c2 (GMOS deg 5, 1e5 tries), c5 (DEIMOS 1000x1000 bins, 1e6 tries)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--spectra", type=int, default=2048, help="C4 spectra per rank in the many-spectra leg (0 = skip)")

@@ -82,6 +82,24 @@ def c5_deimos():
                   fit=dict(max_tries=300), seed=0)
 
 
+def c5_deimos_full():
+    """BASELINE configs[4] at its stated size: num_slopes x bins = 2000 x (1000 x 1000) - 10^6 Hough lines, which
+    costs the reference ~1-2 minutes of candidate collection (calibrator.py:219-261).  Few tries: this fixture
+    pins K1 (histogram, edges), the ranking and K2 (candidates) at 10^6 bins; the RANSAC trace stays short."""
+    spec = np.array(json.load(open(os.path.join(EX, "data_keck_deimos/keck_deimos_830g_l_PYPIT.json")))["spec"])
+    peaks, _ = find_peaks(spec, prominence=200, distance=10)
+    peaks = util.refine_peaks(spec.copy(), peaks, window_width=3)
+    atlas = Atlas(elements=["Ne", "Ar", "Kr"], min_intensity=1000.0, pressure=70000.0, temperature=285.0,
+                  range_tolerance=500.0, min_atlas_wavelength=6500.0, max_atlas_wavelength=10500.0)
+    G.record_case("c5_deimos_full", np.asarray(peaks, float), np.asarray(atlas.get_lines(), float),
+                  spectrum=np.zeros(len(spec)),
+                  hough=dict(num_slopes=2000, range_tolerance=500.0, linearity_tolerance=50, xbins=1000, ybins=1000,
+                             min_wavelength=6500.0, max_wavelength=10500.0),
+                  ransac=dict(sample_size=5, top_n_candidate=5, linear=True, filter_close=True, ransac_tolerance=5,
+                              candidate_weighted=True, hough_weight=1.0),
+                  fit=dict(max_tries=40), seed=0)
+
+
 def c2_gmos():
     """BASELINE configs[1]: Gemini GMOS longslit CuAr arc, degree 5.  The example's FITS frame is not
     shipped; the reference's own ground-truth effective-pixel spectrum of the same
@@ -109,3 +127,5 @@ if __name__ == "__main__":
         c1_sprat()
     if "c5" in which:
         c5_deimos()
+    if "c5full" in which:
+        c5_deimos_full()

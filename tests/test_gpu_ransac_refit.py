@@ -93,7 +93,7 @@ def test_replay_reference_draws(golden):
 # the assertion allows 10x the measured gap
 COEFF_GAP = {"c3_deg4": 3.6e-7, "poly_linear_deg1": 2.1e-11, "poly_quadratic_deg2": 2e-5, "fine_deg5": 1.2e-7,
              "c1_sprat_xe": 3.1e-7, "c5_deimos": 2.5e-7, "c2_gmos_cuar": 3.7e-9, "c4_npix1024": 1.9e-7,
-             "c4_npix2048": 2.6e-8, "c4_npix4096": 5.5e-6, "synth_nm_deg4": 2e-5}
+             "c4_npix2048": 2.6e-8, "c4_npix4096": 5.5e-6, "synth_nm_deg4": 2e-5, "c5_deimos_full": 2e-5}
 
 
 def test_replay_selects_reference_winner(golden, request):
