@@ -361,6 +361,173 @@ WORKLOAD_NAME = WORKLOADS["c3"]
 # ---------------------------------------------------------------------------
 
 
+def fp64_peak_tflops(lib, engine, torch, sms):
+    """FP64 roofline denominator: DFMA microbenchmark (rb2_dfma_burn) timed with CUDA events in this run."""
+    sink = torch.zeros(1, dtype=torch.float64, device="cuda")
+    blocks, iters = sms * 16, 1 << 15
+    for _ in range(2):
+        lib.rb2_dfma_burn(blocks, iters, sink.data_ptr(), engine.current_stream_ptr())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    lib.rb2_dfma_burn(blocks, iters, sink.data_ptr(), engine.current_stream_ptr())
+    b.record()
+    torch.cuda.synchronize()
+    return 2.0 * 8 * iters * blocks * 256 / (a.elapsed_time(b) * 1e-3) / 1e12
+
+
+def config_bench(args, torch, dist, rank, world, local, group):
+    """`--config c2|c5`: the real-data BASELINE configs at their stated sizes through the UNCHANGED public
+    signature - do_hough_transform() + fit(max_tries=..., fit_deg=...) - plus the stage times on resident
+    inputs.  A step = one calibration.  `e2e` = hypotheses drawn / wall time of the public calls from host arrays;
+    `value` = the same draws through K3 + exchange + K4 with the candidate tables resident."""
+    from rascal_b200 import _native, engine, parallel
+    from rascal_b200.calibrator import Calibrator, LineList
+
+    lib = _native.load()
+    name = args.config
+    w = config_input(name)
+    tries = int(w["tries"])
+    deg, ssz = int(w["fit"].get("fit_deg", 4)), int(w["ransac"].get("sample_size", 5))
+
+    def new_calibrator(seed):
+        c = Calibrator(w["peaks"], spectrum=np.zeros(w["npix"]))
+        c.set_calibrator_properties(seed=seed)
+        c.set_hough_properties(**w["hough"])
+        c.set_ransac_properties(**w["ransac"])
+        c.set_atlas(LineList(w["atlas"]), candidate_tolerance=10.0)
+        if world > 1:
+            c.use_distributed(None)
+        return c
+
+    # ---- e2e: the public API, host arrays in, 7-tuple out ----
+    for k in range(max(1, args.warmup)):
+        c = new_calibrator(5 + k)
+        c.do_hough_transform()
+        res = c.fit(max_tries=tries, progress=False, **w["fit"])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    engine.TRANSFER["h2d"] = engine.TRANSFER["d2h"] = 0
+    drawn = scored = 0
+    t_hough = t_fit = 0.0
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            c = new_calibrator(100 + k)
+            ta = time.perf_counter()
+            c.do_hough_transform()
+            c.ht.hist  # noqa: B018  (K1 runs when its results are first read)
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            res = c.fit(max_tries=tries, progress=False, **w["fit"])
+            torch.cuda.synchronize()
+            t_hough += tb - ta
+            t_fit += time.perf_counter() - tb
+            drawn += c.ransac_counters["drawn"] + c.ransac_counters["aborted"]
+            scored += c.ransac_counters["scored"] + c.ransac_counters["aborted"]
+        if world > 1:
+            dist.barrier()
+        t_e2e = time.perf_counter() - t0
+    t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e_t.item())
+    e2e = {"value": drawn / t_e2e, "unit": UNIT, "h2d_bytes_per_step": engine.TRANSFER["h2d"] // args.steps,
+           "d2h_bytes_per_step": engine.TRANSFER["d2h"] // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps,
+           "tries_per_s": scored / t_e2e, "completed_tries_per_step": scored // args.steps,
+           "hough_ms_per_step": 1e3 * t_hough / args.steps, "fit_ms_per_step": 1e3 * t_fit / args.steps,
+           "rms": float(res[3]), "n_matched": len(res[1])}
+
+    # ---- resident legs: K1 / K2 alone, then K3 (+ exchange + K4) over the same number of draws ----
+    H = drawn // args.steps
+    c = new_calibrator(0)
+    c.do_hough_transform()
+    c.ht.hist  # noqa: B018
+    hb = c.ht._batch
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    hb.run()
+    torch.cuda.synchronize()
+    e0.record()
+    hb.run()
+    e1.record()
+    c._vote(w["fit"]["candidate_tolerance"])
+    e2.record()
+    torch.cuda.synchronize()
+    k1_ms, k2_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    setup = engine.RansacSetup(
+        c.candidate_peak, c.candidate_arc, fit_deg=deg, sample_size=max(ssz, deg + 1), ransac_tolerance=c.ransac_tolerance,
+        min_intercept=c.min_intercept, max_intercept=c.max_intercept, pixel_list=c.pixel_list, hist=c.ht.hist,
+        xedges=c.ht.xedges, yedges=c.ht.yedges, hough_weight=c.hough_weight, filter_close=c.filter_close,
+        n_peaks_total=len(c.peaks))
+    rb = engine.RansacBatch([setup])
+    lo, hi = parallel.shard_range(H, rank, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(k):
+        rb.run(k * H + lo, hi - lo, seed=2026)
+        rb.exchange(group)
+        rb.refit_async()
+        return rb.fetch()
+
+    for k in range(max(3, args.warmup)):
+        step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    counters = dict.fromkeys(_native.COUNTER_NAMES, 0)
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        kev[k][0].record()
+        rb.run((3 + k) * H + lo, hi - lo, seed=2026)
+        kev[k][1].record()
+        rb.exchange(group)
+        rb.refit_async()
+        win = rb.fetch()[0]
+        ev[k][1].record()
+        for nm, v in engine.counters_dict(win[0]).items():
+            counters[nm] += v
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(total_ms.item()), float(kern_ms.item())
+    peak = fp64_peak_tflops(lib, engine, torch, rb.sm_count)
+    n_u, n_c = len(setup.peaks), len(setup.cand_wave)
+    F, f_i, f_m = flops_per_hypothesis(counters, deg=deg, s=setup.sample_size, n=n_u, k=max(1, n_c // max(1, n_u)))
+    achieved = (hi - lo) * args.steps * F / (kern_ms * 1e-3) / 1e12
+    P_pairs, S, B = len(c.pairs), int(w["hough"]["num_slopes"]), int(w["hough"]["xbins"]) * int(w["hough"]["ybins"])
+    line = {
+        "metric": METRIC, "value": args.steps * H / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "real arc (recorded peaks / NIST lines), random draws",
+        "config": {"workload": WORKLOADS[name], "max_tries": tries, "hypotheses_per_step": H,
+                   "parallelism": "hypothesis-id ranges x%d" % world, "l2": "flushed (256 MiB write) between timed steps"},
+        "clocks": clocks.summary(), "e2e": e2e,
+        "gpu_launches": None,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "K3 staged pipeline (deg %d, sample %d, %d peaks x ~%d candidates)"
+                                                % (deg, setup.sample_size, n_u, max(1, n_c // max(1, n_u))),
+                     "flops_per_hypothesis": F, "f_intercept_pass": f_i, "f_scored": f_m,
+                     "peak_source": "DFMA microbenchmark in this run (rb2_dfma_burn)", "kernel_ms_per_step": kern_ms / args.steps},
+        "stages_resident": {"k1_hough_ms": k1_ms, "k1_evaluations_per_s": S * P_pairs / (k1_ms * 1e-3),
+                            "k2_vote_ms": k2_ms, "k2_bin_pair_tests_per_s": float(B) * P_pairs / (k2_ms * 1e-3),
+                            "hough_lines": B, "pairs": P_pairs, "slopes": S},
+        "counters": counters,
+    }
+    n_chunks = -(-(hi - lo) // (1 << 24))
+    line["gpu_launches"] = (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps
+    if not args.no_cpu and rank == 0:
+        line["cpu_baseline"] = cpu_baseline(name)
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -402,6 +569,13 @@ def main():
     from rascal_b200.calibrator import Calibrator, LineList
 
     lib = _native.load()
+    if args.config != "c3":
+        line = config_bench(args, torch, dist, rank, world, local, group)
+        if rank == 0:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        if world > 1:
+            dist.destroy_process_group()
+        return
     w = c3_input()
     H = int(args.hyp)
 
@@ -470,17 +644,8 @@ def main():
     value = args.steps * H / (total_ms * 1e-3)
 
     # ---- FP64 roofline denominator (DFMA microbenchmark, same box, same run) ----
-    sink = torch.zeros(1, dtype=torch.float64, device="cuda")
     sms = rb.sm_count
-    blocks, iters = sms * 16, 1 << 15
-    for _ in range(2):
-        lib.rb2_dfma_burn(blocks, iters, sink.data_ptr(), engine.current_stream_ptr())
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    lib.rb2_dfma_burn(blocks, iters, sink.data_ptr(), engine.current_stream_ptr())
-    b.record()
-    torch.cuda.synchronize()
-    fp64_peak = 2.0 * 8 * iters * blocks * 256 / (a.elapsed_time(b) * 1e-3) / 1e12
+    fp64_peak = fp64_peak_tflops(lib, engine, torch, sms)
 
     # ---- e2e leg: the public Calibrator API with host buffers, every step ----
     e2e = None
@@ -646,19 +811,19 @@ def main():
         return
     F, f_i, f_m = flops_per_hypothesis(counters)
     per_rank_hyp = (hi - lo)
-    n_chunks = -(-per_rank_hyp // (1 << 22))
+    n_chunks = -(-per_rank_hyp // (1 << 24))
     achieved = per_rank_hyp * args.steps * F / (kern_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d, chunks of 2^22 ids over 3 stream lanes per GPU" % world,
+        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d, chunks of 2^24 ids over 3 stream lanes per GPU" % world,
                    "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
         "clocks": clocks.summary(),
         "e2e": e2e,
-        # K3 = pipe_init + 6 kernels (reset, draw_fit, monotonic, match, cost, record) per 2^22-hypothesis
-        # chunk + pipe_join; + merge after the all-gather (N > 1) + K4 refit
-        "gpu_launches": (2 + 6 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
+        # K3 = pipe_init + 8 kernels (reset, draw_fit, monotonic, match, cost, general weight, exact, record) per
+        # 2^24-hypothesis chunk + pipe_join; + merge after the all-gather (N > 1) + K4 refit
+        "gpu_launches": (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": k3_traffic(),
                      "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant, ~60 % of K3 time) + "
@@ -677,7 +842,7 @@ def main():
     if peak_leg is not None:
         line["peak_finding"] = peak_leg
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline()
+        line["cpu_baseline"] = cpu_baseline("c3")
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

@@ -245,6 +245,19 @@ typedef struct {
   const double *d_bs_ppx, *d_bs_ppy;    /* per knot interval m = 0..n-4 the four non-zero cubic B-splines
                                            N_m..N_m+3 as polynomials in (x - t[m+3]):
                                            [(n-3)][4 basis][4 coefficients, ascending powers]             */
+  /* fit_type 'legendre' / 'chebyshev' (calibrator.py:1625-1631).  The hypothesis polynomial is the same
+     least-squares polynomial whatever basis legfit / chebfit express it in (the coefficients everywhere in this
+     ABI stay MONOMIAL); what the basis changes in the reference is (i) the intercept test, which reads the
+     FIRST COEFFICIENT OF THE BASIS (:578-582), (ii) the "gradient" of the Hough-density weight -
+     util._derivative, the monomial rule, applied to the basis coefficients and evaluated with the basis'
+     polyval (:614-618) - and (iii) K4's residual: the basis' polyval applied to the monomial coefficients
+     that models.robust_polyfit returns (:664-671).  basis != 0 needs the d_bs_* tables (the weight is then
+     always evaluated per pixel). */
+  int32_t basis;                        /* 0 poly, 1 legendre, 2 chebyshev                               */
+  int32_t pad1;
+  const double *d_basis_c0;             /* [deg+1]: first row of the monomial -> basis change matrix      */
+  const double *d_basis_grad;           /* [deg][deg+1]: monomial coefficients of sum_k (k+1) c_(k+1) B_k(x),
+                                           as a linear map of the hypothesis' monomial coefficients       */
 } rb2_ransac_desc;
 
 typedef enum {
@@ -343,7 +356,9 @@ typedef struct {
   int32_t fit_deg;                      /* degree of polyfit / robust refit  */
   double tolerance;
   int32_t robust_refit;                 /* 0: stop after the polyfit         */
-  int32_t pad;
+  int32_t basis;                        /* self.polyval of the fit: 0 poly, 1 legendre, 2 chebyshev - used where
+                                           the reference calls it on `coeffs` (:1831) and on the refit result
+                                           (:1936); polyfit_coeffs stay monomial */
 } rb2_match_desc;
 
 typedef struct {

@@ -188,7 +188,11 @@ class RansacProblem:
                  hist, xedges, yedges, hough_weight=1.0, filter_close=False,
                  minimum_matches=0, minimum_peak_utilisation=0.0,
                  minimum_fit_error=1e-4, n_peaks_total=None,
-                 pix_known=None, wave_known=None):
+                 pix_known=None, wave_known=None, fit_type="poly"):
+        # calibrator.py:1621-1636: the basis only swaps the two callables; everything else (the
+        # monomial util._derivative, the monomial models.robust_polyfit) stays as it is
+        self.fit_type = fit_type
+        self.polyfit, self.polyval = BASES[fit_type]
         x = np.array(cand_peak, dtype=float)
         y = np.array(cand_arc, dtype=float)
         if filter_close:  # calibrator.py:457-464
@@ -236,6 +240,10 @@ class RansacProblem:
 # a9-a13: one hypothesis
 # ---------------------------------------------------------------------------
 
+BASES = {"poly": (P.polyfit, P.polyval),
+         "legendre": (np.polynomial.legendre.legfit, np.polynomial.legendre.legval),
+         "chebyshev": (np.polynomial.chebyshev.chebfit, np.polynomial.chebyshev.chebval)}
+
 ST_ABORT = 0        # impossible draw (try consumed)          :557-566
 ST_INTERCEPT = 1    # intercept test failed                   :578-582
 ST_MONOTONIC = 2    # not strictly increasing                 :585-600
@@ -254,7 +262,7 @@ def match_bijective(prob: RansacProblem, coeffs):
     err = np.empty(n)
     my = np.empty(n)
     for k, peak in enumerate(prob.peaks):
-        fit = P.polyval(peak, coeffs)
+        fit = prob.polyval(peak, coeffs)
         e = np.abs(fit - prob.cands[k])
         i = np.argmin(e)
         err[k] = e[i]
@@ -272,8 +280,8 @@ def match_bijective(prob: RansacProblem, coeffs):
 def hough_weight_sum(prob: RansacProblem, coeffs):
     """hough_weight * sum(spline(intercept, gradient)); calibrator.py:614-627."""
     px = prob.pixel_list
-    wave = P.polyval(px, coeffs)
-    grad = P.polyval(px, deriv_coeffs(coeffs))
+    wave = prob.polyval(px, coeffs)
+    grad = prob.polyval(px, deriv_coeffs(coeffs))
     icpt = wave - grad * px
     return prob.hough_weight * np.sum(prob.spline(icpt, grad, grid=False))
 
@@ -281,7 +289,7 @@ def hough_weight_sum(prob: RansacProblem, coeffs):
 def is_monotonic(prob: RansacProblem, coeffs):
     """calibrator.py:585-596."""
     grid = np.arange(prob.pix_min, prob.pix_max, 1)
-    return bool(np.all(np.diff(P.polyval(grid, coeffs)) > 0))
+    return bool(np.all(np.diff(prob.polyval(grid, coeffs)) > 0))
 
 
 def evaluate_hypothesis(prob: RansacProblem, x_hat, y_hat):
@@ -294,7 +302,7 @@ def evaluate_hypothesis(prob: RansacProblem, x_hat, y_hat):
     if prob.pix_known is not None:
         x_hat = np.concatenate((x_hat, prob.pix_known))
         y_hat = np.concatenate((y_hat, prob.wave_known))
-    c = P.polyfit(x_hat, y_hat, prob.fit_deg)
+    c = prob.polyfit(x_hat, y_hat, prob.fit_deg)
     r = dict(status=ST_SCORED, coeffs=c, cost=np.nan, n_match=0, n_inliers=0)
     if (c[0] < prob.min_intercept) | (c[0] > prob.max_intercept):
         r["status"] = ST_INTERCEPT
@@ -418,7 +426,7 @@ def acceptance(prob: RansacProblem, r, refit=robust_polyfit):
     if len(mp) <= prob.fit_deg:
         return False, None, None, None, mp, ma
     coeffs = refit(mp, ma, prob.fit_deg)
-    res = P.polyval(mp, coeffs) - ma
+    res = prob.polyval(mp, coeffs) - ma  # the basis' polyval on the MONOMIAL refit coefficients (:664)
     res[np.abs(res) > prob.tol] = prob.tol
     rms = np.sqrt(np.mean(res ** 2))
     if rms < prob.minimum_fit_error:
@@ -529,7 +537,7 @@ def run_path(peaks, lines, *, num_pix=None, pixel_list=None, num_slopes=2000,
              candidate_weighted=True, hough_weight=1.0, minimum_matches=0,
              minimum_peak_utilisation=0.0, minimum_fit_error=1e-4,
              max_tries=500, fit_deg=4, candidate_tolerance=2.0, seed=None,
-             refit=robust_polyfit, trace=None, timings=None):
+             refit=robust_polyfit, trace=None, timings=None, fit_type="poly"):
     """do_hough_transform() + fit() of the reference (calibrator.py:1425-1452,
     1552-1715) on explicit inputs.  Returns a dict with every intermediate."""
     import time
@@ -563,7 +571,7 @@ def run_path(peaks, lines, *, num_pix=None, pixel_list=None, num_slopes=2000,
         yedges=ye, hough_weight=hough_weight, filter_close=filter_close,
         minimum_matches=min(minimum_matches, len(lines), len(peaks)),
         minimum_peak_utilisation=minimum_peak_utilisation,
-        minimum_fit_error=minimum_fit_error, n_peaks_total=len(peaks))
+        minimum_fit_error=minimum_fit_error, n_peaks_total=len(peaks), fit_type=fit_type)
     rs = np.random.RandomState(seed)
     best = ransac_sequential(prob, max_tries, rs, refit=refit, trace=trace)
     t3 = time.perf_counter()

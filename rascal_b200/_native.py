@@ -73,6 +73,7 @@ class RansacDesc(C.Structure):
         ("min_fit_error", C.c_double),
         ("bs_nx", C.c_int32), ("bs_ny", C.c_int32), ("d_bs_tx", _vp), ("d_bs_ty", _vp), ("d_bs_c", _vp),
         ("d_bs_ppx", _vp), ("d_bs_ppy", _vp),
+        ("basis", C.c_int32), ("pad1", C.c_int32), ("d_basis_c0", _vp), ("d_basis_grad", _vp),
     ]
 
 
@@ -96,7 +97,7 @@ class MatchDesc(C.Structure):
     _fields_ = [
         ("d_peaks", _vp), ("d_atlas", _vp), ("n_peaks", C.c_int32), ("n_atlas", C.c_int32),
         ("coeffs", C.c_double * NCOEF), ("d_coeffs", _vp), ("n_coef", C.c_int32), ("fit_deg", C.c_int32),
-        ("tolerance", C.c_double), ("robust_refit", C.c_int32), ("pad", C.c_int32),
+        ("tolerance", C.c_double), ("robust_refit", C.c_int32), ("basis", C.c_int32),
     ]
 
 
@@ -144,6 +145,7 @@ REFINE_MAX_WINDOW = 32
 
 STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult, MatchDesc, MatchResult,
            PairsDesc, PrepareDesc, FindPeaksDesc, RefineDesc]
+BASIS_CODES = {"poly": 0, "legendre": 1, "chebyshev": 2}
 COUNTER_NAMES = ("drawn", "aborted", "intercept", "monotonic", "empty", "scored", "eligible", "unsupported")
 
 # every symbol include/rascal_b200.h declares

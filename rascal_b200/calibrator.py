@@ -284,8 +284,12 @@ class Calibrator:
         if self.fit_type == "poly":
             self.polyfit = np.polynomial.polynomial.polyfit
             self.polyval = np.polynomial.polynomial.polyval
-        elif self.fit_type in ("legendre", "chebyshev"):
-            raise NotImplementedError("fit_type '%s' is not on the accelerated path yet" % self.fit_type)
+        elif self.fit_type == "legendre":
+            self.polyfit = np.polynomial.legendre.legfit
+            self.polyval = np.polynomial.legendre.legval
+        elif self.fit_type == "chebyshev":
+            self.polyfit = np.polynomial.chebyshev.chebfit
+            self.polyval = np.polynomial.chebyshev.chebval
         else:
             raise ValueError("fit_type must be: (1) poly, (2) legendre or (3) chebyshev")
         if brute_force:
@@ -352,7 +356,8 @@ class Calibrator:
         mb = engine.MatchBatch([dict(peaks=np.asarray(self.peaks, dtype=np.float64),
                                      lines=np.asarray(self.atlas.get_lines(), dtype=np.float64),
                                      coeffs=fit_coeff, tolerance=tolerance, fit_deg=fit_deg,
-                                     robust_refit=robust_refit)]).run(mode=refit_mode)
+                                     robust_refit=robust_refit,
+                                     fit_type=getattr(self, "fit_type", None) or "poly")]).run(mode=refit_mode)
         res, mx, my, rs = mb.fetch()
         r = res[0]
         m = r.n_matched
@@ -439,7 +444,7 @@ class Calibrator:
         from . import parallel, pipeline
 
         if (self.pix_known is not None or self.constrain_poly or self.filter_close or not self.linear
-                or self.ht._external or self.sample_size != fit_deg + 1):
+                or self.ht._external or self.sample_size != fit_deg + 1 or getattr(self, "fit_type", "poly") != "poly"):
             return None
         pl = np.asarray(self.pixel_list, dtype=np.float64)
         # K1 / K2 / K3 work on the ascending distinct peaks whatever the caller's order (the staged path
@@ -521,7 +526,8 @@ class Calibrator:
             xedges=self.ht.xedges, yedges=self.ht.yedges, hough_weight=self.hough_weight,
             filter_close=self.filter_close, minimum_matches=self.minimum_matches,
             minimum_peak_utilisation=self.minimum_peak_utilisation, minimum_fit_error=self.minimum_fit_error,
-            n_peaks_total=len(self.peaks), pix_known=self.pix_known, wave_known=self.wave_known)
+            n_peaks_total=len(self.peaks), pix_known=self.pix_known, wave_known=self.wave_known,
+            fit_type=getattr(self, "fit_type", "poly"))
         if not setup.enough:  # :468-469
             return best
         if fit_coeff is not None:  # :512-515: only hypotheses that beat the pre-existing fit count

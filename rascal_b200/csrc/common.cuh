@@ -90,4 +90,32 @@ __device__ __forceinline__ double horner_unfused(const double* c, int n, double 
   return r;
 }
 
+// self.polyval of the fit (calibrator.py:1621-1631) on n coefficients: numpy's polyval (Horner), legval or
+// chebval (Clenshaw recurrences), each with numpy's own sequence of separately rounded operations.
+__device__ __forceinline__ double basis_val(int basis, const double* c, int n, double x) {
+  if (basis == 0 || n <= 0) return (n <= 0) ? 0.0 : horner_unfused(c, n, x);
+  double c0, c1;
+  if (n == 1) { c0 = c[0]; c1 = 0.0; }
+  else if (n == 2) { c0 = c[0]; c1 = c[1]; }
+  else if (basis == 1) {  // numpy.polynomial.legendre.legval
+    double nd = (double)n;
+    c0 = c[n - 2]; c1 = c[n - 1];
+    for (int i = 3; i <= n; ++i) {
+      const double tmp = c0;
+      nd = nd - 1.0;
+      c0 = sub(c[n - i], mul(c1, nd - 1.0) / nd);
+      c1 = add(tmp, mul(mul(c1, x), 2.0 * nd - 1.0) / nd);
+    }
+  } else {                // numpy.polynomial.chebyshev.chebval
+    const double x2 = mul(2.0, x);
+    c0 = c[n - 2]; c1 = c[n - 1];
+    for (int i = 3; i <= n; ++i) {
+      const double tmp = c0;
+      c0 = sub(c[n - i], c1);
+      c1 = add(tmp, mul(c1, x2));
+    }
+  }
+  return add(c0, mul(c1, x));
+}
+
 }  // namespace rb2

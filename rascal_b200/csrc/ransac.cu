@@ -1136,7 +1136,14 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
         }
     }
     if (active) {
-      if (!aborted) pass = !((cf[0] < min_i) || (cf[0] > max_i));  // :578-582
+      if (!aborted) {
+        double c0 = cf[0];
+        if (d.basis) {  // the first coefficient of the BASIS the reference fitted in (legfit / chebfit)
+          c0 = 0.0;
+          for (int k = 0; k < ncoef; ++k) c0 = fma(d.d_basis_c0[k], cf[k], c0);
+        }
+        pass = !((c0 < min_i) || (c0 > max_i));  // :578-582
+      }
       if (diag) {
         if (!aborted) {
           if (d.d_out_coeffs)
@@ -1454,6 +1461,15 @@ ransac_weight_general_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pip
       const long long id = (long long)(tag & TAG_ID_MASK);
       const rb2_ransac_desc& d = descs[problem];
       w.deg = deg; w.pix = d.d_pix;
+      if (d.basis) {  // "gradient" = the monomial derivative rule on the basis coefficients (:614-618)
+#pragma unroll
+        for (int k = 0; k <= CAP; ++k) {
+          double g = 0.0;
+          if (k < deg)
+            for (int j = 0; j < ncoef; ++j) g = fma(d.d_basis_grad[k * ncoef + j], w.c[j <= CAP ? j : CAP], g);
+          w.dc[k] = g;
+        }
+      }
       double acc = 0.0;
       for (int i = lane; i < d.n_pix; i += 32) {
         const double x = w.px(i);
@@ -1510,8 +1526,8 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
           const unsigned long long best_hi = *reinterpret_cast<volatile unsigned long long*>(&pipe.best[problem].hi);
           if (cost_key(lb) > best_hi || lb > d.cost_ceiling) need_value = false;
         }
-        double weight;
-        const bool ok = hough_weight_thread<DEG_T>(d, cr, deg, need_value, &weight);
+        double weight = 0.0;
+        const bool ok = d.basis ? false : hough_weight_thread<DEG_T>(d, cr, deg, need_value, &weight);
         if (!ok && d.d_bs_c) {
           // outside the corner regime: the weight is the clamped bicubic spline summed over the pixels -
           // warp-sized work, done by ransac_weight_general_kernel (which also finishes the cost)
@@ -1878,6 +1894,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     if (h.sample_size != h.deg + 1 || h.n_known != 0) fast = false;
     if (h.n_cand < h.n_upeaks || h.n_wids < 1 || h.n_upeaks > 65535 || h.n_cand > A_MAX_CAND) return RB2_ERR_ARG;
     if (h.n_hyp < 0 || h.n_hyp >= (1ll << 40)) return RB2_ERR_ARG;
+    if (h.basis && (h.basis < 0 || h.basis > 2 || !h.d_bs_c || !h.d_basis_c0 || !h.d_basis_grad)) return RB2_ERR_ARG;
     if (h.d_bs_c) {
       if (h.bs_nx < 4 || h.bs_ny < 4 || !h.d_bs_tx || !h.d_bs_ty || !h.d_bs_ppx || !h.d_bs_ppy) return RB2_ERR_ARG;
       general_weight = true;

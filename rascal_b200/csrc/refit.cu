@@ -549,7 +549,7 @@ refit_kernel(const rb2_ransac_desc* __restrict__ descs, const rb2_ransac_result*
   // residual = polyval(matched_peaks, coeffs) - matched_atlas, clipped (:664-671)
   double ss = 0.0;
   for (int i = lane; i < m; i += 32) {
-    double res = sub(horner_unfused(r.coeffs, n, ix[i]), iy[i]);
+    double res = sub(basis_val(d.basis, r.coeffs, n, ix[i]), iy[i]);  // self.polyval on the refit coefficients (:664)
     if (fabs(res) > d.tol) res = d.tol;
     ss = fma(res, res, ss);
     mx_out[(size_t)p * max_up + i] = ix[i];
@@ -626,7 +626,7 @@ match_peaks_kernel(const rb2_match_desc* __restrict__ descs, int mode, int max_p
     double bd = CUDART_INF, bw = 0.0, px = 0.0;
     if (u < n_p) {
       px = d.d_peaks[u];
-      const double x = horner_unfused(cin, d.n_coef, px);
+      const double x = basis_val(d.basis, cin, d.n_coef, px);
       for (int k = 0; k < n_a; ++k) {
         const double w = d.d_atlas[k];
         const double ad = fabs(sub(w, x));
@@ -685,7 +685,7 @@ match_peaks_kernel(const rb2_match_desc* __restrict__ descs, int mode, int max_p
     robust_polyfit_warp(m, n, ix, iy, xn, yn, sw, A, mode, r.refit);
     double ss = 0.0;
     for (int i = lane; i < m; i += 32) {
-      const double res = sub(iy[i], horner_unfused(r.refit.coeffs, n, ix[i]));
+      const double res = sub(iy[i], basis_val(d.basis, r.refit.coeffs, n, ix[i]));
       res_out[(size_t)p * max_p + i] = res;
       ss = fma(res, res, ss);
     }
@@ -750,7 +750,7 @@ extern "C" int rb2_match_peaks(int n_problems, const rb2_match_desc* d_desc, con
   for (int i = 0; i < n_problems; ++i) {
     const rb2_match_desc& h = h_desc[i];
     if (h.n_peaks < 0 || h.n_peaks > max_peaks || h.n_atlas < 0 || h.n_coef < 1 || h.n_coef > RB2_MAX_DEG + 1 ||
-        h.fit_deg < 1 || h.fit_deg > RB2_MAX_DEG || !(h.tolerance >= 0.0))
+        h.fit_deg < 1 || h.fit_deg > RB2_MAX_DEG || !(h.tolerance >= 0.0) || h.basis < 0 || h.basis > 2)
       return RB2_ERR_ARG;
     if ((h.n_peaks && !h.d_peaks) || (h.n_atlas && !h.d_atlas)) return RB2_ERR_ARG;
     max_n = max(max_n, h.fit_deg + 1);

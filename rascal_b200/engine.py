@@ -497,6 +497,34 @@ def sampling_cdf32(peaks):
     return prob, c32
 
 
+def basis_tables(fit_type, deg):
+    """fit_type 'legendre' / 'chebyshev' (calibrator.py:1625-1631) for K3: (code, c0_row[deg+1], grad[deg, deg+1]).
+    c0_row: first row of the monomial -> basis change matrix (the intercept test reads the basis' first
+    coefficient); grad: the monomial coefficients of sum_k (k+1) c_(k+1) B_k(x) - util._derivative applied to
+    the basis coefficients, evaluated with the basis' polyval (:614-618) - as a linear map of the hypothesis'
+    monomial coefficients."""
+    code = N.BASIS_CODES[fit_type]
+    if code == 0:
+        return 0, None, None
+    to_basis, to_poly = ((np.polynomial.legendre.poly2leg, np.polynomial.legendre.leg2poly) if code == 1 else
+                         (np.polynomial.chebyshev.poly2cheb, np.polynomial.chebyshev.cheb2poly))
+    n = deg + 1
+
+    def col(fn, k, size):
+        e = np.zeros(k + 1)
+        e[k] = 1.0
+        out = np.zeros(size)
+        v = np.atleast_1d(fn(e))
+        out[:len(v)] = v
+        return out
+
+    T = np.column_stack([col(to_basis, j, n) for j in range(n)])         # c_basis = T @ a_mono
+    D = np.zeros((deg, n))
+    D[np.arange(deg), np.arange(1, n)] = np.arange(1, n)                  # d_k = (k + 1) c_(k+1)
+    Bk = np.column_stack([col(to_poly, k, deg) for k in range(deg)])      # monomials of sum_k d_k B_k
+    return code, np.ascontiguousarray(T[0]), np.ascontiguousarray(Bk @ D @ T)
+
+
 def bspline_basis_pp(t):
     """The cubic B-spline basis on knots t (first / last four equal) as local polynomials: for every knot
     interval m = 0..n-4 (n = len(t) - 4 basis functions) the four non-zero basis functions N_m..N_m+3 in
@@ -521,7 +549,9 @@ class RansacSetup:
     def __init__(self, cand_peak, cand_arc, *, fit_deg, sample_size, ransac_tolerance, min_intercept,
                  max_intercept, pixel_list, hist, xedges, yedges, hough_weight=1.0, filter_close=False,
                  minimum_matches=0, minimum_peak_utilisation=0.0, minimum_fit_error=1e-4, n_peaks_total=None,
-                 pix_known=None, wave_known=None, cost_ceiling=1e50):
+                 pix_known=None, wave_known=None, cost_ceiling=1e50, fit_type="poly"):
+        self.fit_type = fit_type
+        self.basis, self.basis_c0, self.basis_grad = basis_tables(fit_type, int(fit_deg))
         x = np.array(cand_peak, dtype=np.float64)
         y = np.array(cand_arc, dtype=np.float64)
         if filter_close:  # calibrator.py:457-464: drop the lower wavelength of every close pair
@@ -596,7 +626,12 @@ class RansacSetup:
         coef = np.linalg.solve(np.vander(u, 4, increasing=True), v.T).T / w[:, None] ** np.arange(4)[None, :]
         self.pp_breaks = brk.astype(np.float64)
         self.pp_coef = coef.reshape(-1)
-        # the spline itself for hypotheses outside the corner regime (general evaluation on the device)
+        # the spline itself for hypotheses outside the corner regime (general evaluation on the device); only
+        # where such hypotheses can exist: gradients within reach of the first intercept-bin centre (nm-scale
+        # problems) - on Angstrom scales (centre ~ 3500, gradients ~ 1) the tables would be dead weight
+        self.bs_c = None
+        if not (self.basis or self.ic_min <= 20.0 * max(abs(self.gc_min), abs(self.gc_max))):
+            return  # (a non-monomial basis always takes the per-pixel evaluation, see rb2_ransac_desc.basis)
         ty = spl.get_knots()[1]
         self.bs_tx, self.bs_ty = np.ascontiguousarray(tx, dtype=np.float64), np.ascontiguousarray(ty, dtype=np.float64)
         self.bs_c = np.ascontiguousarray(spl.get_coeffs(), dtype=np.float64)  # [(len(tx)-4) * (len(ty)-4)], x first
@@ -607,7 +642,9 @@ class RansacSetup:
         bijective-match errors of `fit_coeff` (unweighted, unclipped) - the ceiling a hypothesis has to
         beat.  Part of the loop's set-up, evaluated once on the host."""
         c = np.asarray(fit_coeff, dtype=np.float64)
-        fit = np.polynomial.polynomial.polyval(self.peaks, c)
+        polyval = {0: np.polynomial.polynomial.polyval, 1: np.polynomial.legendre.legval,
+                   2: np.polynomial.chebyshev.chebval}[self.basis]  # self.polyval of the fit (:1621-1631)
+        fit = polyval(self.peaks, c)
         best_e, best_w = np.empty(len(self.peaks)), np.empty(len(self.peaks))
         for k in range(len(self.peaks)):
             cand = self.cand_wave[self.cand_off[k]:self.cand_off[k + 1]]
@@ -678,6 +715,8 @@ class RansacBatch:
             o = dict(peaks=ar.add(s.peaks), coff=ar.add(s.cand_off), cwave=ar.add(s.cand_wave),
                      cwid=ar.add(s.cand_wid), cdf=ar.add(s.cdf32), kx=ar.add(s.known_x), ky=ar.add(s.known_y),
                      ppb=ar.add(s.pp_breaks), ppc=ar.add(s.pp_coef))
+            if getattr(s, "basis", 0):
+                o.update(bc0=ar.add(s.basis_c0), bgr=ar.add(s.basis_grad))
             if getattr(s, "bs_c", None) is not None:
                 o.update(btx=ar.add(s.bs_tx), bty=ar.add(s.bs_ty), bc=ar.add(s.bs_c), bpx=ar.add(s.bs_ppx),
                          bpy=ar.add(s.bs_ppy))
@@ -710,6 +749,8 @@ class RansacBatch:
             d.cost_ceiling = s.cost_ceiling
             d.floor_cost, d.floor_id = 0.0, -1
             d.min_fit_error = float(s.minimum_fit_error)
+            if "bc0" in o:
+                d.basis, d.d_basis_c0, d.d_basis_grad = int(s.basis), base + o["bc0"], base + o["bgr"]
             if "bc" in o:
                 d.bs_nx, d.bs_ny = len(s.bs_tx) - 4, len(s.bs_ty) - 4
                 d.d_bs_tx, d.d_bs_ty, d.d_bs_c = base + o["btx"], base + o["bty"], base + o["bc"]
@@ -941,6 +982,7 @@ class MatchBatch:
             d.fit_deg = int(p["fit_deg"]) if p.get("fit_deg") is not None else d.n_coef - 1
             d.tolerance = float(p["tolerance"])
             d.robust_refit = int(bool(p.get("robust_refit", True)))
+            d.basis = int(N.BASIS_CODES[p.get("fit_type", "poly")])
         torch = _torch()
         self.arena = ar
         self._desc_host = torch.empty(C.sizeof(N.MatchDesc) * self.n, dtype=torch.uint8, pin_memory=True)

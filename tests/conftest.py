@@ -9,7 +9,8 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["c3_deg4", "poly_linear_deg1", "poly_quadratic_deg2", "fine_deg5", "c1_sprat_xe", "c5_deimos", "c2_gmos_cuar",
-                "c4_npix1024", "c4_npix2048", "c4_npix4096", "synth_nm_deg4", "c5_deimos_full"]
+                "c4_npix1024", "c4_npix2048", "c4_npix4096", "synth_nm_deg4", "c5_deimos_full", "legendre_deg2",
+                "chebyshev_deg2"]
 
 
 MATCH_CASES = GOLDEN_CASES[:7]  # cases with a match_<case>.npz recording of Calibrator.match_peaks

@@ -109,6 +109,18 @@ class Recorder(logging.Handler):
             return out
 
         np.polynomial.polynomial.polyfit = polyfit
+        # fit_type 'legendre' / 'chebyshev' (calibrator.py:1625-1631) fit with these instead
+        self._legfit, self._chebfit = np.polynomial.legendre.legfit, np.polynomial.chebyshev.chebfit
+
+        def wrap(fn):
+            def fit(x, y, deg, *a, **k):
+                out = fn(x, y, deg, *a, **k)
+                rec.events.append(("fit", np.array(x, float), np.array(y, float), np.array(out)))
+                return out
+            return fit
+
+        np.polynomial.legendre.legfit = wrap(self._legfit)
+        np.polynomial.chebyshev.chebfit = wrap(self._chebfit)
         self._mb = Calibrator._match_bijective
 
         def mb(self_, cands, peaks, coeff):
@@ -143,6 +155,7 @@ class Recorder(logging.Handler):
 
     def remove(self):
         np.polynomial.polynomial.polyfit = self._polyfit
+        np.polynomial.legendre.legfit, np.polynomial.chebyshev.chebfit = self._legfit, self._chebfit
         Calibrator._match_bijective = self._mb
         models.robust_polyfit = self._rp
         rc.interpolate = self._interp

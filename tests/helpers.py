@@ -12,6 +12,7 @@ def oracle_from_golden(g, refit=O.robust_polyfit, max_tries=None, trace=None):
     kw.update(cfg["ransac"])
     assert kw.pop("linear", True)  # the linear candidate search is the path restated here
     kw.update(cfg["fit"])
+    kw.pop("fit_tolerance", None)  # only a warning threshold in Calibrator.fit (:1696)
     if max_tries is not None:
         kw["max_tries"] = max_tries
     return O.run_path(g["peaks"], g["lines"], pixel_list=g["pixel_list"],
@@ -35,4 +36,4 @@ def problem_from_golden(g):
                             len(g["peaks"])),
         minimum_peak_utilisation=r.get("minimum_peak_utilisation", 0.0),
         minimum_fit_error=r.get("minimum_fit_error", 1e-4),
-        n_peaks_total=len(g["peaks"]))
+        n_peaks_total=len(g["peaks"]), fit_type=f.get("fit_type", "poly"))

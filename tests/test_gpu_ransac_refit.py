@@ -29,9 +29,29 @@ def setup_from_golden(g, **over):
               hough_weight=r.get("hough_weight", 1.0), filter_close=r.get("filter_close", False),
               minimum_matches=min(r.get("minimum_matches", 0), len(g["lines"]), len(g["peaks"])),
               minimum_peak_utilisation=r.get("minimum_peak_utilisation", 0.0),
-              minimum_fit_error=r.get("minimum_fit_error", 1e-4), n_peaks_total=len(g["peaks"]))
+              minimum_fit_error=r.get("minimum_fit_error", 1e-4), n_peaks_total=len(g["peaks"]),
+              fit_type=f.get("fit_type", "poly"))
     kw.update(over)
     return engine.RansacSetup(g["candidate_peak"], g["candidate_arc"], **kw)
+
+
+def ref_curve(g, x, coeffs):
+    """The reference's self.polyval on ITS coefficients (basis coefficients for legendre / chebyshev)."""
+    return O.BASES[g["config"]["fit"].get("fit_type", "poly")][1](x, coeffs)
+
+
+def monomial_coeffs(g, coeffs):
+    """Recorded hypothesis coefficients as the monomial coefficients the device ABI carries."""
+    ft = g["config"]["fit"].get("fit_type", "poly")
+    if ft == "poly":
+        return np.asarray(coeffs)
+    conv = np.polynomial.legendre.leg2poly if ft == "legendre" else np.polynomial.chebyshev.cheb2poly
+    c = np.atleast_2d(coeffs)
+    out = np.zeros_like(c)
+    for i, row in enumerate(c):
+        v = conv(row)
+        out[i, :len(v)] = v
+    return out.reshape(np.shape(coeffs))
 
 
 def test_setup_matches_reference_tables(golden):
@@ -68,7 +88,7 @@ def test_replay_reference_draws(golden):
         assert np.max(np.abs(fit - ys)[well]) < 1e-6
     grid = np.linspace(s.pix_min, s.pix_max, 64)
     dev = P.polyval(grid, out["coeffs"][sc].T)
-    ref = P.polyval(grid, g["tr_coeffs"][sc].T)
+    ref = ref_curve(g, grid, g["tr_coeffs"][sc].T)
     assert np.max(np.abs(dev - ref)) < 1e-6  # incl. the 20 % extrapolation beyond the outer peaks
     assert np.array_equal(out["counts"][sc, 0], g["tr_n_match"][sc])
     assert np.array_equal(out["counts"][sc, 1], g["tr_n_inl"][sc])
@@ -93,7 +113,8 @@ def test_replay_reference_draws(golden):
 # the assertion allows 10x the measured gap
 COEFF_GAP = {"c3_deg4": 3.6e-7, "poly_linear_deg1": 2.1e-11, "poly_quadratic_deg2": 2e-5, "fine_deg5": 1.2e-7,
              "c1_sprat_xe": 3.1e-7, "c5_deimos": 2.5e-7, "c2_gmos_cuar": 3.7e-9, "c4_npix1024": 1.9e-7,
-             "c4_npix2048": 2.6e-8, "c4_npix4096": 5.5e-6, "synth_nm_deg4": 2e-5, "c5_deimos_full": 2e-5}
+             "c4_npix2048": 2.6e-8, "c4_npix4096": 5.5e-6, "synth_nm_deg4": 2e-5, "c5_deimos_full": 2e-5, "legendre_deg2": 2e-5,
+             "chebyshev_deg2": 2e-5}
 
 
 def test_replay_selects_reference_winner(golden, request):
@@ -114,7 +135,7 @@ def test_replay_selects_reference_winner(golden, request):
     kw = dict(replay=(g["tr_x_idx"], g["tr_y_idx"]))
     err_sum = g["tr_cost"][ref_id] * (g["tr_weight"][ref_id] + 1e-9) * (g["tr_n_match"][ref_id] - s.deg)
     if err_sum < 1e-8:  # the winner's summed error over ~25 peaks is below 1e-8 A: rounding noise of the fit
-        kw["replay_coeffs"] = g["tr_coeffs"]
+        kw["replay_coeffs"] = monomial_coeffs(g, g["tr_coeffs"])
     rb.run(0, n, **kw)
     win = rb.results()[0]
     for _ in range(8):
@@ -159,6 +180,7 @@ def test_replay_selects_reference_winner(golden, request):
     gap = COEFF_GAP[case]
     assert np.allclose(coeffs, g["fit_coeff"], rtol=gap, atol=atol)
     assert np.allclose(coeffs, exact, rtol=max(gap, 10 * rel(g["fit_coeff"], exact)), atol=atol)
+    # (the returned fit_coeff is models.robust_polyfit's MONOMIAL vector for every fit_type)
     assert np.max(np.abs(P.polyval(g["matched_peaks"], coeffs)
                          - P.polyval(g["matched_peaks"], g["fit_coeff"]))) < 1e-6
     assert abs(o.rms - float(g["rms"])) < 1e-6
@@ -180,10 +202,11 @@ def test_replay_with_reference_coefficients_is_decision_exact(golden):
     s = setup_from_golden(g)
     rb = engine.RansacBatch([s])
     n = len(g["tr_status"])
-    out = rb.run(0, n, replay=(g["tr_x_idx"], g["tr_y_idx"]), replay_coeffs=g["tr_coeffs"], per_hypothesis=True)
+    inj = monomial_coeffs(g, g["tr_coeffs"])
+    out = rb.run(0, n, replay=(g["tr_x_idx"], g["tr_y_idx"]), replay_coeffs=inj, per_hypothesis=True)
     assert np.array_equal(out["status"], g["tr_status"].astype(np.uint8))
     sc = g["tr_status"] == O.ST_SCORED
-    assert np.array_equal(out["coeffs"][sc], g["tr_coeffs"][sc])
+    assert np.array_equal(out["coeffs"][sc], inj[sc])
     assert np.array_equal(out["counts"][sc, 0], g["tr_n_match"][sc])
     assert np.array_equal(out["counts"][sc, 1], g["tr_n_inl"][sc])
     dw = np.abs(out["weight"][sc] - g["tr_weight"][sc])
