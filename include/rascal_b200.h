@@ -378,6 +378,18 @@ int rb2_match_peaks(int n_problems, const rb2_match_desc *d_desc,
                     double *d_matched_y, double *d_residual, int max_peaks,
                     void *stream);
 
+/* Calibrator._adjust_polyfit (calibrator.py:754-820): the objective that match_peaks(refine=True) hands to
+ * scipy.optimize.minimize (:1797-1821), for n_eval trial shifts at once.  Trial e adds d_deltas[e*n_delta + i] to
+ * coefficient i of d_fit (i < n_delta); every peak is paired with its nearest atlas line (first on ties) if that
+ * is closer than `tolerance`; the value is sum((line - polyval(peak))^2) / (n_matched - n_coef - 1), or +inf when
+ * that divisor is < 1, fewer than min_frac * n_peaks peaks are matched, or the polynomial is not strictly
+ * increasing over d_pix_sorted (np.sort(pixel_list)).  basis: self.polyval of the fit (0 poly, 1 legendre,
+ * 2 chebyshev).  One warp per trial. */
+int rb2_adjust_polyfit(int n_eval, const double *d_deltas, int n_delta, const double *d_fit,
+                       int n_coef, int basis, const double *d_peaks, int n_peaks,
+                       const double *d_atlas, int n_atlas, const double *d_pix_sorted, int n_pix,
+                       double tolerance, double min_frac, double *d_out, void *stream);
+
 /* ======================================================================= *
  * Device-resident glue of the many-spectra path: the host work the reference
  * does between its stages, on the device, so that a batch of spectra goes

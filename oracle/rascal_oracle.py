@@ -150,6 +150,49 @@ def candidate_points_linear(lines, pairs, candidate_tolerance, sigma):
 # ---------------------------------------------------------------------------
 
 
+def candidate_points_poly(peaks, lines, fit_coeff, n_lines, range_tolerance, candidate_tolerance, rs,
+                          polyval=P.polyval):
+    """linear=False: Calibrator._get_candidate_points_poly, calibrator.py:263-315 (EXPERIMENTAL there).
+    `rs`: the legacy RandomState the reference's np.random.random call draws from."""
+    peaks = np.asarray(peaks, dtype=float)
+    actual = np.array(lines, dtype=float)
+    out = []
+    delta = rs.random_sample(n_lines) * range_tolerance * 2.0 - range_tolerance
+    for d in delta:
+        predicted = polyval(peaks, fit_coeff) + d
+        diff = np.abs(actual - predicted)
+        mask = diff < candidate_tolerance
+        if np.sum(mask) > 0:
+            weight = np.exp(-((actual[mask] - predicted[mask]) ** 2) / (2 * range_tolerance ** 2 + 1e-9))
+            out.append([peaks[mask], actual[mask], weight])
+    return out
+
+
+def adjust_polyfit(delta, fit, peaks, lines, pixel_list, tolerance, min_frac, polyval=P.polyval):
+    """Calibrator._adjust_polyfit, calibrator.py:754-820: the objective of match_peaks(refine=True)."""
+    fit_new = np.array(fit, dtype=float)
+    atlas_lines = np.asarray(lines, dtype=float)
+    for i, d in enumerate(delta):
+        fit_new[i] += d
+    xm, ym = [], []
+    for p in peaks:
+        x = polyval(p, fit_new)
+        diff_abs = np.abs(atlas_lines - x)
+        idx = np.argmin(diff_abs)
+        if diff_abs[idx] < tolerance:
+            xm.append(p)
+            ym.append(atlas_lines[idx])
+    xm, ym = np.array(xm), np.array(ym)
+    dof = len(xm) - len(fit_new) - 1
+    if dof < 1:
+        return np.inf
+    if len(xm) < len(peaks) * min_frac:
+        return np.inf
+    if not np.all(np.diff(polyval(np.sort(pixel_list), fit_new)) > 0):
+        return np.inf
+    return np.sum((ym - polyval(xm, fit_new)) ** 2.0) / dof
+
+
 def most_common_candidates(candidates, top_n, weighted):
     """(candidate_peak, candidate_arc) lists; calibrator.py:174-217.
 

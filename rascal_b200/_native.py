@@ -164,6 +164,8 @@ EXPORTS = {
     "rb2_ransac_batch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_merge_winners": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "rb2_robust_polyfit": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "rb2_adjust_polyfit": (C.c_int, [C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
+                                     C.c_double, C.c_double, _vp, _vp]),
     "rb2_hough_brute_force": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),
     "rb2_hough_bin_points": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
     "rb2_expand_pairs": (C.c_int, [C.c_int, _vp, _vp, _vp]),

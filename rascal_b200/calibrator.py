@@ -295,8 +295,6 @@ class Calibrator:
         if brute_force:
             raise NotImplementedError("brute_force sampling is not supported (it never terminates on a "
                                       "rejected sample in the reference, calibrator.py:532-534)")
-        if not self.linear:
-            raise NotImplementedError("linear=False (experimental in the reference) is not on the accelerated path")
         if self.sample_size > len(self.atlas):
             self.logger.warning("Size of sample_size is larger than the size of atlas, the sample_size is set to "
                                 "match the size of atlas = " + str(len(self.atlas)) + ".")
@@ -341,18 +339,37 @@ class Calibrator:
 
         Where the reference is defined (no peak has two atlas lines inside the tolerance) the
         7-tuple is the reference's.  Where it raises (an ambiguous peak: TypeError at :1867, see
-        DESIGN.md) the nearest line is taken and a warning is logged.  `refine=True` (the
-        experimental Nelder-Mead pre-step, :1797-1821) is not on the accelerated path."""
+        DESIGN.md) the nearest line is taken and a warning is logged.  `refine=True`: the reference's
+        experimental Nelder-Mead pre-step (:1797-1821) over its objective _adjust_polyfit (:754-820), which runs
+        on the device (rb2_adjust_polyfit); as in the reference its result only reaches the output when
+        robust_refit=False - the association itself is made with the unrefined `fit_coeff` (:1831)."""
         if fit_coeff is None:
             fit_coeff = self.fit_coeff.copy()
         if fit_deg is None:
             fit_deg = len(fit_coeff) - 1
-        if refine:
-            raise NotImplementedError("match_peaks(refine=True) (experimental in the reference, "
-                                      "calibrator.py:1797-1821) is not on the accelerated path")
         if getattr(self, "polyval", None) is None:
             self.polyfit = np.polynomial.polynomial.polyfit
             self.polyval = np.polynomial.polynomial.polyval
+        fit_coeff_new = None
+        if refine:
+            # :1797-1821 (experimental in the reference): Nelder-Mead on the host, exactly the reference's
+            # scipy.optimize.minimize call, over Calibrator._adjust_polyfit evaluated on the device
+            from scipy.optimize import minimize
+
+            fit_coeff = np.asarray(fit_coeff, dtype=np.float64)
+            fit_coeff_new = fit_coeff.copy()
+            if n_delta is None:
+                n_delta = len(fit_coeff_new) - 1
+            objective = engine.AdjustPolyfit(self.peaks, self.atlas.get_lines(), self.pixel_list, fit_coeff, tolerance,
+                                             min_frac, fit_type=getattr(self, "fit_type", None) or "poly")
+            fitted_delta = minimize(objective, fit_coeff_new[: int(n_delta)] * 1e-3, method=method, tol=convergence,
+                                    options={"maxiter": 10000}).x
+            for i, d in enumerate(fitted_delta):
+                fit_coeff_new[i] += d
+            self.refine_evaluations = objective.n_evals
+            if np.any(np.isnan(fit_coeff_new)):
+                self.logger.warning("_adjust_polyfit() returns None. Input solution is returned.")
+                return fit_coeff, None, None, None, None, None, None
         mb = engine.MatchBatch([dict(peaks=np.asarray(self.peaks, dtype=np.float64),
                                      lines=np.asarray(self.atlas.get_lines(), dtype=np.float64),
                                      coeffs=fit_coeff, tolerance=tolerance, fit_deg=fit_deg,
@@ -379,9 +396,9 @@ class Calibrator:
             self.rms = r.refit.rms
             self.refit_nfev = r.refit.huber_iters
         else:
-            # the reference assigns an undefined name here (:1944, UnboundLocalError unless
-            # refine=True); the documented intent is "the current solution": keep the input
-            self.fit_coeff = np.asarray(fit_coeff)
+            # :1944: fit_coeff_new, which only exists after refine=True (UnboundLocalError otherwise in the
+            # reference; the documented intent is "the current solution": then the input is kept)
+            self.fit_coeff = np.asarray(fit_coeff) if fit_coeff_new is None else fit_coeff_new
             self.rms = r.polyfit_rms
         return (self.fit_coeff, self.matched_peaks, self.matched_atlas, self.rms, self.residuals,
                 self.peak_utilisation, self.atlas_utilisation)
@@ -422,6 +439,17 @@ class Calibrator:
         per Hough line in rank order - read by its plotting code (plotting.py:309-349).  The vote (K2) never
         builds this list; it is materialised from the device on first use after a fit."""
         c = self.__dict__.get("_cand_triples")
+        if c is None and not self.linear and self.__dict__.get("_poly_candidates") is not None:
+            # linear=False: one [peaks, lines, weights] entry per random shift that hit anything (:298-315)
+            delta, base, actual, peaks, tol = self._poly_candidates
+            c = []
+            for d in delta:
+                predicted = base + d
+                mask = np.abs(actual - predicted) < tol
+                if np.sum(mask) > 0:
+                    w = np.exp(-((actual[mask] - predicted[mask]) ** 2) / (2 * self.range_tolerance ** 2 + 1e-9))
+                    c.append([peaks[mask], actual[mask], w])
+            self.__dict__["_cand_triples"] = c
         if c is None and self.__dict__.get("_cand_triples_tol") is not None:
             tol = self.__dict__["_cand_triples_tol"]
             sigma = (self.range_tolerance + self.linearity_tolerance) * 1.1775  # :256
@@ -501,6 +529,27 @@ class Calibrator:
         cp, ca = vb.candidates(0)
         self.candidate_peak, self.candidate_arc = list(cp), list(ca)
 
+    def _vote_poly(self, candidate_tolerance):
+        """linear=False (experimental in the reference): _get_candidate_points_poly (calibrator.py:263-315) +
+        _get_most_common_candidates (:154-217).  The reference compares peak i with atlas line i (its
+        `actual - predicted` is elementwise: equal lengths or a broadcasting ValueError) for len(hough_lines)
+        random shifts of the prior solution, so a peak's only possible candidate is its own line - kept iff
+        some shift brings the prediction within the tolerance.  Set-up logic on the host like _generate_pairs;
+        the shifts come from the seeded global NumPy RNG exactly as in the reference."""
+        if self.fit_coeff is None:
+            raise ValueError("A guess solution for a polynomial fit has to be provided as fit_coeff in fit() in "
+                             "order to generate candidates for RANSAC sampling.")
+        peaks = np.asarray(self.peaks, dtype=np.float64)
+        actual = np.array(self.atlas.get_lines())
+        n = int(self.xbins) * int(self.ybins)  # len(self.hough_lines)
+        delta = np.random.random(n) * self.range_tolerance * 2.0 - self.range_tolerance
+        base = self.polyval(peaks, self.fit_coeff)
+        hit = np.abs(actual[None, :] - (base[None, :] + delta[:, None])) < candidate_tolerance  # [shift, peak]
+        keep = hit.any(axis=0)
+        order = np.argsort(peaks[keep], kind="stable")
+        self.candidate_peak, self.candidate_arc = list(peaks[keep][order]), list(actual[keep][order])
+        self._poly_candidates = (delta, base, actual, peaks, candidate_tolerance)
+
     def _solve_candidate_ransac(self, fit_deg, fit_coeff, max_tries, candidate_tolerance, n_hypotheses=None):
         """calibrator.py:382-752 as batched device work (order-independent rule).
 
@@ -517,7 +566,10 @@ class Calibrator:
             fast = self._solve_device_resident(fit_deg, candidate_tolerance, int(n_hypotheses))
             if fast is not None:
                 return fast
-        self._vote(candidate_tolerance)
+        if self.linear:
+            self._vote(candidate_tolerance)
+        else:
+            self._vote_poly(candidate_tolerance)
         best = (None, 1e50, None, 0, False)
         setup = engine.RansacSetup(
             self.candidate_peak, self.candidate_arc, fit_deg=fit_deg, sample_size=self.sample_size,

@@ -696,7 +696,67 @@ match_peaks_kernel(const rb2_match_desc* __restrict__ descs, int mode, int max_p
   if (lane == 0) out[p] = r;
 }
 
+// Calibrator._adjust_polyfit (calibrator.py:754-820), the objective of match_peaks(refine=True): one warp per
+// trial shift `delta` of the first n_delta coefficients.
+__global__ void __launch_bounds__(32)
+adjust_polyfit_kernel(const double* __restrict__ deltas, int n_delta, const double* __restrict__ fit, int n_coef, int basis,
+                      const double* __restrict__ peaks, int n_peaks, const double* __restrict__ atlas, int n_atlas,
+                      const double* __restrict__ pix_sorted, int n_pix, double tolerance, double min_frac,
+                      double* __restrict__ out) {
+  const int e = blockIdx.x, lane = threadIdx.x;
+  double c[NCF];
+  for (int i = 0; i < NCF; ++i) c[i] = (i < n_coef) ? fit[i] : 0.0;
+  for (int i = 0; i < n_delta && i < n_coef; ++i) c[i] = add(c[i], deltas[(size_t)e * n_delta + i]);  // fit_new[i] += d (:786-787)
+  // nearest atlas line per peak (np.argmin: first minimum), kept if closer than the tolerance (:789-797)
+  int n_m = 0;
+  double ss = 0.0;
+  for (int u = lane; u < n_peaks; u += 32) {
+    const double p = peaks[u];
+    const double x = basis_val(basis, c, n_coef, p);
+    double best = CUDART_INF, bw = 0.0;
+    for (int k = 0; k < n_atlas; ++k) {
+      const double da = fabs(sub(atlas[k], x));
+      if (da < best) { best = da; bw = atlas[k]; }
+    }
+    if (best < tolerance) {
+      ++n_m;
+      const double r = sub(bw, x);  // y_matched - polyval(x_matched, fit_new) (:816)
+      ss = add(ss, mul(r, r));
+    }
+  }
+  n_m = __reduce_add_sync(0xffffffffu, n_m);
+  ss = warp_sum(ss);
+  // monotonic over the sorted pixel list (:809-813)
+  int bad = 0;
+  for (int i = lane; i + 1 < n_pix; i += 32)
+    bad |= !(sub(basis_val(basis, c, n_coef, pix_sorted[i + 1]), basis_val(basis, c, n_coef, pix_sorted[i])) > 0.0);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    const int dof = n_m - n_coef - 1;  // :802
+    double v;
+    if (dof < 1 || (double)n_m < (double)n_peaks * min_frac || bad) v = CUDART_INF;
+    else v = ss / (double)dof;
+    out[e] = v;
+  }
+}
+
 }  // namespace rb2
+
+extern "C" int rb2_adjust_polyfit(int n_eval, const double* d_deltas, int n_delta, const double* d_fit, int n_coef, int basis,
+                                  const double* d_peaks, int n_peaks, const double* d_atlas, int n_atlas,
+                                  const double* d_pix_sorted, int n_pix, double tolerance, double min_frac, double* d_out,
+                                  void* stream_) {
+  using namespace rb2;
+  if (n_eval <= 0 || !d_deltas || !d_fit || !d_out || n_delta < 0 || n_coef < 1 || n_coef > RB2_MAX_DEG + 1 || basis < 0 ||
+      basis > 2 || n_peaks < 0 || n_atlas < 0 || n_pix < 0 || (n_peaks && !d_peaks) || (n_atlas && !d_atlas) ||
+      (n_pix && !d_pix_sorted))
+    return RB2_ERR_ARG;
+  adjust_polyfit_kernel<<<n_eval, 32, 0, (cudaStream_t)stream_>>>(d_deltas, n_delta, d_fit, n_coef, basis, d_peaks, n_peaks,
+                                                                 d_atlas, n_atlas, d_pix_sorted, n_pix, tolerance, min_frac,
+                                                                 d_out);
+  RB2_CHECK(cudaGetLastError());
+  return RB2_OK;
+}
 
 extern "C" int rb2_refit_winners(int n_problems, const rb2_ransac_desc* d_desc, const rb2_ransac_desc* h_desc,
                                  const rb2_ransac_result* d_winner, double minimum_fit_error, int mode,

@@ -610,6 +610,21 @@ class RansacSetup:
         self.gc_min, self.gc_max, self.ic_min = float(gc[0]), float(gc[-1]), float(ic[0])
         if not np.isfinite(self.hough_weight):
             raise NotImplementedError("hough_weight must be finite")
+        general = bool(self.basis or hist.size <= 65536 or self.ic_min <= 20.0 * max(abs(self.gc_min), abs(self.gc_max)))
+        self.bs_c = None
+        if not general:
+            # fine binnings (config 5: 10^6 bins) on an Angstrom scale: only the section of the spline along the
+            # first intercept row is ever evaluated - the interpolating cubic spline of
+            # hist[:, 0] (FITPACK's knots are the not-a-knot ones), without fitting the 2-D spline (0.15 s)
+            b = interpolate.make_interp_spline(gc, hist[:, 0], k=3)
+            brk = np.unique(b.t)
+            left = brk[:-1]
+            fact = (1.0, 1.0, 2.0, 6.0)
+            coef = np.stack([b(left, nu=k) / fact[k] for k in range(4)], axis=1)
+            self.h_lo, self.h_hi = float(hist[0, 0]), float(hist[-1, 0])
+            self.pp_breaks = brk.astype(np.float64)
+            self.pp_coef = np.ascontiguousarray(coef.reshape(-1))
+            return
         # the reference's own spline object gives the two clamped corner values and the
         # 1-D section along the first intercept row (evaluated as spline(t, ic_min))
         spl = interpolate.RectBivariateSpline(gc, ic, hist)
@@ -626,12 +641,9 @@ class RansacSetup:
         coef = np.linalg.solve(np.vander(u, 4, increasing=True), v.T).T / w[:, None] ** np.arange(4)[None, :]
         self.pp_breaks = brk.astype(np.float64)
         self.pp_coef = coef.reshape(-1)
-        # the spline itself for hypotheses outside the corner regime (general evaluation on the device); only
-        # where such hypotheses can exist: gradients within reach of the first intercept-bin centre (nm-scale
-        # problems) - on Angstrom scales (centre ~ 3500, gradients ~ 1) the tables would be dead weight
-        self.bs_c = None
-        if not (self.basis or self.ic_min <= 20.0 * max(abs(self.gc_min), abs(self.gc_max))):
-            return  # (a non-monomial basis always takes the per-pixel evaluation, see rb2_ransac_desc.basis)
+        # the spline itself, for hypotheses outside the corner regime (general evaluation on the device): nm-scale
+        # problems, a curvy degree-5 hypothesis now and then on an Angstrom scale too (242 of 490 000 scored ones on
+        # the GMOS arc), and every hypothesis of a non-monomial basis (rb2_ransac_desc.basis)
         ty = spl.get_knots()[1]
         self.bs_tx, self.bs_ty = np.ascontiguousarray(tx, dtype=np.float64), np.ascontiguousarray(ty, dtype=np.float64)
         self.bs_c = np.ascontiguousarray(spl.get_coeffs(), dtype=np.float64)  # [(len(tx)-4) * (len(ty)-4)], x first
@@ -942,6 +954,40 @@ def robust_polyfit(x, y, deg, mode=0):
     outs = [(np.array(r.coeffs[:deg + 1]) if r.accepted else np.full(deg + 1, np.nan), r.rms, r.huber_iters, r.pad)
             for r in res]
     return outs[0] if single else outs
+
+
+class AdjustPolyfit:
+    """Calibrator._adjust_polyfit (calibrator.py:754-820) on the device (rb2_adjust_polyfit): the objective of
+    match_peaks(refine=True).  Peaks, atlas lines and the sorted pixel list are uploaded once; __call__ evaluates
+    one trial shift (what scipy.optimize.minimize asks for), many() a whole array of them."""
+
+    def __init__(self, peaks, lines, pixel_list, fit, tolerance, min_frac, fit_type="poly"):
+        torch = _torch()
+        self.lib = N.load()
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()  # noqa: E731
+        self.peaks, self.lines = up(np.asarray(peaks).reshape(-1)), up(np.asarray(lines).reshape(-1))
+        self.pix, self.fit = up(np.sort(np.asarray(pixel_list, dtype=np.float64))), up(np.asarray(fit).reshape(-1))
+        TRANSFER["h2d"] += 8 * (self.peaks.numel() + self.lines.numel() + self.pix.numel() + self.fit.numel())
+        self.tolerance, self.min_frac, self.basis = float(tolerance), float(min_frac), int(N.BASIS_CODES[fit_type])
+        self.n_evals = 0
+
+    def many(self, deltas):
+        torch = _torch()
+        d = np.ascontiguousarray(np.atleast_2d(np.asarray(deltas, dtype=np.float64)))
+        dd = torch.from_numpy(d).cuda()
+        out = torch.empty(len(d), dtype=torch.float64, device="cuda")
+        rc = self.lib.rb2_adjust_polyfit(len(d), dd.data_ptr(), d.shape[1], self.fit.data_ptr(), self.fit.numel(), self.basis,
+                                         self.peaks.data_ptr(), self.peaks.numel(), self.lines.data_ptr(), self.lines.numel(),
+                                         self.pix.data_ptr(), self.pix.numel(), self.tolerance, self.min_frac, out.data_ptr(),
+                                         current_stream_ptr())
+        N.check(rc, "rb2_adjust_polyfit")
+        TRANSFER["h2d"] += d.nbytes
+        TRANSFER["d2h"] += 8 * len(d)
+        self.n_evals += len(d)
+        return out.cpu().numpy()
+
+    def __call__(self, delta):
+        return float(self.many(np.asarray(delta, dtype=np.float64).reshape(1, -1))[0])
 
 
 class MatchBatch:

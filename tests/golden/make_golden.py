@@ -190,6 +190,8 @@ def _trace_arrays(rec, c, s_total):
                 cur["rejected_reason"] = m
         elif kind == "match":
             err, mx, my = ev[1], ev[2], ev[3]
+            if cur is None:  # the initial cost of a pre-existing fit (calibrator.py:512-515), before any draw
+                continue
             cur["status"] = ST_SCORED if len(mx) else ST_EMPTY
             e = np.minimum(err, c.ransac_tolerance)
             cur["err_clipped"] = e
