@@ -129,3 +129,49 @@ def exchange_device(d_result, n, group=None):
     dist.all_gather_into_tensor(gathered, d_result, group=group)
     rc = N.load().rb2_merge_winners(int(n), world, gathered.data_ptr(), d_result.data_ptr(), engine.current_stream_ptr())
     N.check(rc, "rb2_merge_winners")
+
+
+# ---- many spectra: spectrum i -> rank i mod world, one final gather of fixed-size records ----
+
+RECORD_DOUBLES = 14  # ok, n_inliers, rms, cost, peak_utilisation, atlas_utilisation, coeffs[8]
+
+
+def result_records(results, deg_cap=7):
+    """Fixed-size (112-byte) records of per-spectrum results (batch.calibrate_batch output) for the final gather."""
+    out = np.zeros((len(results), RECORD_DOUBLES))
+    for i, r in enumerate(results):
+        if r.fit_coeff is None:
+            out[i, 3] = np.inf
+            continue
+        c = np.asarray(r.fit_coeff, dtype=np.float64)[: deg_cap + 1]
+        out[i, 0], out[i, 1], out[i, 2], out[i, 3] = 1.0, len(r.matched_peaks), r.rms, r.cost
+        out[i, 4], out[i, 5] = r.peak_utilisation, r.atlas_utilisation
+        out[i, 6:6 + len(c)] = c
+    return out
+
+
+def gather_records(local, n_total, group=None):
+    """All ranks' records in the order of the original batch.  Rank r holds the records of spectra r, r + world,
+    ... (`local`: [n_local, RECORD_DOUBLES]); ONE all_gather_into_tensor of equally padded blocks (NCCL device to
+    device on GPUs, gloo in the CPU tests), then the interleave.  Identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    local = np.ascontiguousarray(local, dtype=np.float64).reshape(-1, RECORD_DOUBLES)
+    rank, world = rank_world(group)
+    if world == 1:
+        assert len(local) == n_total
+        return local
+    per = -(-int(n_total) // world)  # ceil: every rank's block is padded to this many records
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    block = torch.zeros((per, RECORD_DOUBLES), dtype=torch.float64, device=dev)
+    block[: len(local)] = torch.from_numpy(local).to(dev)
+    gathered = torch.empty((world * per, RECORD_DOUBLES), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(gathered, block, group=group)
+    g = gathered.cpu().numpy().reshape(world, per, RECORD_DOUBLES)
+    out = np.empty((int(n_total), RECORD_DOUBLES))
+    for r in range(world):
+        idx = np.arange(r, int(n_total), world)
+        out[idx] = g[r, : len(idx)]
+    return out
+

@@ -67,7 +67,7 @@ def test_facade_fit_recovers_reference_solution(golden):
     assert np.isclose(rms, np.sqrt(np.mean(res ** 2)), rtol=1e-12)
     ref_cost = g["tr_cost"][np.flatnonzero(g["tr_accepted"])[-1]]
     assert c.best_cost <= ref_cost * (1 + 1e-9)
-    assert rms < 5.0
+    assert rms < 5.0 or (f.get("fit_type", "poly") != "poly" and rms <= tol)  # (clipped residuals: see above)
     assert 0 < pu <= 1 and 0 < au <= 1
     # completed tries = scored hypotheses + impossible draws (calibrator.py:557-566, App. A.4)
     assert c.ransac_counters["scored"] + c.ransac_counters["aborted"] >= f["max_tries"]

@@ -126,5 +126,8 @@ def test_facade_match_peaks(case):
     wl = np.polynomial.polynomial.polyval(out[1], out[0])
     ref = np.polynomial.polynomial.polyval(out[1], gm["fit_coeff_" + key])
     assert np.max(np.abs(wl - ref)) < 1e-5
-    with pytest.raises(NotImplementedError):
-        c.match_peaks(fit_coeff=g["fit_coeff"], refine=True)
+    # refine=True (the reference's experimental Nelder-Mead pre-step): with robust_refit its result never reaches
+    # the output (calibrator.py:1831 associates with the unrefined coefficients), so the 7-tuple is the same
+    out_r = c.match_peaks(fit_coeff=g["fit_coeff"], refine=True, tolerance=tol_of(key))
+    assert np.array_equal(out_r[1], out[1]) and np.array_equal(out_r[2], out[2]) and np.allclose(out_r[0], out[0], rtol=1e-12)
+    assert c.refine_evaluations > 0

@@ -100,3 +100,48 @@ def test_merge_rule():
     assert parallel.merge_winners([a, b, c, none]).hyp_id == 2
     assert list(parallel.merge_winners([a, b, c, none]).counters) == [10] * 8
     assert parallel.merge_winners([none]).hyp_id == -1
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import types
+
+    from rascal_b200 import parallel
+
+    n_total = 7  # ragged: rank 0 holds 4 spectra, rank 1 holds 3
+    mine = []
+    for i in range(rank, n_total, world):
+        if i == 4:
+            mine.append(types.SimpleNamespace(fit_coeff=None))
+        else:
+            mine.append(types.SimpleNamespace(fit_coeff=np.arange(5) + 10.0 * i, matched_peaks=[0] * (i + 6), rms=0.1 * i,
+                                              cost=1e-6 * (i + 1), peak_utilisation=0.5, atlas_utilisation=0.25))
+    rec = parallel.gather_records(parallel.result_records(mine), n_total, None)
+    q.put((rank, rec))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_of_result_records():
+    """The final gather of the many-spectra path: spectrum i lives on rank i mod world; afterwards
+    every rank holds all records in batch order."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(got[0], got[1]) and got[0].shape == (7, 14)
+    for i in range(7):
+        if i == 4:
+            assert got[0][i, 0] == 0 and np.isinf(got[0][i, 3])
+        else:
+            assert got[0][i, 0] == 1 and got[0][i, 1] == i + 6 and np.isclose(got[0][i, 2], 0.1 * i)
+            assert np.array_equal(got[0][i, 6:11], np.arange(5) + 10.0 * i)
+
