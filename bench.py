@@ -748,6 +748,22 @@ def main():
            "d2h_bytes_per_step": engine.TRANSFER["d2h"] // e2e_steps,
            "ms_per_step": 1e3 * t_e2e / e2e_steps, "rms": float(res[3]), "n_matched": len(res[1])}
 
+    # ---- the UNCHANGED signature: do_hough_transform() + fit(max_tries=500) as every example of the reference calls
+    # it (its own runtime for this call: 3-8 s) ----
+    api_ms, api_cal = [], None
+    for k in range(4):
+        api_cal = new_calibrator(200 + k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        api_cal.do_hough_transform()
+        api_res = api_cal.fit(max_tries=500, progress=False, **w["fit"])
+        torch.cuda.synchronize()
+        api_ms.append(1e3 * (time.perf_counter() - t0))
+    default_api = {"call": "do_hough_transform() + fit(max_tries=500, fit_deg=4) from host arrays",
+                   "ms_per_calibration": float(np.median(api_ms[1:])), "completed_tries": 500,
+                   "hypotheses_drawn": api_cal.ransac_counters["drawn"] + api_cal.ransac_counters["aborted"],
+                   "rms": float(api_res[3]), "n_matched": len(api_res[1])}
+
     # ---- many-spectra leg (BASELINE configs[3] shape, bounded sample): spectra calibrated/s through
     # rascal_b200.batch.calibrate_batch (K1..K5 per spectrum, host buffers in, results out) ----
     spectra = None
@@ -922,6 +938,7 @@ def main():
         "counters": counters,
         "wall_s_timed_region": t_wall,
     }
+    line["default_api"] = default_api
     if spectra is not None:
         line["spectra_per_sec"] = spectra
     if hough_roof is not None:

@@ -145,6 +145,7 @@ REFINE_MAX_WINDOW = 32
 
 STRUCTS = [HoughDesc, HoughStats, VoteDesc, RansacDesc, RansacResult, RefitResult, MatchDesc, MatchResult,
            PairsDesc, PrepareDesc, FindPeaksDesc, RefineDesc]
+HYP_ABORT, HYP_INTERCEPT, HYP_MONOTONIC, HYP_EMPTY, HYP_SCORED, HYP_UNSUPPORTED = range(6)  # rb2_hyp_status
 BASIS_CODES = {"poly": 0, "legendre": 1, "chebyshev": 2}
 COUNTER_NAMES = ("drawn", "aborted", "intercept", "monotonic", "empty", "scored", "eligible", "unsupported")
 

@@ -529,6 +529,31 @@ class Calibrator:
         cp, ca = vb.candidates(0)
         self.candidate_peak, self.candidate_arc = list(cp), list(ca)
 
+    def _completed_tries_cutoff(self, rb, begin, count, need, key, rank, world):
+        """Length of the prefix of hypothesis ids [begin, begin + count) that holds exactly `need` completed
+        tries (scored hypotheses and impossible draws): every rank re-evaluates its shard with the per-hypothesis
+        status kept on the device, the per-rank counts are exchanged (one tiny all-gather) and the rank that holds
+        the need-th completed try locates it by a prefix sum."""
+        from . import parallel
+
+        torch = engine._torch()
+        lo, hi = parallel.shard_range(count, rank, world)
+        rb.run(begin + lo, hi - lo, seed=key, status_only=True)
+        st = rb.d_status
+        done = ((st == engine.N.HYP_SCORED) | (st == engine.N.HYP_ABORT) | (st == engine.N.HYP_UNSUPPORTED)).to(torch.int32)
+        mine = int(done.sum().item())
+        counts = parallel.allgather_ints([mine], self.dist_group)[:, 0] if world > 1 else np.array([mine])
+        before = int(counts[:rank].sum())
+        cut = count
+        if before < need <= before + mine:
+            k = need - before  # the k-th completed try of this shard
+            pos = int(torch.searchsorted(torch.cumsum(done, 0), torch.tensor([k], device=done.device, dtype=torch.int64)).item())
+            cut = lo + pos + 1
+        if world > 1:
+            cut = int(parallel.allgather_ints([cut], self.dist_group)[:, 0].min())
+        rb.d_status = None
+        return cut
+
     def _vote_poly(self, candidate_tolerance):
         """linear=False (experimental in the reference): _get_candidate_points_poly (calibrator.py:263-315) +
         _get_most_common_candidates (:154-217).  The reference compares peak i with atlas line i (its
@@ -618,13 +643,27 @@ class Calibrator:
             winner = engine.N.RansacResult.from_buffer_copy(bytes(win[0]))
         else:
             # `max_tries` counts completed tries of the reference loop: scored hypotheses (and
-            # impossible draws); rejected draws are redrawn for free (:578-600)
+            # impossible draws); rejected draws are redrawn for free (:578-600).  Spans of hypothesis ids are
+            # evaluated until that many tries are complete; the last span is then cut at the id where the count
+            # is reached EXACTLY, so the outcome is a function of (seed, max_tries) only - not of the span sizes
+            # or of the number of GPUs.
             winner = parallel.merge_winners([])
             done, chunk = 0, max(1 << 14, 64 * int(max_tries))
-            while winner.counters[5] + winner.counters[1] < int(max_tries) and done < (1 << 40):
-                spans.append((done, chunk))
+            while done < (1 << 40):
                 evaluate(done, chunk)
-                winner = parallel.merge_winners([winner, rb.results()[0]])
+                span_win = rb.results()[0]
+                tries = lambda w: w.counters[5] + w.counters[1] + w.counters[7]  # noqa: E731  scored, aborted, unsupported
+                completed = tries(winner)
+                if completed + tries(span_win) >= int(max_tries):
+                    cut = self._completed_tries_cutoff(rb, done, chunk, int(max_tries) - completed, key, rank, world)
+                    if cut < chunk:
+                        evaluate(done, cut)
+                        span_win = rb.results()[0]
+                    spans.append((done, cut))
+                    winner = parallel.merge_winners([winner, span_win])
+                    break
+                spans.append((done, chunk))
+                winner = parallel.merge_winners([winner, span_win])
                 done += chunk
                 if winner.counters[0] == 0 and winner.counters[1] == 0:
                     break

@@ -804,7 +804,7 @@ class RansacBatch:
         self._desc_synced = True
 
     def run(self, hyp_begin, n_hyp, seed=0, replay=None, per_hypothesis=False, floors=None, replay_coeffs=None,
-            samples=False):
+            samples=False, status_only=False):
         """Evaluate hypothesis ids [hyp_begin, hyp_begin + n_hyp) of every problem; the winner
         records stay on the device (results() / fetch() bring them back).
 
@@ -813,7 +813,8 @@ class RansacBatch:
         instead of fitting (the reference's own polyfit output); per_hypothesis=True also returns
         status / cost / weight / coefficients / counts of every hypothesis (one problem);
         samples=True returns the draws themselves, "sample" [n_hyp, s, 2] = (peak index, candidate
-        index inside that peak's list), -1 where the draw was aborted (one problem).
+        index inside that peak's list), -1 where the draw was aborted (one problem); status_only=True
+        keeps the rb2_hyp_status byte of every hypothesis on the device (self.d_status, one problem).
         """
         torch = _torch()
         self._keep = []
@@ -852,6 +853,11 @@ class RansacBatch:
             d.d_out_status, d.d_out_cost = outs["status"].data_ptr(), outs["cost"].data_ptr()
             d.d_out_weight, d.d_out_coeffs = outs["weight"].data_ptr(), outs["coeffs"].data_ptr()
             d.d_out_counts = outs["counts"].data_ptr()
+        self.d_status = None
+        if status_only:
+            assert self.n == 1 and not per_hypothesis
+            self.d_status = torch.full((n_hyp,), 255, dtype=torch.uint8, device="cuda")
+            self.h_desc[0].d_out_status = self.d_status.data_ptr()
         if samples:
             assert self.n == 1
             outs = outs if outs is not None else {}

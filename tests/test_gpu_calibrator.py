@@ -70,7 +70,8 @@ def test_facade_fit_recovers_reference_solution(golden):
     assert rms < 5.0 or (f.get("fit_type", "poly") != "poly" and rms <= tol)  # (clipped residuals: see above)
     assert 0 < pu <= 1 and 0 < au <= 1
     # completed tries = scored hypotheses + impossible draws (calibrator.py:557-566, App. A.4)
-    assert c.ransac_counters["scored"] + c.ransac_counters["aborted"] >= f["max_tries"]
+    # - counted exactly: the last span of hypothesis ids is cut where the count is reached
+    assert c.ransac_counters["scored"] + c.ransac_counters["aborted"] + c.ransac_counters["unsupported"] == f["max_tries"]
     # seed => reproducible
     c2 = make_calibrator(g)
     coeff2 = c2.fit(progress=False, **f)[0]

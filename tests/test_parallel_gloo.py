@@ -119,6 +119,8 @@ def _gather_worker(rank, world, port, q):
             mine.append(types.SimpleNamespace(fit_coeff=np.arange(5) + 10.0 * i, matched_peaks=[0] * (i + 6), rms=0.1 * i,
                                               cost=1e-6 * (i + 1), peak_utilisation=0.5, atlas_utilisation=0.25))
     rec = parallel.gather_records(parallel.result_records(mine), n_total, None)
+    ints = parallel.allgather_ints([10 + rank, 7 * rank], None)
+    assert np.array_equal(ints, [[10, 0], [11, 7]])
     q.put((rank, rec))
     dist.barrier()
     dist.destroy_process_group()
