@@ -529,30 +529,47 @@ class Calibrator:
         cp, ca = vb.candidates(0)
         self.candidate_peak, self.candidate_arc = list(cp), list(ca)
 
-    def _completed_tries_cutoff(self, rb, begin, count, need, key, rank, world):
-        """Length of the prefix of hypothesis ids [begin, begin + count) that holds exactly `need` completed
-        tries (scored hypotheses and impossible draws): every rank re-evaluates its shard with the per-hypothesis
-        status kept on the device, the per-rank counts are exchanged (one tiny all-gather) and the rank that holds
-        the need-th completed try locates it by a prefix sum."""
+    def _span_tries(self, rb, setup, begin, count, need, best, key, rank, world):
+        """Evaluate hypothesis ids [begin, begin + count) (this rank's shard of them) and count the tries of the
+        reference loop they complete: -> (completed tries, length of the prefix that holds `need` of them - `count`
+        if the span holds fewer -, merged winner record of the whole span).
+
+        A try is completed by an impossible draw, by a scored hypothesis whose cost does not beat the best accepted
+        so far, or by one that is accepted (here: passes the inlier-count criteria; the refit-dependent
+        minimum_fit_error test is left to K4's fall-through).  The best-so-far at hypothesis i is the minimum of
+        the accepted costs before it in id order: a prefix minimum on the device, seeded with `best` and, on rank
+        r, with the minima of the ranks before it (one tiny all-gather)."""
         from . import parallel
 
         torch = engine._torch()
+        N = engine.N
         lo, hi = parallel.shard_range(count, rank, world)
-        rb.run(begin + lo, hi - lo, seed=key, status_only=True)
-        st = rb.d_status
-        done = ((st == engine.N.HYP_SCORED) | (st == engine.N.HYP_ABORT) | (st == engine.N.HYP_UNSUPPORTED)).to(torch.int32)
+        out = rb.run(begin + lo, hi - lo, seed=key, per_hypothesis=True, device_outputs=True)
+        rb.exchange(self.dist_group)
+        span_win = rb.results()[0]
+        st, cost, ni = out["status"], out["cost"], out["counts"][:, 1]
+        scored = st == N.HYP_SCORED
+        elig = scored & (ni >= setup.min_inliers) & (ni.to(torch.float64) >= setup.min_inliers_frac) & (cost <= setup.cost_ceiling)
+        inf = torch.full_like(cost, float("inf"))
+        ecost = torch.where(elig, cost, inf)
+        start = best
+        if world > 1:
+            mins = parallel.allgather_doubles([float(ecost.min().item()) if ecost.numel() else float("inf")], self.dist_group)[:, 0]
+            start = min([best] + [float(m) for m in mins[:rank]])
+        run_min = torch.cummin(torch.cat((torch.tensor([start], dtype=cost.dtype, device=cost.device), ecost)), 0).values[:-1]
+        beats = scored & (cost <= run_min)
+        done = ((st == N.HYP_ABORT) | (st == N.HYP_UNSUPPORTED) | (scored & (~beats | elig))).to(torch.int64)
         mine = int(done.sum().item())
         counts = parallel.allgather_ints([mine], self.dist_group)[:, 0] if world > 1 else np.array([mine])
-        before = int(counts[:rank].sum())
+        total, before = int(counts.sum()), int(counts[:rank].sum())
         cut = count
-        if before < need <= before + mine:
-            k = need - before  # the k-th completed try of this shard
+        if total >= need and before < need <= before + mine:
+            k = need - before  # the k-th completed try of this shard ends the budget
             pos = int(torch.searchsorted(torch.cumsum(done, 0), torch.tensor([k], device=done.device, dtype=torch.int64)).item())
             cut = lo + pos + 1
         if world > 1:
             cut = int(parallel.allgather_ints([cut], self.dist_group)[:, 0].min())
-        rb.d_status = None
-        return cut
+        return min(total, need), cut, span_win
 
     def _vote_poly(self, candidate_tolerance):
         """linear=False (experimental in the reference): _get_candidate_points_poly (calibrator.py:263-315) +
@@ -642,32 +659,30 @@ class Calibrator:
             win, fit, mx, my, rs = rb.fetch()
             winner = engine.N.RansacResult.from_buffer_copy(bytes(win[0]))
         else:
-            # `max_tries` counts completed tries of the reference loop: scored hypotheses (and
-            # impossible draws); rejected draws are redrawn for free (:578-600).  Spans of hypothesis ids are
-            # evaluated until that many tries are complete; the last span is then cut at the id where the count
-            # is reached EXACTLY, so the outcome is a function of (seed, max_tries) only - not of the span sizes
-            # or of the number of GPUs.
+            # `max_tries` counts COMPLETED tries of the reference loop: an impossible draw, or a
+            # scored hypothesis that either does not beat the best so far or is accepted; rejected draws and
+            # hypotheses that beat the best but fail the acceptance checks are redrawn for free (:578-700).  Spans
+            # of hypothesis ids are evaluated with their per-hypothesis outcomes kept on the device, where a prefix
+            # minimum over the id order tells which ones completed a try; the last span is cut at the id where the
+            # count reaches max_tries EXACTLY, so the outcome is a function of (seed, max_tries) only - not of the
+            # span sizes or of the number of GPUs.
             winner = parallel.merge_winners([])
-            done, chunk = 0, max(1 << 14, 64 * int(max_tries))
+            done, chunk, completed = 0, max(1 << 14, 64 * int(max_tries)), 0
             while done < (1 << 40):
-                evaluate(done, chunk)
-                span_win = rb.results()[0]
-                tries = lambda w: w.counters[5] + w.counters[1] + w.counters[7]  # noqa: E731  scored, aborted, unsupported
-                completed = tries(winner)
-                if completed + tries(span_win) >= int(max_tries):
-                    cut = self._completed_tries_cutoff(rb, done, chunk, int(max_tries) - completed, key, rank, world)
-                    if cut < chunk:
-                        evaluate(done, cut)
-                        span_win = rb.results()[0]
-                    spans.append((done, cut))
-                    winner = parallel.merge_winners([winner, span_win])
-                    break
-                spans.append((done, chunk))
+                best_so_far = min(setup.cost_ceiling, winner.cost if winner.hyp_id >= 0 else float("inf"))
+                n_done, cut, span_win = self._span_tries(rb, setup, done, chunk, int(max_tries) - completed, best_so_far,
+                                                         key, rank, world)
+                if cut < chunk:  # the budget ends inside this span: its winner is the one of the prefix
+                    evaluate(done, cut)
+                    span_win = rb.results()[0]
+                spans.append((done, cut))
                 winner = parallel.merge_winners([winner, span_win])
+                completed += n_done
                 done += chunk
-                if winner.counters[0] == 0 and winner.counters[1] == 0:
+                if completed >= int(max_tries) or (span_win.counters[0] == 0 and span_win.counters[1] == 0):
                     break
-                chunk = min(chunk * 4, 1 << 28)
+                chunk = min(chunk * 4, 1 << 26)
+            self.completed_tries = completed
             fit, mx, my, rs = rb.refit(one(winner))
         self.ransac_counters = engine.counters_dict(winner)
         if self.ransac_counters["unsupported"]:

@@ -804,7 +804,7 @@ class RansacBatch:
         self._desc_synced = True
 
     def run(self, hyp_begin, n_hyp, seed=0, replay=None, per_hypothesis=False, floors=None, replay_coeffs=None,
-            samples=False, status_only=False):
+            samples=False, status_only=False, device_outputs=False):
         """Evaluate hypothesis ids [hyp_begin, hyp_begin + n_hyp) of every problem; the winner
         records stay on the device (results() / fetch() bring them back).
 
@@ -868,7 +868,7 @@ class RansacBatch:
                                        self.d_result.data_ptr(), self.scratch.data_ptr(), self.blocks_per_problem,
                                        current_stream_ptr())
         N.check(rc, "rb2_ransac_batch")
-        if outs is not None:
+        if outs is not None and not device_outputs:  # device_outputs: the caller post-processes them on the device
             outs = {k: v.cpu().numpy() for k, v in outs.items()}
         return outs
 

@@ -66,6 +66,22 @@ def allgather_ints(values, group=False):
     return out.cpu().numpy().reshape(world, -1)
 
 
+def allgather_doubles(values, group=False):
+    """[world, len(values)] float64 array of every rank's numbers."""
+    rank, world = rank_world(group)
+    v = np.asarray(values, dtype=np.float64).reshape(1, -1)
+    if world == 1:
+        return v
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(v[0].copy()).to(dev)
+    out = torch.empty(world * t.numel(), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().reshape(world, -1)
+
+
 def better(cost_a, id_a, cost_b, id_b):
     """True if (cost_a, id_a) beats (cost_b, id_b): lower cost, later id on ties; id < 0 = none."""
     if id_a < 0:

@@ -70,8 +70,11 @@ def test_facade_fit_recovers_reference_solution(golden):
     assert rms < 5.0 or (f.get("fit_type", "poly") != "poly" and rms <= tol)  # (clipped residuals: see above)
     assert 0 < pu <= 1 and 0 < au <= 1
     # completed tries = scored hypotheses + impossible draws (calibrator.py:557-566, App. A.4)
-    # - counted exactly: the last span of hypothesis ids is cut where the count is reached
-    assert c.ransac_counters["scored"] + c.ransac_counters["aborted"] + c.ransac_counters["unsupported"] == f["max_tries"]
+    # - counted as the reference counts them: the last span of hypothesis ids is cut where the count is reached.
+    # Scored hypotheses that beat the best so far but fail the acceptance checks are redrawn for free there, so
+    # the scored + aborted draws are at least the tries (equal when nothing is ever rejected after scoring)
+    assert c.ransac_counters["scored"] + c.ransac_counters["aborted"] + c.ransac_counters["unsupported"] >= f["max_tries"]
+    assert c.completed_tries == f["max_tries"]
     # seed => reproducible
     c2 = make_calibrator(g)
     coeff2 = c2.fit(progress=False, **f)[0]
@@ -199,7 +202,7 @@ def test_nm_scale_fit_scores_every_hypothesis():
     g = load_golden("synth_nm_deg4")
     c = make_calibrator(g)
     coeff, mp, ma, rms, residual, pu, au = c.fit(max_tries=500, progress=False)
-    assert c.ransac_counters["unsupported"] == 0 and c.ransac_counters["scored"] >= 500
+    assert c.ransac_counters["unsupported"] == 0 and c.completed_tries == 500
     coeff, x_fit, y_fit, rms, residual, pu, au = c.match_peaks(coeff, refine=False, robust_refit=True)
     fit_diff = c.polyval(x_fit, coeff) - y_fit
     assert pu > 0.7 and au > 0.0 and np.sqrt(np.sum(fit_diff ** 2 / len(x_fit))) < 5.0
