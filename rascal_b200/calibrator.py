@@ -544,7 +544,7 @@ class Calibrator:
         torch = engine._torch()
         N = engine.N
         lo, hi = parallel.shard_range(count, rank, world)
-        out = rb.run(begin + lo, hi - lo, seed=key, per_hypothesis=True, device_outputs=True)
+        out = rb.run(begin + lo, hi - lo, seed=key, per_hypothesis=("status", "cost", "counts"), device_outputs=True)
         rb.exchange(self.dist_group)
         span_win = rb.results()[0]
         st, cost, ni = out["status"], out["cost"], out["counts"][:, 1]

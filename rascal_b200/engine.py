@@ -844,15 +844,19 @@ class RansacBatch:
         if per_hypothesis:
             assert self.n == 1
             nc = self.setups[0].deg + 1
-            outs = dict(status=torch.full((n_hyp,), 255, dtype=torch.uint8, device="cuda"),
-                        cost=torch.full((n_hyp,), float("nan"), dtype=torch.float64, device="cuda"),
-                        weight=torch.full((n_hyp,), float("nan"), dtype=torch.float64, device="cuda"),
-                        coeffs=torch.full((n_hyp, nc), float("nan"), dtype=torch.float64, device="cuda"),
-                        counts=torch.zeros((n_hyp, 2), dtype=torch.int32, device="cuda"))
+            # per_hypothesis may name the fields wanted (the rest is not allocated nor written)
+            want = ("status", "cost", "weight", "coeffs", "counts") if per_hypothesis is True else tuple(per_hypothesis)
+            make = dict(status=lambda: torch.full((n_hyp,), 255, dtype=torch.uint8, device="cuda"),
+                        cost=lambda: torch.full((n_hyp,), float("nan"), dtype=torch.float64, device="cuda"),
+                        weight=lambda: torch.full((n_hyp,), float("nan"), dtype=torch.float64, device="cuda"),
+                        coeffs=lambda: torch.full((n_hyp, nc), float("nan"), dtype=torch.float64, device="cuda"),
+                        counts=lambda: torch.zeros((n_hyp, 2), dtype=torch.int32, device="cuda"))
+            outs = {k: make[k]() for k in want}
             d = self.h_desc[0]
-            d.d_out_status, d.d_out_cost = outs["status"].data_ptr(), outs["cost"].data_ptr()
-            d.d_out_weight, d.d_out_coeffs = outs["weight"].data_ptr(), outs["coeffs"].data_ptr()
-            d.d_out_counts = outs["counts"].data_ptr()
+            ptr = lambda k: outs[k].data_ptr() if k in outs else None  # noqa: E731
+            d.d_out_status, d.d_out_cost = ptr("status"), ptr("cost")
+            d.d_out_weight, d.d_out_coeffs = ptr("weight"), ptr("coeffs")
+            d.d_out_counts = ptr("counts")
         self.d_status = None
         if status_only:
             assert self.n == 1 and not per_hypothesis
