@@ -1934,7 +1934,16 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   }
   pipe_init_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(ps, d_result, n_problems);
 
-  const long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
+  // chunk = hypothesis ids per problem and launch.  Large calls use the full queue capacity (fewer, longer
+  // kernels); a call that would fit in a few chunks (a rank's share of a sharded fit, a batch of spectra with
+  // 1e4 hypotheses each) is cut into ~2 chunks per lane, but not below 2^21 hypotheses in total, so that the
+  // stages of consecutive chunks still overlap across the lanes
+  long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
+  {
+    const long long want = (max_hyp + 2 * pipe_lanes() - 1) / (2 * pipe_lanes());
+    const long long floor_pp = max(1ll, (long long)((1u << 21) / (unsigned)n_problems));
+    per_problem = min(per_problem, max(want, floor_pp));
+  }
   const long long n_chunks = (max_hyp + per_problem - 1) / per_problem;
   LaneStreams& ls = lane_streams();
   const int n_lanes = (ls.ok && n_chunks > 1) ? (int)min((long long)ps.n, n_chunks) : 1;

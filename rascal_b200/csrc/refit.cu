@@ -88,9 +88,14 @@ struct TrfWs {        // shared-memory work space of one problem (m points, n pa
 };
 
 // models.py:10-54: y - (a[n-1] + sum_i a[n-1-i] * x**i), each power formed separately
-__device__ __forceinline__ double trf_residual(const double* a, int n, double x, double y) {
+// (NT > 0: the number of coefficients is a compile-time constant - the loops unroll and the small vectors of the
+//  solver live in registers instead of local memory; NT = 0: run-time n, degrees 6 and 7)
+template <int NT>
+__device__ __forceinline__ double trf_residual(const double* a, int n_, double x, double y) {
+  const int n = NT > 0 ? NT : n_;
   double t = a[n - 1];
   double pw = x;
+#pragma unroll
   for (int i = 1; i < n; ++i) {
     t = add(t, mul(a[n - 1 - i], pw));
     pw = mul(pw, x);
@@ -105,17 +110,20 @@ __device__ __forceinline__ void huber_rho(double f, double& r0, double& r1, doub
 }
 
 // f_true (filled) -> J (2-point), robust scaling of J and f, returns cost; g = J^T f
-__device__ double trf_linearise(const double* a, int n, int m, const double* xn, const double* yn, TrfWs& w, double* g) {
+template <int NT>
+__device__ double trf_linearise(const double* a, int n_, int m, const double* xn, const double* yn, TrfWs& w, double* g) {
+  const int n = NT > 0 ? NT : n_;
   const int lane = lane_id();
+#pragma unroll
   for (int j = 0; j < n; ++j) {  // _numdiff._compute_absolute_step / _dense_difference
     const double sign = (a[j] >= 0.0) ? 1.0 : -1.0;
     double h = 1e-5 * sign * fabs(a[j]);
     if (sub(add(a[j], h), a[j]) == 0.0) h = sqrt(TRF_EPS) * sign * fmax(1.0, fabs(a[j]));
     const double dx = sub(add(a[j], h), a[j]);
     double a1[NCF];
-    for (int k = 0; k < n; ++k) a1[k] = a[k];
-    a1[j] = add(a[j], h);
-    for (int i = lane; i < m; i += 32) w.J[j * m + i] = sub(trf_residual(a1, n, xn[i], yn[i]), w.f_true[i]) / dx;
+#pragma unroll
+    for (int k = 0; k < n; ++k) a1[k] = (k == j) ? add(a[j], h) : a[k];
+    for (int i = lane; i < m; i += 32) w.J[j * m + i] = sub(trf_residual<NT>(a1, n, xn[i], yn[i]), w.f_true[i]) / dx;
   }
   double c = 0.0;
   for (int i = lane; i < m; i += 32) {  // common.scale_for_robust_loss_function
@@ -130,6 +138,7 @@ __device__ double trf_linearise(const double* a, int n, int m, const double* xn,
     c += r0;
   }
   __syncwarp();
+#pragma unroll
   for (int j = 0; j < n; ++j) {
     double gj = 0.0;
     for (int i = lane; i < m; i += 32) {
@@ -154,15 +163,19 @@ __device__ int g_k4_rot = 0, g_k4_sweeps = 0;
 // `warm`: V holds the right singular vectors of the previous Jacobian of the same problem; the
 // iteration then starts from U = J V (columns already nearly orthogonal: the Jacobian changes little
 // between trust-region steps), which saves most sweeps.  U S V^T is the same decomposition either way.
-__device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF], bool warm) {
+template <int NT>
+__device__ void trf_svd(int n_, int m, TrfWs& w, double* s, double (*V)[NCF], bool warm) {
+  const int n = NT > 0 ? NT : n_;
   const int lane = lane_id();
   if (!warm) {
     for (int i = lane; i < m * n; i += 32) w.U[i] = w.J[i];
     for (int i = lane; i < n * n; i += 32) V[i / n][i % n] = (i / n == i % n) ? 1.0 : 0.0;
   } else {
     for (int i = lane; i < m; i += 32) {
+#pragma unroll
       for (int j = 0; j < n; ++j) {
         double acc = 0.0;
+#pragma unroll
         for (int k = 0; k < n; ++k) acc = fma(w.J[k * m + i], V[k][j], acc);
         w.U[j * m + i] = acc;
       }
@@ -171,7 +184,9 @@ __device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF], boo
   __syncwarp();
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
+#pragma unroll
     for (int p = 0; p < n - 1; ++p) {
+#pragma unroll
       for (int q = p + 1; q < n; ++q) {
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int i = lane; i < m; i += 32) {
@@ -212,22 +227,29 @@ __device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF], boo
 #endif
     if (!rotated) break;
   }
+#pragma unroll
   for (int j = 0; j < n; ++j) {
     double ss = 0.0;
     for (int i = lane; i < m; i += 32) ss = fma(w.U[j * m + i], w.U[j * m + i], ss);
     s[j] = sqrt(warp_sum(ss));
   }
   // selection sort, descending (stable enough: n <= 8), permuting U columns and V columns
+#pragma unroll
   for (int a = 0; a < n - 1; ++a) {
     int b = a;
-    for (int k = a + 1; k < n; ++k) if (s[k] > s[b]) b = k;
+    double sb = s[a];
+#pragma unroll
+    for (int k = 0; k < NCF; ++k) if (k > a && k < n && s[k] > sb) { b = k; sb = s[k]; }
     if (b != a) {
-      const double ts = s[a]; s[a] = s[b]; s[b] = ts;
+#pragma unroll
+      for (int k = 0; k < NCF; ++k) if (k == b) s[k] = s[a];
+      s[a] = sb;
       for (int i = lane; i < m; i += 32) { const double tu = w.U[a * m + i]; w.U[a * m + i] = w.U[b * m + i]; w.U[b * m + i] = tu; }
       if (lane < n) { const double tv = V[lane][a]; V[lane][a] = V[lane][b]; V[lane][b] = tv; }
     }
   }
   __syncwarp();
+#pragma unroll
   for (int j = 0; j < n; ++j) {
     const double inv = (s[j] > 0.0) ? 1.0 / s[j] : 0.0;
     for (int i = lane; i < m; i += 32) w.U[j * m + i] *= inv;
@@ -235,16 +257,22 @@ __device__ void trf_svd(int n, int m, TrfWs& w, double* s, double (*V)[NCF], boo
   __syncwarp();
 }
 
-__device__ __forceinline__ double vnorm(const double* v, int n) {
+template <int NT = 0>
+__device__ __forceinline__ double vnorm(const double* v, int n_) {
+  const int n = NT > 0 ? NT : n_;
   double s = 0.0;
+#pragma unroll
   for (int i = 0; i < n; ++i) s = fma(v[i], v[i], s);
   return sqrt(s);
 }
 
 // common.solve_lsq_trust_region (scalar: every lane computes the same values)
-__device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, const double (*V)[NCF], double Delta,
+template <int NT>
+__device__ void trf_solve_tr(int n_, int m, const double* uf, const double* s, const double (*V)[NCF], double Delta,
                              double& alpha, double* p) {
+  const int n = NT > 0 ? NT : n_;
   double suf[NCF];
+#pragma unroll
   for (int i = 0; i < n; ++i) suf[i] = s[i] * uf[i];
   auto phi_and_derivative = [&](double al, double& phi, double& phi_prime) {
     double pn = 0.0, sm = 0.0;
@@ -264,15 +292,18 @@ __device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, co
   const bool full_rank = (m >= n) && (s[n - 1] > TRF_EPS * m * s[0]);
   if (full_rank) {
     double gn[NCF];  // Gauss-Newton step in the singular basis
+#pragma unroll
     for (int i = 0; i < n; ++i) gn[i] = uf[i] / s[i];
+#pragma unroll
     for (int k = 0; k < n; ++k) {
       double acc = 0.0;
+#pragma unroll
       for (int i = 0; i < n; ++i) acc = fma(V[k][i], gn[i], acc);
       p[k] = -acc;
     }
-    if (vnorm(p, n) <= Delta) { alpha = 0.0; return; }
+    if (vnorm<NT>(p, n) <= Delta) { alpha = 0.0; return; }
   }
-  double alpha_upper = vnorm(suf, n) / Delta, alpha_lower = 0.0;
+  double alpha_upper = vnorm<NT>(suf, n) / Delta, alpha_lower = 0.0;
   if (full_rank) {
     double phi, phip;
     phi_and_derivative(0.0, phi, phip);
@@ -290,28 +321,34 @@ __device__ void trf_solve_tr(int n, int m, const double* uf, const double* s, co
     if (fabs(phi) < 0.01 * Delta) break;
   }
   double lm[NCF];  // Levenberg-Marquardt step in the singular basis
+#pragma unroll
   for (int i = 0; i < n; ++i) lm[i] = suf[i] / (s[i] * s[i] + alpha);
+#pragma unroll
   for (int k = 0; k < n; ++k) {
     double acc = 0.0;
+#pragma unroll
     for (int i = 0; i < n; ++i) acc = fma(V[k][i], lm[i], acc);
     p[k] = -acc;
   }
-  const double sc = Delta / vnorm(p, n);
+  const double sc = Delta / vnorm<NT>(p, n);
+#pragma unroll
   for (int k = 0; k < n; ++k) p[k] *= sc;
 }
 
 // trf.trf_no_bounds; a[] = solution (high order first, as models.polynomial expects)
-__device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn, TrfWs& w, double* a, int& nfev_out,
+template <int NT>
+__device__ void trf_huber_warp(int n_, int m, const double* xn, const double* yn, TrfWs& w, double* a, int& nfev_out,
                                int& status_out) {
+  const int n = NT > 0 ? NT : n_;
   const int lane = lane_id();
   const double ftol = 1e-8, xtol = 1e-8, gtol = 1e-8;
-  for (int k = 0; k < n; ++k) a[k] = 1.0;
-  for (int i = lane; i < m; i += 32) w.f_true[i] = trf_residual(a, n, xn[i], yn[i]);
+  _Pragma("unroll") for (int k = 0; k < n; ++k) a[k] = 1.0;
+  for (int i = lane; i < m; i += 32) w.f_true[i] = trf_residual<NT>(a, n, xn[i], yn[i]);
   __syncwarp();
   int nfev = 1;
   double g[NCF];
-  double cost = trf_linearise(a, n, m, xn, yn, w, g);
-  double Delta = vnorm(a, n);
+  double cost = trf_linearise<NT>(a, n, m, xn, yn, w, g);
+  double Delta = vnorm<NT>(a, n);
   if (Delta == 0.0) Delta = 1.0;
   const int max_nfev = 100 * n;
   double alpha = 0.0;
@@ -330,12 +367,12 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
 #endif
   for (;;) {
     double g_norm = 0.0;
-    for (int k = 0; k < n; ++k) g_norm = fmax(g_norm, fabs(g[k]));
+    _Pragma("unroll") for (int k = 0; k < n; ++k) g_norm = fmax(g_norm, fabs(g[k]));
     if (g_norm < gtol) status = 1;
     if (status >= 0 || nfev == max_nfev) break;
     K4_TIC();
-    trf_svd(n, m, w, s, V, svd_count++ > 0);
-    for (int j = 0; j < n; ++j) {
+    trf_svd<NT>(n, m, w, s, V, svd_count++ > 0);
+    _Pragma("unroll") for (int j = 0; j < n; ++j) {
       double acc = 0.0;
       for (int i = lane; i < m; i += 32) acc = fma(w.U[j * m + i], w.f[i], acc);
       uf[j] = warp_sum(acc);
@@ -347,22 +384,22 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
     K4_TIC();
     double actual_reduction = -1.0, cost_new = cost;
     while (actual_reduction <= 0.0 && nfev < max_nfev) {
-      trf_solve_tr(n, m, uf, s, V, Delta, alpha, step);
+      trf_solve_tr<NT>(n, m, uf, s, V, Delta, alpha, step);
       double q = 0.0;  // evaluate_quadratic
       for (int i = lane; i < m; i += 32) {
         double js = 0.0;
-        for (int k = 0; k < n; ++k) js = fma(w.J[k * m + i], step[k], js);
+        _Pragma("unroll") for (int k = 0; k < n; ++k) js = fma(w.J[k * m + i], step[k], js);
         q = fma(js, js, q);
       }
       q = warp_sum(q);
       double l = 0.0;
-      for (int k = 0; k < n; ++k) l = fma(step[k], g[k], l);
+      _Pragma("unroll") for (int k = 0; k < n; ++k) l = fma(step[k], g[k], l);
       const double predicted_reduction = -(0.5 * q + l);
-      for (int k = 0; k < n; ++k) a_new[k] = a[k] + step[k];
+      _Pragma("unroll") for (int k = 0; k < n; ++k) a_new[k] = a[k] + step[k];
       double c = 0.0;
       int bad = 0;
       for (int i = lane; i < m; i += 32) {
-        const double fn = trf_residual(a_new, n, xn[i], yn[i]);
+        const double fn = trf_residual<NT>(a_new, n, xn[i], yn[i]);
         w.f_new[i] = fn;
         bad |= !isfinite(fn);
         double r0, r1, r2;
@@ -370,7 +407,7 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
         c += r0;
       }
       ++nfev;
-      const double step_norm = vnorm(step, n);
+      const double step_norm = vnorm<NT>(step, n);
       if (__any_sync(0xffffffffu, bad)) { Delta = 0.25 * step_norm; continue; }
       cost_new = 0.5 * warp_sum(c);
       actual_reduction = cost - cost_new;
@@ -382,7 +419,7 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
       if (ratio < 0.25) Delta_new = 0.25 * step_norm;
       else if (ratio > 0.75 && step_norm > 0.95 * Delta) Delta_new = Delta * 2.0;
       const bool ftol_ok = (actual_reduction < ftol * cost) && (ratio > 0.25);
-      const bool xtol_ok = step_norm < xtol * (xtol + vnorm(a, n));
+      const bool xtol_ok = step_norm < xtol * (xtol + vnorm<NT>(a, n));
       if (ftol_ok && xtol_ok) status = 4; else if (ftol_ok) status = 2; else if (xtol_ok) status = 3;
       if (status >= 0) break;
       alpha *= Delta / Delta_new;
@@ -390,13 +427,13 @@ __device__ void trf_huber_warp(int n, int m, const double* xn, const double* yn,
     }
     K4_TOC(t_inner);
     if (actual_reduction > 0.0) {
-      for (int k = 0; k < n; ++k) a[k] = a_new[k];
+      _Pragma("unroll") for (int k = 0; k < n; ++k) a[k] = a_new[k];
       __syncwarp();
       for (int i = lane; i < m; i += 32) w.f_true[i] = w.f_new[i];
       __syncwarp();
       cost = cost_new;
       K4_TIC();
-      trf_linearise(a, n, m, xn, yn, w, g);
+      trf_linearise<NT>(a, n, m, xn, yn, w, g);
       K4_TOC(t_lin);
     }
   }
@@ -435,7 +472,14 @@ __device__ void robust_polyfit_warp(int m, int n, const double* ix, const double
     ws.f = ws.f_true + m; ws.f_new = ws.f + m; ws.js = sw;
     double ah[NCF];
     int nfev = 0, status = 0;
-    trf_huber_warp(n, m, xn, yn, ws, ah, nfev, status);
+    switch (n) {  // compile-time coefficient counts for the degrees in use (1..5)
+      case 2: trf_huber_warp<2>(n, m, xn, yn, ws, ah, nfev, status); break;
+      case 3: trf_huber_warp<3>(n, m, xn, yn, ws, ah, nfev, status); break;
+      case 4: trf_huber_warp<4>(n, m, xn, yn, ws, ah, nfev, status); break;
+      case 5: trf_huber_warp<5>(n, m, xn, yn, ws, ah, nfev, status); break;
+      case 6: trf_huber_warp<6>(n, m, xn, yn, ws, ah, nfev, status); break;
+      default: trf_huber_warp<0>(n, m, xn, yn, ws, ah, nfev, status); break;
+    }
     for (int j = 0; j < n; ++j) a[j] = ah[n - 1 - j];  // low order first
     iters = nfev;
     r.pad = status;
