@@ -548,17 +548,22 @@ class Calibrator:
         rb.exchange(self.dist_group)
         span_win = rb.results()[0]
         st, cost, ni = out["status"], out["cost"], out["counts"][:, 1]
-        scored = st == N.HYP_SCORED
-        elig = scored & (ni >= setup.min_inliers) & (ni.to(torch.float64) >= setup.min_inliers_frac) & (cost <= setup.cost_ceiling)
-        inf = torch.full_like(cost, float("inf"))
-        ecost = torch.where(elig, cost, inf)
+        # everything below works on the scored hypotheses only (~1 % of the draws): ids ascending, their cost,
+        # whether they pass the inlier-count criteria
+        sc_idx = torch.nonzero(st == N.HYP_SCORED).squeeze(1)
+        sc_cost, sc_ni = cost[sc_idx], ni[sc_idx]
+        sc_elig = (sc_ni >= setup.min_inliers) & (sc_ni.to(torch.float64) >= setup.min_inliers_frac) & (sc_cost <= setup.cost_ceiling)
+        e_cost = sc_cost[sc_elig]
         start = best
         if world > 1:
-            mins = parallel.allgather_doubles([float(ecost.min().item()) if ecost.numel() else float("inf")], self.dist_group)[:, 0]
+            mins = parallel.allgather_doubles([float(e_cost.min().item()) if e_cost.numel() else float("inf")], self.dist_group)[:, 0]
             start = min([best] + [float(m) for m in mins[:rank]])
-        run_min = torch.cummin(torch.cat((torch.tensor([start], dtype=cost.dtype, device=cost.device), ecost)), 0).values[:-1]
-        beats = scored & (cost <= run_min)
-        done = ((st == N.HYP_ABORT) | (st == N.HYP_UNSUPPORTED) | (scored & (~beats | elig))).to(torch.int64)
+        # cm[k] = best accepted cost after the first k eligible hypotheses of this shard (a scan over ~1e5 values)
+        cm = torch.cummin(torch.cat((torch.tensor([start], dtype=cost.dtype, device=cost.device), e_cost)), 0).values
+        n_elig_before = torch.cumsum(sc_elig.to(torch.int64), 0) - sc_elig.to(torch.int64)
+        beats = sc_cost <= cm[n_elig_before]
+        done = ((st == N.HYP_ABORT) | (st == N.HYP_UNSUPPORTED)).to(torch.int64)
+        done[sc_idx] = (~beats | sc_elig).to(torch.int64)
         mine = int(done.sum().item())
         counts = parallel.allgather_ints([mine], self.dist_group)[:, 0] if world > 1 else np.array([mine])
         total, before = int(counts.sum()), int(counts[:rank].sum())
