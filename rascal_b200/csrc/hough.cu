@@ -616,6 +616,165 @@ hough_rank_scatter_kernel(const rb2_hough_desc* __restrict__ descs, rb2_hough_st
 }
 }  // namespace rb2
 
+namespace rb2 {
+// Ranking of ONE fine-binned spectrum (config 5: 10^6 bins) - too many bins for the counting kernel above, and the
+// single-CTA radix sort walks them tile after tile (26 ms).  The same stable LSD radix sort spread over the GPU:
+// per 8-bit pass (a) every CTA histograms the digits of its tile of 1024 inputs, (b) per digit a CTA scans the tile
+// counts, a last warp scans the digit totals, (c) every CTA ranks its tile's inputs inside their digit (in input
+// order: warp match + prefix over the warps, as in hough_rank_kernel) and scatters them.
+constexpr int RANKM_T = 1024;
+__global__ void __launch_bounds__(RANKM_T)
+rank_multi_hist_kernel(const unsigned* __restrict__ hist, const int* __restrict__ src, int B, int sh,
+                       unsigned* __restrict__ tile_hist /* [256][tiles] */, int tiles) {
+  __shared__ unsigned cnt[256];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 256) cnt[tid] = 0u;
+  __syncthreads();
+  const int e = blockIdx.x * RANKM_T + tid;
+  const bool valid = e < B;
+  unsigned dg = 0;
+  if (valid) dg = 255u - ((hist[src ? src[e] : (B - 1 - e)] >> sh) & 255u);
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, dg);
+    if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&cnt[dg], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  if (tid < 256) tile_hist[(size_t)tid * tiles + blockIdx.x] = cnt[tid];
+}
+// one CTA per digit: exclusive scan of that digit's counts over the tiles (in place), total -> digit_total
+__global__ void __launch_bounds__(RANKM_T)
+rank_multi_scan_kernel(unsigned* __restrict__ tile_hist, int tiles, unsigned* __restrict__ digit_total) {
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned carry;
+  unsigned* row = tile_hist + (size_t)blockIdx.x * tiles;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0u;
+  __syncthreads();
+  for (int t0 = 0; t0 < tiles; t0 += RANKM_T) {
+    const int t = t0 + tid;
+    const unsigned v = (t < tiles) ? row[t] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = wsum[lane], iw = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, iw, o); if (lane >= o) iw += x; }
+      wsum[lane] = iw - w;
+    }
+    __syncthreads();
+    const unsigned excl = carry + wsum[warp] + incl - v;
+    if (t < tiles) row[t] = excl;
+    __syncthreads();
+    if (tid == RANKM_T - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) digit_total[blockIdx.x] = carry;
+}
+__global__ void rank_multi_base_kernel(unsigned* __restrict__ digit_total) {  // <<<1, 32>>>: exclusive scan of 256 totals
+  const int lane = threadIdx.x;
+  unsigned v[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = digit_total[lane * 8 + j]; sum += v[j]; }
+  unsigned incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+  unsigned run = incl - sum;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { digit_total[lane * 8 + j] = run; run += v[j]; }
+}
+__global__ void __launch_bounds__(RANKM_T)
+rank_multi_place_kernel(const unsigned* __restrict__ hist, const int* __restrict__ src, int* __restrict__ dst, int B, int sh,
+                        const unsigned* __restrict__ tile_off /* [256][tiles], scanned */, int tiles,
+                        const unsigned* __restrict__ digit_base) {
+  __shared__ __align__(16) unsigned short wcnt[32][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  reinterpret_cast<uint4*>(&wcnt[0][0])[tid] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const int e = blockIdx.x * RANKM_T + tid;
+  const bool valid = e < B;
+  int idx = 0;
+  unsigned dg = 0;
+  if (valid) {
+    idx = src ? src[e] : (B - 1 - e);
+    dg = 255u - ((hist[idx] >> sh) & 255u);
+  }
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  unsigned rank_in_warp = 0;
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, dg);
+    rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (rank_in_warp == 0) wcnt[warp][dg] = (unsigned short)__popc(peers);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {  // exclusive prefix over the 32 warps, per digit; warp w owns digits 8w..8w+7
+    const int dgt = warp * 8 + j;
+    const unsigned v = wcnt[lane][dgt];
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+    wcnt[lane][dgt] = (unsigned short)(incl - v);
+  }
+  __syncthreads();
+  if (valid) dst[digit_base[dg] + tile_off[(size_t)dg * tiles + blockIdx.x] + wcnt[warp][dg] + rank_in_warp] = idx;
+}
+__global__ void rank_multi_finish_kernel(const int* __restrict__ sorted, int* __restrict__ rank, int* __restrict__ rankpos, int B) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x) {
+    const int e = sorted[r];
+    if (rank != sorted) rank[r] = e;
+    rankpos[e] = r;
+  }
+}
+__global__ void __launch_bounds__(256)
+rank_multi_max_kernel(const unsigned* __restrict__ hist, int B, rb2_hough_stats* __restrict__ stats) {
+  unsigned mx = 0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B; e += gridDim.x * blockDim.x) mx = max(mx, hist[e]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&stats->max_count, mx);
+}
+}  // namespace rb2
+
+// multi-CTA radix ranking of one spectrum; h.d_sort_tmp holds B ints, `scratch` (256 * tiles + 256 unsigned) comes
+// from the caller.  Needs the maximum count on the host to know the number of passes: one small D2H inside.
+static cudaError_t launch_rank_multi(const rb2_hough_desc& h, rb2_hough_stats* d_stats, unsigned* scratch, cudaStream_t stream) {
+  using namespace rb2;
+  const int B = h.xbins * h.ybins;
+  const int tiles = (B + RANKM_T - 1) / RANKM_T;
+  rank_multi_max_kernel<<<256, 256, 0, stream>>>(h.d_hist, B, d_stats);
+  unsigned mx = 0;
+  cudaError_t e = cudaMemcpyAsync(&mx, &d_stats->max_count, sizeof(unsigned), cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return e;
+  int passes = 0;
+  while (passes < 4 && (mx >> (8 * passes)) != 0) ++passes;
+  unsigned* tile_hist = scratch;
+  unsigned* digit_total = scratch + (size_t)256 * tiles;
+  const int* src = nullptr;
+  int* bufs[2] = {h.d_rank, h.d_sort_tmp};
+  for (int ps = 0; ps < passes; ++ps) {
+    int* dst = bufs[(passes - 1 - ps) & 1];  // the last pass lands in d_rank
+    rank_multi_hist_kernel<<<tiles, RANKM_T, 0, stream>>>(h.d_hist, src, B, 8 * ps, tile_hist, tiles);
+    rank_multi_scan_kernel<<<256, RANKM_T, 0, stream>>>(tile_hist, tiles, digit_total);
+    rank_multi_base_kernel<<<1, 32, 0, stream>>>(digit_total);
+    rank_multi_place_kernel<<<tiles, RANKM_T, 0, stream>>>(h.d_hist, src, dst, B, 8 * ps, tile_hist, tiles, digit_total);
+    src = dst;
+  }
+  if (passes == 0) {  // an empty histogram: descending flat index
+    rank_multi_hist_kernel<<<tiles, RANKM_T, 0, stream>>>(h.d_hist, nullptr, B, 0, tile_hist, tiles);
+    rank_multi_scan_kernel<<<256, RANKM_T, 0, stream>>>(tile_hist, tiles, digit_total);
+    rank_multi_base_kernel<<<1, 32, 0, stream>>>(digit_total);
+    rank_multi_place_kernel<<<tiles, RANKM_T, 0, stream>>>(h.d_hist, nullptr, h.d_rank, B, 0, tile_hist, tiles, digit_total);
+  }
+  rank_multi_finish_kernel<<<256, 256, 0, stream>>>(h.d_rank, h.d_rank, h.d_rankpos, B);
+  return cudaGetLastError();
+}
+
 static cudaError_t launch_rank(int n_problems, const rb2_hough_desc* d_desc, const rb2_hough_desc* h_desc,
                                rb2_hough_stats* d_stats, cudaStream_t stream) {
   using namespace rb2;
@@ -638,6 +797,22 @@ static cudaError_t launch_rank(int n_problems, const rb2_hough_desc* d_desc, con
     hough_rank_pairs_kernel<<<dim3(tiles, split, n_problems), RANKP_T, 0, stream>>>(d_desc, src_chunk);
     hough_rank_scatter_kernel<<<dim3(min(tiles, 64), n_problems), RANKP_T, 0, stream>>>(d_desc, d_stats);
     return cudaGetLastError();
+  }
+  if (n_problems == 1 && max_bins > 65536) {  // one fine-binned spectrum: radix passes over the whole GPU
+    static unsigned* scratch[64] = {};
+    static size_t scratch_n[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    const size_t need = (size_t)256 * ((max_bins + RANKM_T - 1) / RANKM_T) + 256;
+    if (need > scratch_n[dev]) {
+      if (scratch[dev]) cudaFree(scratch[dev]);
+      e = cudaMalloc(&scratch[dev], need * sizeof(unsigned));
+      if (e != cudaSuccess) { scratch[dev] = nullptr; scratch_n[dev] = 0; return e; }
+      scratch_n[dev] = need;
+    }
+    return launch_rank_multi(h_desc[0], d_stats, scratch[dev], stream);
   }
   const int smem_bins = (max_bins <= RANK_SMEM_MAX_BINS) ? max_bins : 0;  // 0: sort in global memory
   const size_t smem = (size_t)smem_bins * 12;
