@@ -38,7 +38,25 @@ class HoughTransform:
             xb, yb = self._lazy_bins
             self._lazy_bins = None
             self._bin_now(xb, yb)
+        if self._res[name] is None and name != "batch" and self._res["batch"] is not None:
+            self._fetch(name)  # each host copy is made when somebody reads it (10^6 Hough lines are 16 MB of tuples)
         return self._res[name]
+
+    def _fetch(self, name):
+        batch = self._res["batch"]
+        if name == "hist":
+            self._res["hist"] = batch.hist(0).astype(np.float64)
+        elif name == "xedges":
+            self._res["xedges"] = batch.xedges(0)
+        elif name == "yedges":
+            self._res["yedges"] = batch.yedges(0)
+        else:  # hist_sorted_arg / hough_lines: the ranking (houghtransform.py:190-210)
+            xb, yb = batch._dims(0)
+            i, j = np.unravel_index(batch.rank(0), (xb, yb))
+            self._res["hist_sorted_arg"] = np.column_stack((i, j))
+            xe, ye = self._get("xedges"), self._get("yedges")
+            # bin-centre lines in rank order (:197-210); an [B,2] array instead of a list of tuples
+            self._res["hough_lines"] = np.column_stack((xe[i] + (xe[1] - xe[0]) / 2, ye[j] + (ye[1] - ye[0]) / 2))
 
     def _set(self, name, value):
         self._res[name] = value
@@ -132,16 +150,9 @@ class HoughTransform:
             batch = engine.PointsHoughBatch([dict(points=self._points, xbins=int(xbins), ybins=int(ybins))]).run()
         else:
             batch = engine.HoughBatch([self._problem(xbins, ybins)]).run()
+        for k in ("hist", "xedges", "yedges", "hist_sorted_arg", "hough_lines"):
+            self._res[k] = None  # host copies are fetched from the batch on first use (_fetch)
         self._batch = batch
-        self.hist = batch.hist(0).astype(np.float64)
-        self.xedges = batch.xedges(0)
-        self.yedges = batch.yedges(0)
-        order = batch.rank(0)
-        i, j = np.unravel_index(order, self.hist.shape)
-        self.hist_sorted_arg = np.column_stack((i, j))
-        # bin-centre lines in rank order (:197-210); an [B,2] array instead of a list of tuples
-        self.hough_lines = np.column_stack((self.xedges[i] + (self.xedges[1] - self.xedges[0]) / 2,
-                                            self.yedges[j] + (self.yedges[1] - self.yedges[0]) / 2))
 
     # ---- reference: houghtransform.py:212-339 ------------------------------
     def save(self, filename="hough_transform", fileformat="npy", delimiter="+", to_disk=True):
