@@ -130,12 +130,21 @@ class Calibrator:
             self.pixel_list = np.asarray(pixel_list)
         elif self.pixel_list is None:
             self.pixel_list = np.arange(self.num_pix)
-        self.pix_to_rawpix = interpolate.interp1d(self.pixel_list, np.arange(len(self.pixel_list)),
-                                                  fill_value="extrapolate")
+        self.__dict__["_pix_to_rawpix"] = None  # (:941-946) built when somebody asks: see the property
         if seed is not None:
             self.seed = seed
             np.random.seed(seed)
         self.plotting_library = _keep(plotting_library, self.plotting_library, "matplotlib")
+
+    @property
+    def pix_to_rawpix(self):
+        """interp1d(pixel_list -> raw pixel index) (calibrator.py:941-946), built on first use: only the
+        reference's plotting and effective-pixel helpers read it, a fit never does."""
+        f = self.__dict__.get("_pix_to_rawpix")
+        if f is None:
+            f = self.__dict__["_pix_to_rawpix"] = interpolate.interp1d(self.pixel_list, np.arange(len(self.pixel_list)),
+                                                                       fill_value="extrapolate")
+        return f
 
     def set_hough_properties(self, num_slopes=None, xbins=None, ybins=None, min_wavelength=None,
                              max_wavelength=None, range_tolerance=None, linearity_tolerance=None):

@@ -25,6 +25,7 @@ from . import engine
 
 _ALIGN = 16
 _CACHE = {}  # device-resident constants and scratch reused across calls
+_PLANS = {}  # arena layouts + descriptor templates per batch shape (run_async)
 
 
 _DT = {}
@@ -248,36 +249,9 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
         _CACHE[key] = (torch.from_numpy(op).cuda(), torch.from_numpy(brk).cuda(), len(brk) - 1)
     d_op, d_brk, npp = _CACHE[key]
     max_p = max(int(n_p.max()), ssz)  # stride of the per-spectrum outputs; K3's descriptors carry >= ssz peaks
-
-    # ---- layout: [inputs | descriptors] (H2D)  [work] (device only)  [results] (D2H) ----
-    L = _Layout()
-    o_peaks, o_lines = L.many(8 * n_p), L.many(8 * n_a)
     dts = dict(pairs=_dt(N.PairsDesc), hough=_dt(N.HoughDesc), vote=_dt(N.VoteDesc), prep=_dt(N.PrepareDesc),
                ransac=_dt(N.RansacDesc), match=_dt(N.MatchDesc))
-    o_desc = {k: L.one(dt.itemsize * n) for k, dt in dts.items()}
-    h2d_bytes = L.size
-    o_px, o_py, o_pwid = L.many(8 * P), L.many(8 * P), L.many(4 * P)
-    o_poff, o_lo, o_hi = L.many(4 * (n_p + 1)), L.many(4 * P), L.many(4 * P)
-    o_hist, o_rank, o_rpos, o_tmp = (L.one(4 * B * n) + 4 * B * np.arange(n) for _ in range(4))
-    o_xe, o_ye = L.one(8 * (xb + 1) * n) + 8 * (xb + 1) * np.arange(n), L.one(8 * (yb + 1) * n) + 8 * (yb + 1) * np.arange(n)
-    zero_begin = L.size
-    o_cw, o_cp, o_cn = L.many(8 * n_p * top_n), L.many(4 * n_p * top_n), L.many(4 * n_p)
-    zero_end = L.size
-    res_begin = L.size  # with keep_tables the D2H region starts here and includes the K3 tables
-    o_up, o_coff, o_cwave = L.many(8 * n_p), L.many(4 * (n_p + 1)), L.many(8 * n_p * top_n)
-    o_cwid, o_cdf = L.many(4 * n_p * top_n), L.many(4 * n_p)
-    o_ppb, o_ppc = L.one(8 * (npp + 1) * n) + 8 * (npp + 1) * np.arange(n), L.one(32 * npp * n) + 32 * npp * np.arange(n)
-    o_kdesc = L.one(dts["ransac"].itemsize * n)  # the descriptors as rb2_ransac_prepare completed them
-    if not keep_tables:
-        res_begin = L.size
     rsz, fsz, msz = C.sizeof(N.RansacResult), C.sizeof(N.RefitResult), C.sizeof(N.MatchResult)
-    o_res, o_fit = L.one(rsz * n), L.one(fsz * n)
-    o_mx, o_my, o_rs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
-    o_mres = L.one(msz * n)
-    o_mmx, o_mmy, o_mrs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
-    o_enough, o_vstat = L.one(4 * n), L.one(4 * n)
-    o_hstat = L.one(C.sizeof(N.HoughStats) * n)
-    res_end = L.size
 
     # grow-only device arena and pinned staging buffers, reused across calls (cudaHostAlloc of tens of MB
     # costs more than the whole batch); results own their memory, only k3_tables() reads the arena later
@@ -288,94 +262,149 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
             t = _CACHE[name] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, **kw)
         return t
 
-    buf = cached("arena", L.size, device="cuda")[:L.size]
+    # The layout of the arena and every descriptor field that only depends on the SHAPE of the batch (sizes,
+    # pointers into the arena, Hough / RANSAC dimensions) is a plan, built once per shape and arena and kept:
+    # a repeated call - the fits of a survey, the timed loop of a benchmark - copies the descriptor block and
+    # overwrites the handful of fields that carry this call's values.
+    plan_key = (slot, n, n_p.tobytes(), n_a.tobytes(), S, xb, yb, top_n, deg, ssz, weighted, bool(keep_tables),
+                match_tolerance is not None, d_op.data_ptr())
+    pl = _PLANS.get(plan_key)
+    if pl is not None and cached("arena", pl.size, device="cuda").data_ptr() != pl.base:
+        pl = None  # the arena moved (it grew for another shape): the pointers in the plan are stale
+    fresh = pl is None
+    if fresh:
+        pl = types.SimpleNamespace()
+        # ---- layout: [inputs | descriptors] (H2D)  [work] (device only)  [results] (D2H) ----
+        L = _Layout()
+        pl.o_peaks, pl.o_lines = L.many(8 * n_p), L.many(8 * n_a)
+        pl.o_desc = {k: L.one(dt.itemsize * n) for k, dt in dts.items()}
+        pl.h2d_bytes = L.size
+        pl.o_px, pl.o_py, pl.o_pwid = L.many(8 * P), L.many(8 * P), L.many(4 * P)
+        pl.o_poff, pl.o_lo, pl.o_hi = L.many(4 * (n_p + 1)), L.many(4 * P), L.many(4 * P)
+        pl.o_hist, pl.o_rank, pl.o_rpos, pl.o_tmp = (L.one(4 * B * n) + 4 * B * np.arange(n) for _ in range(4))
+        pl.o_xe = L.one(8 * (xb + 1) * n) + 8 * (xb + 1) * np.arange(n)
+        pl.o_ye = L.one(8 * (yb + 1) * n) + 8 * (yb + 1) * np.arange(n)
+        pl.zero_begin = L.size
+        pl.o_cw, pl.o_cp, pl.o_cn = L.many(8 * n_p * top_n), L.many(4 * n_p * top_n), L.many(4 * n_p)
+        pl.zero_end = L.size
+        pl.res_begin = L.size  # with keep_tables the D2H region starts here and includes the K3 tables
+        pl.o_up, pl.o_coff, pl.o_cwave = L.many(8 * n_p), L.many(4 * (n_p + 1)), L.many(8 * n_p * top_n)
+        pl.o_cwid, pl.o_cdf = L.many(4 * n_p * top_n), L.many(4 * n_p)
+        pl.o_ppb = L.one(8 * (npp + 1) * n) + 8 * (npp + 1) * np.arange(n)
+        pl.o_ppc = L.one(32 * npp * n) + 32 * npp * np.arange(n)
+        pl.o_kdesc = L.one(dts["ransac"].itemsize * n)  # the descriptors as rb2_ransac_prepare completed them
+        if not keep_tables:
+            pl.res_begin = L.size
+        pl.o_res, pl.o_fit = L.one(rsz * n), L.one(fsz * n)
+        pl.o_mx, pl.o_my, pl.o_rs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
+        pl.o_mres = L.one(msz * n)
+        pl.o_mmx, pl.o_mmy, pl.o_mrs = L.one(8 * n * max_p), L.one(8 * n * max_p), L.one(8 * n * max_p)
+        pl.o_enough, pl.o_vstat = L.one(4 * n), L.one(4 * n)
+        pl.o_hstat = L.one(C.sizeof(N.HoughStats) * n)
+        pl.res_end = L.size
+        pl.size = L.size
+        pl.base = cached("arena", pl.size, device="cuda").data_ptr()
+        pl.desc_begin = min(pl.o_desc.values())
+        # peaks / lines: offsets are 16-byte aligned, so scatter by index arrays
+        pl.idx_p = np.repeat(pl.o_peaks // 8 - np.concatenate(([0], np.cumsum(n_p)[:-1])), n_p) + np.arange(int(n_p.sum()))
+        pl.idx_l = np.repeat(pl.o_lines // 8 - np.concatenate(([0], np.cumsum(n_a)[:-1])), n_a) + np.arange(int(n_a.sum()))
+
+    buf = cached("arena", pl.size, device="cuda")[:pl.size]
     base = buf.data_ptr()
+    h2d_bytes = pl.h2d_bytes
     host = cached("stage_in", h2d_bytes, pin_memory=True)[:h2d_bytes]
     hv = host.numpy()
-    # peaks / lines: offsets are 16-byte aligned, so scatter by index arrays
-    pk = np.concatenate([sp["peaks"] for sp in specs])
-    ln = np.concatenate([sp["lines"] for sp in specs])
     h64 = hv.view(np.float64)
-    idx_p = np.repeat(o_peaks // 8 - np.concatenate(([0], np.cumsum(n_p)[:-1])), n_p) + np.arange(len(pk))
-    idx_l = np.repeat(o_lines // 8 - np.concatenate(([0], np.cumsum(n_a)[:-1])), n_a) + np.arange(len(ln))
-    h64[idx_p] = pk
-    h64[idx_l] = ln
-
-    hv[min(o_desc.values()):h2d_bytes] = 0  # descriptor fields not set below are NULL / 0 (pinned memory is recycled)
+    h64[pl.idx_p] = np.concatenate([sp["peaks"] for sp in specs])
+    h64[pl.idx_l] = np.concatenate([sp["lines"] for sp in specs])
 
     def view(name):
-        o = o_desc[name]
+        o = pl.o_desc[name]
         return hv[o:o + dts[name].itemsize * n].view(dts[name])
 
     dp, dh, dv, dr, dk, dm = (view(k) for k in ("pairs", "hough", "vote", "prep", "ransac", "match"))
-    u = lambda a: (base + np.asarray(a, dtype=np.int64)).astype(np.uint64)  # noqa: E731
-    dp["d_peaks"], dp["d_lines"], dp["n_peaks"], dp["n_lines"] = u(o_peaks), u(o_lines), n_p, n_a
-    dp["d_pair_x"], dp["d_pair_y"], dp["d_pair_wid"], dp["d_pair_off"] = u(o_px), u(o_py), u(o_pwid), u(o_poff)
+    if fresh:
+        hv[pl.desc_begin:h2d_bytes] = 0  # descriptor fields not set below are NULL / 0 (pinned memory is recycled)
+        u = lambda a: (base + np.asarray(a, dtype=np.int64)).astype(np.uint64)  # noqa: E731
+        dp["d_peaks"], dp["d_lines"], dp["n_peaks"], dp["n_lines"] = u(pl.o_peaks), u(pl.o_lines), n_p, n_a
+        dp["d_pair_x"], dp["d_pair_y"], dp["d_pair_wid"], dp["d_pair_off"] = u(pl.o_px), u(pl.o_py), u(pl.o_pwid), u(pl.o_poff)
 
+        dh["n_slopes"], dh["xbins"], dh["ybins"], dh["n_pairs"] = S, xb, yb, P
+        dh["d_pair_x"], dh["d_pair_y"], dh["d_lo"], dh["d_hi"] = u(pl.o_px), u(pl.o_py), u(pl.o_lo), u(pl.o_hi)
+        dh["d_xedges"], dh["d_yedges"], dh["d_hist"], dh["d_rank"] = u(pl.o_xe), u(pl.o_ye), u(pl.o_hist), u(pl.o_rank)
+        dh["d_rankpos"], dh["d_sort_tmp"] = u(pl.o_rpos), u(pl.o_tmp)
+
+        dv["n_upeaks"], dv["n_uwaves"], dv["xbins"], dv["ybins"] = n_p, n_a, xb, yb
+        dv["top_n"], dv["weighted"] = top_n, weighted
+        dv["d_upeak_x"], dv["d_pair_off"], dv["d_pair_y"], dv["d_pair_wid"] = u(pl.o_peaks), u(pl.o_poff), u(pl.o_py), u(pl.o_pwid)
+        dv["d_xedges"], dv["d_yedges"], dv["d_rankpos"] = u(pl.o_xe), u(pl.o_ye), u(pl.o_rpos)
+        dv["d_rank"] = u(pl.o_rank)
+        dv["d_cand_wave"], dv["d_cand_pair"], dv["d_cand_n"] = u(pl.o_cw), u(pl.o_cp), u(pl.o_cn)
+        dv["d_agg"], dv["d_cnt"], dv["d_status"] = 0, 0, u(pl.o_vstat + 4 * np.arange(n))
+
+        dr["d_upeak_x"], dr["d_cand_wave"], dr["d_cand_n"], dr["n_peaks"], dr["top_n"] = u(pl.o_peaks), u(pl.o_cw), u(pl.o_cn), n_p, top_n
+        dr["d_xedges"], dr["d_yedges"], dr["d_hist"], dr["xbins"], dr["ybins"] = u(pl.o_xe), u(pl.o_ye), u(pl.o_hist), xb, yb
+        dr["d_spline_op"], dr["d_spline_brk"], dr["n_pp"] = d_op.data_ptr(), d_brk.data_ptr(), npp
+        dr["d_enough"] = u(pl.o_enough + 4 * np.arange(n))
+
+        # K3 descriptors: pointers + host-known scalars; sizes are upper bounds until rb2_ransac_prepare ran
+        dk["n_upeaks"], dk["n_wids"], dk["n_cand"] = np.maximum(n_p, ssz), n_p * top_n, np.maximum(n_p, ssz) * top_n
+        dk["d_peaks"], dk["d_cand_off"], dk["d_cand_wave"], dk["d_cand_wid"] = u(pl.o_up), u(pl.o_coff), u(pl.o_cwave), u(pl.o_cwid)
+        dk["d_cdf32"], dk["deg"], dk["sample_size"] = u(pl.o_cdf), deg, ssz
+        dk["n_pp"], dk["d_pp_breaks"], dk["d_pp_coef"] = npp, u(pl.o_ppb), u(pl.o_ppc)
+        dk["d_pix"] = 0
+        dk["cost_ceiling"], dk["floor_cost"], dk["floor_id"] = 1e50, 0.0, -1
+
+        if match_tolerance is not None:
+            dm["d_peaks"], dm["d_atlas"], dm["n_peaks"], dm["n_atlas"] = u(pl.o_peaks), u(pl.o_lines), n_p, n_a
+            dm["d_coeffs"], dm["n_coef"], dm["fit_deg"] = u(pl.o_fit + fsz * np.arange(n)), deg + 1, deg
+            dm["robust_refit"] = 1
+        pl.template = hv[pl.desc_begin:h2d_bytes].copy()
+        _PLANS[plan_key] = pl
+        if len(_PLANS) > 64:
+            _PLANS.pop(next(iter(_PLANS)))
+    else:
+        hv[pl.desc_begin:h2d_bytes] = pl.template
+    # this call's values
     dh["min_slope"], dh["max_slope"], dh["min_intercept"], dh["max_intercept"] = lim[:, 0], lim[:, 1], lim[:, 2], lim[:, 3]
-    dh["n_slopes"], dh["xbins"], dh["ybins"], dh["n_pairs"] = S, xb, yb, P
-    dh["d_pair_x"], dh["d_pair_y"], dh["d_lo"], dh["d_hi"] = u(o_px), u(o_py), u(o_lo), u(o_hi)
-    dh["d_xedges"], dh["d_yedges"], dh["d_hist"], dh["d_rank"] = u(o_xe), u(o_ye), u(o_hist), u(o_rank)
-    dh["d_rankpos"], dh["d_sort_tmp"] = u(o_rpos), u(o_tmp)
-
-    dv["n_upeaks"], dv["n_uwaves"], dv["xbins"], dv["ybins"] = n_p, n_a, xb, yb
-    dv["top_n"], dv["weighted"], dv["tol"], dv["gauss_denom"] = top_n, weighted, ctol, 2 * sigma ** 2 + 1e-9
-    dv["d_upeak_x"], dv["d_pair_off"], dv["d_pair_y"], dv["d_pair_wid"] = u(o_peaks), u(o_poff), u(o_py), u(o_pwid)
-    dv["d_xedges"], dv["d_yedges"], dv["d_rankpos"] = u(o_xe), u(o_ye), u(o_rpos)
-    dv["d_rank"] = u(o_rank)
-    dv["d_cand_wave"], dv["d_cand_pair"], dv["d_cand_n"] = u(o_cw), u(o_cp), u(o_cn)
-    dv["d_agg"], dv["d_cnt"], dv["d_status"] = 0, 0, u(o_vstat + 4 * np.arange(n))
-
-    dr["d_upeak_x"], dr["d_cand_wave"], dr["d_cand_n"], dr["n_peaks"], dr["top_n"] = u(o_peaks), u(o_cw), u(o_cn), n_p, top_n
-    dr["d_xedges"], dr["d_yedges"], dr["d_hist"], dr["xbins"], dr["ybins"] = u(o_xe), u(o_ye), u(o_hist), xb, yb
-    dr["d_spline_op"], dr["d_spline_brk"], dr["n_pp"] = d_op.data_ptr(), d_brk.data_ptr(), npp
-    dr["d_enough"] = u(o_enough + 4 * np.arange(n))
-
-    # K3 descriptors: pointers + host-known scalars; sizes are upper bounds until rb2_ransac_prepare ran
-    dk["n_upeaks"], dk["n_wids"], dk["n_cand"] = np.maximum(n_p, ssz), n_p * top_n, np.maximum(n_p, ssz) * top_n
-    dk["d_peaks"], dk["d_cand_off"], dk["d_cand_wave"], dk["d_cand_wid"] = u(o_up), u(o_coff), u(o_cwave), u(o_cwid)
-    dk["d_cdf32"], dk["deg"], dk["sample_size"] = u(o_cdf), deg, ssz
+    dv["tol"], dv["gauss_denom"] = ctol, 2 * sigma ** 2 + 1e-9
     dk["min_intercept"], dk["max_intercept"], dk["tol"], dk["hough_weight"] = lim[:, 2], lim[:, 3], tol, hw
-    dk["n_pp"], dk["d_pp_breaks"], dk["d_pp_coef"] = npp, u(o_ppb), u(o_ppc)
-    dk["n_pix"], dk["d_pix"] = n_pix, 0
+    dk["n_pix"] = n_pix
     dk["min_inliers"] = np.maximum(deg + 1, np.minimum(np.minimum(mm, n_a), n_p))
-    dk["min_inliers_frac"], dk["cost_ceiling"], dk["floor_cost"], dk["floor_id"] = mpu * n_p, 1e50, 0.0, -1
+    dk["min_inliers_frac"] = mpu * n_p
     dk["hyp_begin"], dk["n_hyp"], dk["seed"] = int(hyp_begin), int(n_hypotheses), int(seed)
     dk["min_fit_error"] = mfe
-
     if match_tolerance is not None:
-        dm["d_peaks"], dm["d_atlas"], dm["n_peaks"], dm["n_atlas"] = u(o_peaks), u(o_lines), n_p, n_a
-        dm["d_coeffs"], dm["n_coef"], dm["fit_deg"] = u(o_fit + fsz * np.arange(n)), deg + 1, deg
-        dm["tolerance"], dm["robust_refit"] = float(match_tolerance), 1
+        dm["tolerance"] = float(match_tolerance)
 
     buf[:h2d_bytes].copy_(host, non_blocking=True)
     engine.TRANSFER["h2d"] += h2d_bytes
-    buf[zero_begin:zero_end].zero_()
-    buf[o_vstat:o_vstat + 4 * n].zero_()
+    buf[pl.zero_begin:pl.zero_end].zero_()
+    buf[pl.o_vstat:pl.o_vstat + 4 * n].zero_()
     stream = engine.current_stream_ptr()
-    hptr = lambda name: hv.ctypes.data + o_desc[name]  # noqa: E731
-    dptr = lambda name: base + o_desc[name]  # noqa: E731
+    hptr = lambda name: hv.ctypes.data + pl.o_desc[name]  # noqa: E731
+    dptr = lambda name: base + pl.o_desc[name]  # noqa: E731
     t1 = time.perf_counter()
 
     N.check(lib.rb2_expand_pairs(n, dptr("pairs"), hptr("pairs"), stream), "rb2_expand_pairs")
-    N.check(lib.rb2_hough_accumulate(n, dptr("hough"), hptr("hough"), base + o_hstat, 0, stream), "rb2_hough_accumulate")
+    N.check(lib.rb2_hough_accumulate(n, dptr("hough"), hptr("hough"), base + pl.o_hstat, 0, stream), "rb2_hough_accumulate")
     N.check(lib.rb2_candidate_vote(n, dptr("vote"), hptr("vote"), stream), "rb2_candidate_vote")
     N.check(lib.rb2_ransac_prepare(n, dptr("prep"), hptr("prep"), dptr("ransac"), stream), "rb2_ransac_prepare")
     scratch = engine.ransac_scratch(lib.rb2_ransac_scratch_bytes(n, 0))
-    N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + o_res, scratch.data_ptr(), 0, stream),
+    N.check(lib.rb2_ransac_batch(n, dptr("ransac"), hptr("ransac"), base + pl.o_res, scratch.data_ptr(), 0, stream),
             "rb2_ransac_batch")
     if exchange is not None:
-        exchange(buf[o_res:o_res + rsz * n], n)
-    N.check(lib.rb2_refit_winners(n, dptr("ransac"), hptr("ransac"), base + o_res, float("nan"), int(refit_mode), base + o_fit,
-                                  base + o_mx, base + o_my, base + o_rs, max_p, stream), "rb2_refit_winners")
+        exchange(buf[pl.o_res:pl.o_res + rsz * n], n)
+    N.check(lib.rb2_refit_winners(n, dptr("ransac"), hptr("ransac"), base + pl.o_res, float("nan"), int(refit_mode), base + pl.o_fit,
+                                  base + pl.o_mx, base + pl.o_my, base + pl.o_rs, max_p, stream), "rb2_refit_winners")
     if match_tolerance is not None:
-        N.check(lib.rb2_match_peaks(n, dptr("match"), hptr("match"), int(refit_mode), base + o_mres, base + o_mmx,
-                                    base + o_mmy, base + o_mrs, max_p, stream), "rb2_match_peaks")
-    raw = cached("stage_out", res_end - res_begin, pin_memory=True)[:res_end - res_begin]
+        N.check(lib.rb2_match_peaks(n, dptr("match"), hptr("match"), int(refit_mode), base + pl.o_mres, base + pl.o_mmx,
+                                    base + pl.o_mmy, base + pl.o_mrs, max_p, stream), "rb2_match_peaks")
+    raw = cached("stage_out", pl.res_end - pl.res_begin, pin_memory=True)[:pl.res_end - pl.res_begin]
     if keep_tables:
         nb = dts["ransac"].itemsize * n
-        buf[o_kdesc:o_kdesc + nb].copy_(buf[o_desc["ransac"]:o_desc["ransac"] + nb], non_blocking=True)
-    raw.copy_(buf[res_begin:res_end], non_blocking=True)
+        buf[pl.o_kdesc:pl.o_kdesc + nb].copy_(buf[pl.o_desc["ransac"]:pl.o_desc["ransac"] + nb], non_blocking=True)
+    raw.copy_(buf[pl.res_begin:pl.res_end], non_blocking=True)
     done = torch.cuda.Event()
     done.record()
     engine.TRANSFER["d2h"] += raw.numel()
@@ -388,19 +417,19 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
 
     def unpack(r, t2):
         def region(off, nbytes):
-            return r[off - res_begin:off - res_begin + nbytes]
+            return r[off - pl.res_begin:off - pl.res_begin + nbytes]
 
-        hstat = region(o_hstat, C.sizeof(N.HoughStats) * n).view(_dt(N.HoughStats))
-        vstat = region(o_vstat, 4 * n).view(np.int32)
+        hstat = region(pl.o_hstat, C.sizeof(N.HoughStats) * n).view(_dt(N.HoughStats))
+        vstat = region(pl.o_vstat, 4 * n).view(np.int32)
         for st, what in ((hstat["status"], "rb2_hough_accumulate"), (vstat, "rb2_candidate_vote")):
             bad = np.flatnonzero(st != 0)
             if len(bad):
                 N.check(int(st[bad[0]]), what + " (device status)")
-        win = region(o_res, rsz * n).view(_dt(N.RansacResult))
-        fit = region(o_fit, fsz * n).view(_dt(N.RefitResult))
+        win = region(pl.o_res, rsz * n).view(_dt(N.RansacResult))
+        fit = region(pl.o_fit, fsz * n).view(_dt(N.RefitResult))
         out = BatchResults(n)
         out.deg, out.n_p, out.n_a = deg, n_p, n_a
-        enough = region(o_enough, 4 * n).view(np.int32)
+        enough = region(pl.o_enough, 4 * n).view(np.int32)
         out.enough = enough > 0
         out.law_error = enough < 0  # the reference raises ValueError("probabilities contain NaN") for these
         out.counters, out.cost = win["counters"], win["cost"]
@@ -409,22 +438,22 @@ def run_async(specs, n_hypotheses, seed=0, refit_mode=0, match_tolerance=None, t
         out.ok = out.enough & (win["hyp_id"] >= 0) & (fit["accepted"] != 0)
         out.coeffs, out.rms, out.n_inliers = fit["coeffs"], fit["rms"], fit["n_inliers"]
         shp = (n, max_p)
-        out.mx = region(o_mx, 8 * n * max_p).view(np.float64).reshape(shp)
-        out.my = region(o_my, 8 * n * max_p).view(np.float64).reshape(shp)
-        out.rs = region(o_rs, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.mx = region(pl.o_mx, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.my = region(pl.o_my, 8 * n * max_p).view(np.float64).reshape(shp)
+        out.rs = region(pl.o_rs, 8 * n * max_p).view(np.float64).reshape(shp)
         out.match_ok = None
         if match_tolerance is not None:
-            mres = region(o_mres, msz * n).view(_dt(N.MatchResult))
+            mres = region(pl.o_mres, msz * n).view(_dt(N.MatchResult))
             out.match_ok = out.ok & (mres["refit"]["accepted"] != 0)
             out.m_n, out.m_amb = mres["n_matched"], mres["n_ambiguous"]
             out.m_coeffs, out.m_rms = mres["refit"]["coeffs"], mres["refit"]["rms"]
-            out.mmx = region(o_mmx, 8 * n * max_p).view(np.float64).reshape(shp)
-            out.mmy = region(o_mmy, 8 * n * max_p).view(np.float64).reshape(shp)
-            out.mrs = region(o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
-        out._tables = dict(buf=buf, up=o_up, coff=o_coff, cwave=o_cwave, cwid=o_cwid, cdf=o_cdf, ppb=o_ppb, ppc=o_ppc,
-                           npp=npp, desc=o_desc["ransac"], top_n=top_n)
+            out.mmx = region(pl.o_mmx, 8 * n * max_p).view(np.float64).reshape(shp)
+            out.mmy = region(pl.o_mmy, 8 * n * max_p).view(np.float64).reshape(shp)
+            out.mrs = region(pl.o_mrs, 8 * n * max_p).view(np.float64).reshape(shp)
+        out._tables = dict(buf=buf, up=pl.o_up, coff=pl.o_coff, cwave=pl.o_cwave, cwid=pl.o_cwid, cdf=pl.o_cdf, ppb=pl.o_ppb, ppc=pl.o_ppc,
+                           npp=npp, desc=pl.o_desc["ransac"], top_n=top_n)
         if keep_tables:  # own copy: later runs reuse the arena
-            out._tables.update(host=r, host_base=res_begin, desc=o_kdesc)
+            out._tables.update(host=r, host_base=pl.res_begin, desc=pl.o_kdesc)
         if timings is not None:
             timings.update(pack=t1 - t0, launch=t_launch - t1, device=t2 - t1, unpack=time.perf_counter() - t2)
         return out
