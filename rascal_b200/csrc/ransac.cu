@@ -156,21 +156,39 @@ __device__ __forceinline__ int real_roots(const double (&a)[CAP + 1], int n, dou
 }
 
 // ---- monotonicity test (calibrator.py:585-600) -------------------------------
-// all(diff(polyval(arange(pix_min, pix_max, 1), c)) > 0)
+// all(diff(polyval(arange(pix_min, pix_max, 1), c)) > 0), in two parts so that stage B can run the second one
+// on a compacted list: mono_ends() tests the first and the last difference (most non-monotonic hypotheses fail
+// there), mono_interior() the grid points around every critical point of the difference polynomial.
 template <int DEG>
-__device__ __forceinline__ bool monotonic_test(const double (&c)[deg_cap(DEG) + 1], int deg_rt, double pix_min, double pix_max) {
-  constexpr int CAP = deg_cap(DEG);
-  const int deg = DEG > 0 ? DEG : deg_rt;
-  const double gl = ceil((pix_max - pix_min) / 1.0);  // numpy arange length
-  if (!(gl >= 2.0)) return true;                      // diff of <2 points is empty
-  const long long G = (long long)gl;
-  const long long kmax = G - 2;                       // D_k for k in [0, kmax]
-  auto D = [&](long long k) {
+struct MonoGrid {
+  static constexpr int CAP = deg_cap(DEG);
+  long long kmax;  // D_k for k in [0, kmax]; < 0: fewer than two grid points
+  double pix_min;
+  __device__ __forceinline__ MonoGrid(double pmin, double pmax) : pix_min(pmin) {
+    const double gl = ceil((pmax - pmin) / 1.0);  // numpy arange length
+    kmax = (gl >= 2.0) ? (long long)gl - 2 : -1;  // diff of <2 points is empty
+  }
+  __device__ __forceinline__ double D(const double (&c)[CAP + 1], int deg, long long k) const {
     const double t0 = add(pix_min, (double)k), t1 = add(pix_min, (double)(k + 1));
     return sub(horner_ref<CAP>(c, deg + 1, t1), horner_ref<CAP>(c, deg + 1, t0));
-  };
-  if (!(D(0) > 0.0) || !(D(kmax) > 0.0)) return false;
-  if (deg <= 2) return true;  // q is linear: extremes at the ends
+  }
+};
+
+template <int DEG>
+__device__ __forceinline__ bool mono_ends(const double (&c)[deg_cap(DEG) + 1], int deg_rt, double pix_min, double pix_max) {
+  const int deg = DEG > 0 ? DEG : deg_rt;
+  const MonoGrid<DEG> g(pix_min, pix_max);
+  if (g.kmax < 0) return true;
+  return (g.D(c, deg, 0) > 0.0) && (g.D(c, deg, g.kmax) > 0.0);
+}
+
+template <int DEG>
+__device__ __forceinline__ bool mono_interior(const double (&c)[deg_cap(DEG) + 1], int deg_rt, double pix_min, double pix_max) {
+  constexpr int CAP = deg_cap(DEG);
+  const int deg = DEG > 0 ? DEG : deg_rt;
+  const MonoGrid<DEG> g(pix_min, pix_max);
+  if (g.kmax < 0 || deg <= 2) return true;  // q is linear: extremes at the ends
+  const long long kmax = g.kmax;
   // p~(tau) = p(pix_min + tau): Taylor shift
   double ps[CAP + 1];
 #pragma unroll
@@ -200,7 +218,7 @@ __device__ __forceinline__ bool monotonic_test(const double (&c)[deg_cap(DEG) + 
     const long long kf = (long long)floor(roots[r]);
     for (long long k = kf - 1; k <= kf + 2; ++k) {
       if (k < 0 || k > kmax) continue;
-      if (!(D(k) > 0.0)) return false;
+      if (!(g.D(c, deg, k) > 0.0)) return false;
     }
   }
   return true;
@@ -891,11 +909,16 @@ struct Pipe {  // device pointers of the staged pipeline (one per rb2_ransac_bat
   unsigned char* res_flag;          // per queue-B entry: RES_* bits
   rb2_ransac_result* win;           // [n_problems] winner records written by THIS lane's stage D
   unsigned cap; int qs;
+  unsigned cap_a;                   // capacity of queue A: cap + the slack of the paged reservation (stage A)
 };
 enum : unsigned char { RES_ELIGIBLE = 1, RES_NEAR_FLOOR = 2, RES_EXACT = 4, RES_GENERAL = 8 };
 // two costs computed from the same coefficients differ only by the summation order of <= n_peaks clipped
 // errors (a few ulp); anything within this relative margin of the running best is re-summed exactly
 constexpr double COST_MARGIN = 1e-12;
+
+constexpr unsigned QA_PAGE = 32u;                    // slots a warp of stage A reserves at a time
+constexpr unsigned QA_SLACK = 1u << 20;              // extra queue-A slots for the unfilled ends of the pages (<= 2 pages per warp)
+constexpr unsigned long long QA_HOLE = ~0ull;        // tag of a reserved slot that holds no hypothesis
 
 constexpr int PIPE_MAX_LANES = 4;
 struct PipeSet { Pipe p[PIPE_MAX_LANES]; int n; };
@@ -950,7 +973,7 @@ __device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigne
 template <int DEG_T, bool LSQ = false>
 __global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 && !LSQ ? RB2_A_CTAS : 2)
 ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
-                       rb2_ransac_result* __restrict__ result, const PhiloxKey pkey) {
+                       rb2_ransac_result* __restrict__ result, const PhiloxKey pkey, const int paged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ rb2_ransac_desc s_desc;
   __shared__ unsigned s_cnt[3];
@@ -1032,6 +1055,13 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane);
   unsigned qn = 0u;  // hypotheses in this warp's deferred queue (warp-uniform)
   unsigned* const s_q = s_defer[warp];
+  // Queue-A slots.  One returning atomic per warp iteration on ONE address was the largest single stall of this
+  // kernel (99.6 % of the iterations have a survivor; the warp waited ~1 us for its slot).  Paged: a warp owns a
+  // page of QA_PAGE slots and holds the NEXT page already - its atomic was issued a page earlier, so the reply is
+  // there when it is needed.  Slots of the last two pages that stay empty are tagged QA_HOLE (stage B skips them).
+  unsigned pg_base = 0u, pg_used = QA_PAGE, pg_next = 0u;  // pg_next: lane 0 only (raw reply of the prefetch)
+  bool pg_have = false;
+  if (paged && lane == 0) pg_next = atomicAdd(&pipe.counts[0], QA_PAGE);
   for (;;) {
     const bool stream_left = base < chunk_len;
     bool slow = false, active = false;
@@ -1159,18 +1189,39 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
     c_abort += active && aborted;
     c_icpt += active && !aborted && !pass;
     if (pm) {  // warp-aggregated push
-      unsigned slot0 = 0;
-      if (lane == 0) slot0 = atomicAdd(&pipe.counts[0], (unsigned)__popc(pm));
-      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-      if (pass) {
-        const unsigned slot = slot0 + __popc(pm & ((1u << lane) - 1u));
-        if (slot < pipe.cap) {
-          double* q = pipe.qa + (size_t)slot * qs;
-#pragma unroll
-          for (int i = 0; i < NCOEF; ++i) if (i < ncoef) q[i] = cf[i];
-          q[ncoef] = __longlong_as_double((long long)(((unsigned long long)problem << 40) | (unsigned long long)id));
+      const unsigned n_push = (unsigned)__popc(pm), rank = (unsigned)__popc(pm & ((1u << lane) - 1u));
+      unsigned slot;
+      if (paged) {
+        const unsigned room = QA_PAGE - pg_used;
+        unsigned nb = 0u;
+        if (n_push > room) {  // warp-uniform: the held page becomes the current one, the next is requested
+          nb = __shfl_sync(0xffffffffu, pg_next, 0);
+          if (lane == 0) pg_next = atomicAdd(&pipe.counts[0], QA_PAGE);
         }
+        slot = (rank < room) ? pg_base + pg_used + rank : nb + (rank - room);
+        if (n_push > room) { pg_base = nb; pg_used = n_push - room; pg_have = true; }
+        else pg_used += n_push;
+      } else {
+        unsigned slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&pipe.counts[0], n_push);
+        slot = __shfl_sync(0xffffffffu, slot0, 0) + rank;
       }
+      if (pass && slot < pipe.cap_a) {
+        double* q = pipe.qa + (size_t)slot * qs;
+#pragma unroll
+        for (int i = 0; i < NCOEF; ++i) if (i < ncoef) q[i] = cf[i];
+        q[ncoef] = __longlong_as_double((long long)(((unsigned long long)problem << 40) | (unsigned long long)id));
+      }
+    }
+  }
+  if (paged) {  // unused slots of the current page and the whole held page
+    const unsigned nb = __shfl_sync(0xffffffffu, pg_next, 0);
+    for (unsigned k = lane; k < 2u * QA_PAGE; k += 32u) {
+      const bool cur = k < QA_PAGE;
+      const unsigned off = cur ? k : k - QA_PAGE;
+      if (cur && (!pg_have || off < pg_used)) continue;
+      const unsigned slot = (cur ? pg_base : nb) + off;
+      if (slot < pipe.cap_a) pipe.qa[(size_t)slot * qs + ncoef] = __longlong_as_double((long long)QA_HOLE);
     }
   }
   // counters: warp -> block -> global
@@ -1187,56 +1238,87 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
 }
 
 // ---- stage B ---------------------------------------------------------------------------
+// Thread per queue-A entry for the end-point test (86 % of the entries stop there); the entries that pass it
+// are parked in a per-warp list and their interior test - roots of the difference polynomial's derivative,
+// data-dependent and ~10x the work - runs on 32 parked entries at a time, so that its lanes are all busy
+// (as one fused test it ran with 9 of 32 lanes).
 template <int DEG_T>
 __global__ void __launch_bounds__(256)
 ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
-  const unsigned n = min(pipe.counts[0], pipe.cap);
+  __shared__ unsigned s_pend[256 / 32][64];
+  const unsigned n = min(pipe.counts[0], pipe.cap_a);
   const int lane = threadIdx.x & 31;
-  const int qs = pipe.qs;
+  const int qs = pipe.qs, ncoef = qs - 1;
   const unsigned total = gridDim.x * blockDim.x;
+  unsigned* const pend = s_pend[threadIdx.x >> 5];
+  unsigned np = 0u;  // parked entries (warp-uniform)
   int acc_problem = -1;
   unsigned acc_n = 0;
-  for (unsigned i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += total) {
-    const unsigned i = i0 + lane;
-    const bool have = i < n;
+  auto reject = [&](int problem, const rb2_ransac_desc* d, unsigned long long tag) {
+    if (d->d_out_status) d->d_out_status[tag & TAG_ID_MASK] = (uint8_t)RB2_HYP_MONOTONIC;
+    if (problem != acc_problem) {  // per-thread run-length counter, flushed when the problem changes
+      if (acc_n) add_counter(result + acc_problem, 3, acc_n);
+      acc_problem = problem; acc_n = 0;
+    }
+    ++acc_n;
+  };
+  auto load = [&](unsigned i, double (&c)[deg_cap(DEG_T) + 1]) {
+    const double* q = pipe.qa + (size_t)i * qs;
+#pragma unroll
+    for (int k = 0; k <= deg_cap(DEG_T); ++k) c[k] = (k < ncoef) ? q[k] : 0.0;
+  };
+  auto interior = [&](unsigned count) {  // the last `count` (<= 32) parked entries
+    const bool have = (unsigned)lane < count;
     bool mono = false;
-    int problem = -1;
     double c[deg_cap(DEG_T) + 1];
     unsigned long long tag = 0;
     if (have) {
-      const double* q = pipe.qa + (size_t)i * qs;
-      const int ncoef = qs - 1;
-#pragma unroll
-      for (int k = 0; k <= deg_cap(DEG_T); ++k) c[k] = (k < ncoef) ? q[k] : 0.0;
-      tag = (unsigned long long)__double_as_longlong(q[ncoef]);
-      problem = (int)(tag >> 40);
+      const unsigned i = pend[np - count + lane];
+      load(i, c);
+      tag = (unsigned long long)__double_as_longlong(pipe.qa[(size_t)i * qs + ncoef]);
+      const int problem = (int)(tag >> 40);
       const rb2_ransac_desc* d = descs + problem;
-      const int deg = DEG_T > 0 ? DEG_T : d->deg;
-      mono = monotonic_test<DEG_T>(c, deg, d->pix_min, d->pix_max);
-      if (!mono && d->d_out_status) d->d_out_status[tag & TAG_ID_MASK] = (uint8_t)RB2_HYP_MONOTONIC;
+      mono = mono_interior<DEG_T>(c, DEG_T > 0 ? DEG_T : d->deg, d->pix_min, d->pix_max);
+      if (!mono) reject(problem, d, tag);
     }
-    const unsigned pm = __ballot_sync(0xffffffffu, have && mono);
-    if (have && !mono) {  // rejected: per-thread run-length counter, flushed when the problem changes
-      if (problem != acc_problem) {
-        if (acc_n) add_counter(result + acc_problem, 3, acc_n);
-        acc_problem = problem; acc_n = 0;
-      }
-      ++acc_n;
-    }
+    np -= count;
+    const unsigned pm = __ballot_sync(0xffffffffu, mono);
     if (pm) {
       unsigned slot0 = 0;
       if (lane == 0) slot0 = atomicAdd(&pipe.counts[1], (unsigned)__popc(pm));
       slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-      if (have && mono) {
+      if (mono) {
         const unsigned slot = slot0 + __popc(pm & ((1u << lane) - 1u));
         double* q = pipe.qb + (size_t)slot * qs;
-        const int ncoef = qs - 1;
 #pragma unroll
         for (int k = 0; k <= deg_cap(DEG_T); ++k) if (k < ncoef) q[k] = c[k];
         q[ncoef] = __longlong_as_double((long long)tag);
       }
     }
+    __syncwarp();
+  };
+  for (unsigned i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += total) {
+    const unsigned i = i0 + lane;
+    bool have = i < n, park = false;
+    if (have) {
+      const unsigned long long tag = (unsigned long long)__double_as_longlong(pipe.qa[(size_t)i * qs + ncoef]);
+      have = tag != QA_HOLE;  // an unfilled slot of stage A's paged reservation
+      if (have) {
+        double c[deg_cap(DEG_T) + 1];
+        load(i, c);
+        const int problem = (int)(tag >> 40);
+        const rb2_ransac_desc* d = descs + problem;
+        park = mono_ends<DEG_T>(c, DEG_T > 0 ? DEG_T : d->deg, d->pix_min, d->pix_max);
+        if (!park) reject(problem, d, tag);
+      }
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, park);
+    if (park) pend[np + __popc(km & ((1u << lane) - 1u))] = i;
+    np += __popc(km);
+    __syncwarp();
+    if (np >= 32u) interior(32u);
   }
+  if (np > 0u) interior(np);
   // final flush, aggregated over the lanes that hold the same problem
   const unsigned holders = __ballot_sync(0xffffffffu, acc_n > 0);
   if (acc_n > 0) {
@@ -1758,7 +1840,7 @@ static PipeLayout pipe_layout(int n_problems) {
   L.lane0 = lane0;
   L.counts = o - lane0; o = up(o + 16);
   L.win = o - lane0; o = up(o + (size_t)n_problems * sizeof(rb2_ransac_result));
-  L.qa = o - lane0; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
+  L.qa = o - lane0; o = up(o + ((size_t)PIPE_CHUNK + QA_SLACK) * (NCOEF + 1) * 8);
   L.qb = o - lane0; o = up(o + (size_t)PIPE_CHUNK * (NCOEF + 1) * 8);
   L.res_cost = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
   L.res_esum = o - lane0; o = up(o + (size_t)PIPE_CHUNK * 8);
@@ -1808,6 +1890,7 @@ struct ChunkArgs {
   dim3 grid_a; size_t smem_a, smem_c, smem_x; int max_wids, max_up, single, sms; cudaStream_t stream;
   const rb2_ransac_desc* d_desc; Pipe pipe; long long chunk_begin, chunk_len; rb2_ransac_result* d_result;
   PhiloxKey key;
+  int paged;  // stage A reserves queue slots page-wise (the grid's warps x 2 pages fit QA_SLACK)
   bool general_weight;  // some problem carries the spline tables of the general Hough-density weight
 };
 
@@ -1843,7 +1926,7 @@ static int launch_chunk(const ChunkArgs& a) {
   static const int nb = knob("RB2_B_CTAS_PER_SM", 8), nc1 = knob("RB2_C1_CTAS_PER_SM", 4), nc2 = knob("RB2_C2_CTAS_PER_SM", 8);
   pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(a.pipe);
   ransac_draw_fit_kernel<DEG_T, LSQ><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(a.d_desc, a.pipe, a.chunk_begin, a.chunk_len,
-                                                                                 a.d_result, a.key);
+                                                                                 a.d_result, a.key, a.paged);
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
   ransac_monotonic_kernel<DEG_T><<<sms * nb, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
@@ -1930,6 +2013,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     pipe.res_esum = (double*)(lb + L.res_esum);
     pipe.res_cnt = (int2*)(lb + L.res_cnt);
     pipe.cap = PIPE_CHUNK;
+    pipe.cap_a = PIPE_CHUNK + QA_SLACK;
     pipe.qs = deg + 2;
   }
   pipe_init_kernel<<<(n_problems + 255) / 256, 256, 0, stream>>>(ps, d_result, n_problems);
@@ -1967,6 +2051,11 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     ChunkArgs ca;
     ca.grid_a = dim3(bpp, n_problems); ca.smem_a = smem_a; ca.smem_c = smem_c; ca.smem_x = smem_x;
     ca.max_wids = max_wids; ca.max_up = max_up; ca.single = single; ca.sms = sms; ca.stream = cstream;
+    static const bool no_pages = getenv("RB2_A_UNPAGED") != nullptr;  // A/B knob
+    // paged only where the pages' empty ends (<= 2 pages per warp) are few next to the survivors (~16 % of the chunk):
+    // a rank's share of a sharded fit and batches of small problems keep the per-iteration atomic
+    const unsigned long long page_slots = (unsigned long long)bpp * n_problems * RS_WARPS * 2ull * QA_PAGE;
+    ca.paged = (!no_pages && page_slots <= QA_SLACK && (unsigned long long)len * n_problems >= 48ull * page_slots) ? 1 : 0;
     ca.d_desc = d_desc; ca.pipe = pipe; ca.chunk_begin = c0; ca.chunk_len = len; ca.d_result = d_result; ca.key = key; ca.general_weight = general_weight;
     int rc;
     switch ((fast ? 0 : 8) + (deg <= 5 ? deg : 0)) {
