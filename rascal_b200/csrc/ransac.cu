@@ -1335,6 +1335,7 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
 // error with an atomicMin on the wavelength's slot, then the peak whose error IS the minimum
 // claims the slot with a CAS that also resets it (equal errors: either peak, same cost).
 // Output per entry: sum of the clipped errors, match count, inlier count.
+constexpr int MATCH_UNROLL = 5;  // the reference's default top_n_candidate
 template <int DEG_T>
 __global__ void __launch_bounds__(RS_THREADS, 4)
 ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up, int single) {
@@ -1390,9 +1391,19 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
       const int o0 = g_coff[u], o1 = g_coff[u + 1];
       double be = CUDART_INF;
       int bk = -1;
-      for (int k = o0; k < o1; ++k) {
+      // the first MATCH_UNROLL candidates as straight-line predicated code (top-N lists are that short: the loop
+      // control was a sixth of this kernel's instructions), the rest in a loop
+#pragma unroll
+      for (int j = 0; j < MATCH_UNROLL; ++j) {
+        const int k = o0 + j;
+        if (k < o1) {
+          const double er = fabs(sub(fit, g_cwave[k]));
+          if (er < be) { be = er; bk = k; }  // first minimum wins
+        }
+      }
+      for (int k = o0 + MATCH_UNROLL; k < o1; ++k) {
         const double er = fabs(sub(fit, g_cwave[k]));
-        if (er < be) { be = er; bk = k; }  // first minimum wins
+        if (er < be) { be = er; bk = k; }
       }
       const int bw = (bk >= 0) ? g_cwid[bk] : -1;
       s_be[u] = be; s_bw[u] = bw;
