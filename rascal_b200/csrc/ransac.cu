@@ -2031,12 +2031,15 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
 
   // chunk = hypothesis ids per problem and launch.  Large calls use the full queue capacity (fewer, longer
   // kernels); a call that would fit in a few chunks (a rank's share of a sharded fit, a batch of spectra with
-  // 1e4 hypotheses each) is cut into ~2 chunks per lane, but not below 2^21 hypotheses in total, so that the
-  // stages of consecutive chunks still overlap across the lanes
+  // 1e4 hypotheses each) is cut into one chunk per lane, but not below 2^23 hypotheses in total: below that the
+  // ramp-up, tail and per-CTA table set-up of the seven kernels of a chunk cost more than the overlap of
+  // consecutive chunks gains (measured on B200, C3, K3 alone: 1.25e7 hypotheses 0.79 -> 0.68 ms, 2.5e7 1.32 -> 1.23 ms,
+  // 5e7 2.39 -> 2.34 ms against two chunks per lane with a 2^21 floor)
   long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
   {
-    const long long want = (max_hyp + 2 * pipe_lanes() - 1) / (2 * pipe_lanes());
-    const long long floor_pp = max(1ll, (long long)((1u << 21) / (unsigned)n_problems));
+    static const int per_lane = knob("RB2_CHUNKS_PER_LANE", 1), floor_log2 = knob("RB2_CHUNK_FLOOR_LOG2", 23);
+    const long long want = (max_hyp + per_lane * pipe_lanes() - 1) / (per_lane * pipe_lanes());
+    const long long floor_pp = max(1ll, (long long)((1u << floor_log2) / (unsigned)n_problems));
     per_problem = min(per_problem, max(want, floor_pp));
   }
   const long long n_chunks = (max_hyp + per_problem - 1) / per_problem;

@@ -182,11 +182,13 @@ __device__ void trf_svd(int n_, int m, TrfWs& w, double* s, double (*V)[NCF], bo
     }
   }
   __syncwarp();
+  // (the pair loops are NOT unrolled: nothing in a pair step needs p or q at compile time, and ten copies of
+  //  its ~300 instructions - the kernel is one warp - left it waiting for instruction fetches 44 % of the time)
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < n - 1; ++p) {
-#pragma unroll
+#pragma unroll 1
       for (int q = p + 1; q < n; ++q) {
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int i = lane; i < m; i += 32) {
