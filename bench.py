@@ -425,6 +425,15 @@ def k3_traffic():
     return k3_profile("dram_bytes_per_chunk")
 
 
+def k3_chunk_plan(lib, n_hyp):
+    """(chunks, lanes, ids per chunk) rb2_ransac_batch uses for one problem of n_hyp hypothesis ids."""
+    import ctypes as C
+
+    pp, nc, nl = C.c_longlong(0), C.c_int(0), C.c_int(0)
+    lib.rb2_ransac_chunk_plan(1, int(n_hyp), C.byref(pp), C.byref(nc), C.byref(nl))
+    return nc.value, nl.value, pp.value
+
+
 WORKLOAD_NAME = WORKLOADS["c3"]
 
 
@@ -593,7 +602,7 @@ def config_bench(args, torch, dist, rank, world, local, group):
                             "hough_lines": B, "pairs": P_pairs, "slopes": S},
         "counters": counters,
     }
-    n_chunks = -(-(hi - lo) // (1 << 24))
+    n_chunks = k3_chunk_plan(lib, hi - lo)[0]
     line["gpu_launches"] = (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps
     if not args.no_cpu and rank == 0:
         line["cpu_baseline"] = cpu_baseline(name)
@@ -914,13 +923,13 @@ def main():
         return
     F, f_i, f_m = flops_per_hypothesis(counters)
     per_rank_hyp = (hi - lo)
-    n_chunks = -(-per_rank_hyp // (1 << 24))
+    n_chunks, n_lanes, chunk_ids = k3_chunk_plan(lib, per_rank_hyp)
     achieved = per_rank_hyp * args.steps * F / (kern_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d, chunks of 2^24 ids over 3 stream lanes per GPU" % world,
+        "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d, %d chunks of %d ids over %d stream lanes per GPU" % (world, n_chunks, chunk_ids, n_lanes),
                    "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
         "clocks": clocks.summary(),
         "e2e": e2e,

@@ -277,7 +277,7 @@ typedef struct {
   uint64_t counters[8];                 /* drawn, aborted, intercept, monotonic, empty, scored, eligible, unsupported */
 } rb2_ransac_result;
 
-/* Chunks of 2^22 hypothesis ids alternate over internal stream lanes that fork
+/* Chunks of up to 2^24 hypothesis ids alternate over internal stream lanes that fork
  * from and join back into `stream` (events; capturable); everything the call
  * enqueues is ordered after prior work on `stream` and before later work on it.
  * One host thread per device drives this entry point.
@@ -285,6 +285,11 @@ typedef struct {
  * for one problem).  d_block_scratch must hold rb2_ransac_scratch_bytes().
  * All problems of one call share deg, sample_size and seed (else RB2_ERR_ARG). */
 size_t rb2_ransac_scratch_bytes(int n_problems, int blocks_per_problem);
+/* How rb2_ransac_batch cuts a call of n_problems x max_hyp hypothesis ids: ids per problem and chunk, the number
+ * of chunks (each = 7 kernel launches, 8 with the general Hough weight) and the stream lanes they alternate over
+ * (any output pointer may be NULL).  The reference has no counterpart: its loop (calibrator.py:525-735) is
+ * one hypothesis at a time. */
+int rb2_ransac_chunk_plan(int n_problems, long long max_hyp, long long *per_problem, int *n_chunks, int *n_lanes);
 int rb2_ransac_batch(int n_problems, const rb2_ransac_desc *d_desc,
                      const rb2_ransac_desc *h_desc, rb2_ransac_result *d_result,
                      void *d_block_scratch, int blocks_per_problem, void *stream);

@@ -162,6 +162,7 @@ EXPORTS = {
     "rb2_candidate_vote": (C.c_int, [C.c_int, _vp, _vp, _vp]),
     "rb2_candidate_points": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "rb2_ransac_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rb2_ransac_chunk_plan": (C.c_int, [C.c_int, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rb2_ransac_batch": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rb2_merge_winners": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "rb2_robust_polyfit": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),

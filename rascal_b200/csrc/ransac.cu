@@ -1897,6 +1897,15 @@ static int knob(const char* name, int dflt) {
   return v < 1 ? dflt : v;
 }
 
+// hypothesis ids per problem and chunk (see rb2_ransac_batch)
+static long long chunk_len(int n_problems, long long max_hyp) {
+  long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
+  static const int per_lane = knob("RB2_CHUNKS_PER_LANE", 1), floor_log2 = knob("RB2_CHUNK_FLOOR_LOG2", 23);
+  const long long want = (max_hyp + per_lane * pipe_lanes() - 1) / (per_lane * pipe_lanes());
+  const long long floor_pp = max(1ll, (long long)((1u << floor_log2) / (unsigned)n_problems));
+  return min(per_problem, max(want, floor_pp));
+}
+
 struct ChunkArgs {
   dim3 grid_a; size_t smem_a, smem_c, smem_x; int max_wids, max_up, single, sms; cudaStream_t stream;
   const rb2_ransac_desc* d_desc; Pipe pipe; long long chunk_begin, chunk_len; rb2_ransac_result* d_result;
@@ -1962,6 +1971,16 @@ extern "C" size_t rb2_ransac_scratch_bytes(int n_problems, int blocks_per_proble
   (void)blocks_per_problem;
   if (n_problems <= 0) return 0;
   return rb2::pipe_layout(n_problems).total;
+}
+
+extern "C" int rb2_ransac_chunk_plan(int n_problems, long long max_hyp, long long* per_problem, int* n_chunks, int* n_lanes) {
+  if (n_problems <= 0 || max_hyp < 0 || (unsigned)n_problems > PIPE_CHUNK) return RB2_ERR_ARG;
+  const long long pp = rb2::chunk_len(n_problems, max_hyp);
+  const long long nc = (max_hyp + pp - 1) / pp;
+  if (per_problem) *per_problem = pp;
+  if (n_chunks) *n_chunks = (int)nc;
+  if (n_lanes) *n_lanes = (int)(nc > 1 ? (nc < rb2::pipe_lanes() ? nc : rb2::pipe_lanes()) : 1);
+  return RB2_OK;
 }
 
 extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, const rb2_ransac_desc* h_desc,
@@ -2035,13 +2054,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   // ramp-up, tail and per-CTA table set-up of the seven kernels of a chunk cost more than the overlap of
   // consecutive chunks gains (measured on B200, C3, K3 alone: 1.25e7 hypotheses 0.79 -> 0.68 ms, 2.5e7 1.32 -> 1.23 ms,
   // 5e7 2.39 -> 2.34 ms against two chunks per lane with a 2^21 floor)
-  long long per_problem = max(1ll, (long long)(PIPE_CHUNK / (unsigned)n_problems));
-  {
-    static const int per_lane = knob("RB2_CHUNKS_PER_LANE", 1), floor_log2 = knob("RB2_CHUNK_FLOOR_LOG2", 23);
-    const long long want = (max_hyp + per_lane * pipe_lanes() - 1) / (per_lane * pipe_lanes());
-    const long long floor_pp = max(1ll, (long long)((1u << floor_log2) / (unsigned)n_problems));
-    per_problem = min(per_problem, max(want, floor_pp));
-  }
+  const long long per_problem = rb2::chunk_len(n_problems, max_hyp);
   const long long n_chunks = (max_hyp + per_problem - 1) / per_problem;
   LaneStreams& ls = lane_streams();
   const int n_lanes = (ls.ok && n_chunks > 1) ? (int)min((long long)ps.n, n_chunks) : 1;
