@@ -412,8 +412,9 @@ def reference_arm(args):
 
 def k3_profile(key):
     """Figures of the K3 stage kernels from the committed `ncu --set full` capture (profiles/k3_traffic.json):
-    "dram_bytes_per_chunk" = DRAM read + write bytes per 2^22-hypothesis chunk, "issue_slots_busy_pct" = issue-slot
-    utilisation per stage kernel; None if the file is absent."""
+    "dram_bytes_per_chunk" = DRAM read + write bytes of the six stage kernels of one chunk ("hypotheses_per_chunk" ids,
+    2^24 in a 1e8-hypothesis step), "issue_slots_busy_pct" = issue-slot utilisation per stage kernel; None if the
+    file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
             return json.load(f)[key]
@@ -938,8 +939,9 @@ def main():
         "gpu_launches": (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": k3_traffic(),
-                     "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant, ~60 % of K3 time) + "
-                               "monotonic + match + cost + record, timed together per step",
+                     "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant: 65 % of K3's instructions) + "
+                               "monotonic + match + cost + exact + record, timed together per step; traffic = DRAM "
+                               "bytes of one 2^24-hypothesis chunk's six kernels (ncu, caches flushed)",
                      "issue_slots_busy_pct": k3_profile("issue_slots_busy_pct"),
                      "flops_per_hypothesis": F, "f_intercept_pass": f_i,
                      "f_scored": f_m, "peak_source": "DFMA microbenchmark in this run (rb2_dfma_burn); FP64 is not in MEASURED_PEAKS.json",
