@@ -275,6 +275,40 @@ def test_philox_hypotheses_agree_with_oracle():
         assert c0 < prob.min_intercept or c0 > prob.max_intercept
 
 
+def test_large_call_equals_its_small_parts():
+    """A call big enough for 2^24-id chunks - stage A then reserves queue-A slots a page ahead and leaves
+    tagged holes for stage B to skip (ransac.cu, QA_PAGE) - selects the same winner and counts the same
+    outcomes as the same id range evaluated in small calls, which use the per-iteration atomic and other
+    chunk lengths (rb2_ransac_chunk_plan)."""
+    import ctypes as C
+
+    from rascal_b200 import _native, engine
+
+    g = load_golden("c3_deg4")
+    s = setup_from_golden(g)
+    n, parts = 40_000_000, 8
+    lib = _native.load()
+    pp = C.c_longlong(0)
+    assert lib.rb2_ransac_chunk_plan(1, n, C.byref(pp), None, None) == 0 and pp.value >= 48 * 3 * 148 * 8 * 64
+    assert lib.rb2_ransac_chunk_plan(1, n // parts, C.byref(pp), None, None) == 0 and pp.value < 10_000_000
+    rb = engine.RansacBatch([s])
+    rb.run(0, n, seed=11)
+    whole = rb.results()[0]
+    best, counters = None, [0] * 8
+    for k in range(parts):
+        rb.run(k * (n // parts), n // parts, seed=11)
+        r = rb.results()[0]
+        counters = [x + y for x, y in zip(counters, r.counters)]
+        if r.hyp_id >= 0 and (best is None or (r.cost, -r.hyp_id) < (best.cost, -best.hyp_id)):
+            best = _native.RansacResult.from_buffer_copy(bytes(r))
+    assert list(whole.counters) == counters
+    c = engine.counters_dict(whole)
+    assert c["drawn"] + c["aborted"] == n
+    assert c["intercept"] + c["monotonic"] + c["empty"] + c["scored"] + c["unsupported"] == c["drawn"]
+    assert (whole.hyp_id, whole.cost, whole.n_match, whole.n_inliers) == (best.hyp_id, best.cost, best.n_match, best.n_inliers)
+    assert list(whole.coeffs) == list(best.coeffs)
+
+
 def test_philox_sharding_independent():
     """Hypothesis-id ranges are independent of the launch split: best over [0,N) ==
     merge of the bests over [0,N/2) and [N/2,N) (what the multi-GPU path relies on)."""
