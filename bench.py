@@ -9,7 +9,12 @@ A step = one pass of the hot path over one batch of hypotheses: H hypothesis ids
 the Philox stream (default 1e8, the configuration the target is quoted on), split
 evenly over the N ranks (strong scaling: total work fixed), each rank running K3
 (draw -> fit -> intercept/monotonicity tests -> bijective match -> M-SAC cost ->
-block-best), ONE all-gather of the per-rank winner records, and K4 (winner refit).
+block-best), ONE all-gather of the per-rank winner records, K4 (winner refit) and the
+D2H copy of the result.  The K timed steps run back to back the way a service that
+calibrates one spectrum after the other runs them: the exchange, K4 (one warp) and the
+D2H of step k sit on a side stream and overlap K3 of step k + 1; every result is on the
+host before the closing event.  `sequential` reports the same K steps one at a time
+(the latency of a resident fit).
 Hough + candidate vote (K1, K2) run once per spectrum and are part of the e2e leg,
 which goes through the public Calibrator API with host buffers every step.
 
@@ -694,36 +699,91 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+
+    # ---- (1) one fit after the other: the latency of a step (K3 -> exchange -> K4 -> D2H, the host waits for the
+    # result before the next step starts).  Reported as `sequential`. ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (inputs are KBs, far below L2)
+        ev[k][0].record()
+        rb.run((args.warmup + k) * H + lo, hi - lo, seed=2026)
+        rb.exchange(group)
+        rb.refit_async()
+        rb.fetch()
+        ev[k][1].record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    seq_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(seq_ms, op=dist.ReduceOp.MAX)
+    seq_ms = float(seq_ms.item())
+
+    # ---- (2) the timed job: the same K steps back to back, as a service that calibrates one spectrum after the other
+    # runs them - K3 of step k on the main stream; the exchange, K4 and the D2H of step k on a side stream, where they
+    # overlap K3 of step k + 1 (K4 is ONE warp: a dependent chain that no rank count shrinks).  Two sets of result
+    # buffers alternate; every step's result is on the host before the closing event.  `value` = K * H / this time. ----
+    rbs = [rb, engine.RansacBatch([setup])]
+    side = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    for k in range(2):  # warm the second buffer set
+        rbs[1].run(k * H + lo, hi - lo, seed=2026)
+        rbs[1].exchange(group)
+        rbs[1].refit_async()
+        rbs[1].fetch()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     counters = dict.fromkeys(_native.COUNTER_NAMES, 0)
+    results = []
+
+    def collect(r, done):
+        win, fit, mx, my, rs = r.fetch_wait(done)
+        results.append((win[0].hyp_id, fit[0].accepted))
+        for name, v in engine.counters_dict(win[0]).items():
+            counters[name] += v
+
     with ClockSampler(local) as clocks:
         t_wall0 = time.perf_counter()
+        t_begin.record()
+        pending = None
         for k in range(args.steps):
-            flush.zero_()  # L2 flush between timed iterations (inputs are KBs, far below L2)
-            ev[k][0].record()
+            r = rbs[k % 2]
+            flush.zero_()  # L2 flush between timed iterations
             kev[k][0].record()
-            rb.run((args.warmup + k) * H + lo, hi - lo, seed=2026)  # K3 main + finalize
+            r.run((args.warmup + k) * H + lo, hi - lo, seed=2026)  # K3 (main stream)
             kev[k][1].record()
-            rb.exchange(group)
-            rb.refit_async()  # K4
-            win, fit, mx, my, rs = rb.fetch()
-            ev[k][1].record()
-            for name, v in engine.counters_dict(win[0]).items():
-                counters[name] += v
+            k3_done = torch.cuda.Event()
+            k3_done.record()
+            with torch.cuda.stream(side):
+                side.wait_event(k3_done)
+                r.exchange(group)          # NCCL all-gather + device merge (no-op at N=1)
+                r.refit_async()            # K4
+                done = r.fetch_async()     # the step's single D2H copy
+            if pending is not None:
+                collect(*pending)          # step k - 1: it finished while K3 of step k was queued / running
+            pending = (r, done)
+        collect(*pending)
+        main_stream.wait_stream(side)
+        t_end.record()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    assert len(results) == args.steps
     ms_kernel = [a.elapsed_time(b) for a, b in kev]
-    total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device="cuda")
+    total_ms = torch.tensor([t_begin.elapsed_time(t_end)], dtype=torch.float64, device="cuda")
     kern_ms = torch.tensor([sum(ms_kernel)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = float(total_ms.item()), float(kern_ms.item())
     value = args.steps * H / (total_ms * 1e-3)
+    sequential = {"value": args.steps * H / (seq_ms * 1e-3), "unit": UNIT, "ms_per_step": seq_ms / args.steps,
+                  "what": "the same K steps one after the other (the host waits for a step's result before it starts "
+                          "the next): latency of one resident fit"}
 
     # ---- FP64 roofline denominator (DFMA microbenchmark, same box, same run) ----
     sms = rb.sm_count
@@ -931,9 +991,12 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "hypotheses_per_step": H, "parallelism": "hypothesis-id ranges x%d, %d chunks of %d ids over %d stream lanes per GPU" % (world, n_chunks, chunk_ids, n_lanes),
-                   "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026},
+                   "l2": "flushed (256 MiB write) between timed steps", "philox_seed": 2026,
+                   "steps": "back to back: exchange + K4 + D2H of step k on a side stream overlap K3 of step k+1; "
+                            "`sequential` = one step at a time"},
         "clocks": clocks.summary(),
         "e2e": e2e,
+        "sequential": sequential,
         # K3 = pipe_init + 8 kernels (reset, draw_fit, monotonic, match, cost, general weight, exact, record) per
         # 2^24-hypothesis chunk + pipe_join; + merge after the all-gather (N > 1) + K4 refit
         "gpu_launches": (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,

@@ -914,13 +914,21 @@ class RansacBatch:
                                         self.max_up, current_stream_ptr())
         N.check(rc, "rb2_refit_winners")
 
-    def fetch(self):
-        """ONE device->host copy of everything a fit produced:
-        (winner records, refit results, matched_x, matched_y, residual)."""
+    def fetch_async(self):
+        """Enqueue the ONE device->host copy of everything a fit produced on the current stream and return the
+        event that marks its end (fetch_wait(event) reads the copy).  Lets a caller that runs fits back to back
+        put K4 + this copy of fit k on a side stream while K3 of fit k + 1 runs (bench.py)."""
         torch = _torch()
         self.h_out.copy_(self.d_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        ev = torch.cuda.Event()
+        ev.record()
         TRANSFER["d2h"] += self.h_out.numel()
+        return ev
+
+    def fetch_wait(self, event=None):
+        """(winner records, refit results, matched_x, matched_y, residual) from the pinned host copy."""
+        if event is not None:
+            event.synchronize()
         raw = self.h_out.numpy()
         win = (N.RansacResult * self.n).from_buffer_copy(raw[self._o_res:self._o_fit].tobytes())
         fit = (N.RefitResult * self.n).from_buffer_copy(raw[self._o_fit:self._o_mx].tobytes())
@@ -929,6 +937,11 @@ class RansacBatch:
         my = raw[self._o_my:self._o_rs].view(np.float64).reshape(shp).copy()
         rs = raw[self._o_rs:].view(np.float64).reshape(shp).copy()
         return win, fit, mx, my, rs
+
+    def fetch(self):
+        """ONE device->host copy of everything a fit produced:
+        (winner records, refit results, matched_x, matched_y, residual)."""
+        return self.fetch_wait(self.fetch_async())
 
     def refit(self, winners=None, mode=0):
         """K4 on the current winners (or on explicitly supplied RansacResult structs)."""
