@@ -624,7 +624,7 @@ def main():
     ap.add_argument("--hyp", type=float, default=1e8, help="hypotheses per step over all ranks")
     ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"],
                     help="BASELINE config: c3 (headline, default), c2 (GMOS deg 5, 1e5 tries), c5 (DEIMOS 1000x1000 bins, 1e6 tries)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="fits in the e2e leg (0 = --steps)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--spectra", type=int, default=2048, help="C4 spectra per rank in the many-spectra leg (0 = skip)")
     args = ap.parse_args()
@@ -791,7 +791,7 @@ def main():
 
     # ---- e2e leg: the public Calibrator API with host buffers, every step ----
     e2e = None
-    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    e2e_steps = max(1, min(args.e2e_steps or args.steps, args.steps))
     for k in range(2):  # warm the public path the timed loop takes (allocations, spline operator, NCCL)
         wc = new_calibrator(5 + k)
         wc.do_hough_transform()
