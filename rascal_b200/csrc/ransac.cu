@@ -970,7 +970,10 @@ __device__ __forceinline__ void add_counter(rb2_ransac_result* r, int k, unsigne
 // Work items of a warp are either the next 32 hypothesis ids of its stream (fast sampler) or 32
 // hypotheses from its deferred queue (those whose fast draw needs a redraw: slow sampler, all lanes
 // busy again); draw, fit, intercept test and the queue push are the same code for both.
-template <int DEG_T, bool LSQ = false>
+// PLAIN = the production launch: no replayed draws, no per-hypothesis outputs, monomial basis - the tests of
+// those switches and the code behind them are compiled out (they were ~5 % of the instructions of a launch that
+// uses none of them).
+template <int DEG_T, bool LSQ = false, bool PLAIN = false>
 __global__ void __launch_bounds__(RS_THREADS, DEG_T > 0 && DEG_T <= 4 && !LSQ ? RB2_A_CTAS : 2)
 ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, long long chunk_begin, long long chunk_len,
                        rb2_ransac_result* __restrict__ result, const PhiloxKey pkey, const int paged) {
@@ -1041,7 +1044,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   tb.prec = s_prec; tb.okt = s_okt; tb.cwave = s_cwave; tb.lut = s_lut; tb.n_u = n_u;
   tb.uni = (s_kmin == s_kmax && s_kmax > 0) ? ((unsigned)s_kmax | ((65536u % (unsigned)s_kmax) << 8)) : 0u;
 
-  const bool replay = d.d_replay_x != nullptr;
+  const bool replay = !PLAIN && d.d_replay_x != nullptr;
   const int s = FAST ? DEG_T + 1 : d.sample_size;
   const double min_i = d.min_intercept, max_i = d.max_intercept;
   const long long n_hyp = d.n_hyp;
@@ -1049,7 +1052,9 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   const double lsq_xsc = (d.pix_max > d.pix_min) ? 2.0 / (d.pix_max - d.pix_min) : 1.0;
   const int qs = pipe.qs;
   unsigned c_drawn = 0, c_abort = 0, c_icpt = 0;
-  const bool diag = d.d_out_status != nullptr || d.d_out_coeffs != nullptr || d.d_out_sample != nullptr;  // parity / diagnostics launches only
+  const bool diag = !PLAIN && (d.d_out_status != nullptr || d.d_out_coeffs != nullptr || d.d_out_sample != nullptr);  // parity / diagnostics launches only
+  const bool out_sample = !PLAIN && d.d_out_sample != nullptr;
+  const bool other_basis = !PLAIN && d.basis != 0;
 
   const long long stride = (long long)gridDim.x * RS_THREADS;
   long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane);
@@ -1127,7 +1132,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
           for (int k = 0; k <= DEG_T; ++k) cf[k] = cc[k];
         }
       }
-      if (active && d.d_out_sample) {
+      if (active && out_sample) {
 #pragma unroll
         for (int k = 0; k <= DEG_T; ++k) {
           d.d_out_sample[(id * (DEG_T + 1) + k) * 2] = aborted ? -1 : pi[k];
@@ -1159,7 +1164,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
           }
         }
       }
-      if (d.d_out_sample)
+      if (out_sample)
         for (int k = 0; k < s; ++k) {
           d.d_out_sample[(id * s + k) * 2] = aborted ? -1 : pi[k];
           d.d_out_sample[(id * s + k) * 2 + 1] = aborted ? -1 : ci[k] - (int)(tb.okt[pi[k]] & 0xffffu);
@@ -1168,7 +1173,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
     if (active) {
       if (!aborted) {
         double c0 = cf[0];
-        if (d.basis) {  // the first coefficient of the BASIS the reference fitted in (legfit / chebfit)
+        if (other_basis) {  // the first coefficient of the BASIS the reference fitted in (legfit / chebfit)
           c0 = 0.0;
           for (int k = 0; k < ncoef; ++k) c0 = fma(d.d_basis_c0[k], cf[k], c0);
         }
@@ -1911,6 +1916,7 @@ struct ChunkArgs {
   const rb2_ransac_desc* d_desc; Pipe pipe; long long chunk_begin, chunk_len; rb2_ransac_result* d_result;
   PhiloxKey key;
   int paged;  // stage A reserves queue slots page-wise (the grid's warps x 2 pages fit QA_SLACK)
+  int plain;  // no problem replays draws, asks for per-hypothesis outputs or fits in another basis
   bool general_weight;  // some problem carries the spline tables of the general Hough-density weight
 };
 
@@ -1923,6 +1929,8 @@ static int launch_chunk(const ChunkArgs& a) {
   dev = (dev >= 0 && dev < 64) ? dev : 0;
   if (a.smem_a > cfg_a[dev]) {
     RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_a)));
+    if (!LSQ && DEG_T > 0)
+      RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ, (!LSQ && DEG_T > 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_a)));
     cfg_a[dev] = a.smem_a;
   }
   if (a.smem_c > cfg_c[dev]) {
@@ -1945,8 +1953,12 @@ static int launch_chunk(const ChunkArgs& a) {
   // CTAs per SM of the small stages (tuning knobs; the defaults are the measured optimum)
   static const int nb = knob("RB2_B_CTAS_PER_SM", 8), nc1 = knob("RB2_C1_CTAS_PER_SM", 4), nc2 = knob("RB2_C2_CTAS_PER_SM", 8);
   pipe_reset_counts_kernel<<<1, 32, 0, stream>>>(a.pipe);
-  ransac_draw_fit_kernel<DEG_T, LSQ><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(a.d_desc, a.pipe, a.chunk_begin, a.chunk_len,
-                                                                                 a.d_result, a.key, a.paged);
+  if (!LSQ && DEG_T > 0 && a.plain)
+    ransac_draw_fit_kernel<DEG_T, LSQ, (!LSQ && DEG_T > 0)><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(
+        a.d_desc, a.pipe, a.chunk_begin, a.chunk_len, a.d_result, a.key, a.paged);
+  else
+    ransac_draw_fit_kernel<DEG_T, LSQ><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(a.d_desc, a.pipe, a.chunk_begin, a.chunk_len,
+                                                                                   a.d_result, a.key, a.paged);
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
   ransac_monotonic_kernel<DEG_T><<<sms * nb, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
@@ -1994,7 +2006,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
   if (rb2_sm_count(&sms) != RB2_OK) return RB2_ERR_NO_DEVICE;
   // all problems of one call share degree / sample size (one kernel instantiation) and the Philox key
   const int deg = h_desc[0].deg, s = h_desc[0].sample_size;
-  bool fast = true, general_weight = false;
+  bool fast = true, general_weight = false, plain = true;
   size_t smem_a = 0;
   int max_wids = 1, max_up = 1;
   long long max_hyp = 0;
@@ -2012,6 +2024,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
       if (h.bs_nx < 4 || h.bs_ny < 4 || !h.d_bs_tx || !h.d_bs_ty || !h.d_bs_ppx || !h.d_bs_ppy) return RB2_ERR_ARG;
       general_weight = true;
     }
+    if (h.d_replay_x || h.d_out_status || h.d_out_coeffs || h.d_out_sample || h.basis) plain = false;
     smem_a = max(smem_a, stage_a_smem(h));
     max_wids = max(max_wids, h.n_wids);
     max_up = max(max_up, h.n_upeaks);
@@ -2083,7 +2096,7 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
     // a rank's share of a sharded fit and batches of small problems keep the per-iteration atomic
     const unsigned long long page_slots = (unsigned long long)bpp * n_problems * RS_WARPS * 2ull * QA_PAGE;
     ca.paged = (!no_pages && page_slots <= QA_SLACK && (unsigned long long)len * n_problems >= 48ull * page_slots) ? 1 : 0;
-    ca.d_desc = d_desc; ca.pipe = pipe; ca.chunk_begin = c0; ca.chunk_len = len; ca.d_result = d_result; ca.key = key; ca.general_weight = general_weight;
+    ca.d_desc = d_desc; ca.pipe = pipe; ca.chunk_begin = c0; ca.chunk_len = len; ca.d_result = d_result; ca.key = key; ca.general_weight = general_weight; ca.plain = plain ? 1 : 0;
     int rc;
     switch ((fast ? 0 : 8) + (deg <= 5 ? deg : 0)) {
       case 1: rc = launch_chunk<1>(ca); break;
