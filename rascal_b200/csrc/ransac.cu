@@ -1247,7 +1247,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
 // are parked in a per-warp list and their interior test - roots of the difference polynomial's derivative,
 // data-dependent and ~10x the work - runs on 32 parked entries at a time, so that its lanes are all busy
 // (as one fused test it ran with 9 of 32 lanes).
-template <int DEG_T>
+template <int DEG_T, bool PLAIN = false>
 __global__ void __launch_bounds__(256)
 ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
   __shared__ unsigned s_pend[256 / 32][64];
@@ -1260,7 +1260,7 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
   int acc_problem = -1;
   unsigned acc_n = 0;
   auto reject = [&](int problem, const rb2_ransac_desc* d, unsigned long long tag) {
-    if (d->d_out_status) d->d_out_status[tag & TAG_ID_MASK] = (uint8_t)RB2_HYP_MONOTONIC;
+    if (!PLAIN && d->d_out_status) d->d_out_status[tag & TAG_ID_MASK] = (uint8_t)RB2_HYP_MONOTONIC;
     if (problem != acc_problem) {  // per-thread run-length counter, flushed when the problem changes
       if (acc_n) add_counter(result + acc_problem, 3, acc_n);
       acc_problem = problem; acc_n = 0;
@@ -1341,9 +1341,10 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
 // claims the slot with a CAS that also resets it (equal errors: either peak, same cost).
 // Output per entry: sum of the clipped errors, match count, inlier count.
 constexpr int MATCH_UNROLL = 5;  // the reference's default top_n_candidate
-template <int DEG_T>
+template <int DEG_T, bool SINGLE = false>  // SINGLE: one problem in the call, its tables staged in shared memory
 __global__ void __launch_bounds__(RS_THREADS, 4)
-ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up, int single) {
+ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up) {
+  constexpr bool single = SINGLE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1463,16 +1464,19 @@ __device__ __forceinline__ void best_update(BestKey* slot, const BestKey& mine) 
 }
 
 // status / counts of a scored hypothesis (parity outputs)
+template <bool PLAIN = false>
 __device__ __forceinline__ void cost_report(const rb2_ransac_desc& d, long long id, int nm, int ni) {
+  if (PLAIN) return;
   if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_SCORED;
   if (d.d_out_counts) { d.d_out_counts[2 * id] = nm; d.d_out_counts[2 * id + 1] = ni; }
 }
 // cost of a scored hypothesis from its (tree-summed) errors and its weight, eligibility, running best;
 // returns the entry's RES_* flag
+template <bool PLAIN = false>
 __device__ __forceinline__ unsigned char cost_tail(const rb2_ransac_desc& d, Pipe& pipe, unsigned e, long long id,
                                                    int problem, int nm, int ni, double esum, double weight,
                                                    bool counts_ok, int ncoef) {
-  cost_report(d, id, nm, ni);
+  cost_report<PLAIN>(d, id, nm, ni);
   const long long gid = d.hyp_begin + id;
   const double denom = (double)(nm - ncoef + 1);
   const double cost = esum / denom / (weight + 1e-9);  // :629-633
@@ -1483,8 +1487,8 @@ __device__ __forceinline__ unsigned char cost_tail(const rb2_ransac_desc& d, Pip
     near_floor = fabs(cost - d.floor_cost) <= slack;
     elig = near_floor || cost > d.floor_cost;
   }
-  if (d.d_out_cost) d.d_out_cost[id] = cost;
-  if (d.d_out_weight) d.d_out_weight[id] = weight;
+  if (!PLAIN && d.d_out_cost) d.d_out_cost[id] = cost;
+  if (!PLAIN && d.d_out_weight) d.d_out_weight[id] = weight;
   if (!elig) return 0;
   pipe.res_cost[e] = cost;
   pipe.res_w[e] = weight;
@@ -1586,7 +1590,7 @@ ransac_weight_general_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pip
   }
 }
 
-template <int DEG_T>
+template <int DEG_T, bool PLAIN = false>
 __global__ void __launch_bounds__(128, 4)
 ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
   const unsigned n = pipe.counts[1];
@@ -1612,11 +1616,11 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
       unsigned char flag = 0;
       if (nm == 0) {  // :607-608
         kind = 0;
-        if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY;
+        if (!PLAIN && d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_EMPTY;
       } else {
         const long long gid = d.hyp_begin + id;
         const bool counts_ok = (ni >= d.min_inliers) && ((double)ni >= d.min_inliers_frac);
-        const bool wants_all = d.d_out_cost || d.d_out_weight;  // parity / diagnostics: every cost is reported
+        const bool wants_all = !PLAIN && (d.d_out_cost || d.d_out_weight);  // parity / diagnostics: every cost is reported
         bool need_value = wants_all || counts_ok;
         const double denom = (double)(nm - ncoef + 1);
         if (need_value && !wants_all && d.w_upper > 0.0) {
@@ -1625,7 +1629,7 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
           if (cost_key(lb) > best_hi || lb > d.cost_ceiling) need_value = false;
         }
         double weight = 0.0;
-        const bool ok = d.basis ? false : hough_weight_thread<DEG_T>(d, cr, deg, need_value, &weight);
+        const bool ok = (!PLAIN && d.basis) ? false : hough_weight_thread<DEG_T>(d, cr, deg, need_value, &weight);
         if (!ok && d.d_bs_c) {
           // outside the corner regime: the weight is the clamped bicubic spline summed over the pixels -
           // warp-sized work, done by ransac_weight_general_kernel (which also finishes the cost)
@@ -1633,11 +1637,11 @@ ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ran
           flag = RES_GENERAL;
         } else if (!ok) {
           kind = 3;
-          if (d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED;
+          if (!PLAIN && d.d_out_status) d.d_out_status[id] = (uint8_t)RB2_HYP_UNSUPPORTED;
         } else {
           kind = counts_ok ? 2 : 1;
-          if (need_value) flag = cost_tail(d, pipe, e, id, problem, nm, ni, esum, weight, counts_ok, ncoef);
-          else cost_report(d, id, nm, ni);
+          if (need_value) flag = cost_tail<PLAIN>(d, pipe, e, id, problem, nm, ni, esum, weight, counts_ok, ncoef);
+          else cost_report<PLAIN>(d, id, nm, ni);
         }
       }
       pipe.res_flag[e] = flag;
@@ -1935,6 +1939,7 @@ static int launch_chunk(const ChunkArgs& a) {
   }
   if (a.smem_c > cfg_c[dev]) {
     RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_c));
+    RB2_CHECK((cudaFuncSetAttribute(ransac_match_kernel<DEG_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_c)));
     cfg_c[dev] = a.smem_c;
   }
   if (a.smem_x > cfg_x[dev] && a.smem_x > 48 * 1024) {
@@ -1960,11 +1965,14 @@ static int launch_chunk(const ChunkArgs& a) {
     ransac_draw_fit_kernel<DEG_T, LSQ><<<a.grid_a, RS_THREADS, a.smem_a, stream>>>(a.d_desc, a.pipe, a.chunk_begin, a.chunk_len,
                                                                                    a.d_result, a.key, a.paged);
   if (!stage_ok("A draw_fit")) return RB2_ERR_CUDA;
-  ransac_monotonic_kernel<DEG_T><<<sms * nb, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
+  if (a.plain) ransac_monotonic_kernel<DEG_T, true><<<sms * nb, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
+  else ransac_monotonic_kernel<DEG_T><<<sms * nb, 256, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("B monotonic")) return RB2_ERR_CUDA;
-  ransac_match_kernel<DEG_T><<<sms * nc1, RS_THREADS, a.smem_c, stream>>>(a.d_desc, a.pipe, a.max_wids, a.max_up, a.single);
+  if (a.single) ransac_match_kernel<DEG_T, true><<<sms * nc1, RS_THREADS, a.smem_c, stream>>>(a.d_desc, a.pipe, a.max_wids, a.max_up);
+  else ransac_match_kernel<DEG_T><<<sms * nc1, RS_THREADS, a.smem_c, stream>>>(a.d_desc, a.pipe, a.max_wids, a.max_up);
   if (!stage_ok("C1 match")) return RB2_ERR_CUDA;
-  ransac_cost_kernel<DEG_T><<<sms * nc2, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
+  if (a.plain) ransac_cost_kernel<DEG_T, true><<<sms * nc2, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
+  else ransac_cost_kernel<DEG_T><<<sms * nc2, 128, 0, stream>>>(a.d_desc, a.pipe, a.d_result);
   if (!stage_ok("C2 cost")) return RB2_ERR_CUDA;
   if (a.general_weight) {
     ransac_weight_general_kernel<DEG_T><<<sms * 4, 256, 0, stream>>>(a.d_desc, a.pipe);
@@ -2024,7 +2032,8 @@ extern "C" int rb2_ransac_batch(int n_problems, const rb2_ransac_desc* d_desc, c
       if (h.bs_nx < 4 || h.bs_ny < 4 || !h.d_bs_tx || !h.d_bs_ty || !h.d_bs_ppx || !h.d_bs_ppy) return RB2_ERR_ARG;
       general_weight = true;
     }
-    if (h.d_replay_x || h.d_out_status || h.d_out_coeffs || h.d_out_sample || h.basis) plain = false;
+    if (h.d_replay_x || h.d_out_status || h.d_out_coeffs || h.d_out_sample || h.d_out_cost || h.d_out_weight || h.d_out_counts ||
+        h.basis) plain = false;
     smem_a = max(smem_a, stage_a_smem(h));
     max_wids = max(max_wids, h.n_wids);
     max_up = max(max_up, h.n_upeaks);
