@@ -611,7 +611,10 @@ constexpr int A_MAX_K = 255, A_MAX_CAND = 65535;  // limits of the packed okt wo
 // the top LUT_BITS bits.  A cell stores the index of its first value; bit 15 marks the few cells (about n_u
 // of 2^LUT_BITS) that a CDF boundary may cross - only those walk the records, so a warp usually takes the
 // two-load path with all lanes.
-constexpr int LUT_BITS = 12;
+#ifndef RB2_LUT_BITS
+#define RB2_LUT_BITS 12
+#endif
+constexpr int LUT_BITS = RB2_LUT_BITS;
 constexpr unsigned short LUT_CHECK = 0x8000u;
 __device__ __forceinline__ int find_peak(const TablesA& t, unsigned u, PeakRec& r) {
   const unsigned short e = t.lut[u >> (32 - LUT_BITS)];
@@ -1051,7 +1054,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   const double lsq_xc = 0.5 * (d.pix_min + d.pix_max);
   const double lsq_xsc = (d.pix_max > d.pix_min) ? 2.0 / (d.pix_max - d.pix_min) : 1.0;
   const int qs = pipe.qs;
-  unsigned c_drawn = 0, c_abort = 0, c_icpt = 0;
+  unsigned c_drawn = 0, c_abort = 0, c_icpt = 0, w_pass = 0;  // w_pass: survivors of this warp (warp-uniform)
   const bool diag = !PLAIN && (d.d_out_status != nullptr || d.d_out_coeffs != nullptr || d.d_out_sample != nullptr);  // parity / diagnostics launches only
   const bool out_sample = !PLAIN && d.d_out_sample != nullptr;
   const bool other_basis = !PLAIN && d.basis != 0;
@@ -1190,9 +1193,14 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
       }
     }
     const unsigned pm = __ballot_sync(0xffffffffu, pass);
-    c_drawn += active && !aborted;
-    c_abort += active && aborted;
-    c_icpt += active && !aborted && !pass;
+    if constexpr (FAST && PLAIN) {  // drawn / intercept follow from the ids this warp owns (closed form below)
+      if (slow) c_abort += active && aborted;
+      w_pass += (unsigned)__popc(pm);
+    } else {
+      c_drawn += active && !aborted;
+      c_abort += active && aborted;
+      c_icpt += active && !aborted && !pass;
+    }
     if (pm) {  // warp-aggregated push
       const unsigned n_push = (unsigned)__popc(pm), rank = (unsigned)__popc(pm & ((1u << lane) - 1u));
       unsigned slot;
@@ -1230,9 +1238,24 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
     }
   }
   // counters: warp -> block -> global
-  c_drawn = __reduce_add_sync(0xffffffffu, c_drawn);
   c_abort = __reduce_add_sync(0xffffffffu, c_abort);
-  c_icpt = __reduce_add_sync(0xffffffffu, c_icpt);
+  if constexpr (FAST && PLAIN) {
+    // every id of the warp's strided ranges below the end of the chunk / of the call is handled exactly once
+    // (in a stream round, or in a deferred round): 32 per full round + the one partial round
+    long long L = min(chunk_len, n_hyp - chunk_begin);
+    const long long b0 = (long long)blockIdx.x * RS_THREADS + (tid - lane);
+    long long owned = 0;
+    if (L > b0) {
+      const long long n_full = (L - b0 >= 32) ? (L - b0 - 32) / stride + 1 : 0;
+      const long long start = b0 + n_full * stride;
+      owned = 32 * n_full + ((start < L) ? min(32ll, L - start) : 0ll);
+    }
+    c_drawn = (unsigned)owned - c_abort;
+    c_icpt = c_drawn - w_pass;
+  } else {
+    c_drawn = __reduce_add_sync(0xffffffffu, c_drawn);
+    c_icpt = __reduce_add_sync(0xffffffffu, c_icpt);
+  }
   if (lane == 0) { atomicAdd(&s_cnt[0], c_drawn); atomicAdd(&s_cnt[1], c_abort); atomicAdd(&s_cnt[2], c_icpt); }
   __syncthreads();
   if (tid == 0) {
