@@ -1399,6 +1399,74 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
   }
   __syncwarp();
   const unsigned total_warps = gridDim.x * RS_WARPS;
+  if constexpr (SINGLE) {
+    // One problem with at most 64 peaks (every single-spectrum fit): a lane always handles the same two peaks,
+    // so their pixels and the first MATCH_UNROLL entries of their candidate lists stay in REGISTERS for the whole
+    // kernel - an entry costs no table loads and no per-peak staging, only the polynomial, the comparisons and the
+    // two 64-bit minima (half the instructions of the general loop below).  Same arithmetic, same order of the
+    // per-lane error sums.
+    if (n_u <= 64) {
+      const int u0 = lane, u1 = lane + 32;
+      const bool v0 = u0 < n_u, v1 = u1 < n_u;
+      const double x0 = v0 ? t_peaks[u0] : 0.0, x1 = v1 ? t_peaks[u1] : 0.0;
+      const int ob0 = v0 ? t_coff[u0] : 0, oe0 = v0 ? t_coff[u0 + 1] : 0;
+      const int ob1 = v1 ? t_coff[u1] : 0, oe1 = v1 ? t_coff[u1 + 1] : 0;
+      double cw0[MATCH_UNROLL], cw1[MATCH_UNROLL];
+      int wi0[MATCH_UNROLL], wi1[MATCH_UNROLL];
+#pragma unroll
+      for (int j = 0; j < MATCH_UNROLL; ++j) {  // a missing entry: +inf never is a (strict) minimum
+        cw0[j] = (ob0 + j < oe0) ? t_cwave[ob0 + j] : CUDART_INF; wi0[j] = (ob0 + j < oe0) ? t_cwid[ob0 + j] : -1;
+        cw1[j] = (ob1 + j < oe1) ? t_cwave[ob1 + j] : CUDART_INF; wi1[j] = (ob1 + j < oe1) ? t_cwid[ob1 + j] : -1;
+      }
+      auto nearest = [&](double fit, const double (&cw)[MATCH_UNROLL], const int (&wi)[MATCH_UNROLL], int ob, int oe,
+                         double& be, int& bw) {
+        be = CUDART_INF; bw = -1;
+#pragma unroll
+        for (int j = 0; j < MATCH_UNROLL; ++j) {
+          const double er = fabs(sub(fit, cw[j]));
+          if (er < be) { be = er; bw = wi[j]; }  // first minimum wins (calibrator.py:341-354)
+        }
+        for (int k = ob + MATCH_UNROLL; k < oe; ++k) {  // lists longer than the default top-N
+          const double er = fabs(sub(fit, t_cwave[k]));
+          if (er < be) { be = er; bw = t_cwid[k]; }
+        }
+      };
+      for (unsigned e = blockIdx.x * RS_WARPS + warp; e < n; e += total_warps) {
+        const double* q = pipe.qb + (size_t)e * qs;
+        double cr[deg_cap(DEG_T) + 1];
+#pragma unroll
+        for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? q[k] : 0.0;
+        double be0, be1;
+        int bw0, bw1;
+        nearest(horner_ref<deg_cap(DEG_T)>(cr, ncoef, x0), cw0, wi0, ob0, oe0, be0, bw0);
+        nearest(horner_ref<deg_cap(DEG_T)>(cr, ncoef, x1), cw1, wi1, ob1, oe1, be1, bw1);
+        const unsigned long long bits0 = (unsigned long long)__double_as_longlong(be0);
+        const unsigned long long bits1 = (unsigned long long)__double_as_longlong(be1);
+        if (bw0 >= 0) atomicMin(&berr[bw0], bits0);
+        if (bw1 >= 0) atomicMin(&berr[bw1], bits1);
+        __syncwarp();
+        double esum = 0.0;
+        int nm = 0, ni = 0;
+        if (bw0 >= 0 && berr[bw0] == bits0 && atomicCAS(&berr[bw0], bits0, INF_BITS) == bits0) {
+          double er = be0;
+          if (er > tol) er = tol;  // M-SAC clip (:611)
+          esum += er; ++nm; ni += (er < tol);
+        }
+        if (bw1 >= 0 && berr[bw1] == bits1 && atomicCAS(&berr[bw1], bits1, INF_BITS) == bits1) {
+          double er = be1;
+          if (er > tol) er = tol;
+          esum += er; ++nm; ni += (er < tol);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+        nm = __reduce_add_sync(0xffffffffu, nm);
+        ni = __reduce_add_sync(0xffffffffu, ni);
+        if (lane == 0) { pipe.res_esum[e] = esum; pipe.res_cnt[e] = make_int2(nm, ni); }
+        __syncwarp();
+      }
+      return;
+    }
+  }
   for (unsigned e = blockIdx.x * RS_WARPS + warp; e < n; e += total_warps) {
     const double* q = pipe.qb + (size_t)e * qs;
     double cr[deg_cap(DEG_T) + 1];
