@@ -1406,6 +1406,10 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
     // two 64-bit minima (half the instructions of the general loop below).  Same arithmetic, same order of the
     // per-lane error sums.
     if (n_u <= 64) {
+      unsigned* const t_hi = reinterpret_cast<unsigned*>(berr);  // [max_wids] high words, 0xffffffff = empty
+      unsigned* const t_lo = t_hi + max_wids;                    // [max_wids] low words
+      for (int i = lane; i < 2 * max_wids; i += 32) t_hi[i] = 0xffffffffu;
+      __syncwarp();
       const int u0 = lane, u1 = lane + 32;
       const bool v0 = u0 < n_u, v1 = u1 < n_u;
       const double x0 = v0 ? t_peaks[u0] : 0.0, x1 = v1 ? t_peaks[u1] : 0.0;
@@ -1440,19 +1444,30 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
         int bw0, bw1;
         nearest(horner_ref<deg_cap(DEG_T)>(cr, ncoef, x0), cw0, wi0, ob0, oe0, be0, bw0);
         nearest(horner_ref<deg_cap(DEG_T)>(cr, ncoef, x1), cw1, wi1, ob1, oe1, be1, bw1);
-        const unsigned long long bits0 = (unsigned long long)__double_as_longlong(be0);
-        const unsigned long long bits1 = (unsigned long long)__double_as_longlong(be1);
-        if (bw0 >= 0) atomicMin(&berr[bw0], bits0);
-        if (bw1 >= 0) atomicMin(&berr[bw1], bits1);
+        // 64-bit minimum per wavelength from NATIVE 32-bit shared atomics (a 64-bit shared atomicMin is a
+        // compare-and-swap loop: it was a quarter of this path's instructions): errors are non-negative doubles, so
+        // their bit patterns order like the values - minimum of the high words, then, among the peaks that hold it,
+        // minimum of the low words; the peak that holds both claims the line with a CAS on the high word that also
+        // resets the slot (equal errors: either peak, same cost).
+        const unsigned hi0 = (unsigned)__double2hiint(be0), lo0 = (unsigned)__double2loint(be0);
+        const unsigned hi1 = (unsigned)__double2hiint(be1), lo1 = (unsigned)__double2loint(be1);
+        if (bw0 >= 0) atomicMin(&t_hi[bw0], hi0);
+        if (bw1 >= 0) atomicMin(&t_hi[bw1], hi1);
+        __syncwarp();
+        const bool f0 = bw0 >= 0 && t_hi[bw0] == hi0, f1 = bw1 >= 0 && t_hi[bw1] == hi1;
+        if (f0) atomicMin(&t_lo[bw0], lo0);
+        if (f1) atomicMin(&t_lo[bw1], lo1);
         __syncwarp();
         double esum = 0.0;
         int nm = 0, ni = 0;
-        if (bw0 >= 0 && berr[bw0] == bits0 && atomicCAS(&berr[bw0], bits0, INF_BITS) == bits0) {
+        if (f0 && t_lo[bw0] == lo0 && atomicCAS(&t_hi[bw0], hi0, 0xffffffffu) == hi0) {
+          t_lo[bw0] = 0xffffffffu;
           double er = be0;
           if (er > tol) er = tol;  // M-SAC clip (:611)
           esum += er; ++nm; ni += (er < tol);
         }
-        if (bw1 >= 0 && berr[bw1] == bits1 && atomicCAS(&berr[bw1], bits1, INF_BITS) == bits1) {
+        if (f1 && t_lo[bw1] == lo1 && atomicCAS(&t_hi[bw1], hi1, 0xffffffffu) == hi1) {
+          t_lo[bw1] = 0xffffffffu;
           double er = be1;
           if (er > tol) er = tol;
           esum += er; ++nm; ni += (er < tol);
