@@ -1053,14 +1053,17 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   const long long n_hyp = d.n_hyp;
   const double lsq_xc = 0.5 * (d.pix_min + d.pix_max);
   const double lsq_xsc = (d.pix_max > d.pix_min) ? 2.0 / (d.pix_max - d.pix_min) : 1.0;
-  const int qs = pipe.qs;
+  const int qs = FAST ? DEG_T + 2 : pipe.qs;
   unsigned c_drawn = 0, c_abort = 0, c_icpt = 0, w_pass = 0;  // w_pass: survivors of this warp (warp-uniform)
   const bool diag = !PLAIN && (d.d_out_status != nullptr || d.d_out_coeffs != nullptr || d.d_out_sample != nullptr);  // parity / diagnostics launches only
   const bool out_sample = !PLAIN && d.d_out_sample != nullptr;
   const bool other_basis = !PLAIN && d.basis != 0;
 
   const long long stride = (long long)gridDim.x * RS_THREADS;
-  long long base = (long long)blockIdx.x * RS_THREADS + (tid - lane);
+  // ids of this chunk that exist (a chunk is at most 2^26 ids: 32-bit arithmetic in the loop)
+  const unsigned limit = (unsigned)max(0ll, min(chunk_len, n_hyp - chunk_begin));
+  const unsigned stride32 = (unsigned)stride;
+  unsigned base = (unsigned)(blockIdx.x * RS_THREADS + (tid - lane));
   unsigned qn = 0u;  // hypotheses in this warp's deferred queue (warp-uniform)
   unsigned* const s_q = s_defer[warp];
   // Queue-A slots.  One returning atomic per warp iteration on ONE address was the largest single stall of this
@@ -1071,7 +1074,7 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
   bool pg_have = false;
   if (paged && lane == 0) pg_next = atomicAdd(&pipe.counts[0], QA_PAGE);
   for (;;) {
-    const bool stream_left = base < chunk_len;
+    const bool stream_left = base < limit;
     bool slow = false, active = false;
     unsigned rel = 0u;  // hypothesis index inside the chunk
     if (FAST && (qn >= 32u || (!stream_left && qn > 0u))) {
@@ -1082,9 +1085,9 @@ ransac_draw_fit_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, lon
       qn -= take;
       __syncwarp();
     } else if (stream_left) {
-      rel = (unsigned)(base + lane);
-      active = (base + lane < chunk_len) && (chunk_begin + base + lane < n_hyp);
-      base += stride;
+      rel = base + (unsigned)lane;
+      active = rel < limit;
+      base += stride32;
     } else {
       break;
     }
@@ -1276,7 +1279,7 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
   __shared__ unsigned s_pend[256 / 32][64];
   const unsigned n = min(pipe.counts[0], pipe.cap_a);
   const int lane = threadIdx.x & 31;
-  const int qs = pipe.qs, ncoef = qs - 1;
+  const int qs = DEG_T > 0 ? DEG_T + 2 : pipe.qs, ncoef = qs - 1;
   const unsigned total = gridDim.x * blockDim.x;
   unsigned* const pend = s_pend[threadIdx.x >> 5];
   unsigned np = 0u;  // parked entries (warp-uniform)
@@ -1364,15 +1367,18 @@ ransac_monotonic_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb
 // claims the slot with a CAS that also resets it (equal errors: either peak, same cost).
 // Output per entry: sum of the clipped errors, match count, inlier count.
 constexpr int MATCH_UNROLL = 5;  // the reference's default top_n_candidate
+#ifndef RB2_C1_MIN_CTAS
+#define RB2_C1_MIN_CTAS 4
+#endif
 template <int DEG_T, bool SINGLE = false>  // SINGLE: one problem in the call, its tables staged in shared memory
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, RB2_C1_MIN_CTAS)
 ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int max_wids, int max_up) {
   constexpr bool single = SINGLE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned n = pipe.counts[1];
-  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1;
+  const int qs = DEG_T > 0 ? DEG_T + 2 : pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1;
   const size_t per_warp = (size_t)max_wids + max_up + (max_up + 1) / 2;  // in doubles
   unsigned long long* berr = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * per_warp;
   double* s_be = reinterpret_cast<double*>(berr + max_wids);
@@ -1435,11 +1441,23 @@ ransac_match_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
           if (er < be) { be = er; bw = t_cwid[k]; }
         }
       };
+      double cn[deg_cap(DEG_T) + 1];  // the NEXT entry's coefficients: loaded one entry ahead (queue B is in L2 / DRAM)
+      {
+        const unsigned e0 = blockIdx.x * RS_WARPS + warp;
+#pragma unroll
+        for (int k = 0; k <= deg_cap(DEG_T); ++k) cn[k] = (k < ncoef && e0 < n) ? pipe.qb[(size_t)e0 * qs + k] : 0.0;
+      }
       for (unsigned e = blockIdx.x * RS_WARPS + warp; e < n; e += total_warps) {
-        const double* q = pipe.qb + (size_t)e * qs;
         double cr[deg_cap(DEG_T) + 1];
 #pragma unroll
-        for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = (k < ncoef) ? q[k] : 0.0;
+        for (int k = 0; k <= deg_cap(DEG_T); ++k) cr[k] = cn[k];
+        {
+          const unsigned en = e + total_warps;
+          if (en < n) {
+#pragma unroll
+            for (int k = 0; k <= deg_cap(DEG_T); ++k) if (k < ncoef) cn[k] = pipe.qb[(size_t)en * qs + k];
+          }
+        }
         double be0, be1;
         int bw0, bw1;
         nearest(horner_ref<deg_cap(DEG_T)>(cr, ncoef, x0), cw0, wi0, ob0, oe0, be0, bw0);
@@ -1648,7 +1666,7 @@ __global__ void __launch_bounds__(256)
 ransac_weight_general_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned n = pipe.counts[1];
-  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
+  const int qs = DEG_T > 0 ? DEG_T + 2 : pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
   const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
   for (unsigned g = blockIdx.x * (blockDim.x >> 5) + warp; g * 32u < n; g += total_warps) {
     const unsigned e = g * 32u + lane;
@@ -1701,7 +1719,7 @@ __global__ void __launch_bounds__(128, 4)
 ransac_cost_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, rb2_ransac_result* __restrict__ result) {
   const unsigned n = pipe.counts[1];
   const int lane = threadIdx.x & 31;
-  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
+  const int qs = DEG_T > 0 ? DEG_T + 2 : pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1, deg = ncoef - 1;
   const unsigned total = gridDim.x * blockDim.x;
   for (unsigned e0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); e0 < n; e0 += total) {
     const unsigned e = e0 + lane;
@@ -1779,7 +1797,7 @@ ransac_exact_kernel(const rb2_ransac_desc* __restrict__ descs, Pipe pipe, int ma
   constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned n = pipe.counts[1];
-  const int qs = pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1;
+  const int qs = DEG_T > 0 ? DEG_T + 2 : pipe.qs, ncoef = DEG_T > 0 ? DEG_T + 1 : qs - 1;
   unsigned long long* berr = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * max_wids;
   for (int i = lane; i < max_wids; i += 32) berr[i] = INF_BITS;
   __syncwarp();
