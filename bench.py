@@ -418,7 +418,7 @@ def reference_arm(args):
 def k3_profile(key):
     """Figures of the K3 stage kernels from the committed `ncu --set full` capture (profiles/k3_traffic.json):
     "dram_bytes_per_chunk" = DRAM read + write bytes of the six stage kernels of one chunk ("hypotheses_per_chunk" ids,
-    2^24 in a 1e8-hypothesis step), "issue_slots_busy_pct" = issue-slot utilisation per stage kernel; None if the
+    3.3e7 in a 1e8-hypothesis step), "issue_slots_busy_pct" = issue-slot utilisation per stage kernel; None if the
     file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
@@ -998,13 +998,13 @@ def main():
         "e2e": e2e,
         "sequential": sequential,
         # K3 = pipe_init + 8 kernels (reset, draw_fit, monotonic, match, cost, general weight, exact, record) per
-        # 2^24-hypothesis chunk + pipe_join; + merge after the all-gather (N > 1) + K4 refit
+        # chunk + pipe_join; + merge after the all-gather (N > 1) + K4 refit
         "gpu_launches": (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": k3_traffic(),
                      "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant: 65 % of K3's instructions) + "
                                "monotonic + match + cost + exact + record, timed together per step; traffic = DRAM "
-                               "bytes of one 2^24-hypothesis chunk's six kernels (ncu, caches flushed)",
+                               "bytes of one chunk's six kernels (profiles/k3_traffic.json: hypotheses_per_chunk; ncu, caches flushed)",
                      "issue_slots_busy_pct": k3_profile("issue_slots_busy_pct"),
                      "flops_per_hypothesis": F, "f_intercept_pass": f_i,
                      "f_scored": f_m, "peak_source": "DFMA microbenchmark in this run (rb2_dfma_burn); FP64 is not in MEASURED_PEAKS.json",

@@ -277,7 +277,7 @@ typedef struct {
   uint64_t counters[8];                 /* drawn, aborted, intercept, monotonic, empty, scored, eligible, unsupported */
 } rb2_ransac_result;
 
-/* Chunks of up to 2^24 hypothesis ids alternate over internal stream lanes that fork
+/* Chunks of up to 2^25 hypothesis ids alternate over internal stream lanes that fork
  * from and join back into `stream` (events; capturable); everything the call
  * enqueues is ordered after prior work on `stream` and before later work on it.
  * One host thread per device drives this entry point.

@@ -1954,7 +1954,9 @@ namespace rb2 {
 static unsigned pipe_chunk() {
   static const unsigned n = [] {
     const char* e = getenv("RB2_PIPE_CHUNK_LOG2");
-    const int v = e ? atoi(e) : 24;  // measured on B200 (C3, 1e8 hypotheses): 2^21 1.61, 2^22 1.76, 2^23 1.87, 2^24 1.89 e10 hyp/s
+    // measured on B200 (C3, 1e8 hypotheses, K3 alone): 2^23 4.03, 2^24 3.84, 2^25 3.61, 2^26 3.65 ms - a 1e8-hypothesis
+    // call is then ONE chunk of 3.3e7 ids per lane (the queues of the three lanes take 18 GB of the 180 GB)
+    const int v = e ? atoi(e) : 25;
     return 1u << (v < 12 ? 12 : (v > 26 ? 26 : v));
   }();
   return n;

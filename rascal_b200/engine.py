@@ -699,7 +699,7 @@ _SCRATCH = {}
 
 
 def ransac_scratch(nbytes):
-    """K3's survivor queues (rb2_ransac_scratch_bytes: several GB at the default chunk of 2^24 hypotheses):
+    """K3's survivor queues (rb2_ransac_scratch_bytes: 18 GB at the default chunk capacity of 2^25 hypotheses and three lanes):
     ONE grow-only buffer per device and process.  Every K3 call is ordered on the caller's stream, so calls
     can share it; allocating it per call would cost more than most fits."""
     torch = _torch()

@@ -276,7 +276,7 @@ def test_philox_hypotheses_agree_with_oracle():
 
 
 def test_large_call_equals_its_small_parts():
-    """A call big enough for 2^24-id chunks - stage A then reserves queue-A slots a page ahead and leaves
+    """A call big enough for large (> 1e7-id) chunks - stage A then reserves queue-A slots a page ahead and leaves
     tagged holes for stage B to skip (ransac.cu, QA_PAGE) - selects the same winner and counts the same
     outcomes as the same id range evaluated in small calls, which use the per-iteration atomic and other
     chunk lengths (rb2_ransac_chunk_plan)."""

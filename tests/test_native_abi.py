@@ -60,16 +60,16 @@ def test_argument_validation_without_device(lib):
 
 def test_chunk_plan_covers_every_call(lib):
     """rb2_ransac_chunk_plan is host logic (no device): the chunks cover the call, one chunk never exceeds the queue
-    capacity of 2^24 entries over all problems, small calls are not cut below 2^23 ids in total."""
+    capacity of 2^25 entries over all problems, small calls are not cut below 2^23 ids in total."""
     pp, nc, nl = C.c_longlong(0), C.c_int(0), C.c_int(0)
     for n_problems, max_hyp in [(1, 100_000_000), (1, 12_500_000), (1, 1), (1, 0), (2048, 10_000), (7, 3_000_001),
                                 (1 << 20, 5), (1, (1 << 40) - 1)]:
         assert lib.rb2_ransac_chunk_plan(n_problems, max_hyp, C.byref(pp), C.byref(nc), C.byref(nl)) == 0
-        assert pp.value >= 1 and pp.value * n_problems <= max(1 << 24, n_problems)
+        assert pp.value >= 1 and pp.value * n_problems <= max(1 << 25, n_problems)
         assert nc.value * pp.value >= max_hyp and (nc.value - 1) * pp.value < max(max_hyp, 1)
         assert 1 <= nl.value <= 4 and nl.value <= max(nc.value, 1)
         if nc.value > 1:
-            assert pp.value * n_problems > (1 << 23) - n_problems or pp.value == (1 << 24) // n_problems
+            assert pp.value * n_problems > (1 << 23) - n_problems or pp.value == (1 << 25) // n_problems
     assert lib.rb2_ransac_chunk_plan(0, 10, None, None, None) == -2
     assert lib.rb2_ransac_chunk_plan(1, -1, None, None, None) == -2
 
