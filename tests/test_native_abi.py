@@ -36,6 +36,12 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, name), name
 
 
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md shows, per entry point, the reference code it replaces: none may be missing."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [f for f in header_functions() if f not in doc] == []
+
+
 def test_struct_layouts(lib):
     from rascal_b200 import _native
 
