@@ -18,10 +18,14 @@ deterministic).  Third-party arithmetic (``np.histogram2d``, ``polyfit``,
 ``RandomState``) is *called*, not restated, exactly as the reference calls it.
 
 Every function cites the reference lines (``src/rascal/...``) it follows.
-Deliberate canonicalisation (one place only): bin ranking ties.  The reference
-uses NumPy's default unstable argsort; we use
+Deliberate canonicalisation (two places): ties of the reference's two default
+(unstable, build- and CPU-dependent) argsorts.  Bin ranking: we use
 ``argsort(kind='stable')[::-1]`` = descending count, ties by descending flat
-index.
+index.  Per-peak aggregate ranking in
+``most_common_candidates`` (calibrator.py:212): ``argsort(-agg, kind='stable')``;
+ties only occur in practice with ``candidate_weighted=False`` (integer counts).
+``tests/test_oracle_live_reference.py`` holds this module to the live reference
+on new random problems.
 """
 
 from __future__ import annotations
