@@ -2050,25 +2050,38 @@ struct ChunkArgs {
   bool general_weight;  // some problem carries the spline tables of the general Hough-density weight
 };
 
+// Dynamic shared memory each kernel has been opted in for, per device.  The attribute is a CAP once set - a
+// later launch that asks for more fails with "invalid argument" even below the 48 KB a kernel may use without any
+// opt-in - so it only ever grows and never sits below 48 KB, and the record is kept per KERNEL: the match and the
+// exact kernel are shared by the exactly determined and the least-squares instantiation of launch_chunk (a call
+// sequence exact / over-determined / exact at one degree used to lower the cap under the third call's request).
+template <int DEG_T> struct SmemOptIn { static size_t c[64], x[64]; };
+template <int DEG_T> size_t SmemOptIn<DEG_T>::c[64] = {};
+template <int DEG_T> size_t SmemOptIn<DEG_T>::x[64] = {};
+constexpr size_t SMEM_NO_OPT_IN = 48 * 1024;
+
 template <int DEG_T, bool LSQ = false>
 static int launch_chunk(const ChunkArgs& a) {
-  // the opt-in for dynamic shared memory is per function and per device and only grows
-  static size_t cfg_a[64] = {}, cfg_c[64] = {}, cfg_x[64] = {};
+  static size_t cfg_a[64] = {};  // ransac_draw_fit_kernel<DEG_T, LSQ, *>: kernels of this instantiation only
+  size_t* const cfg_c = SmemOptIn<DEG_T>::c;
+  size_t* const cfg_x = SmemOptIn<DEG_T>::x;
   int dev = 0;
   RB2_CHECK(cudaGetDevice(&dev));
   dev = (dev >= 0 && dev < 64) ? dev : 0;
   if (a.smem_a > cfg_a[dev]) {
-    RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_a)));
+    const size_t cap = max(a.smem_a, SMEM_NO_OPT_IN);
+    RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap)));
     if (!LSQ && DEG_T > 0)
-      RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ, (!LSQ && DEG_T > 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_a)));
-    cfg_a[dev] = a.smem_a;
+      RB2_CHECK((cudaFuncSetAttribute(ransac_draw_fit_kernel<DEG_T, LSQ, (!LSQ && DEG_T > 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap)));
+    cfg_a[dev] = cap;
   }
   if (a.smem_c > cfg_c[dev]) {
-    RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_c));
-    RB2_CHECK((cudaFuncSetAttribute(ransac_match_kernel<DEG_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_c)));
-    cfg_c[dev] = a.smem_c;
+    const size_t cap = max(a.smem_c, SMEM_NO_OPT_IN);
+    RB2_CHECK(cudaFuncSetAttribute(ransac_match_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    RB2_CHECK((cudaFuncSetAttribute(ransac_match_kernel<DEG_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap)));
+    cfg_c[dev] = cap;
   }
-  if (a.smem_x > cfg_x[dev] && a.smem_x > 48 * 1024) {
+  if (a.smem_x > cfg_x[dev] && a.smem_x > SMEM_NO_OPT_IN) {
     RB2_CHECK(cudaFuncSetAttribute(ransac_exact_kernel<DEG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_x));
     cfg_x[dev] = a.smem_x;
   }

@@ -177,7 +177,7 @@ def test_replay_selects_reference_winner(golden, request):
     case = request.node.callspec.id
     print("COEFF_GAP %s: device-recording %.2e  device-exact %.2e  recording-exact %.2e  scipy(now)-recording %.2e"
           % (case, rel(coeffs, g["fit_coeff"]), rel(coeffs, exact), rel(g["fit_coeff"], exact), rel(ref, g["fit_coeff"])))
-    gap = COEFF_GAP[case]
+    gap = COEFF_GAP.get(case, 2e-5)  # cases without a measured entry: the widest measured gap
     assert np.allclose(coeffs, g["fit_coeff"], rtol=gap, atol=atol)
     assert np.allclose(coeffs, exact, rtol=max(gap, 10 * rel(g["fit_coeff"], exact)), atol=atol)
     # (the returned fit_coeff is models.robust_polyfit's MONOMIAL vector for every fit_type)

@@ -1,0 +1,28 @@
+"""The oracle against the recordings of the random problems tests/live_problems.py::LIVE_CASES (unweighted vote,
+filter_close, over-determined samples, hough_weight != 1, Legendre / Chebyshev at degree 3 / 4): the same bit-exact
+bars as tests/test_oracle_golden.py.  The fixtures exist so that the DEVICE path meets these problems on the GPU
+box (tests/test_gpu_live_cases.py); tests/test_oracle_live_reference.py draws further ones against the live
+reference where its checkout exists."""
+import pytest
+
+from tests import test_oracle_golden as T
+from tests.conftest import load_golden
+from tests.live_problems import LIVE_CASES
+
+
+@pytest.fixture(scope="module", params=LIVE_CASES)
+def live(request):
+    return load_golden("live_%d" % request.param)
+
+
+def test_hough_and_candidates(live):
+    T.test_limits_and_pairs(live)
+    T.test_hough_points_and_histogram(live)
+    T.test_reference_order_is_a_valid_ranking(live)
+    T.test_candidates(live)
+
+
+def test_draws_loop_and_final_model(live, request):
+    T.test_replayed_hypotheses(live)
+    T.test_seeded_loop_reproduces_reference(live, request)
+    T.test_order_independent_rule(live)
