@@ -1,0 +1,136 @@
+"""Host side of the facade against the LIVE reference (no device needed; build container only).
+
+The reference's `Calibrator` and `rascal_b200.calibrator.Calibrator` receive the same random SCRIPT of setter calls -
+constructor with / without a spectrum, `set_calibrator_properties` (num_pix, custom pixel lists with gaps),
+repeated `set_hough_properties` / `set_ransac_properties` calls with partial arguments (explicit value > previous
+value > default, calibrator.py:984-1283), `set_atlas` with and without the polygon constraint (:86-133),
+`set_known_pairs` - and must end in the same state: detector, Hough limits, pair list, every RANSAC property,
+`pix_to_rawpix`.  The reference runs in a subprocess (it needs the numpy-2 shims of tests/golden/make_golden.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN_DIR, ROOT
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src/rascal"),
+                                reason="needs the reference checkout (build container only)")
+
+SCALARS = ["num_pix", "num_slopes", "xbins", "ybins", "min_wavelength", "max_wavelength", "range_tolerance",
+           "linearity_tolerance", "min_slope", "max_slope", "min_intercept", "max_intercept", "sample_size",
+           "top_n_candidate", "linear", "filter_close", "ransac_tolerance", "candidate_weighted", "hough_weight",
+           "minimum_matches", "minimum_peak_utilisation", "minimum_fit_error", "candidate_tolerance", "constrain_poly"]
+
+APPLY = '''
+def apply(Calibrator, make_atlas, script):
+    import numpy as np
+    sp = script["spectrum_len"]
+    c = Calibrator(np.array(script["peaks"]), spectrum=None if sp is None else np.zeros(sp))
+    for name, kw in script["calls"]:
+        if name == "set_atlas":
+            kw = dict(kw)
+            c.set_atlas(make_atlas(kw.pop("lines")), **kw)
+        else:
+            getattr(c, name)(**kw)
+    return c
+
+
+def state(c, scalars, probe):
+    import numpy as np
+    out = {k: (None if getattr(c, k, None) is None else float(getattr(c, k))) for k in scalars}
+    out["pixel_list"] = np.asarray(c.pixel_list, dtype=float).tolist()
+    out["pairs"] = np.asarray(c.pairs, dtype=float).reshape(-1, 2).tolist()
+    out["pix_known"] = None if c.pix_known is None else np.asarray(c.pix_known, dtype=float).tolist()
+    out["wave_known"] = None if c.wave_known is None else np.asarray(c.wave_known, dtype=float).tolist()
+    out["rawpix"] = np.asarray(c.pix_to_rawpix(np.array(probe)), dtype=float).tolist()
+    return out
+'''
+
+REFERENCE_SIDE = APPLY + '''
+import json, sys
+sys.path.insert(0, GOLDEN_DIR)
+import make_golden as M          # the shims + the reference import
+from rascal.atlas import Atlas
+
+def make_atlas(lines):
+    a = Atlas()
+    a.add_user_atlas(elements=["X"] * len(lines), wavelengths=lines)
+    return a
+
+script = json.load(open(SCRIPT))
+print("STATE" + json.dumps(state(apply(M.Calibrator, make_atlas, script), SCALARS, script["probe"])))
+'''
+
+
+def random_script(seed):
+    rng = np.random.default_rng(seed)
+    npix = int(rng.choice([512, 1024, 2048]))
+    peaks = np.sort(rng.uniform(5, npix - 5, int(rng.integers(8, 20))))
+    lines = np.sort(rng.uniform(3800, 8200, int(rng.integers(10, 30))))
+    calls = []
+    mode = int(rng.integers(0, 4))  # how the detector is described
+    spectrum_len = npix if mode in (0, 3) else None
+    if mode == 1:
+        calls.append(("set_calibrator_properties", dict(num_pix=npix)))
+    elif mode == 2:  # neither: 1.1 * max(peaks)
+        calls.append(("set_calibrator_properties", dict(seed=int(rng.integers(0, 99)))))
+    elif mode == 3:  # effective pixels: a chip gap in the pixel list
+        gap = int(rng.integers(20, 60))
+        half = npix // 2
+        calls.append(("set_calibrator_properties",
+                      dict(pixel_list=np.concatenate((np.arange(half), np.arange(half, npix) + gap)).astype(float).tolist())))
+
+    def hough_kw():
+        full = dict(num_slopes=int(rng.choice([500, 2000, 5000])), xbins=int(rng.choice([50, 100, 200])),
+                    ybins=int(rng.choice([50, 100, 200])), min_wavelength=float(rng.uniform(3500, 4500)),
+                    max_wavelength=float(rng.uniform(7500, 8500)), range_tolerance=float(rng.choice([200, 500])),
+                    linearity_tolerance=float(rng.choice([50, 100])))
+        return {k: v for k, v in full.items() if rng.random() < 0.6}
+
+    def ransac_kw():
+        full = dict(sample_size=int(rng.integers(3, 9)), top_n_candidate=int(rng.integers(2, 9)), linear=bool(rng.random() < 0.8),
+                    filter_close=bool(rng.random() < 0.5), ransac_tolerance=float(rng.choice([1, 5, 10])),
+                    candidate_weighted=bool(rng.random() < 0.5), hough_weight=float(rng.choice([0.5, 1.0, 2.0])),
+                    minimum_matches=int(rng.integers(1, 12)), minimum_peak_utilisation=float(rng.uniform(0, 1)),
+                    minimum_fit_error=float(rng.choice([1e-12, 1e-4, 1e-2])))
+        return {k: v for k, v in full.items() if rng.random() < 0.5}
+
+    calls.append(("set_hough_properties", hough_kw()))
+    calls.append(("set_ransac_properties", ransac_kw()))
+    calls.append(("set_atlas", dict(lines=lines.tolist(), candidate_tolerance=float(rng.choice([2.0, 10.0])),
+                                    constrain_poly=bool(rng.random() < 0.5))))
+    if rng.random() < 0.7:  # changing the Hough limits after the atlas regenerates the pairs (:1118-1119)
+        calls.append(("set_hough_properties", hough_kw()))
+    if rng.random() < 0.7:
+        calls.append(("set_ransac_properties", ransac_kw()))
+    if rng.random() < 0.5:
+        k = int(rng.integers(1, 4))
+        calls.append(("set_known_pairs", dict(pix=rng.uniform(0, npix, k).tolist(), wave=rng.uniform(4000, 8000, k).tolist())))
+    return dict(peaks=peaks.tolist(), spectrum_len=spectrum_len, calls=calls,
+                probe=rng.uniform(0, npix, 7).tolist())
+
+
+@pytest.mark.parametrize("seed", range(4100, 4112))
+def test_setter_scripts_end_in_the_reference_state(seed, tmp_path):
+    script = random_script(seed)
+    path = os.path.join(tmp_path, "script.json")
+    with open(path, "w") as f:
+        json.dump(script, f)
+    head = "GOLDEN_DIR, SCRIPT, SCALARS = %r, %r, %r\n" % (GOLDEN_DIR, path, SCALARS)
+    r = subprocess.run([sys.executable, "-c", head + REFERENCE_SIDE], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("STATE")][-1][5:])
+
+    from rascal_b200.calibrator import Calibrator, LineList
+
+    ns = {}
+    exec(APPLY, ns)
+    mine = ns["state"](ns["apply"](Calibrator, LineList, json.loads(json.dumps(script))), SCALARS, script["probe"])
+    for k in SCALARS + ["pix_known", "wave_known"]:
+        assert mine[k] == ref[k], (k, mine[k], ref[k], script["calls"])
+    assert np.array_equal(mine["pixel_list"], ref["pixel_list"])
+    assert np.array_equal(np.array(mine["pairs"]), np.array(ref["pairs"])), script["calls"]
+    assert np.array_equal(mine["rawpix"], ref["rawpix"])
