@@ -26,3 +26,12 @@ def test_draws_loop_and_final_model(live, request):
     T.test_replayed_hypotheses(live)
     T.test_seeded_loop_reproduces_reference(live, request)
     T.test_order_independent_rule(live)
+
+
+def test_host_setup_tables(live):
+    """engine.RansacSetup (the host side of K3's set-up, calibrator.py:441-523) on the same problems: peaks,
+    candidate lists, sampling law, monotonicity range and the Hough-weight spline tables against the oracle."""
+    from tests import test_host_logic as H
+
+    H.test_ransac_setup_tables(live)
+    H.test_weight_tables_reproduce_the_reference_spline(live)

@@ -1,0 +1,97 @@
+"""oracle.match_peaks against the LIVE reference's Calibrator.match_peaks on new random problems (build container
+only): same association, same refit, same residuals / RMS / utilisations where the reference is defined - and the
+reference raises exactly where the oracle reports an ambiguous peak (calibrator.py:1841-1876)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import rascal_oracle as O
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src/rascal"),
+                                reason="needs the reference checkout (build container only)")
+
+REFERENCE_SIDE = '''
+import json, sys, types, warnings
+import numpy as np
+warnings.filterwarnings("ignore")
+sys.modules.setdefault("pynverse", types.ModuleType("pynverse"))
+sys.path.insert(0, "/root/reference/src")
+from rascal.atlas import Atlas
+from rascal.calibrator import Calibrator
+
+out = []
+for p in json.load(open(PROBLEMS)):
+    c = Calibrator(np.array(p["peaks"]), spectrum=np.zeros(p["npix"]))
+    c.set_calibrator_properties(log_level="critical")
+    a = Atlas()
+    a.add_user_atlas(["X"] * len(p["lines"]), list(p["lines"]))
+    c.atlas = a
+    c.polyfit = np.polynomial.polynomial.polyfit   # what fit(fit_type="poly") installs, :1621-1623
+    c.polyval = np.polynomial.polynomial.polyval
+    try:
+        r = c.match_peaks(fit_coeff=np.array(p["coeff"]), tolerance=p["tolerance"], fit_deg=p["fit_deg"])
+    except Exception as e:
+        out.append(dict(error=type(e).__name__))
+        continue
+    out.append(dict(fit_coeff=np.asarray(r[0]).tolist(), matched_peaks=np.asarray(r[1]).tolist(),
+                    matched_atlas=np.asarray(r[2]).tolist(), rms=float(r[3]), residuals=np.asarray(r[4]).tolist(),
+                    peak_utilisation=float(r[5]), atlas_utilisation=float(r[6])))
+print("RESULT" + json.dumps(out))
+'''
+
+
+def random_problems(seed, n):
+    rng = np.random.default_rng(seed)
+    probs = []
+    for _ in range(n):
+        npix = int(rng.choice([1024, 2048]))
+        deg = int(rng.choice([1, 2, 3, 4]))
+        co = [float(rng.uniform(3500, 6000)), float(rng.uniform(1.0, 2.5)), float(rng.uniform(-3e-5, 3e-5)),
+              float(rng.uniform(-4e-9, 4e-9)), float(rng.uniform(-5e-13, 5e-13))][:deg + 1]
+        px = np.sort(rng.uniform(10, npix - 10, int(rng.integers(12, 40))))
+        px = px[np.concatenate(([True], np.diff(px) > 6.0))]
+        true = np.polynomial.polynomial.polyval(px, co)
+        have = rng.random(len(px)) > 0.2
+        extra = rng.uniform(true.min() - 100, true.max() + 100, int(rng.integers(0, 25)))
+        lines = np.sort(np.concatenate((true[have] + rng.normal(0, 0.3, int(have.sum())), extra)))
+        if rng.random() < 0.7:  # mostly the separated atlases on which the reference is defined
+            gap = np.diff(lines)
+            lines = lines[np.concatenate(([True], gap > 25.0))]
+        guess = np.array(co) * (1 + rng.normal(0, 2e-4, deg + 1))  # the solution handed to match_peaks is a bit off
+        probs.append(dict(npix=npix, peaks=(px + rng.normal(0, 0.05, len(px))).tolist(), lines=lines.tolist(), coeff=guess.tolist(),
+                          tolerance=float(rng.choice([2.0, 5.0, 10.0])), fit_deg=deg))
+    return probs
+
+
+@pytest.mark.parametrize("seed", [71, 72, 73])
+def test_match_peaks_equals_the_live_reference(seed, tmp_path):
+    probs = random_problems(seed, 20)
+    path = os.path.join(tmp_path, "problems.json")
+    with open(path, "w") as f:
+        json.dump(probs, f)
+    r = subprocess.run([sys.executable, "-c", "PROBLEMS = %r\n" % path + REFERENCE_SIDE], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][-1][6:])
+    defined = 0
+    for p, want in zip(probs, ref):
+        o = O.match_peaks(np.array(p["peaks"]), np.array(p["lines"]), np.array(p["coeff"]), tolerance=p["tolerance"],
+                          fit_deg=p["fit_deg"])
+        if "error" in want:
+            # the reference only raises for an ambiguous peak or for an association too small to fit
+            assert o["n_ambiguous"] > 0 or len(o["matched_peaks"]) <= p["fit_deg"], (want, o["n_ambiguous"])
+            continue
+        assert o["n_ambiguous"] == 0
+        defined += 1
+        assert np.array_equal(o["matched_peaks"], want["matched_peaks"])
+        assert np.array_equal(o["matched_atlas"], want["matched_atlas"])
+        assert np.array_equal(o["fit_coeff"], want["fit_coeff"])      # the same SciPy call on the same points
+        assert np.array_equal(o["residuals"], want["residuals"]) and o["rms"] == want["rms"]
+        assert want["peak_utilisation"] == len(want["matched_peaks"]) / len(p["peaks"])
+        assert want["atlas_utilisation"] == len(want["matched_peaks"]) / len(p["lines"])
+    assert defined >= 5
