@@ -65,7 +65,11 @@ def enorm(v):
                 s1 = 1.0 + s1 * (x1max / xabs) ** 2
                 x1max = xabs
             else:
-                s1 += (xabs / x1max) ** 2
+                # (a NaN component lands here with x1max still 0: IEEE arithmetic, as in the Fortran / C original,
+                #  gives NaN - Python's float division would raise instead)
+                s1 += (xabs / x1max) ** 2 if x1max != 0.0 else float("nan")
+    if s1 != s1:  # a NaN component: every IEEE evaluation order of the line below gives NaN
+        return float("nan")
     if s1 != 0.0:
         return x1max * math.sqrt(s1 + (s2 / x1max) / x1max)
     if s2 != 0.0:
