@@ -584,7 +584,8 @@ def run_path(peaks, lines, *, num_pix=None, pixel_list=None, num_slopes=2000,
              candidate_weighted=True, hough_weight=1.0, minimum_matches=0,
              minimum_peak_utilisation=0.0, minimum_fit_error=1e-4,
              max_tries=500, fit_deg=4, candidate_tolerance=2.0, seed=None,
-             refit=robust_polyfit, trace=None, timings=None, fit_type="poly"):
+             refit=robust_polyfit, trace=None, timings=None, fit_type="poly",
+             pix_known=None, wave_known=None):
     """do_hough_transform() + fit() of the reference (calibrator.py:1425-1452,
     1552-1715) on explicit inputs.  Returns a dict with every intermediate."""
     import time
@@ -618,7 +619,8 @@ def run_path(peaks, lines, *, num_pix=None, pixel_list=None, num_slopes=2000,
         yedges=ye, hough_weight=hough_weight, filter_close=filter_close,
         minimum_matches=min(minimum_matches, len(lines), len(peaks)),
         minimum_peak_utilisation=minimum_peak_utilisation,
-        minimum_fit_error=minimum_fit_error, n_peaks_total=len(peaks), fit_type=fit_type)
+        minimum_fit_error=minimum_fit_error, n_peaks_total=len(peaks), fit_type=fit_type,
+        pix_known=pix_known, wave_known=wave_known)
     rs = np.random.RandomState(seed)
     best = ransac_sequential(prob, max_tries, rs, refit=refit, trace=trace)
     t3 = time.perf_counter()

@@ -242,11 +242,13 @@ def _trace_arrays(rec, c, s_total):
 
 
 def record_case(name, peaks, lines, *, spectrum=None, calib=None, hough=None,
-                ransac=None, fit=None, seed=0, atlas_kw=None):
+                ransac=None, fit=None, seed=0, atlas_kw=None, known=None):
     calib, hough, ransac, fit = (dict(calib or {}), dict(hough or {}),
                                  dict(ransac or {}), dict(fit or {}))
     cfg = dict(calib=calib, hough=hough, ransac=ransac, fit=fit, seed=seed,
                atlas_kw=atlas_kw or {})
+    if known is not None:  # set_known_pairs (calibrator.py:1507-1550): appended to every sample (:568-573)
+        cfg["known"] = [list(map(float, known[0])), list(map(float, known[1]))]
 
     def build():
         c = Calibrator(peaks, spectrum=spectrum)
@@ -256,6 +258,8 @@ def record_case(name, peaks, lines, *, spectrum=None, calib=None, hough=None,
         a = Atlas()
         a.add_user_atlas(elements=["X"] * len(lines), wavelengths=lines)
         c.set_atlas(a, **(atlas_kw or {}))
+        if known is not None:
+            c.set_known_pairs(known[0], known[1])
         return c
 
     # (1) the reference exactly as shipped: its own (unstable) ranking

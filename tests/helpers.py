@@ -15,6 +15,8 @@ def oracle_from_golden(g, refit=O.robust_polyfit, max_tries=None, trace=None):
     kw.pop("fit_tolerance", None)  # only a warning threshold in Calibrator.fit (:1696)
     if max_tries is not None:
         kw["max_tries"] = max_tries
+    if cfg.get("known"):
+        kw["pix_known"], kw["wave_known"] = (np.array(v, dtype=float) for v in cfg["known"])
     return O.run_path(g["peaks"], g["lines"], pixel_list=g["pixel_list"],
                       seed=cfg["seed"], refit=refit, trace=trace, **kw)
 
@@ -36,4 +38,6 @@ def problem_from_golden(g):
                             len(g["peaks"])),
         minimum_peak_utilisation=r.get("minimum_peak_utilisation", 0.0),
         minimum_fit_error=r.get("minimum_fit_error", 1e-4),
-        n_peaks_total=len(g["peaks"]), fit_type=f.get("fit_type", "poly"))
+        n_peaks_total=len(g["peaks"]), fit_type=f.get("fit_type", "poly"),
+        pix_known=None if not cfg.get("known") else np.array(cfg["known"][0], dtype=float),
+        wave_known=None if not cfg.get("known") else np.array(cfg["known"][1], dtype=float))

@@ -8,7 +8,7 @@ import numpy as np
 LIVE_CASES = [20262, 20264, 30002, 30003, 30006, 30008, 30010, 31003, 31007]
 
 
-def random_problem(seed):
+def random_problem(seed, with_known=False):
     """A small synthetic arc in the style of SURVEY.md 8d (true lines + distractors + spurious peaks), every
     setting drawn from `seed`."""
     rng = np.random.default_rng(seed)
@@ -38,4 +38,10 @@ def random_problem(seed):
     fit_type = str(rng.choice(["poly", "poly", "legendre", "chebyshev"]))  # drawn last: earlier draws keep their values
     if fit_type != "poly":
         spec["fit"]["fit_type"] = fit_type
+    if with_known and rng.random() < 0.6:
+        # set_known_pairs (calibrator.py:1507-1550): a few (pixel, wavelength) pairs the user is sure of, appended to
+        # every sample before the fit (:568-573).  (Not part of the recorded LIVE_CASES fixtures.)
+        k = int(rng.integers(1, 4))
+        kp = rng.uniform(20, npix - 20, k)
+        spec["known"] = [kp.tolist(), (lam(kp) + rng.normal(0, 0.05, k)).tolist()]
     return spec

@@ -2,7 +2,7 @@
 
 The committed goldens pin the oracle on a fixed set of inputs.  Where the reference checkout exists (the build
 container: /root/reference; never the GPU box) these tests draw NEW random problems - peaks, atlas, detector size,
-Hough shape, degree, sample size, tolerances, seed - let the unmodified reference solve them in a subprocess under
+Hough shape, degree, sample size, basis, tolerances, known pairs, seed - let the unmodified reference solve them in a subprocess under
 the recording hooks of tests/golden/make_golden.py, and hold the oracle to the recording exactly as
 tests/test_oracle_golden.py holds it to the fixtures: Hough points (SHA-256), histogram, edges, candidates, the
 complete seeded draw stream with per-draw status / cost, and the final model, bit for bit.
@@ -51,14 +51,14 @@ if {stable_ties}:
     rc.np = StableTies()
 M.record_case(spec["name"], np.array(spec["peaks"]), np.array(spec["lines"]), spectrum=np.zeros(spec["npix"]),
               hough=spec["hough"], ransac=spec["ransac"], fit=spec["fit"], seed=spec["seed"],
-              atlas_kw=dict(candidate_tolerance=spec["fit"]["candidate_tolerance"]))
+              atlas_kw=dict(candidate_tolerance=spec["fit"]["candidate_tolerance"]), known=spec.get("known"))
 """
 
 
 @pytest.fixture(scope="module", params=[20261, 20262, 20263, 20264, 20265, 20266])
 def live(request, tmp_path_factory):
     d = tmp_path_factory.mktemp("live_reference")
-    spec = random_problem(request.param)
+    spec = random_problem(request.param, with_known=True)
     spec_path = os.path.join(d, "spec.json")
     with open(spec_path, "w") as f:
         json.dump(spec, f)
