@@ -55,7 +55,7 @@ M.record_case(spec["name"], np.array(spec["peaks"]), np.array(spec["lines"]), sp
 """
 
 
-@pytest.fixture(scope="module", params=[20261, 20262, 20263, 20264, 20265, 20266])
+@pytest.fixture(scope="module", params=[32000, 32001, 32002, 32003, 32004, 32005])
 def live(request, tmp_path_factory):
     d = tmp_path_factory.mktemp("live_reference")
     spec = random_problem(request.param, with_known=True)
