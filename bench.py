@@ -1002,7 +1002,7 @@ def main():
         "gpu_launches": (2 + 8 * n_chunks + (1 if world > 1 else 0) + 1) * args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": k3_traffic(),
-                     "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant: 65 % of K3's instructions) + "
+                     "kernel": "K3 staged pipeline: ransac_draw_fit_kernel<4> (dominant: 71 % of K3's instructions) + "
                                "monotonic + match + cost + exact + record, timed together per step; traffic = DRAM "
                                "bytes of one chunk's six kernels (profiles/k3_traffic.json: hypotheses_per_chunk; ncu, caches flushed)",
                      "issue_slots_busy_pct": k3_profile("issue_slots_busy_pct"),
