@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Fixtures live_<seed>.npz: the random problems tests/live_problems.py::LIVE_CASES, solved by the UNMODIFIED
+"""Fixtures live_<seed>.npz / live_known_<seed>.npz: the random problems tests/live_problems.py::LIVE_CASES and
+KNOWN_CASES (the latter with set_known_pairs), solved by the UNMODIFIED
 reference under the recording hooks of make_golden.py (same arrays as every other golden).
 
     python tests/golden/make_golden_live.py     # build container only (needs /root/reference)
@@ -18,7 +19,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import make_golden as G  # noqa: E402  (installs the shims, imports the reference)
 import rascal.calibrator as rc  # noqa: E402
-from tests.live_problems import LIVE_CASES, random_problem  # noqa: E402
+from tests.live_problems import KNOWN_CASES, LIVE_CASES, random_problem  # noqa: E402
 
 
 class StableTies:
@@ -32,13 +33,15 @@ class StableTies:
 
 
 def main():
-    for seed in LIVE_CASES:
-        spec = random_problem(seed)
+    for seed, with_known in [(s, False) for s in LIVE_CASES] + [(s, True) for s in KNOWN_CASES]:
+        spec = random_problem(seed, with_known=with_known)
+        assert with_known == ("known" in spec)
         rc.np = np if spec["ransac"]["candidate_weighted"] else StableTies()
         try:
-            G.record_case(spec["name"], np.array(spec["peaks"]), np.array(spec["lines"]), spectrum=np.zeros(spec["npix"]),
+            G.record_case(("live_known_%d" % seed) if with_known else spec["name"], np.array(spec["peaks"]),
+                          np.array(spec["lines"]), spectrum=np.zeros(spec["npix"]),
                           hough=spec["hough"], ransac=spec["ransac"], fit=spec["fit"], seed=spec["seed"],
-                          atlas_kw=dict(candidate_tolerance=spec["fit"]["candidate_tolerance"]))
+                          atlas_kw=dict(candidate_tolerance=spec["fit"]["candidate_tolerance"]), known=spec.get("known"))
         finally:
             rc.np = np
 

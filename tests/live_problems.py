@@ -6,6 +6,8 @@ import numpy as np
 # seeds of the committed fixtures tests/golden/live_<seed>.npz - chosen to cover what the other goldens are thin on:
 # candidate_weighted=False, filter_close, over-determined samples, hough_weight != 1 and the other bases at degree 3 / 4
 LIVE_CASES = [20262, 20264, 30002, 30003, 30006, 30008, 30010, 31003, 31007]
+# the same with set_known_pairs (random_problem(seed, with_known=True)): fixtures tests/golden/live_known_<seed>.npz
+KNOWN_CASES = [32000, 32001, 32005]
 
 
 def random_problem(seed, with_known=False):

@@ -8,7 +8,7 @@ import pytest
 from tests import test_gpu_hough_vote as HV
 from tests import test_gpu_ransac_refit as RR
 from tests.conftest import load_golden
-from tests.live_problems import LIVE_CASES
+from tests.live_problems import KNOWN_CASES, LIVE_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -53,3 +53,16 @@ def test_shared_memory_opt_in_survives_mixed_calls():
         n = min(len(g["tr_status"]), 2000)
         out = rb.run(0, n, replay=(g["tr_x_idx"][:n], g["tr_y_idx"][:n]), per_hypothesis=("status",))
         assert (out["status"] == g["tr_status"][:n].astype("uint8")).all(), case
+
+
+@pytest.mark.parametrize("seed", KNOWN_CASES)
+def test_known_pairs(seed, request):
+    """set_known_pairs (calibrator.py:1507-1550, :568-573): the user's (pixel, wavelength) pairs are appended to every
+    sample, so every hypothesis is a least-squares fit over sample + known rows (rb2_ransac_desc.n_known).  Recorded
+    from the reference with known pairs set; replayed draw for draw, winner and K4's model as for every golden."""
+    g = load_golden("live_known_%d" % seed)
+    assert g["config"]["known"]
+    RR.test_setup_matches_reference_tables(g)
+    RR.test_replay_reference_draws(g)
+    RR.test_replay_with_reference_coefficients_is_decision_exact(g)
+    RR.test_replay_selects_reference_winner(g, request)

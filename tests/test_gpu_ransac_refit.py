@@ -31,6 +31,8 @@ def setup_from_golden(g, **over):
               minimum_peak_utilisation=r.get("minimum_peak_utilisation", 0.0),
               minimum_fit_error=r.get("minimum_fit_error", 1e-4), n_peaks_total=len(g["peaks"]),
               fit_type=f.get("fit_type", "poly"))
+    if cfg.get("known"):  # set_known_pairs: rows appended to every sample (calibrator.py:568-573)
+        kw.update(pix_known=np.array(cfg["known"][0], dtype=float), wave_known=np.array(cfg["known"][1], dtype=float))
     kw.update(over)
     return engine.RansacSetup(g["candidate_peak"], g["candidate_arc"], **kw)
 
@@ -78,7 +80,7 @@ def test_replay_reference_draws(golden):
     # ill-conditioned (numpy's gelsd and any other solver then differ), so: (i) every exactly
     # determined fit passes through its own sample points, (ii) the scored (well-behaved)
     # hypotheses trace the reference's curve over the detector.
-    if s.sample_size == s.deg + 1:
+    if s.sample_size == s.deg + 1 and len(s.known_x) == 0:
         xs = s.peaks[g["tr_x_idx"]]
         ys = np.array([[s.cand_wave[s.cand_off[k] + j] for k, j in zip(rx, ry)]
                        for rx, ry in zip(g["tr_x_idx"], g["tr_y_idx"])])

@@ -7,12 +7,12 @@ import pytest
 
 from tests import test_oracle_golden as T
 from tests.conftest import load_golden
-from tests.live_problems import LIVE_CASES
+from tests.live_problems import KNOWN_CASES, LIVE_CASES
 
 
-@pytest.fixture(scope="module", params=LIVE_CASES)
+@pytest.fixture(scope="module", params=["live_%d" % s for s in LIVE_CASES] + ["live_known_%d" % s for s in KNOWN_CASES])
 def live(request):
-    return load_golden("live_%d" % request.param)
+    return load_golden(request.param)
 
 
 def test_hough_and_candidates(live):
