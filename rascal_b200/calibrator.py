@@ -308,8 +308,12 @@ class Calibrator:
             self.logger.warning("Size of sample_size is larger than the size of atlas, the sample_size is set to "
                                 "match the size of atlas = " + str(len(self.atlas)) + ".")
             self.sample_size = len(self.atlas)
-        if self.sample_size <= self.fit_deg:
-            self.sample_size = self.fit_deg + 1
+        # the reference compares with the fit_deg ARGUMENT (:1651) even when fit_coeff has just set self.fit_deg; where
+        # that would leave a sample smaller than the fitted degree + 1 (a rank-deficient polyfit there) the degree
+        # actually fitted decides
+        need = max(int(fit_deg), int(self.fit_deg))
+        if self.sample_size <= need:
+            self.sample_size = need + 1
         if not self._hough_done:
             self.do_hough_transform()
         if self.minimum_matches > len(self.atlas):
