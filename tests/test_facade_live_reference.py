@@ -175,3 +175,50 @@ def test_setter_scripts_end_in_the_reference_state(seed, tmp_path):
     assert np.array_equal(mine["pixel_list"], ref["pixel_list"])
     assert np.array_equal(np.array(mine["pairs"]), np.array(ref["pairs"])), script["calls"]
     assert np.array_equal(mine["rawpix"], ref["rawpix"])
+
+
+ERROR_CALLS = [
+    ("set_known_pairs", dict(pix=[1.0, 2.0], wave=[3.0])),
+    ("set_known_pairs", dict(pix=[float("nan")], wave=[5000.0])),
+    ("set_known_pairs", dict(pix=["a"], wave=[1.0])),
+    ("set_known_pairs", dict(pix=[100.0], wave=[5000.0])),
+    ("set_known_pairs", dict(pix=100, wave=5000)),
+    ("set_ransac_properties", dict(minimum_matches=0)),
+    ("set_ransac_properties", dict(minimum_peak_utilisation=1.5)),
+    ("set_ransac_properties", dict(minimum_peak_utilisation=-0.1)),
+    ("set_ransac_properties", dict(minimum_fit_error=-1.0)),
+    ("set_ransac_properties", dict(minimum_matches=3, minimum_peak_utilisation=1.0, minimum_fit_error=0.0)),
+    ("set_calibrator_properties", dict(log_level="debug")),
+    ("set_hough_properties", dict(num_slopes=10.0)),
+]
+
+ERROR_SIDE = '''
+def outcomes(Calibrator, calls):
+    import numpy as np
+    out = []
+    for name, kw in calls:
+        c = Calibrator(np.arange(10.0) * 10.0, spectrum=np.zeros(200))
+        try:
+            getattr(c, name)(**kw)
+            out.append("ok")
+        except Exception as e:
+            out.append(type(e).__name__)
+    return out
+'''
+
+
+def test_bad_arguments_raise_what_the_reference_raises(tmp_path):
+    code = ("import json, sys\nsys.path.insert(0, %r)\nimport make_golden as M\n" % GOLDEN_DIR + ERROR_SIDE
+            + "print('RESULT' + json.dumps(outcomes(M.Calibrator, %r)))\n" % (ERROR_CALLS,))
+    r = subprocess.run([sys.executable, "-c", code.replace("nan", "float('nan')")], cwd=ROOT, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][-1][6:])
+
+    from rascal_b200.calibrator import Calibrator
+
+    ns = {}
+    exec(ERROR_SIDE, ns)
+    got = ns["outcomes"](Calibrator, ERROR_CALLS)
+    assert got == want, list(zip([c[0] for c in ERROR_CALLS], got, want))
+    assert "ok" in want and "ValueError" in want and "AssertionError" in want
