@@ -87,9 +87,14 @@ def test_match_peaks_equals_the_live_reference(seed, tmp_path):
             assert o["n_ambiguous"] > 0 or len(o["matched_peaks"]) <= p["fit_deg"], (want, o["n_ambiguous"])
             continue
         assert o["n_ambiguous"] == 0
-        defined += 1
         assert np.array_equal(o["matched_peaks"], want["matched_peaks"])
         assert np.array_equal(o["matched_atlas"], want["matched_atlas"])
+        if len(want["matched_peaks"]) <= p["fit_deg"]:
+            # documented deviation: the reference goes on with a rank-deficient polyfit (RankWarning)
+            # and returns its minimum-norm solution; oracle / K5 / facade stop at the association (ValueError)
+            assert o["fit_coeff"] is None
+            continue
+        defined += 1
         assert np.array_equal(o["fit_coeff"], want["fit_coeff"])      # the same SciPy call on the same points
         assert np.array_equal(o["residuals"], want["residuals"]) and o["rms"] == want["rms"]
         assert want["peak_utilisation"] == len(want["matched_peaks"]) / len(p["peaks"])
